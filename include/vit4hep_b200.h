@@ -1,0 +1,190 @@
+/*
+ * vit4hep_b200 - C ABI of the B200-native CFM-ViT hot path.
+ *
+ * The reference (luigifvr/vit4hep) is 100 % Python and has no FFI of its own; the
+ * boundary it exposes for this path is the nn.Module contract of
+ *   - nn.vit.ViT.forward(x, t, c)                      reference nn/vit.py:185-206
+ *   - CaloChallengeCFM.to_patches / from_patches       reference experiments/calochallenge/calochallenge_cfm/model.py:40-60
+ *   - CFM._batch_loss                                  reference models/base_model.py:203-218
+ *   - CaloChallengeCFM.sample_batch (torchdiffeq rk4)  reference experiments/calochallenge/calochallenge_cfm/model.py:68-94
+ * Each entry point below names the reference interface it stands in for.  The Python
+ * host in vit4hep_b200/ binds these with ctypes and mirrors the
+ * reference's module/class names above them.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - all memory is owned by the caller (PyTorch); nothing here allocates device memory
+ *     except the small per-plan tables created by v4h_plan_create/v4h_geometry_create;
+ *   - every launch goes to the cudaStream_t passed in; calls are asynchronous;
+ *   - return value 0 = success, otherwise a V4H_ERR_* code; v4h_last_error() gives the
+ *     message for the calling thread;
+ *   - there is no CPU fallback: a device that is not sm_100 fails with V4H_ERR_ARCH.
+ */
+#ifndef VIT4HEP_B200_H
+#define VIT4HEP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* v4h_stream_t; /* cudaStream_t */
+
+enum {
+  V4H_OK = 0,
+  V4H_ERR_INVALID = 1,     /* bad shape / null pointer / misalignment */
+  V4H_ERR_CUDA = 2,        /* a CUDA runtime call failed */
+  V4H_ERR_ARCH = 3,        /* device is not sm_100 (B200) */
+  V4H_ERR_UNSUPPORTED = 4  /* a knob the reference never enables (dropout, qk_norm, causal mask ...) */
+};
+
+enum { V4H_FP32 = 0, V4H_BF16 = 1 }; /* arithmetic of the GEMM operands / saved activations */
+
+#define V4H_MAX_DEPTH 32
+#define V4H_MAX_SEGMENTS 16
+
+const char* v4h_last_error(void);
+int v4h_version(void);
+/* 0 when device `dev` is sm_100 and usable, else V4H_ERR_ARCH / V4H_ERR_CUDA */
+int v4h_check_device(int dev);
+
+/* ------------------------------------------------------------------------------------
+ * Geometry: 3D patchify / unpatchify over (layer, angular, radial) voxel grids.
+ * Replaces einops.rearrange in to_patches/from_patches (reference
+ * calochallenge_cfm/model.py:40-60 regular grid; :146-173, experiments/calogan/model.py:60-87,
+ * experiments/calohadronic/model.py:59-86 segmented).  Bit-exact copies.
+ * ------------------------------------------------------------------------------------ */
+typedef struct v4h_geometry v4h_geometry;
+
+/* shapes/patches: n_segments x 3 ints (L, A, R) / (P1, P2, P3); flat_input: the wrapper's
+ * input is (B, C, sum V) split at the segment edges instead of (B, C, L, A, R). */
+int v4h_geometry_create(const int32_t* shapes_host, const int32_t* patches_host, int32_t n_segments,
+                        int32_t in_channels, int32_t flat_input, v4h_geometry** out);
+void v4h_geometry_destroy(v4h_geometry* g);
+int32_t v4h_geometry_tokens(const v4h_geometry* g);
+int32_t v4h_geometry_patch_dim(const v4h_geometry* g);
+int32_t v4h_geometry_voxels(const v4h_geometry* g); /* per sample, channels included */
+/* copies the host-side gather table (tokens.flat[j] = x.flat[table[j]]) for inspection */
+int v4h_geometry_table_host(const v4h_geometry* g, int32_t* table_out_host, int32_t n);
+
+/* to_patches: (B, C, *grid) fp32 -> (B, T, P) fp32 */
+int v4h_to_patches(const v4h_geometry* g, const float* x, float* tokens, int64_t batch, v4h_stream_t s);
+/* from_patches: (B, T, P) fp32 -> (B, C, *grid) fp32 */
+int v4h_from_patches(const v4h_geometry* g, const float* tokens, float* x, int64_t batch, v4h_stream_t s);
+
+/* ------------------------------------------------------------------------------------
+ * The ViT velocity network (reference nn/vit.py ViT / DiTBlock / FinalLayer /
+ * TimestepEmbedder / Attention).  Parameters stay in the caller's nn.Module with the
+ * reference's state_dict names; these structs only carry their device addresses.
+ * ------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t hidden_dim;   /* D   */
+  int32_t depth;
+  int32_t num_heads;    /* H, D % H == 0 */
+  int32_t mlp_hidden;   /* int(D * mlp_ratio) */
+  int32_t patch_dim;    /* P   */
+  int32_t out_dim;      /* P * out_channels */
+  int32_t cond_dim;     /* K   */
+  int32_t tokens;       /* T   */
+  int32_t freq_dim;     /* TimestepEmbedder.frequency_embedding_size (256) */
+  int32_t learn_pos_embed; /* 1: pos_embed_freqs + pos_{z,y,x}; 0: fixed (T, D) table */
+  int32_t precision;    /* V4H_FP32 | V4H_BF16 */
+} v4h_vit_dims;
+
+typedef struct {
+  float *qkv_w, *qkv_b;     /* blocks.i.attn.qkv      (3D, D), (3D) */
+  float *proj_w, *proj_b;   /* blocks.i.attn.proj     (D, D), (D) */
+  float *fc1_w, *fc1_b;     /* blocks.i.mlp.fc1       (Hm, D), (Hm) */
+  float *fc2_w, *fc2_b;     /* blocks.i.mlp.fc2       (D, Hm), (D) */
+  float *ada_w, *ada_b;     /* blocks.i.adaLN_modulation.1  (6D, D), (6D) */
+} v4h_block_params;
+
+/* Used both for the weights (read-only) and for the gradients (written). */
+typedef struct {
+  float *pos_embed_freqs;           /* (D/6)   - null when learn_pos_embed == 0 */
+  float *pos_z, *pos_y, *pos_x;     /* (T) buffers, no gradient */
+  float *pos_embed;                 /* (T, D) fixed table when learn_pos_embed == 0 */
+  float *x_w, *x_b;                 /* x_embedder (D, P), (D) */
+  float *c0_w, *c0_b, *c2_w, *c2_b; /* c_embedder.0 (D, K), c_embedder.2 (D, D) */
+  float *t0_w, *t0_b, *t2_w, *t2_b; /* t_embedder.mlp.0 (D, 256), .2 (D, D) */
+  float *final_w, *final_b;         /* final_layer.linear (out_dim, D) */
+  float *final_ada_w, *final_ada_b; /* final_layer.adaLN_modulation.1 (2D, D) */
+  v4h_block_params blocks[V4H_MAX_DEPTH];
+} v4h_vit_params;
+
+typedef struct v4h_plan v4h_plan;
+
+int v4h_plan_create(const v4h_vit_dims* dims, v4h_plan** out);
+void v4h_plan_destroy(v4h_plan* p);
+
+/* bytes of caller-provided scratch for one forward (save_for_backward = 0) or one
+ * forward + backward (= 1) at this batch size */
+size_t v4h_vit_workspace_bytes(const v4h_plan* p, int64_t batch, int32_t save_for_backward);
+/* bytes of the bf16 weight arena (0 in fp32 precision) */
+size_t v4h_vit_weight_arena_bytes(const v4h_plan* p);
+/* (re)build the bf16 operand copies of the GEMM weights; call whenever a parameter changed */
+int v4h_vit_prepare_weights(v4h_plan* p, const v4h_vit_params* w, void* arena, v4h_stream_t s);
+
+/* ViT.forward: x (B, T, P), t (B, 1), c (B, K) -> out (B, T, out_dim), all fp32.
+ * shared_t != 0: every sample has the same t (ODE sampling, reference
+ * calochallenge_cfm/model.py:81-83) - t then points to ONE float. */
+int v4h_vit_forward(v4h_plan* p, const v4h_vit_params* w, const void* arena,
+                    const float* x, const float* t, const float* c, float* out,
+                    int64_t batch, int32_t shared_t, int32_t save_for_backward,
+                    void* workspace, size_t workspace_bytes, v4h_stream_t s);
+
+/* Backward of the forward that last wrote `workspace` with save_for_backward = 1.
+ * dout (B, T, out_dim) fp32.  Gradients of every parameter are ADDED into `grads`
+ * (same layout as the weights; caller zeroes them).  block_hi/block_lo select a range of
+ * the backward chain so the caller can overlap gradient all-reduce buckets with the rest:
+ * stages run from `stage_begin` down to `stage_end` inclusive where stage depth+1 is the
+ * final layer, stages depth..1 are blocks depth-1..0 and stage 0 is embeddings +
+ * conditioning (the only stage that reads the forward inputs x (B, T, P) and c (B, K)).
+ * Pass (depth+1, 0) for the whole backward. */
+int v4h_vit_backward(v4h_plan* p, const v4h_vit_params* w, const void* arena,
+                     const v4h_vit_params* grads, const float* x, const float* c,
+                     const float* dout, int64_t batch,
+                     int32_t stage_begin, int32_t stage_end,
+                     void* workspace, size_t workspace_bytes, v4h_stream_t s);
+
+/* ------------------------------------------------------------------------------------
+ * CFM training step pieces (reference models/base_model.py:203-218, models/trajectories.py:5-8)
+ * ------------------------------------------------------------------------------------ */
+/* x_t = (1-t) x0 + t x1 and x_t_dot = x1 - x0, both emitted directly in token layout
+ * (B, T, P) through the geometry's gather table; x0/x1 are voxel-layout fp32, t is (B). */
+int v4h_cfm_prepare(const v4h_geometry* g, const float* x1, const float* x0, const float* t,
+                    float* xt_tokens, float* target_tokens, int64_t batch, v4h_stream_t s);
+/* loss = mean((v - target)^2) over n elements -> loss_out[0] (fp32, overwritten);
+ * dv = 2 (v - target) / n * grad_scale (pass dv = NULL to skip) */
+int v4h_cfm_loss(const float* v, const float* target, int64_t n, float grad_scale,
+                 float* loss_out, float* dv, v4h_stream_t s);
+
+/* ------------------------------------------------------------------------------------
+ * ODE sampling, torchdiffeq fixed-grid 'rk4' = 3/8 rule (reference
+ * calochallenge_cfm/model.py:85-92).  out = y + a0*k0 + a1*k1 + a2*k2 + a3*k3 (null k = skipped):
+ * one fused kernel per RK stage/combination.
+ * ------------------------------------------------------------------------------------ */
+int v4h_axpy4(float* out, const float* y, const float* k0, float a0, const float* k1, float a1,
+              const float* k2, float a2, const float* k3, float a3, int64_t n, v4h_stream_t s);
+
+/* ------------------------------------------------------------------------------------
+ * Kernel-level test hooks (used by tests/ to localise parity failures; not needed by a host).
+ * ------------------------------------------------------------------------------------ */
+/* C (m, n) fp32 = op(A) op(B) with row-major inputs.  layout: 0 = NT (A (m,k), B (n,k)),
+ * 1 = NN (A (m,k), B (k,n)), 2 = TN (A (k,m), B (k,n)).  engine: 0 = SIMT fp32 inputs,
+ * 1 = tcgen05 bf16 inputs (A, B are bf16 then). */
+int v4h_test_gemm(int32_t engine, int32_t layout, const void* A, const void* B, float* C,
+                  int32_t m, int32_t n, int32_t k, v4h_stream_t s);
+/* qkv (B, T, 3, H, dh) -> o (B, T, H, dh), lse (B, H, T); precision picks fp32 / bf16 buffers */
+int v4h_test_attention_fwd(int32_t precision, int32_t engine, const void* qkv, void* o, float* lse,
+                           int32_t batch, int32_t tokens, int32_t heads, int32_t head_dim, v4h_stream_t s);
+int v4h_test_attention_bwd(int32_t precision, int32_t engine, const void* qkv, const void* o,
+                           const float* lse, const void* d_o, void* dqkv, int32_t batch, int32_t tokens,
+                           int32_t heads, int32_t head_dim, v4h_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIT4HEP_B200_H */

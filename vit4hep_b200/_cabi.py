@@ -1,0 +1,119 @@
+"""ctypes binding of libvit4hep_b200.so (include/vit4hep_b200.h).
+
+This is the only place the Python host touches native code.  There is no CPU fallback: if the
+library is missing it is built with nvcc; if that is impossible, or a call fails, a
+RuntimeError carrying ``v4h_last_error()`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+V4H_OK = 0
+V4H_FP32, V4H_BF16 = 0, 1
+V4H_MAX_DEPTH = 32
+V4H_MAX_SEGMENTS = 16
+
+_f32p = C.c_void_p  # device pointers travel as integers
+
+
+class VitDims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "hidden_dim", "depth", "num_heads", "mlp_hidden", "patch_dim", "out_dim", "cond_dim",
+        "tokens", "freq_dim", "learn_pos_embed", "precision")]
+
+
+class BlockParams(C.Structure):
+    _fields_ = [(n, _f32p) for n in (
+        "qkv_w", "qkv_b", "proj_w", "proj_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b", "ada_w", "ada_b")]
+
+
+class VitParams(C.Structure):
+    _fields_ = [(n, _f32p) for n in (
+        "pos_embed_freqs", "pos_z", "pos_y", "pos_x", "pos_embed", "x_w", "x_b",
+        "c0_w", "c0_b", "c2_w", "c2_b", "t0_w", "t0_b", "t2_w", "t2_b",
+        "final_w", "final_b", "final_ada_w", "final_ada_b")] + [("blocks", BlockParams * V4H_MAX_DEPTH)]
+
+
+# name -> (restype, argtypes); every symbol include/vit4hep_b200.h declares
+_i32, _i64, _sz, _vp, _fl = C.c_int32, C.c_int64, C.c_size_t, C.c_void_p, C.c_float
+SIGNATURES = {
+    "v4h_last_error": (C.c_char_p, []),
+    "v4h_version": (C.c_int, []),
+    "v4h_check_device": (C.c_int, [C.c_int]),
+    "v4h_geometry_create": (C.c_int, [C.POINTER(_i32), C.POINTER(_i32), _i32, _i32, _i32, C.POINTER(_vp)]),
+    "v4h_geometry_destroy": (None, [_vp]),
+    "v4h_geometry_tokens": (_i32, [_vp]),
+    "v4h_geometry_patch_dim": (_i32, [_vp]),
+    "v4h_geometry_voxels": (_i32, [_vp]),
+    "v4h_geometry_table_host": (C.c_int, [_vp, C.POINTER(_i32), _i32]),
+    "v4h_to_patches": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "v4h_from_patches": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "v4h_plan_create": (C.c_int, [C.POINTER(VitDims), C.POINTER(_vp)]),
+    "v4h_plan_destroy": (None, [_vp]),
+    "v4h_vit_workspace_bytes": (_sz, [_vp, _i64, _i32]),
+    "v4h_vit_weight_arena_bytes": (_sz, [_vp]),
+    "v4h_vit_prepare_weights": (C.c_int, [_vp, C.POINTER(VitParams), _vp, _vp]),
+    "v4h_vit_forward": (C.c_int, [_vp, C.POINTER(VitParams), _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32,
+                                  _vp, _sz, _vp]),
+    "v4h_vit_backward": (C.c_int, [_vp, C.POINTER(VitParams), _vp, C.POINTER(VitParams), _vp, _vp, _vp,
+                                   _i64, _i32, _i32, _vp, _sz, _vp]),
+    "v4h_cfm_prepare": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "v4h_cfm_loss": (C.c_int, [_vp, _vp, _i64, _fl, _vp, _vp, _vp]),
+    "v4h_axpy4": (C.c_int, [_vp, _vp, _vp, _fl, _vp, _fl, _vp, _fl, _vp, _fl, _i64, _vp]),
+    "v4h_test_gemm": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "v4h_test_attention_fwd": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "v4h_test_attention_bwd": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def lib_path() -> str:
+    from . import build as _build
+    return _build.LIB_PATH
+
+
+def load(build_if_missing: bool = True):
+    """Return the loaded library (ctypes.CDLL) with typed entry points."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = lib_path()
+        if not os.path.isfile(path):
+            if not build_if_missing:
+                raise RuntimeError(f"{path} is missing: run `python -m vit4hep_b200.build` (no CPU fallback)")
+            from . import build as _build
+            _build.build()
+        lib = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError here = header and library out of sync
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return load().v4h_last_error().decode(errors="replace")
+
+
+def check(rc: int) -> None:
+    if rc != V4H_OK:
+        raise RuntimeError(f"vit4hep_b200 native call failed (code {rc}): {last_error()}")
+
+
+_device_ok = set()
+
+
+def require_device(index: int) -> None:
+    """Raise unless CUDA device `index` is a B200-class (sm_100) GPU."""
+    if index in _device_ok:
+        return
+    check(load().v4h_check_device(int(index)))
+    _device_ok.add(index)

@@ -1,0 +1,272 @@
+// extern "C" surface of libvit4hep_b200.so (declared in include/vit4hep_b200.h).
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace v4h {
+
+char* last_error_buffer() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+struct Plan;
+int plan_create(const v4h_vit_dims* dims, Plan** out);
+void plan_destroy(Plan* p);
+size_t plan_workspace_bytes(const Plan* p, int64_t B, bool train);
+size_t plan_arena_bytes(const Plan* p);
+int plan_prepare_weights(Plan* p, const v4h_vit_params* w, void* arena, cudaStream_t s);
+int plan_forward(Plan* p, const v4h_vit_params* w, const void* arena, const float* x, const float* t,
+                 const float* c, float* out, int64_t B, bool shared_t, bool train, void* workspace,
+                 size_t workspace_bytes, cudaStream_t s);
+int plan_backward(Plan* p, const v4h_vit_params* w, const void* arena, const v4h_vit_params* grads,
+                  const float* x, const float* c, const float* dout, int64_t B, int stage_begin, int stage_end,
+                  void* workspace, size_t workspace_bytes, cudaStream_t s);
+
+// ---------------------------------------------------------------- geometry
+struct Geometry {
+  int tokens = 0, patch_dim = 0, voxels = 0;  // voxels: per sample, channels included
+  std::vector<int32_t> table, inverse, chunks;  // host copies
+  int max_chunk = 0;
+  int32_t *table_dev = nullptr, *inverse_dev = nullptr, *chunks_dev = nullptr;
+  int num_chunks = 0;  // 0 -> plain gather kernel
+  std::mutex upload_mutex;
+  int device = -1;  // device that holds the tables (uploaded on first launch)
+
+  // The host tables are built at creation (no GPU needed, so the index map can be inspected
+  // anywhere); the device copies are made on the first launch, on the then-current device.
+  int ensure_device() {
+    std::lock_guard<std::mutex> lock(upload_mutex);
+    int dev = 0;
+    V4H_CUDA(cudaGetDevice(&dev));
+    if (device == dev) return V4H_OK;
+    if (device >= 0)
+      return fail(V4H_ERR_INVALID, "geometry was uploaded to device %d but is used on device %d", device, dev);
+    V4H_TRY(v4h_check_device(dev));
+    const size_t nb = sizeof(int32_t) * voxels;
+    V4H_CUDA(cudaMalloc(&table_dev, nb));
+    V4H_CUDA(cudaMalloc(&inverse_dev, nb));
+    V4H_CUDA(cudaMalloc(&chunks_dev, sizeof(int32_t) * std::max<size_t>(1, chunks.size())));
+    V4H_CUDA(cudaMemcpy(table_dev, table.data(), nb, cudaMemcpyHostToDevice));
+    V4H_CUDA(cudaMemcpy(inverse_dev, inverse.data(), nb, cudaMemcpyHostToDevice));
+    if (!chunks.empty())
+      V4H_CUDA(cudaMemcpy(chunks_dev, chunks.data(), sizeof(int32_t) * chunks.size(), cudaMemcpyHostToDevice));
+    device = dev;
+    return V4H_OK;
+  }
+};
+
+}  // namespace v4h
+
+using namespace v4h;
+
+extern "C" {
+
+const char* v4h_last_error(void) { return last_error_buffer(); }
+int v4h_version(void) { return 100; }
+
+int v4h_check_device(int dev) {
+  cudaDeviceProp prop;
+  V4H_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return fail(V4H_ERR_ARCH, "device %d is sm_%d%d; this library contains sm_100a code only (no fallback)", dev,
+                prop.major, prop.minor);
+  return V4H_OK;
+}
+
+// ------------------------------------------------------------------------------------ geometry
+int v4h_geometry_create(const int32_t* shapes, const int32_t* patches, int32_t n_segments, int32_t in_channels,
+                        int32_t flat_input, v4h_geometry** out) {
+  V4H_REQUIRE(shapes && patches && out, "geometry_create: null argument");
+  V4H_REQUIRE(n_segments >= 1 && n_segments <= V4H_MAX_SEGMENTS, "geometry_create: %d segments", n_segments);
+  V4H_REQUIRE(in_channels >= 1, "geometry_create: in_channels must be >= 1");
+  V4H_REQUIRE(flat_input || n_segments == 1, "geometry_create: a non-flat input has exactly one segment");
+  const int C = in_channels;
+  int64_t V = 0;
+  int patch_vol = -1;
+  for (int k = 0; k < n_segments; ++k) {
+    int vol = 1;
+    for (int a = 0; a < 3; ++a) {
+      const int sdim = shapes[3 * k + a], pdim = patches[3 * k + a];
+      V4H_REQUIRE(sdim > 0 && pdim > 0, "geometry_create: non-positive extent");
+      // same check as the reference's asserts (calochallenge_cfm/model.py:33-36)
+      V4H_REQUIRE(sdim % pdim == 0, "Input size (%d) should be divisible by patch size (%d) in axis %d.", sdim, pdim, a);
+      vol *= pdim;
+    }
+    V4H_REQUIRE(patch_vol < 0 || patch_vol == vol, "geometry_create: patch volume differs between segments");
+    patch_vol = vol;
+    V += (int64_t)shapes[3 * k] * shapes[3 * k + 1] * shapes[3 * k + 2];
+  }
+  V4H_REQUIRE(V * C < (1ll << 30), "geometry_create: sample too large");
+  Geometry* g = new Geometry();
+  g->voxels = (int)(V * C);
+  g->patch_dim = patch_vol * C;
+  g->table.reserve(g->voxels);
+  std::vector<int32_t> slab_bounds;  // token-order offsets where a slab (one patch-layer of a segment) starts
+  int64_t seg_off = 0;
+  for (int k = 0; k < n_segments; ++k) {
+    const int L = shapes[3 * k], A = shapes[3 * k + 1], R = shapes[3 * k + 2];
+    const int P1 = patches[3 * k], P2 = patches[3 * k + 1], P3 = patches[3 * k + 2];
+    const int nl = L / P1, na = A / P2, nr = R / P3;
+    g->tokens += nl * na * nr;
+    for (int l = 0; l < nl; ++l) {
+      slab_bounds.push_back((int32_t)g->table.size());
+      for (int a = 0; a < na; ++a)
+        for (int r = 0; r < nr; ++r)
+          for (int p1 = 0; p1 < P1; ++p1)
+            for (int p2 = 0; p2 < P2; ++p2)
+              for (int p3 = 0; p3 < P3; ++p3)
+                for (int c = 0; c < C; ++c) {
+                  const int64_t vox = ((int64_t)(l * P1 + p1) * A + (a * P2 + p2)) * R + (r * P3 + p3);
+                  g->table.push_back((int32_t)(c * V + seg_off + vox));
+                }
+    }
+    seg_off += (int64_t)L * A * R;
+  }
+  slab_bounds.push_back((int32_t)g->table.size());
+  g->inverse.assign(g->voxels, 0);
+  for (int j = 0; j < g->voxels; ++j) g->inverse[g->table[j]] = j;
+  // chunks = groups of whole slabs; valid only when every slab is a permutation of its own range (C == 1)
+  bool block_diagonal = (C == 1);
+  const int target = 2048, cap = 12288 - 64;
+  if (block_diagonal) {
+    g->chunks.push_back(0);
+    int begin = 0;
+    for (size_t i = 1; i < slab_bounds.size(); ++i) {
+      const int here = slab_bounds[i];
+      const bool last = i + 1 == slab_bounds.size();
+      const int next = last ? here : slab_bounds[i + 1];
+      if (last || next - begin > target) {
+        g->chunks.push_back(here);
+        g->max_chunk = std::max(g->max_chunk, here - begin);
+        begin = here;
+      }
+    }
+    if (g->max_chunk > cap) block_diagonal = false;
+  }
+  g->num_chunks = block_diagonal ? (int)g->chunks.size() - 1 : 0;
+  *out = reinterpret_cast<v4h_geometry*>(g);
+  return V4H_OK;
+}
+
+void v4h_geometry_destroy(v4h_geometry* gg) {
+  Geometry* g = reinterpret_cast<Geometry*>(gg);
+  if (!g) return;
+  if (g->device >= 0) { cudaFree(g->table_dev); cudaFree(g->inverse_dev); cudaFree(g->chunks_dev); }
+  delete g;
+}
+int32_t v4h_geometry_tokens(const v4h_geometry* g) { return reinterpret_cast<const Geometry*>(g)->tokens; }
+int32_t v4h_geometry_patch_dim(const v4h_geometry* g) { return reinterpret_cast<const Geometry*>(g)->patch_dim; }
+int32_t v4h_geometry_voxels(const v4h_geometry* g) { return reinterpret_cast<const Geometry*>(g)->voxels; }
+int v4h_geometry_table_host(const v4h_geometry* gg, int32_t* out, int32_t n) {
+  const Geometry* g = reinterpret_cast<const Geometry*>(gg);
+  V4H_REQUIRE(g && out && n == g->voxels, "geometry_table_host: bad arguments");
+  memcpy(out, g->table.data(), sizeof(int32_t) * n);
+  return V4H_OK;
+}
+
+int v4h_to_patches(const v4h_geometry* gg, const float* x, float* tokens, int64_t batch, v4h_stream_t s) {
+  Geometry* g = const_cast<Geometry*>(reinterpret_cast<const Geometry*>(gg));
+  V4H_REQUIRE(g && x && tokens && batch >= 0, "to_patches: bad arguments");
+  V4H_TRY(g->ensure_device());
+  return patch_permute(x, tokens, g->table_dev, g->chunks_dev, g->num_chunks, g->max_chunk, batch, g->voxels,
+                       (cudaStream_t)s);
+}
+int v4h_from_patches(const v4h_geometry* gg, const float* tokens, float* x, int64_t batch, v4h_stream_t s) {
+  Geometry* g = const_cast<Geometry*>(reinterpret_cast<const Geometry*>(gg));
+  V4H_REQUIRE(g && x && tokens && batch >= 0, "from_patches: bad arguments");
+  V4H_TRY(g->ensure_device());
+  return patch_permute(tokens, x, g->inverse_dev, g->chunks_dev, g->num_chunks, g->max_chunk, batch, g->voxels,
+                       (cudaStream_t)s);
+}
+
+// ------------------------------------------------------------------------------------ network
+int v4h_plan_create(const v4h_vit_dims* dims, v4h_plan** out) {
+  return plan_create(dims, reinterpret_cast<Plan**>(out));
+}
+void v4h_plan_destroy(v4h_plan* p) { plan_destroy(reinterpret_cast<Plan*>(p)); }
+size_t v4h_vit_workspace_bytes(const v4h_plan* p, int64_t batch, int32_t save_for_backward) {
+  return plan_workspace_bytes(reinterpret_cast<const Plan*>(p), batch, save_for_backward != 0);
+}
+size_t v4h_vit_weight_arena_bytes(const v4h_plan* p) { return plan_arena_bytes(reinterpret_cast<const Plan*>(p)); }
+int v4h_vit_prepare_weights(v4h_plan* p, const v4h_vit_params* w, void* arena, v4h_stream_t s) {
+  return plan_prepare_weights(reinterpret_cast<Plan*>(p), w, arena, (cudaStream_t)s);
+}
+int v4h_vit_forward(v4h_plan* p, const v4h_vit_params* w, const void* arena, const float* x, const float* t,
+                    const float* c, float* out, int64_t batch, int32_t shared_t, int32_t save_for_backward,
+                    void* workspace, size_t workspace_bytes, v4h_stream_t s) {
+  return plan_forward(reinterpret_cast<Plan*>(p), w, arena, x, t, c, out, batch, shared_t != 0,
+                      save_for_backward != 0, workspace, workspace_bytes, (cudaStream_t)s);
+}
+int v4h_vit_backward(v4h_plan* p, const v4h_vit_params* w, const void* arena, const v4h_vit_params* grads,
+                     const float* x, const float* c, const float* dout, int64_t batch, int32_t stage_begin,
+                     int32_t stage_end, void* workspace, size_t workspace_bytes, v4h_stream_t s) {
+  return plan_backward(reinterpret_cast<Plan*>(p), w, arena, grads, x, c, dout, batch, stage_begin, stage_end,
+                       workspace, workspace_bytes, (cudaStream_t)s);
+}
+
+// ------------------------------------------------------------------------------------ CFM / ODE
+int v4h_cfm_prepare(const v4h_geometry* gg, const float* x1, const float* x0, const float* t, float* xt_tokens,
+                    float* target_tokens, int64_t batch, v4h_stream_t s) {
+  Geometry* g = const_cast<Geometry*>(reinterpret_cast<const Geometry*>(gg));
+  V4H_REQUIRE(g && x1 && x0 && t && xt_tokens && target_tokens && batch > 0 && batch <= 65535,
+              "cfm_prepare: bad arguments");
+  V4H_TRY(g->ensure_device());
+  return cfm_prepare(x1, x0, t, g->table_dev, xt_tokens, target_tokens, batch, g->voxels, (cudaStream_t)s);
+}
+int v4h_cfm_loss(const float* v, const float* target, int64_t n, float grad_scale, float* loss_out, float* dv,
+                 v4h_stream_t s) {
+  V4H_REQUIRE(v && target && loss_out && n > 0, "cfm_loss: bad arguments");
+  return cfm_loss(v, target, n, grad_scale, loss_out, dv, (cudaStream_t)s);
+}
+int v4h_axpy4(float* out, const float* y, const float* k0, float a0, const float* k1, float a1, const float* k2,
+              float a2, const float* k3, float a3, int64_t n, v4h_stream_t s) {
+  V4H_REQUIRE(out && y && n > 0, "axpy4: bad arguments");
+  return axpy4(out, y, k0, a0, k1, a1, k2, a2, k3, a3, n, (cudaStream_t)s);
+}
+
+// ------------------------------------------------------------------------------------ test hooks
+int v4h_test_gemm(int32_t engine, int32_t layout, const void* A, const void* B, float* C, int32_t m, int32_t n,
+                  int32_t k, v4h_stream_t s) {
+  V4H_REQUIRE(A && B && C && layout >= 0 && layout <= 2, "test_gemm: bad arguments");
+  GemmDesc g;
+  g.layout = layout; g.A = A; g.B = B; g.M = m; g.N = n; g.K = k;
+  g.lda = layout == GEMM_TN ? m : k;
+  g.ldb = layout == GEMM_NT ? k : n;
+  g.out_dtype = DT_F32; g.ep.out = C; g.ep.ldo = n;
+  if (engine == 0) {
+    return gemm_simt(g, (cudaStream_t)s);
+  }
+  g.a_dtype = g.b_dtype = DT_BF16;
+  static UmmaContext* ctx = umma_context_create();
+  if (layout == GEMM_TN) {  // weight-gradient form: split-K with atomics into a zeroed C
+    g.epi = EPI_ATOMIC;
+    V4H_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)m * n, (cudaStream_t)s));
+  }
+  if (!gemm_umma_supported(g)) return fail(V4H_ERR_UNSUPPORTED, "test_gemm: shape not supported by the tcgen05 GEMM");
+  return gemm_umma(ctx, g, (cudaStream_t)s);
+}
+
+int v4h_test_attention_fwd(int32_t precision, int32_t engine, const void* qkv, void* o, float* lse, int32_t batch,
+                           int32_t tokens, int32_t heads, int32_t head_dim, v4h_stream_t s) {
+  V4H_REQUIRE(qkv && o && lse, "test_attention_fwd: null argument");
+  if (engine != 0) return fail(V4H_ERR_UNSUPPORTED, "test_attention_fwd: tcgen05 attention not built yet");
+  if (precision == V4H_BF16)
+    return attention_fwd_simt<bf16>((const bf16*)qkv, (bf16*)o, lse, batch, tokens, heads, head_dim, (cudaStream_t)s);
+  return attention_fwd_simt<float>((const float*)qkv, (float*)o, lse, batch, tokens, heads, head_dim, (cudaStream_t)s);
+}
+int v4h_test_attention_bwd(int32_t precision, int32_t engine, const void* qkv, const void* o, const float* lse,
+                           const void* d_o, void* dqkv, int32_t batch, int32_t tokens, int32_t heads,
+                           int32_t head_dim, v4h_stream_t s) {
+  V4H_REQUIRE(qkv && o && lse && d_o && dqkv, "test_attention_bwd: null argument");
+  if (engine != 0) return fail(V4H_ERR_UNSUPPORTED, "test_attention_bwd: tcgen05 attention not built yet");
+  if (precision == V4H_BF16)
+    return attention_bwd_simt<bf16>((const bf16*)qkv, (const bf16*)o, lse, (const bf16*)d_o, (bf16*)dqkv, batch,
+                                    tokens, heads, head_dim, (cudaStream_t)s);
+  return attention_bwd_simt<float>((const float*)qkv, (const float*)o, lse, (const float*)d_o, (float*)dqkv, batch,
+                                   tokens, heads, head_dim, (cudaStream_t)s);
+}
+
+}  // extern "C"

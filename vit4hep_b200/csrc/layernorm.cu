@@ -1,0 +1,209 @@
+// LayerNorm (no affine, eps 1e-6, biased variance) fused with adaLN modulation, and its
+// backward fused with the gate backward of the next branch in the chain.
+// Restates: reference nn/vit.py:309-311 (norm1/norm2), :457-458 (modulate), :331-332 (gated residual).
+// One warp per token row; the per-sample reductions (d shift, d scale, d gate) are done per CTA in
+// registers/shared memory and published with one atomicAdd per (CTA, column).
+#include "kernels.cuh"
+
+namespace v4h {
+
+namespace {
+
+constexpr float LN_EPS = 1e-6f;
+constexpr int MAXV = 16;  // columns per lane -> D <= 512
+constexpr int WARPS = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(WARPS * 32) ln_mod_fwd_kernel(
+    const float* __restrict__ h, const float* __restrict__ shift, const float* __restrict__ scale,
+    int mod_stride, T* __restrict__ a, float2* __restrict__ stats, int M, int D, int rows_per_sample) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float* hr = h + (size_t)row * D;
+  float v[MAXV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int d = lane + i * 32;
+    v[i] = d < D ? hr[d] : 0.f;
+    sum += v[i];
+  }
+  const float mean = warp_sum(sum) / D;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int d = lane + i * 32;
+    float c = d < D ? v[i] - mean : 0.f;
+    sq += c * c;
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / D + LN_EPS);
+  if (lane == 0 && stats) stats[row] = make_float2(mean, rstd);
+  const int b = row / rows_per_sample;
+  const float* sh = shift + (size_t)b * mod_stride;
+  const float* sc = scale + (size_t)b * mod_stride;
+  T* ar = a + (size_t)row * D;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int d = lane + i * 32;
+    if (d < D) ar[d] = from_f<T>((v[i] - mean) * rstd * (1.f + sc[d]) + sh[d]);
+  }
+}
+
+// grid (chunks, B); each CTA owns rows [chunk*rows_per_cta, ...) of ONE sample.
+template <typename T, bool HAS_LN, bool HAS_GATE>
+__global__ void __launch_bounds__(WARPS * 32) ln_mod_bwd_kernel(
+    const T* __restrict__ da, const float* __restrict__ h, const float2* __restrict__ stats,
+    const float* __restrict__ scale, int mod_stride, float* __restrict__ dh, bool dh_accumulate,
+    float* __restrict__ dshift, float* __restrict__ dscale, int dmod_stride, const T* __restrict__ y,
+    const float* __restrict__ gate, T* __restrict__ dy, float* __restrict__ dgate,
+    float* __restrict__ dbias, int D, int rows_per_sample, int rows_per_cta) {
+  __shared__ float red[WARPS][MAXV * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int r_begin = blockIdx.x * rows_per_cta;
+  const int r_end = min(rows_per_sample, r_begin + rows_per_cta);
+
+  float sc1[MAXV], gt[MAXV];
+  float acc_shift[MAXV], acc_scale[MAXV], acc_gate[MAXV], acc_bias[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int d = lane + i * 32;
+    sc1[i] = (HAS_LN && d < D) ? 1.f + scale[(size_t)b * mod_stride + d] : 0.f;
+    gt[i] = (HAS_GATE && d < D) ? gate[(size_t)b * mod_stride + d] : 0.f;
+    acc_shift[i] = acc_scale[i] = acc_gate[i] = acc_bias[i] = 0.f;
+  }
+
+  for (int r = r_begin + warp; r < r_end; r += WARPS) {
+    const size_t row = (size_t)b * rows_per_sample + r;
+    float dx[MAXV];
+    if (HAS_LN) {
+      const float2 st = stats[row];
+      float g[MAXV], xh[MAXV];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        int d = lane + i * 32;
+        if (d < D) {
+          float dav = to_f(da[row * D + d]);
+          xh[i] = (h[row * D + d] - st.x) * st.y;
+          g[i] = dav * sc1[i];
+          acc_shift[i] += dav;
+          acc_scale[i] += dav * xh[i];
+          s1 += g[i];
+          s2 += g[i] * xh[i];
+        } else {
+          xh[i] = 0.f; g[i] = 0.f;
+        }
+      }
+      s1 = warp_sum(s1) / D;
+      s2 = warp_sum(s2) / D;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) dx[i] = st.y * (g[i] - s1 - xh[i] * s2);
+    }
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      int d = lane + i * 32;
+      if (d < D) {
+        float dhn;
+        if (HAS_LN) {
+          dhn = dx[i] + (dh_accumulate ? dh[row * D + d] : 0.f);
+          dh[row * D + d] = dhn;
+        } else {
+          dhn = dh[row * D + d];
+        }
+        if (HAS_GATE) {
+          float dyv = gt[i] * dhn;
+          dy[row * D + d] = from_f<T>(dyv);
+          acc_gate[i] += dhn * to_f(y[row * D + d]);
+          acc_bias[i] += dyv;
+        }
+      }
+    }
+  }
+
+  // cross-warp reduction, one quantity at a time
+  auto publish = [&](float (&acc)[MAXV], float* dst) {
+    if (dst == nullptr) return;  // uniform across the CTA
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) red[warp][lane + i * 32] = acc[i];
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += WARPS * 32) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) t += red[w][d];
+      atomicAdd(dst + d, t);
+    }
+  };
+  if (HAS_LN) {
+    publish(acc_shift, dshift ? dshift + (size_t)b * dmod_stride : nullptr);
+    publish(acc_scale, dscale ? dscale + (size_t)b * dmod_stride : nullptr);
+  }
+  if (HAS_GATE) {
+    publish(acc_gate, dgate ? dgate + (size_t)b * dmod_stride : nullptr);
+    publish(acc_bias, dbias);
+  }
+}
+
+}  // namespace
+
+template <typename T>
+int ln_modulate_fwd(const float* h, const float* shift, const float* scale, int mod_stride, T* a,
+                    float2* stats, int M, int D, int rows_per_sample, cudaStream_t s) {
+  if (D > MAXV * 32) return fail(V4H_ERR_UNSUPPORTED, "ln_modulate: hidden_dim %d > %d", D, MAXV * 32);
+  ln_mod_fwd_kernel<T><<<(unsigned)ceil_div(M, WARPS), WARPS * 32, 0, s>>>(h, shift, scale, mod_stride, a,
+                                                                          stats, M, D, rows_per_sample);
+  V4H_LAUNCH_CHECK();
+  return V4H_OK;
+}
+
+template <typename T>
+int ln_modulate_bwd(const T* da, const float* h, const float2* stats, const float* scale, int mod_stride,
+                    float* dh, bool dh_accumulate, float* dshift, float* dscale, int dmod_stride,
+                    const T* y, const float* gate, T* dy, float* dgate, float* dbias, int M, int D,
+                    int rows_per_sample, cudaStream_t s) {
+  if (D > MAXV * 32) return fail(V4H_ERR_UNSUPPORTED, "ln_modulate: hidden_dim %d > %d", D, MAXV * 32);
+  const int B = M / rows_per_sample;
+  const int rows_per_cta = 32;
+  dim3 grid((unsigned)ceil_div(rows_per_sample, rows_per_cta), (unsigned)B);
+  if (gate != nullptr) {
+    ln_mod_bwd_kernel<T, true, true><<<grid, WARPS * 32, 0, s>>>(
+        da, h, stats, scale, mod_stride, dh, dh_accumulate, dshift, dscale, dmod_stride, y, gate, dy, dgate,
+        dbias, D, rows_per_sample, rows_per_cta);
+  } else {
+    ln_mod_bwd_kernel<T, true, false><<<grid, WARPS * 32, 0, s>>>(
+        da, h, stats, scale, mod_stride, dh, dh_accumulate, dshift, dscale, dmod_stride, nullptr, nullptr,
+        nullptr, nullptr, nullptr, D, rows_per_sample, rows_per_cta);
+  }
+  V4H_LAUNCH_CHECK();
+  return V4H_OK;
+}
+
+template <typename T>
+int gate_bwd(const float* dh, const T* y, const float* gate, int mod_stride, T* dy, float* dgate,
+             int dmod_stride, float* dbias, int M, int D, int rows_per_sample, cudaStream_t s) {
+  if (D > MAXV * 32) return fail(V4H_ERR_UNSUPPORTED, "gate_bwd: hidden_dim %d > %d", D, MAXV * 32);
+  const int B = M / rows_per_sample;
+  const int rows_per_cta = 32;
+  dim3 grid((unsigned)ceil_div(rows_per_sample, rows_per_cta), (unsigned)B);
+  ln_mod_bwd_kernel<T, false, true><<<grid, WARPS * 32, 0, s>>>(
+      nullptr, nullptr, nullptr, nullptr, mod_stride, const_cast<float*>(dh), false, nullptr, nullptr,
+      dmod_stride, y, gate, dy, dgate, dbias, D, rows_per_sample, rows_per_cta);
+  V4H_LAUNCH_CHECK();
+  return V4H_OK;
+}
+
+#define INST(T)                                                                                          \
+  template int ln_modulate_fwd<T>(const float*, const float*, const float*, int, T*, float2*, int, int, \
+                                  int, cudaStream_t);                                                    \
+  template int ln_modulate_bwd<T>(const T*, const float*, const float2*, const float*, int, float*,    \
+                                  bool, float*, float*, int, const T*, const float*, T*, float*,        \
+                                  float*, int, int, int, cudaStream_t);                                  \
+  template int gate_bwd<T>(const float*, const T*, const float*, int, T*, float*, int, float*, int, int, \
+                           int, cudaStream_t);
+INST(float)
+INST(bf16)
+#undef INST
+
+}  // namespace v4h

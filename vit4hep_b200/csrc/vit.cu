@@ -1,0 +1,552 @@
+// Orchestration of the ViT velocity network forward / backward (reference nn/vit.py:185-206 forward,
+// :327-333 DiTBlock, :347-351 FinalLayer; backward derived in SURVEY.md appendix A) on top of the
+// kernels in this directory.  Nothing here allocates activations: every buffer is a slice of the
+// caller's workspace, laid out by Workspace::layout().
+#include <cstdlib>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace v4h {
+
+struct Plan {
+  v4h_vit_dims d;
+  int Nmod = 0;           // depth * 6D + 2D columns of the concatenated adaLN output
+  bool bf16 = false;
+  bool use_umma = false;  // tcgen05 GEMMs (bf16 precision only)
+  bool use_umma_attn = false;
+  UmmaContext* umma = nullptr;
+  // bf16 weight arena layout (element offsets in bf16 units, then the fp32 bias tail in bytes)
+  struct BlockArena { size_t qkv, proj, fc1, fc2; } arena_blocks[V4H_MAX_DEPTH];
+  size_t arena_ada = 0;           // bf16 (Nmod, D)
+  size_t arena_bf16_elems = 0;
+  size_t arena_ada_bias_bytes = 0;  // byte offset of fp32 (Nmod) concatenated adaLN biases
+  size_t arena_bytes = 0;
+  // device + pinned staging for the multi-tensor cast job table
+  CastJob* jobs_dev = nullptr;
+  CastJob* jobs_host = nullptr;
+  int njobs = 0;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// workspace layout
+// ------------------------------------------------------------------------------------------
+struct BlockBufs {
+  void *a, *qkv, *o, *y1, *m, *u, *g, *y2;  // TA
+  float* lse;
+  float2 *stats1, *stats2;
+};
+
+struct Workspace {
+  // conditioning
+  float *pe, *temb_in, *t_h_pre, *t_h, *te, *c_h_pre, *c_h, *cond, *sc, *mod;
+  bf16* sc_bf16;
+  // residual stream (fp32): training keeps 2*depth+1 copies, inference 1
+  std::vector<float*> h;
+  std::vector<BlockBufs> blk;  // training: depth entries; inference: 1 shared entry
+  void* a_f;
+  float2* stats_f;
+  // backward scratch
+  float *dh, *dmod, *dsc, *dcond, *dvec;
+  bf16* dmod_bf16;
+  void *dy, *du, *dm, *dqkv;
+  size_t bytes = 0;
+
+  void layout(const Plan& p, char* base, int64_t B, bool train) {
+    const v4h_vit_dims& d = p.d;
+    const size_t M = (size_t)B * d.tokens, D = d.hidden_dim, Hm = d.mlp_hidden;
+    const size_t ta = p.bf16 ? 2 : 4;
+    size_t off = 0;
+    auto take = [&](size_t nbytes) -> char* {
+      char* ptr = base ? base + off : nullptr;
+      off += align_up(nbytes, 256);
+      return ptr;
+    };
+    pe = (float*)take((size_t)d.tokens * D * 4);
+    temb_in = (float*)take((size_t)B * d.freq_dim * 4);
+    t_h_pre = (float*)take(B * D * 4); t_h = (float*)take(B * D * 4); te = (float*)take(B * D * 4);
+    c_h_pre = (float*)take(B * D * 4); c_h = (float*)take(B * D * 4);
+    cond = (float*)take(B * D * 4); sc = (float*)take(B * D * 4);
+    sc_bf16 = (bf16*)take(B * D * 2);
+    mod = (float*)take((size_t)B * p.Nmod * 4);
+    const int nh = train ? 2 * d.depth + 1 : 1;
+    h.resize(nh);
+    for (int i = 0; i < nh; ++i) h[i] = (float*)take(M * D * 4);
+    const int nb = train ? d.depth : 1;
+    blk.resize(nb);
+    for (int i = 0; i < nb; ++i) {
+      BlockBufs& b = blk[i];
+      b.a = take(M * D * ta); b.qkv = take(M * 3 * D * ta); b.o = take(M * D * ta);
+      b.y1 = train ? take(M * D * ta) : nullptr;
+      b.m = take(M * D * ta);
+      b.u = train ? take(M * Hm * ta) : nullptr;
+      b.g = take(M * Hm * ta);
+      b.y2 = train ? take(M * D * ta) : nullptr;
+      b.lse = (float*)take((size_t)B * d.num_heads * d.tokens * 4);
+      b.stats1 = (float2*)take(M * 8); b.stats2 = (float2*)take(M * 8);
+    }
+    a_f = take(M * D * ta);
+    stats_f = (float2*)take(M * 8);
+    if (train) {
+      dh = (float*)take(M * D * 4);
+      dmod = (float*)take((size_t)B * p.Nmod * 4);
+      dmod_bf16 = (bf16*)take((size_t)B * p.Nmod * 2);
+      dsc = (float*)take(B * D * 4); dcond = (float*)take(B * D * 4); dvec = (float*)take(B * D * 4);
+      dy = take(M * D * ta); du = take(M * Hm * ta); dm = take(M * D * ta); dqkv = take(M * 3 * D * ta);
+    } else {
+      dh = dmod = dsc = dcond = dvec = nullptr; dmod_bf16 = nullptr;
+      dy = du = dm = dqkv = nullptr;
+    }
+    bytes = off;
+  }
+};
+
+inline int hidx(bool train, int i) { return train ? i : 0; }
+
+// ------------------------------------------------------------------------------------------
+// GEMM dispatch
+// ------------------------------------------------------------------------------------------
+int run_gemm(const Plan& p, const GemmDesc& g, cudaStream_t s) {
+  if (p.use_umma && g.a_dtype == DT_BF16 && g.b_dtype == DT_BF16 && gemm_umma_supported(g))
+    return gemm_umma(p.umma, g, s);
+  return gemm_simt(g, s);
+}
+
+GemmDesc linear_fwd(const void* A, int a_dt, int lda, const void* W, int w_dt, int ldw, int M, int N, int K) {
+  GemmDesc g;
+  g.layout = GEMM_NT; g.A = A; g.a_dtype = a_dt; g.lda = lda; g.B = W; g.b_dtype = w_dt; g.ldb = ldw;
+  g.M = M; g.N = N; g.K = K;
+  return g;
+}
+
+// number of K splits that brings a weight-gradient GEMM to at least ~2 CTAs per SM
+int wgrad_splits(int M_out, int N_out, int K, int tile_m, int tile_n, int min_k) {
+  const int64_t tiles = ceil_div(M_out, tile_m) * ceil_div(N_out, tile_n);
+  int splits = (int)ceil_div(296, tiles);
+  const int max_splits = (int)std::max<int64_t>(1, K / min_k);
+  if (splits > max_splits) splits = max_splits;
+  return splits < 1 ? 1 : splits;
+}
+
+// dW (M_out x N_out) += A^T B with A (K, M_out), B (K, N_out)
+int wgrad(const Plan& p, const void* A, int a_dt, int lda, const void* B, int b_dt, int ldb, float* dW,
+          int M_out, int N_out, int K, cudaStream_t s) {
+  GemmDesc g;
+  g.layout = GEMM_TN; g.A = A; g.a_dtype = a_dt; g.lda = lda; g.B = B; g.b_dtype = b_dt; g.ldb = ldb;
+  g.M = M_out; g.N = N_out; g.K = K;
+  g.epi = EPI_ATOMIC; g.out_dtype = DT_F32;
+  g.ep.out = dW; g.ep.ldo = N_out;
+  g.splitk = wgrad_splits(M_out, N_out, K, 64, 64, 256);
+  return run_gemm(p, g, s);
+}
+
+template <typename T>
+int forward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const float* x, const float* t,
+                 const float* c, float* out, int64_t B64, bool shared_t, bool train, Workspace& ws,
+                 cudaStream_t s) {
+  const v4h_vit_dims& d = p.d;
+  const int B = (int)B64, Tn = d.tokens, D = d.hidden_dim, Hm = d.mlp_hidden, M = B * Tn;
+  const int TA = p.bf16 ? DT_BF16 : DT_F32;
+  const int Bt = shared_t ? 1 : B;
+  const bf16* wa = reinterpret_cast<const bf16*>(arena);
+
+  // ---- positional embedding + patch embedding: h0 = x Wx^T + bx + PE   (nn/vit.py:192-195)
+  const float* pe = w.pos_embed;
+  if (d.learn_pos_embed) {
+    V4H_TRY(pos_embedding_fwd(w.pos_embed_freqs, w.pos_z, w.pos_y, w.pos_x, ws.pe, Tn, D / 6, s));
+    pe = ws.pe;
+  }
+  {
+    GemmDesc g = linear_fwd(x, DT_F32, d.patch_dim, w.x_w, DT_F32, d.patch_dim, M, D, d.patch_dim);
+    g.ep.bias = w.x_b; g.ep.out = ws.h[0]; g.ep.ldo = D;
+    g.ep.addend = pe; g.ep.addend_rows = Tn; g.ep.ld_addend = D;
+    V4H_TRY(gemm_simt(g, s));
+  }
+  // ---- conditioning: cond = t_embedder(t) + c_embedder(c); sc = SiLU(cond)   (nn/vit.py:197-199)
+  V4H_TRY(timestep_embedding(t, shared_t ? 1 : 0, ws.temb_in, Bt, d.freq_dim, s));
+  {
+    GemmDesc g = linear_fwd(ws.temb_in, DT_F32, d.freq_dim, w.t0_w, DT_F32, d.freq_dim, Bt, D, d.freq_dim);
+    g.act = ACT_SILU; g.ep.bias = w.t0_b; g.ep.out = ws.t_h; g.ep.out2 = ws.t_h_pre; g.ep.ldo = D;
+    V4H_TRY(gemm_simt(g, s));
+    g = linear_fwd(ws.t_h, DT_F32, D, w.t2_w, DT_F32, D, Bt, D, D);
+    g.ep.bias = w.t2_b; g.ep.out = ws.te; g.ep.ldo = D;
+    V4H_TRY(gemm_simt(g, s));
+    g = linear_fwd(c, DT_F32, d.cond_dim, w.c0_w, DT_F32, d.cond_dim, B, D, d.cond_dim);
+    g.act = ACT_SILU; g.ep.bias = w.c0_b; g.ep.out = ws.c_h; g.ep.out2 = ws.c_h_pre; g.ep.ldo = D;
+    V4H_TRY(gemm_simt(g, s));
+    g = linear_fwd(ws.c_h, DT_F32, D, w.c2_w, DT_F32, D, B, D, D);
+    g.act = ACT_SILU; g.ep.bias = w.c2_b; g.ep.out = ws.sc; g.ep.out2 = ws.cond; g.ep.ldo = D;
+    g.ep.addend = ws.te; g.ep.addend_rows = shared_t ? 1 : 0; g.ep.ld_addend = D;
+    V4H_TRY(gemm_simt(g, s));
+  }
+  // ---- every adaLN modulation of the network in one pass: mod = sc Wada^T + bada   (nn/vit.py:328-330, :348)
+  if (p.bf16 && p.use_umma) {
+    V4H_TRY(cast_f32_to_bf16(ws.sc, ws.sc_bf16, (int64_t)B * D, s));
+    GemmDesc g = linear_fwd(ws.sc_bf16, DT_BF16, D, wa + p.arena_ada, DT_BF16, D, B, p.Nmod, D);
+    g.ep.bias = reinterpret_cast<const float*>(arena + p.arena_ada_bias_bytes);
+    g.ep.out = ws.mod; g.ep.ldo = p.Nmod; g.out_dtype = DT_F32;
+    V4H_TRY(run_gemm(p, g, s));
+  } else {
+    for (int i = 0; i <= d.depth; ++i) {
+      const bool fin = i == d.depth;
+      const int n = fin ? 2 * D : 6 * D;
+      GemmDesc g = linear_fwd(ws.sc, DT_F32, D, fin ? w.final_ada_w : w.blocks[i].ada_w, DT_F32, D, B, n, D);
+      g.ep.bias = fin ? w.final_ada_b : w.blocks[i].ada_b;
+      g.ep.out = ws.mod + (size_t)i * 6 * D; g.ep.ldo = p.Nmod;
+      V4H_TRY(gemm_simt(g, s));
+    }
+  }
+  // ---- transformer blocks   (nn/vit.py:327-333)
+  for (int i = 0; i < d.depth; ++i) {
+    const v4h_block_params& bw = w.blocks[i];
+    BlockBufs& bb = ws.blk[train ? i : 0];
+    float* hin = ws.h[hidx(train, 2 * i)];
+    float* hmid = ws.h[hidx(train, 2 * i + 1)];
+    float* hout = ws.h[hidx(train, 2 * i + 2)];
+    const float* mod = ws.mod + (size_t)i * 6 * D;
+    const void* Wqkv = p.bf16 ? (const void*)(wa + p.arena_blocks[i].qkv) : (const void*)bw.qkv_w;
+    const void* Wproj = p.bf16 ? (const void*)(wa + p.arena_blocks[i].proj) : (const void*)bw.proj_w;
+    const void* Wfc1 = p.bf16 ? (const void*)(wa + p.arena_blocks[i].fc1) : (const void*)bw.fc1_w;
+    const void* Wfc2 = p.bf16 ? (const void*)(wa + p.arena_blocks[i].fc2) : (const void*)bw.fc2_w;
+
+    V4H_TRY(ln_modulate_fwd<T>(hin, mod + 0 * D, mod + 1 * D, p.Nmod, (T*)bb.a, bb.stats1, M, D, Tn, s));
+    {
+      GemmDesc g = linear_fwd(bb.a, TA, D, Wqkv, TA, D, M, 3 * D, D);
+      g.ep.bias = bw.qkv_b; g.ep.out = bb.qkv; g.ep.ldo = 3 * D; g.out_dtype = TA;
+      V4H_TRY(run_gemm(p, g, s));
+    }
+    V4H_TRY(attention_fwd_simt<T>((const T*)bb.qkv, (T*)bb.o, bb.lse, B, Tn, d.num_heads, D / d.num_heads, s));
+    {
+      GemmDesc g = linear_fwd(bb.o, TA, D, Wproj, TA, D, M, D, D);
+      g.epi = EPI_GATE_RES; g.out_dtype = TA;
+      g.ep.bias = bw.proj_b; g.ep.out2 = bb.y1; g.ep.ldo = D;
+      g.ep.gate = mod + 2 * D; g.ep.mod_stride = p.Nmod; g.ep.rows_per_sample = Tn;
+      g.ep.res_in = hin; g.ep.res_out = hmid;
+      V4H_TRY(run_gemm(p, g, s));
+    }
+    V4H_TRY(ln_modulate_fwd<T>(hmid, mod + 3 * D, mod + 4 * D, p.Nmod, (T*)bb.m, bb.stats2, M, D, Tn, s));
+    {
+      GemmDesc g = linear_fwd(bb.m, TA, D, Wfc1, TA, D, M, Hm, D);
+      g.act = ACT_GELU_TANH; g.out_dtype = TA;
+      g.ep.bias = bw.fc1_b; g.ep.out = bb.g; g.ep.out2 = bb.u; g.ep.ldo = Hm;
+      V4H_TRY(run_gemm(p, g, s));
+    }
+    {
+      GemmDesc g = linear_fwd(bb.g, TA, Hm, Wfc2, TA, Hm, M, D, Hm);
+      g.epi = EPI_GATE_RES; g.out_dtype = TA;
+      g.ep.bias = bw.fc2_b; g.ep.out2 = bb.y2; g.ep.ldo = D;
+      g.ep.gate = mod + 5 * D; g.ep.mod_stride = p.Nmod; g.ep.rows_per_sample = Tn;
+      g.ep.res_in = hmid; g.ep.res_out = hout;
+      V4H_TRY(run_gemm(p, g, s));
+    }
+  }
+  // ---- final layer   (nn/vit.py:347-351)
+  {
+    const float* mod = ws.mod + (size_t)d.depth * 6 * D;
+    float* hl = ws.h[hidx(train, 2 * d.depth)];
+    V4H_TRY(ln_modulate_fwd<T>(hl, mod, mod + D, p.Nmod, (T*)ws.a_f, ws.stats_f, M, D, Tn, s));
+    GemmDesc g = linear_fwd(ws.a_f, TA, D, w.final_w, DT_F32, D, M, d.out_dim, D);
+    g.ep.bias = w.final_b; g.ep.out = out; g.ep.ldo = d.out_dim; g.out_dtype = DT_F32;
+    V4H_TRY(gemm_simt(g, s));
+  }
+  return V4H_OK;
+}
+
+// dX (M x Nin) = dY (M x Nout) W (Nout x Nin)
+GemmDesc dgrad(const void* dY, int dy_dt, int ld_dy, const void* W, int w_dt, int ldw, int M, int Nin, int Nout) {
+  GemmDesc g;
+  g.layout = GEMM_NN; g.A = dY; g.a_dtype = dy_dt; g.lda = ld_dy; g.B = W; g.b_dtype = w_dt; g.ldb = ldw;
+  g.M = M; g.N = Nin; g.K = Nout;
+  return g;
+}
+
+template <typename T>
+int backward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const v4h_vit_params& gr,
+                  const float* dout, int64_t B64, int stage_begin, int stage_end, Workspace& ws,
+                  cudaStream_t s) {
+  const v4h_vit_dims& d = p.d;
+  const int B = (int)B64, Tn = d.tokens, D = d.hidden_dim, Hm = d.mlp_hidden, M = B * Tn;
+  const int TA = p.bf16 ? DT_BF16 : DT_F32;
+  const bf16* wa = reinterpret_cast<const bf16*>(arena);
+  const int H = d.num_heads, dh = D / H;
+
+  for (int stage = stage_begin; stage >= stage_end; --stage) {
+    if (stage == d.depth + 1) {
+      // ---------------- final layer
+      V4H_CUDA(cudaMemsetAsync(ws.dmod, 0, (size_t)B * p.Nmod * sizeof(float), s));
+      const size_t offF = (size_t)d.depth * 6 * D;
+      V4H_TRY(wgrad(p, dout, DT_F32, d.out_dim, ws.a_f, TA, D, gr.final_w, d.out_dim, D, M, s));
+      V4H_TRY(colsum_add<float>(dout, d.out_dim, gr.final_b, M, d.out_dim, s));
+      {
+        GemmDesc g = dgrad(dout, DT_F32, d.out_dim, w.final_w, DT_F32, D, M, D, d.out_dim);
+        g.ep.out = ws.dm; g.ep.ldo = D; g.out_dtype = TA;
+        V4H_TRY(gemm_simt(g, s));
+      }
+      const int last = d.depth - 1;
+      const float* modL = ws.mod + (size_t)last * 6 * D;
+      float* dmodL = ws.dmod + (size_t)last * 6 * D;
+      V4H_TRY(ln_modulate_bwd<T>((const T*)ws.dm, ws.h[2 * d.depth], ws.stats_f, ws.mod + offF + D, p.Nmod,
+                                 ws.dh, false, ws.dmod + offF, ws.dmod + offF + D, p.Nmod,
+                                 (const T*)ws.blk[last].y2, modL + 5 * D, (T*)ws.dy, dmodL + 5 * D,
+                                 gr.blocks[last].fc2_b, M, D, Tn, s));
+    } else if (stage >= 1) {
+      // ---------------- transformer block i
+      const int i = stage - 1;
+      const v4h_block_params& bw = w.blocks[i];
+      const v4h_block_params& bg = gr.blocks[i];
+      BlockBufs& bb = ws.blk[i];
+      const float* mod = ws.mod + (size_t)i * 6 * D;
+      float* dmod = ws.dmod + (size_t)i * 6 * D;
+      const void* Wqkv = p.bf16 ? (const void*)(wa + p.arena_blocks[i].qkv) : (const void*)bw.qkv_w;
+      const void* Wproj = p.bf16 ? (const void*)(wa + p.arena_blocks[i].proj) : (const void*)bw.proj_w;
+      const void* Wfc1 = p.bf16 ? (const void*)(wa + p.arena_blocks[i].fc1) : (const void*)bw.fc1_w;
+      const void* Wfc2 = p.bf16 ? (const void*)(wa + p.arena_blocks[i].fc2) : (const void*)bw.fc2_w;
+
+      // MLP branch: dy = gate_mlp * dh is ready in ws.dy
+      V4H_TRY(wgrad(p, ws.dy, TA, D, bb.g, TA, Hm, bg.fc2_w, D, Hm, M, s));
+      {
+        GemmDesc g = dgrad(ws.dy, TA, D, Wfc2, TA, Hm, M, Hm, D);
+        g.epi = EPI_DACT; g.act = ACT_GELU_TANH; g.out_dtype = TA;
+        g.ep.out = ws.du; g.ep.ldo = Hm; g.ep.aux = bb.u; g.ep.ld_aux = Hm;
+        V4H_TRY(run_gemm(p, g, s));
+      }
+      V4H_TRY(colsum_add<T>((const T*)ws.du, Hm, bg.fc1_b, M, Hm, s));
+      V4H_TRY(wgrad(p, ws.du, TA, Hm, bb.m, TA, D, bg.fc1_w, Hm, D, M, s));
+      {
+        GemmDesc g = dgrad(ws.du, TA, Hm, Wfc1, TA, D, M, D, Hm);
+        g.ep.out = ws.dm; g.ep.ldo = D; g.out_dtype = TA;
+        V4H_TRY(run_gemm(p, g, s));
+      }
+      V4H_TRY(ln_modulate_bwd<T>((const T*)ws.dm, ws.h[2 * i + 1], bb.stats2, mod + 4 * D, p.Nmod, ws.dh, true,
+                                 dmod + 3 * D, dmod + 4 * D, p.Nmod, (const T*)bb.y1, mod + 2 * D, (T*)ws.dy,
+                                 dmod + 2 * D, bg.proj_b, M, D, Tn, s));
+      // attention branch: dy = gate_msa * dh
+      V4H_TRY(wgrad(p, ws.dy, TA, D, bb.o, TA, D, bg.proj_w, D, D, M, s));
+      {
+        GemmDesc g = dgrad(ws.dy, TA, D, Wproj, TA, D, M, D, D);
+        g.ep.out = ws.dm; g.ep.ldo = D; g.out_dtype = TA;
+        V4H_TRY(run_gemm(p, g, s));
+      }
+      V4H_TRY(attention_bwd_simt<T>((const T*)bb.qkv, (const T*)bb.o, bb.lse, (const T*)ws.dm, (T*)ws.dqkv, B, Tn,
+                                    H, dh, s));
+      V4H_TRY(colsum_add<T>((const T*)ws.dqkv, 3 * D, bg.qkv_b, M, 3 * D, s));
+      V4H_TRY(wgrad(p, ws.dqkv, TA, 3 * D, bb.a, TA, D, bg.qkv_w, 3 * D, D, M, s));
+      {
+        GemmDesc g = dgrad(ws.dqkv, TA, 3 * D, Wqkv, TA, D, M, D, 3 * D);
+        g.ep.out = ws.dm; g.ep.ldo = D; g.out_dtype = TA;
+        V4H_TRY(run_gemm(p, g, s));
+      }
+      if (i > 0) {
+        const float* modP = ws.mod + (size_t)(i - 1) * 6 * D;
+        float* dmodP = ws.dmod + (size_t)(i - 1) * 6 * D;
+        V4H_TRY(ln_modulate_bwd<T>((const T*)ws.dm, ws.h[2 * i], bb.stats1, mod + 1 * D, p.Nmod, ws.dh, true,
+                                   dmod + 0 * D, dmod + 1 * D, p.Nmod, (const T*)ws.blk[i - 1].y2, modP + 5 * D,
+                                   (T*)ws.dy, dmodP + 5 * D, gr.blocks[i - 1].fc2_b, M, D, Tn, s));
+      } else {
+        V4H_TRY(ln_modulate_bwd<T>((const T*)ws.dm, ws.h[0], bb.stats1, mod + 1 * D, p.Nmod, ws.dh, true,
+                                   dmod + 0 * D, dmod + 1 * D, p.Nmod, (const T*)nullptr, nullptr, (T*)nullptr,
+                                   nullptr, nullptr, M, D, Tn, s));
+      }
+    } else {
+      // ---------------- stage 0: embeddings and conditioning.  ws.dh = d loss / d h0
+      // x_embedder and the positional frequencies; the layer input x is not differentiated
+      // (training feeds leaf tensors without grad)
+      return fail(V4H_ERR_INVALID, "internal: stage 0 must be run through backward_stage0");
+    }
+  }
+  return V4H_OK;
+}
+
+int backward_stage0(Plan& p, const v4h_vit_params& w, const v4h_vit_params& gr, const float* x,
+                    const float* c, int64_t B64, Workspace& ws, cudaStream_t s) {
+  const v4h_vit_dims& d = p.d;
+  const int B = (int)B64, Tn = d.tokens, D = d.hidden_dim, M = B * Tn;
+  V4H_TRY(wgrad(p, ws.dh, DT_F32, D, x, DT_F32, d.patch_dim, gr.x_w, D, d.patch_dim, M, s));
+  V4H_TRY(colsum_add<float>(ws.dh, D, gr.x_b, M, D, s));
+  if (d.learn_pos_embed)
+    V4H_TRY(pos_embedding_bwd(ws.dh, w.pos_embed_freqs, w.pos_z, w.pos_y, w.pos_x, gr.pos_embed_freqs, B, Tn,
+                              D / 6, s));
+  // adaLN Linears: d W = dmod^T sc, d b = colsum(dmod), d sc += dmod W
+  V4H_CUDA(cudaMemsetAsync(ws.dsc, 0, (size_t)B * D * sizeof(float), s));
+  for (int i = 0; i <= d.depth; ++i) {
+    const bool fin = i == d.depth;
+    const int n = fin ? 2 * D : 6 * D;
+    const float* dmod = ws.dmod + (size_t)i * 6 * D;
+    float* dW = fin ? gr.final_ada_w : gr.blocks[i].ada_w;
+    float* db = fin ? gr.final_ada_b : gr.blocks[i].ada_b;
+    const float* W = fin ? w.final_ada_w : w.blocks[i].ada_w;
+    {
+      GemmDesc g;
+      g.layout = GEMM_TN; g.A = dmod; g.a_dtype = DT_F32; g.lda = p.Nmod; g.B = ws.sc; g.b_dtype = DT_F32;
+      g.ldb = D; g.M = n; g.N = D; g.K = B; g.epi = EPI_ATOMIC; g.ep.out = dW; g.ep.ldo = D; g.splitk = 1;
+      V4H_TRY(gemm_simt(g, s));
+    }
+    V4H_TRY(colsum_add<float>(dmod, p.Nmod, db, B, n, s));
+    {
+      GemmDesc g = dgrad(dmod, DT_F32, p.Nmod, W, DT_F32, D, B, D, n);
+      g.epi = EPI_ATOMIC; g.ep.out = ws.dsc; g.ep.ldo = D; g.splitk = std::max(1, n / 240);
+      V4H_TRY(gemm_simt(g, s));
+    }
+  }
+  V4H_TRY(dsilu_mul(ws.dsc, ws.cond, ws.dcond, (int64_t)B * D, s));
+  // c_embedder (nn/vit.py:77-81) and t_embedder.mlp (nn/vit.py:361-365): Linear -> SiLU -> Linear
+  struct Mlp { const float *in, *h_pre, *h; int in_dim; const float* w2; float *dw0, *db0, *dw2, *db2; };
+  Mlp mlps[2] = {
+      {c, ws.c_h_pre, ws.c_h, d.cond_dim, w.c2_w, gr.c0_w, gr.c0_b, gr.c2_w, gr.c2_b},
+      {ws.temb_in, ws.t_h_pre, ws.t_h, d.freq_dim, w.t2_w, gr.t0_w, gr.t0_b, gr.t2_w, gr.t2_b}};
+  for (const Mlp& m : mlps) {
+    V4H_TRY(wgrad(p, ws.dcond, DT_F32, D, m.h, DT_F32, D, m.dw2, D, D, B, s));
+    V4H_TRY(colsum_add<float>(ws.dcond, D, m.db2, B, D, s));
+    GemmDesc g = dgrad(ws.dcond, DT_F32, D, m.w2, DT_F32, D, B, D, D);
+    g.epi = EPI_DACT; g.act = ACT_SILU; g.ep.out = ws.dvec; g.ep.ldo = D; g.ep.aux = m.h_pre; g.ep.ld_aux = D;
+    V4H_TRY(gemm_simt(g, s));
+    V4H_TRY(wgrad(p, ws.dvec, DT_F32, D, m.in, DT_F32, m.in_dim, m.dw0, D, m.in_dim, B, s));
+    V4H_TRY(colsum_add<float>(ws.dvec, D, m.db0, B, D, s));
+  }
+  return V4H_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------
+int plan_create(const v4h_vit_dims* dims, Plan** out) {
+  V4H_REQUIRE(dims && out, "plan_create: null argument");
+  const v4h_vit_dims& d = *dims;
+  V4H_REQUIRE(d.hidden_dim > 0 && d.depth > 0 && d.depth <= V4H_MAX_DEPTH && d.num_heads > 0 &&
+                  d.hidden_dim % d.num_heads == 0 && d.mlp_hidden > 0 && d.patch_dim > 0 && d.out_dim > 0 &&
+                  d.cond_dim > 0 && d.tokens > 0 && d.freq_dim >= 2,
+              "plan_create: invalid dimensions");
+  V4H_REQUIRE(!d.learn_pos_embed || d.hidden_dim % 6 == 0, "plan_create: hidden_dim must be a multiple of 6");
+  V4H_REQUIRE(d.precision == V4H_FP32 || d.precision == V4H_BF16, "plan_create: unknown precision");
+  if (d.hidden_dim > 512)
+    return fail(V4H_ERR_UNSUPPORTED, "hidden_dim %d > 512 is not supported by the LayerNorm kernels", d.hidden_dim);
+  if (d.hidden_dim / d.num_heads > 128)
+    return fail(V4H_ERR_UNSUPPORTED, "head_dim %d > 128 is not supported", d.hidden_dim / d.num_heads);
+  Plan* p = new Plan();
+  p->d = d;
+  p->Nmod = d.depth * 6 * d.hidden_dim + 2 * d.hidden_dim;
+  p->bf16 = d.precision == V4H_BF16;
+  const char* no_umma = getenv("V4H_DISABLE_UMMA");
+  p->use_umma = p->bf16 && !(no_umma && no_umma[0] == '1');
+  if (p->use_umma) p->umma = umma_context_create();
+  if (p->bf16) {
+    const size_t D = d.hidden_dim, Hm = d.mlp_hidden;
+    size_t off = 0;
+    auto take = [&](size_t n) { size_t o = off; off += align_up(n, 128); return o; };
+    for (int i = 0; i < d.depth; ++i) {
+      p->arena_blocks[i].qkv = take(3 * D * D);
+      p->arena_blocks[i].proj = take(D * D);
+      p->arena_blocks[i].fc1 = take(Hm * D);
+      p->arena_blocks[i].fc2 = take(D * Hm);
+    }
+    p->arena_ada = take((size_t)p->Nmod * D);
+    p->arena_bf16_elems = off;
+    p->arena_ada_bias_bytes = align_up(off * 2, 256);
+    p->arena_bytes = p->arena_ada_bias_bytes + align_up((size_t)p->Nmod * 4, 256);
+    p->njobs = 4 * d.depth + d.depth + 1;
+    if (cudaMalloc(&p->jobs_dev, sizeof(CastJob) * p->njobs) != cudaSuccess ||
+        cudaMallocHost(&p->jobs_host, sizeof(CastJob) * p->njobs) != cudaSuccess) {
+      delete p;
+      return fail(V4H_ERR_CUDA, "plan_create: cannot allocate the cast job table");
+    }
+    memset(p->jobs_host, 0, sizeof(CastJob) * p->njobs);
+  }
+  *out = p;
+  return V4H_OK;
+}
+
+void plan_destroy(Plan* p) {
+  if (!p) return;
+  if (p->jobs_dev) cudaFree(p->jobs_dev);
+  if (p->jobs_host) cudaFreeHost(p->jobs_host);
+  if (p->umma) umma_context_destroy(p->umma);
+  delete p;
+}
+
+size_t plan_workspace_bytes(const Plan* p, int64_t B, bool train) {
+  Workspace ws;
+  ws.layout(*p, nullptr, B, train);
+  return ws.bytes;
+}
+
+size_t plan_arena_bytes(const Plan* p) { return p->arena_bytes; }
+
+int plan_prepare_weights(Plan* p, const v4h_vit_params* w, void* arena, cudaStream_t s) {
+  if (!p->bf16) return V4H_OK;
+  V4H_REQUIRE(w && arena, "prepare_weights: null argument");
+  const v4h_vit_dims& d = p->d;
+  const size_t D = d.hidden_dim, Hm = d.mlp_hidden;
+  bf16* wa = reinterpret_cast<bf16*>(arena);
+  std::vector<CastJob> jobs;
+  int64_t max_n = 0;
+  auto add = [&](const float* src, bf16* dst, size_t n) {
+    jobs.push_back(CastJob{src, dst, (int64_t)n});
+    if ((int64_t)n > max_n) max_n = (int64_t)n;
+  };
+  for (int i = 0; i < d.depth; ++i) {
+    const v4h_block_params& b = w->blocks[i];
+    V4H_REQUIRE(b.qkv_w && b.proj_w && b.fc1_w && b.fc2_w && b.ada_w && b.ada_b, "prepare_weights: null block weight");
+    add(b.qkv_w, wa + p->arena_blocks[i].qkv, 3 * D * D);
+    add(b.proj_w, wa + p->arena_blocks[i].proj, D * D);
+    add(b.fc1_w, wa + p->arena_blocks[i].fc1, Hm * D);
+    add(b.fc2_w, wa + p->arena_blocks[i].fc2, D * Hm);
+    add(b.ada_w, wa + p->arena_ada + (size_t)i * 6 * D * D, 6 * D * D);
+  }
+  add(w->final_ada_w, wa + p->arena_ada + (size_t)d.depth * 6 * D * D, 2 * D * D);
+  if (memcmp(jobs.data(), p->jobs_host, sizeof(CastJob) * jobs.size()) != 0) {
+    // parameter storage moved: wait for earlier uses of the staging table, then refresh it
+    V4H_CUDA(cudaStreamSynchronize(s));
+    memcpy(p->jobs_host, jobs.data(), sizeof(CastJob) * jobs.size());
+    V4H_CUDA(cudaMemcpyAsync(p->jobs_dev, p->jobs_host, sizeof(CastJob) * jobs.size(), cudaMemcpyHostToDevice, s));
+  }
+  V4H_TRY(cast_many_f32_to_bf16(p->jobs_dev, (int)jobs.size(), max_n, s));
+  float* bias = reinterpret_cast<float*>(reinterpret_cast<char*>(arena) + p->arena_ada_bias_bytes);
+  for (int i = 0; i < d.depth; ++i)
+    V4H_CUDA(cudaMemcpyAsync(bias + (size_t)i * 6 * D, w->blocks[i].ada_b, 6 * D * 4, cudaMemcpyDeviceToDevice, s));
+  V4H_CUDA(cudaMemcpyAsync(bias + (size_t)d.depth * 6 * D, w->final_ada_b, 2 * D * 4, cudaMemcpyDeviceToDevice, s));
+  return V4H_OK;
+}
+
+int plan_forward(Plan* p, const v4h_vit_params* w, const void* arena, const float* x, const float* t,
+                 const float* c, float* out, int64_t B, bool shared_t, bool train, void* workspace,
+                 size_t workspace_bytes, cudaStream_t s) {
+  V4H_REQUIRE(p && w && x && t && c && out && workspace, "vit_forward: null argument");
+  V4H_REQUIRE(B > 0 && B * p->d.tokens < (1ll << 31) / 4096, "vit_forward: batch out of range");
+  V4H_REQUIRE(!p->bf16 || arena, "vit_forward: bf16 precision needs the weight arena");
+  Workspace ws;
+  ws.layout(*p, reinterpret_cast<char*>(workspace), B, train);
+  V4H_REQUIRE(ws.bytes <= workspace_bytes, "vit_forward: workspace too small (%zu < %zu)", workspace_bytes, ws.bytes);
+  if (p->bf16)
+    return forward_impl<bf16>(*p, *w, (const char*)arena, x, t, c, out, B, shared_t, train, ws, s);
+  return forward_impl<float>(*p, *w, (const char*)arena, x, t, c, out, B, shared_t, train, ws, s);
+}
+
+int plan_backward(Plan* p, const v4h_vit_params* w, const void* arena, const v4h_vit_params* grads,
+                  const float* x, const float* c, const float* dout, int64_t B, int stage_begin, int stage_end,
+                  void* workspace, size_t workspace_bytes, cudaStream_t s) {
+  V4H_REQUIRE(p && w && grads && workspace, "vit_backward: null argument");
+  V4H_REQUIRE(stage_begin <= p->d.depth + 1 && stage_end >= 0 && stage_begin >= stage_end,
+              "vit_backward: bad stage range [%d, %d]", stage_begin, stage_end);
+  V4H_REQUIRE(stage_begin != p->d.depth + 1 || dout, "vit_backward: dout is null");
+  Workspace ws;
+  ws.layout(*p, reinterpret_cast<char*>(workspace), B, true);
+  V4H_REQUIRE(ws.bytes <= workspace_bytes, "vit_backward: workspace too small (%zu < %zu)", workspace_bytes, ws.bytes);
+  const int lo = stage_end < 1 ? 1 : stage_end;
+  if (stage_begin >= lo) {
+    if (p->bf16)
+      V4H_TRY(backward_impl<bf16>(*p, *w, (const char*)arena, *grads, dout, B, stage_begin, lo, ws, s));
+    else
+      V4H_TRY(backward_impl<float>(*p, *w, (const char*)arena, *grads, dout, B, stage_begin, lo, ws, s));
+  }
+  if (stage_end == 0) {
+    V4H_REQUIRE(x && c, "vit_backward: stage 0 needs the forward inputs x and c");
+    V4H_TRY(backward_stage0(*p, *w, *grads, x, c, B, ws, s));
+  }
+  return V4H_OK;
+}
+
+}  // namespace v4h
