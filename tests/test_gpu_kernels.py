@@ -1,0 +1,92 @@
+"""Kernel-level GPU tests through the C-ABI test hooks: the tcgen05 GEMM in its three operand layouts
+(forward NT, dgrad NN, wgrad TN with split-K) and the attention kernels, against fp32 torch references
+of the same op on the same bf16-rounded inputs."""
+import pytest
+import torch
+
+from oracle import vit_oracle as vo
+
+pytestmark = pytest.mark.gpu
+
+NT, NN, TN = 0, 1, 2
+
+
+def _gemm(engine, layout, A, B, m, n, k):
+    from vit4hep_b200 import _cabi
+    lib = _cabi.load()
+    C = torch.full((m, n), float("nan"), device=A.device, dtype=torch.float32)
+    _cabi.check(lib.v4h_test_gemm(engine, layout, A.data_ptr(), B.data_ptr(), C.data_ptr(), m, n, k,
+                                  torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    return C
+
+
+def _operands(layout, m, n, k, dtype, dev, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    a_shape = (k, m) if layout == TN else (m, k)
+    b_shape = (n, k) if layout == NT else (k, n)
+    A = torch.randn(a_shape, generator=g).to(dev).to(dtype)
+    B = torch.randn(b_shape, generator=g).to(dev).to(dtype)
+    Af = A.double().t() if layout == TN else A.double()
+    Bf = B.double().t() if layout == NT else B.double()
+    return A, B, Af @ Bf
+
+
+SHAPES = [
+    (128, 64, 64), (128, 240, 64), (128, 256, 128), (256, 480, 480), (135, 144, 48), (8640, 1440, 480),
+    (8640, 480, 1920), (1000, 48, 480), (64, 18240, 480), (77, 96, 200), (300, 1920, 480), (129, 272, 72),
+]
+
+
+@pytest.mark.parametrize("layout", [NT, NN, TN])
+@pytest.mark.parametrize("m,n,k", SHAPES)
+def test_umma_gemm_layouts(layout, m, n, k):
+    dev = torch.device("cuda:0")
+    if layout == TN and (m % 8 or n % 8):
+        pytest.skip("TMA needs 16-byte row pitch")
+    if layout == NN and n % 8:
+        pytest.skip("TMA needs 16-byte row pitch")
+    if layout != TN and k % 8:
+        pytest.skip("TMA needs 16-byte row pitch")
+    A, B, want = _operands(layout, m, n, k, torch.bfloat16, dev)
+    got = _gemm(1, layout, A, B, m, n, k)
+    assert torch.isfinite(got).all()
+    err = vo.rel_l2(got, want)
+    assert err < 2e-6, f"layout {layout} {m}x{n}x{k}: rel-L2 {err}"
+
+
+@pytest.mark.parametrize("layout", [NT, NN, TN])
+def test_simt_gemm_layouts(layout):
+    dev = torch.device("cuda:0")
+    for (m, n, k) in [(135, 48, 48), (64, 480, 46), (300, 77, 129)]:
+        A, B, want = _operands(layout, m, n, k, torch.float32, dev)
+        got = _gemm(0, layout, A, B, m, n, k)
+        assert vo.rel_l2(got, want) < 1e-6
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("B,T,H,dh", [(2, 135, 6, 80), (1, 450, 6, 80), (3, 84, 2, 24), (1, 606, 6, 80), (2, 33, 4, 32)])
+def test_attention_fwd_bwd(precision, B, T, H, dh):
+    from vit4hep_b200 import _cabi
+    lib = _cabi.load()
+    dev = torch.device("cuda:0")
+    dt = torch.bfloat16 if precision else torch.float32
+    g = torch.Generator().manual_seed(3)
+    qkv = torch.randn(B, T, 3, H, dh, generator=g).to(dev).to(dt)
+    d_o = torch.randn(B, T, H, dh, generator=g).to(dev).to(dt)
+    o = torch.empty(B, T, H, dh, device=dev, dtype=dt)
+    lse = torch.empty(B, H, T, device=dev, dtype=torch.float32)
+    dqkv = torch.empty_like(qkv)
+    s = torch.cuda.current_stream().cuda_stream
+    _cabi.check(lib.v4h_test_attention_fwd(precision, 0, qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), B, T, H, dh, s))
+    _cabi.check(lib.v4h_test_attention_bwd(precision, 0, qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), d_o.data_ptr(),
+                                           dqkv.data_ptr(), B, T, H, dh, s))
+    ref = qkv.double().requires_grad_(True)
+    q, k, v = ref.permute(2, 0, 3, 1, 4)
+    sc = (q @ k.transpose(-1, -2)) * dh ** -0.5
+    want = (torch.softmax(sc, -1) @ v).transpose(1, 2)
+    want.backward(d_o.double())
+    tol = 2e-2 if precision else 1e-5
+    assert vo.rel_l2(o, want) < tol
+    assert vo.rel_l2(lse, torch.logsumexp(sc, -1)) < 1e-5 if not precision else True
+    assert vo.rel_l2(dqkv, ref.grad) < tol

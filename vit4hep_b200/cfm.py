@@ -93,14 +93,17 @@ class PatchGeometry:
 
     def _check(self, name, v, per_sample):
         _require_cuda_f32(name, v)
-        if v.dim() < 2 or v[0].numel() != per_sample:
-            raise ValueError(f"{name} has {v[0].numel() if v.dim() else 0} values per sample, expected {per_sample}")
+        got = math.prod(v.shape[1:]) if v.dim() >= 2 else -1
+        if got != per_sample:
+            raise ValueError(f"{name} has {got} values per sample, expected {per_sample}")
 
     def to_patches(self, x: torch.Tensor) -> torch.Tensor:
         self._check("x", x, self.voxels)
         x = x.contiguous()
         B = x.shape[0]
         out = torch.empty((B, self.tokens, self.patch_dim), dtype=torch.float32, device=x.device)
+        if B == 0:
+            return out
         with torch.cuda.device(x.device):
             _cabi.check(_cabi.load().v4h_to_patches(self._handle, x.data_ptr(), out.data_ptr(), B, _stream(x.device)))
         return out
@@ -110,6 +113,8 @@ class PatchGeometry:
         tok = tok.contiguous()
         B = tok.shape[0]
         out = torch.empty((B, *self.sample_shape), dtype=torch.float32, device=tok.device)
+        if B == 0:
+            return out
         with torch.cuda.device(tok.device):
             _cabi.check(_cabi.load().v4h_from_patches(self._handle, tok.data_ptr(), out.data_ptr(), B,
                                                       _stream(tok.device)))

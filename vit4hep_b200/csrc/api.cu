@@ -243,6 +243,7 @@ int v4h_test_gemm(int32_t engine, int32_t layout, const void* A, const void* B, 
   static UmmaContext* ctx = umma_context_create();
   if (layout == GEMM_TN) {  // weight-gradient form: split-K with atomics into a zeroed C
     g.epi = EPI_ATOMIC;
+    g.splitk = 0;
     V4H_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)m * n, (cudaStream_t)s));
   }
   if (!gemm_umma_supported(g)) return fail(V4H_ERR_UNSUPPORTED, "test_gemm: shape not supported by the tcgen05 GEMM");

@@ -93,7 +93,17 @@ int launch(const GemmDesc& d, cudaStream_t s) {
     case GEMM_NN: g.sam = d.lda; g.sak = 1; g.sbk = d.ldb; g.sbn = 1; break;
     default:      g.sam = 1; g.sak = d.lda; g.sbk = d.ldb; g.sbn = 1; break;
   }
-  int splits = (EPI == EPI_ATOMIC) ? max(1, d.splitk) : 1;
+  int splits = 1;
+  if (EPI == EPI_ATOMIC) {
+    splits = d.splitk;
+    if (splits <= 0) {  // auto: about two CTAs per SM, at least 256 of K each
+      const long tiles = ceil_div(d.M, BM) * ceil_div(d.N, BN);
+      splits = (int)ceil_div(296, tiles);
+      const int cap = d.K / 256 > 0 ? d.K / 256 : 1;
+      if (splits > cap) splits = cap;
+    }
+    if (splits < 1) splits = 1;
+  }
   int kper = (int)ceil_div(ceil_div(d.K, splits), BK) * BK;
   splits = (int)ceil_div(d.K, kper);
   g.k_per_split = kper;

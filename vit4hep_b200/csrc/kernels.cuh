@@ -25,7 +25,7 @@ struct GemmDesc {
   int epi = EPI_BIAS_ACT;
   int act = ACT_NONE;
   int out_dtype = DT_F32;
-  int splitk = 1;  // >1 only with EPI_ATOMIC
+  int splitk = 1;  // EPI_ATOMIC only: number of K ranges, 0 = let the engine choose
   EpiParams ep;
 };
 

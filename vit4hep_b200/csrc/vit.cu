@@ -121,15 +121,6 @@ GemmDesc linear_fwd(const void* A, int a_dt, int lda, const void* W, int w_dt, i
   return g;
 }
 
-// number of K splits that brings a weight-gradient GEMM to at least ~2 CTAs per SM
-int wgrad_splits(int M_out, int N_out, int K, int tile_m, int tile_n, int min_k) {
-  const int64_t tiles = ceil_div(M_out, tile_m) * ceil_div(N_out, tile_n);
-  int splits = (int)ceil_div(296, tiles);
-  const int max_splits = (int)std::max<int64_t>(1, K / min_k);
-  if (splits > max_splits) splits = max_splits;
-  return splits < 1 ? 1 : splits;
-}
-
 // dW (M_out x N_out) += A^T B with A (K, M_out), B (K, N_out)
 int wgrad(const Plan& p, const void* A, int a_dt, int lda, const void* B, int b_dt, int ldb, float* dW,
           int M_out, int N_out, int K, cudaStream_t s) {
@@ -138,7 +129,7 @@ int wgrad(const Plan& p, const void* A, int a_dt, int lda, const void* B, int b_
   g.M = M_out; g.N = N_out; g.K = K;
   g.epi = EPI_ATOMIC; g.out_dtype = DT_F32;
   g.ep.out = dW; g.ep.ldo = N_out;
-  g.splitk = wgrad_splits(M_out, N_out, K, 64, 64, 256);
+  g.splitk = 0;  // auto
   return run_gemm(p, g, s);
 }
 
