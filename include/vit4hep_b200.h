@@ -170,6 +170,24 @@ int v4h_axpy4(float* out, const float* y, const float* k0, float a0, const float
               const float* k2, float a2, const float* k3, float a3, int64_t n, v4h_stream_t s);
 
 /* ------------------------------------------------------------------------------------
+ * Measurement hooks (bench.py): how many kernels the library launched, and per-kernel-class device
+ * time from CUDA events recorded on the launching stream around each launch.
+ * ------------------------------------------------------------------------------------ */
+typedef struct {
+  char name[32];     /* kernel class, e.g. "gemm.fc1", "attn.fwd", "ln.fwd" */
+  int64_t launches;  /* bracketed regions (one or a few kernel launches each) */
+  double ms;         /* summed device time */
+  double flops;      /* summed algorithmic flops (2 M N K per GEMM, 4 H T^2 dh per attention forward) */
+  double bytes;      /* summed algorithmic bytes (operands read + results written once) */
+} v4h_profile_entry;
+
+int64_t v4h_launch_count(void);
+/* start booking; every later launch is bracketed by two events until v4h_profile_end */
+int v4h_profile_begin(void);
+/* synchronises the device, aggregates by name into out[0..*n) (at most max entries), stops booking */
+int v4h_profile_end(v4h_profile_entry* out, int32_t max, int32_t* n);
+
+/* ------------------------------------------------------------------------------------
  * Kernel-level test hooks (used by tests/ to localise parity failures; not needed by a host).
  * ------------------------------------------------------------------------------------ */
 /* C (m, n) fp32 = op(A) op(B) with row-major inputs.  layout: 0 = NT (A (m,k), B (n,k)),

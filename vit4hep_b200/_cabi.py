@@ -36,6 +36,11 @@ class VitParams(C.Structure):
         "final_w", "final_b", "final_ada_w", "final_ada_b")] + [("blocks", BlockParams * V4H_MAX_DEPTH)]
 
 
+class ProfileEntry(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("ms", C.c_double), ("flops", C.c_double),
+                ("bytes", C.c_double)]
+
+
 # name -> (restype, argtypes); every symbol include/vit4hep_b200.h declares
 _i32, _i64, _sz, _vp, _fl = C.c_int32, C.c_int64, C.c_size_t, C.c_void_p, C.c_float
 SIGNATURES = {
@@ -62,6 +67,9 @@ SIGNATURES = {
     "v4h_cfm_prepare": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "v4h_cfm_loss": (C.c_int, [_vp, _vp, _i64, _fl, _vp, _vp, _vp]),
     "v4h_axpy4": (C.c_int, [_vp, _vp, _vp, _fl, _vp, _fl, _vp, _fl, _vp, _fl, _i64, _vp]),
+    "v4h_launch_count": (C.c_int64, []),
+    "v4h_profile_begin": (C.c_int, []),
+    "v4h_profile_end": (C.c_int, [C.POINTER(ProfileEntry), _i32, C.POINTER(_i32)]),
     "v4h_test_gemm": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "v4h_test_attention_fwd": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "v4h_test_attention_bwd": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
@@ -117,3 +125,16 @@ def require_device(index: int) -> None:
         return
     check(load().v4h_check_device(int(index)))
     _device_ok.add(index)
+
+
+def profile_begin() -> None:
+    check(load().v4h_profile_begin())
+
+
+def profile_end(max_entries: int = 64):
+    """[{name, launches, ms, flops, bytes}] per kernel class since profile_begin()."""
+    buf = (ProfileEntry * max_entries)()
+    n = C.c_int32(0)
+    check(load().v4h_profile_end(buf, max_entries, C.byref(n)))
+    return [dict(name=buf[i].name.decode(), launches=buf[i].launches, ms=buf[i].ms, flops=buf[i].flops,
+                 bytes=buf[i].bytes) for i in range(n.value)]

@@ -1,6 +1,9 @@
 // extern "C" surface of libvit4hep_b200.so (declared in include/vit4hep_b200.h).
 #include <algorithm>
+#include <atomic>
+#include <map>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "kernels.cuh"
@@ -10,6 +13,42 @@ namespace v4h {
 char* last_error_buffer() {
   static thread_local char buf[512] = {0};
   return buf;
+}
+
+// ---------------------------------------------------------------- launch counter / profiler
+static std::atomic<int64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+namespace {
+struct ProfRecord { std::string tag; double flops, bytes; cudaEvent_t e0, e1; };
+struct Profiler {
+  std::mutex mu;
+  std::atomic<bool> on{false};
+  std::vector<ProfRecord> records;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get_event() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+};
+Profiler& profiler() { static Profiler p; return p; }
+}  // namespace
+
+bool profiling_enabled() { return profiler().on.load(std::memory_order_relaxed); }
+void profile_open(const char* tag, double flops, double bytes, cudaStream_t s, int* slot) {
+  Profiler& p = profiler();
+  std::lock_guard<std::mutex> lock(p.mu);
+  ProfRecord r{tag, flops, bytes, p.get_event(), p.get_event()};
+  cudaEventRecord(r.e0, s);
+  p.records.push_back(r);
+  *slot = (int)p.records.size() - 1;
+}
+void profile_close(int slot, cudaStream_t s) {
+  Profiler& p = profiler();
+  std::lock_guard<std::mutex> lock(p.mu);
+  if (slot >= 0 && slot < (int)p.records.size()) cudaEventRecord(p.records[slot].e1, s);
 }
 
 struct Plan;
@@ -225,6 +264,50 @@ int v4h_axpy4(float* out, const float* y, const float* k0, float a0, const float
               float a2, const float* k3, float a3, int64_t n, v4h_stream_t s) {
   V4H_REQUIRE(out && y && n > 0, "axpy4: bad arguments");
   return axpy4(out, y, k0, a0, k1, a1, k2, a2, k3, a3, n, (cudaStream_t)s);
+}
+
+// ------------------------------------------------------------------------------------ measurement
+int64_t v4h_launch_count(void) { return g_launches.load(); }
+
+int v4h_profile_begin(void) {
+  Profiler& p = profiler();
+  std::lock_guard<std::mutex> lock(p.mu);
+  for (ProfRecord& r : p.records) { p.pool.push_back(r.e0); p.pool.push_back(r.e1); }
+  p.records.clear();
+  p.on.store(true);
+  return V4H_OK;
+}
+
+int v4h_profile_end(v4h_profile_entry* out, int32_t max, int32_t* n) {
+  V4H_REQUIRE(out && n && max > 0, "profile_end: bad arguments");
+  Profiler& p = profiler();
+  p.on.store(false);
+  V4H_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lock(p.mu);
+  std::map<std::string, v4h_profile_entry> agg;
+  std::vector<std::string> order;
+  for (ProfRecord& r : p.records) {
+    float ms = 0.f;
+    V4H_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    auto it = agg.find(r.tag);
+    if (it == agg.end()) {
+      v4h_profile_entry e;
+      memset(&e, 0, sizeof(e));
+      strncpy(e.name, r.tag.c_str(), sizeof(e.name) - 1);
+      it = agg.emplace(r.tag, e).first;
+      order.push_back(r.tag);
+    }
+    it->second.launches += 1; it->second.ms += ms; it->second.flops += r.flops; it->second.bytes += r.bytes;
+    p.pool.push_back(r.e0); p.pool.push_back(r.e1);
+  }
+  p.records.clear();
+  int32_t k = 0;
+  for (const std::string& name : order) {
+    if (k >= max) break;
+    out[k++] = agg[name];
+  }
+  *n = k;
+  return V4H_OK;
 }
 
 // ------------------------------------------------------------------------------------ test hooks

@@ -34,7 +34,31 @@ inline int fail(int code, const char* fmt, ...) {
                          cudaGetErrorString(_e));                                        \
   } while (0)
 
-#define V4H_LAUNCH_CHECK() V4H_CUDA(cudaGetLastError())
+// every kernel launch in the library is followed by this: counts the launch (v4h_launch_count) and
+// surfaces launch errors
+void count_launch();  // api.cu
+#define V4H_LAUNCH_CHECK()       \
+  do {                           \
+    ::v4h::count_launch();       \
+    V4H_CUDA(cudaGetLastError()); \
+  } while (0)
+
+// Optional per-kernel-class timing (v4h_profile_begin / v4h_profile_end): when enabled, a ProfScope
+// brackets the launches made during its lifetime with CUDA events on the launching stream and books
+// their algorithmic flops / bytes under `tag`.  Disabled: a single branch.
+bool profiling_enabled();
+void profile_open(const char* tag, double flops, double bytes, cudaStream_t s, int* slot);
+void profile_close(int slot, cudaStream_t s);
+struct ProfScope {
+  int slot = -1;
+  cudaStream_t stream;
+  ProfScope(const char* tag, double flops, double bytes, cudaStream_t s) : stream(s) {
+    if (profiling_enabled()) profile_open(tag, flops, bytes, s, &slot);
+  }
+  ~ProfScope() {
+    if (slot >= 0) profile_close(slot, stream);
+  }
+};
 
 #define V4H_REQUIRE(cond, ...)                                    \
   do {                                                            \

@@ -25,6 +25,7 @@ struct GemmDesc {
   int epi = EPI_BIAS_ACT;
   int act = ACT_NONE;
   int out_dtype = DT_F32;
+  const char* tag = "gemm";  // kernel class for v4h_profile_*
   int splitk = 1;  // EPI_ATOMIC only: number of K ranges, 0 = let the engine choose
   EpiParams ep;
 };

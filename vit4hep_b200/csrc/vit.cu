@@ -105,10 +105,21 @@ struct Workspace {
 
 inline int hidx(bool train, int i) { return train ? i : 0; }
 
+// run `f` (a launcher) inside a profiling scope
+template <typename F>
+int prof(const char* tag, double flops, double bytes, cudaStream_t s, F&& f) {
+  ProfScope ps(tag, flops, bytes, s);
+  return f();
+}
+
 // ------------------------------------------------------------------------------------------
 // GEMM dispatch
 // ------------------------------------------------------------------------------------------
 int run_gemm(const Plan& p, const GemmDesc& g, cudaStream_t s) {
+  const double esz_a = g.a_dtype == DT_BF16 ? 2 : 4, esz_b = g.b_dtype == DT_BF16 ? 2 : 4;
+  const double esz_o = g.epi == EPI_ATOMIC ? 4 : (g.out_dtype == DT_BF16 ? 2 : 4);
+  ProfScope ps(g.tag, 2.0 * g.M * g.N * g.K,
+               esz_a * g.M * g.K + esz_b * g.N * g.K + esz_o * (double)g.M * g.N, s);
   if (p.use_umma && g.a_dtype == DT_BF16 && g.b_dtype == DT_BF16 && gemm_umma_supported(g))
     return gemm_umma(p.umma, g, s);
   return gemm_simt(g, s);
@@ -123,8 +134,9 @@ GemmDesc linear_fwd(const void* A, int a_dt, int lda, const void* W, int w_dt, i
 
 // dW (M_out x N_out) += A^T B with A (K, M_out), B (K, N_out)
 int wgrad(const Plan& p, const void* A, int a_dt, int lda, const void* B, int b_dt, int ldb, float* dW,
-          int M_out, int N_out, int K, cudaStream_t s) {
+          int M_out, int N_out, int K, cudaStream_t s, const char* tag = "wgrad") {
   GemmDesc g;
+  g.tag = tag;
   g.layout = GEMM_TN; g.A = A; g.a_dtype = a_dt; g.lda = lda; g.B = B; g.b_dtype = b_dt; g.ldb = ldb;
   g.M = M_out; g.N = N_out; g.K = K;
   g.epi = EPI_ATOMIC; g.out_dtype = DT_F32;
@@ -153,29 +165,31 @@ int forward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const floa
     GemmDesc g = linear_fwd(x, DT_F32, d.patch_dim, w.x_w, DT_F32, d.patch_dim, M, D, d.patch_dim);
     g.ep.bias = w.x_b; g.ep.out = ws.h[0]; g.ep.ldo = D;
     g.ep.addend = pe; g.ep.addend_rows = Tn; g.ep.ld_addend = D;
-    V4H_TRY(gemm_simt(g, s));
+    g.tag = "gemm.x_embed";
+    V4H_TRY(run_gemm(p, g, s));
   }
   // ---- conditioning: cond = t_embedder(t) + c_embedder(c); sc = SiLU(cond)   (nn/vit.py:197-199)
   V4H_TRY(timestep_embedding(t, shared_t ? 1 : 0, ws.temb_in, Bt, d.freq_dim, s));
   {
     GemmDesc g = linear_fwd(ws.temb_in, DT_F32, d.freq_dim, w.t0_w, DT_F32, d.freq_dim, Bt, D, d.freq_dim);
-    g.act = ACT_SILU; g.ep.bias = w.t0_b; g.ep.out = ws.t_h; g.ep.out2 = ws.t_h_pre; g.ep.ldo = D;
-    V4H_TRY(gemm_simt(g, s));
-    g = linear_fwd(ws.t_h, DT_F32, D, w.t2_w, DT_F32, D, Bt, D, D);
+    g.tag = "gemm.cond"; g.act = ACT_SILU; g.ep.bias = w.t0_b; g.ep.out = ws.t_h; g.ep.out2 = ws.t_h_pre; g.ep.ldo = D;
+    V4H_TRY(run_gemm(p, g, s));
+    g = linear_fwd(ws.t_h, DT_F32, D, w.t2_w, DT_F32, D, Bt, D, D); g.tag = "gemm.cond";
     g.ep.bias = w.t2_b; g.ep.out = ws.te; g.ep.ldo = D;
-    V4H_TRY(gemm_simt(g, s));
-    g = linear_fwd(c, DT_F32, d.cond_dim, w.c0_w, DT_F32, d.cond_dim, B, D, d.cond_dim);
+    V4H_TRY(run_gemm(p, g, s));
+    g = linear_fwd(c, DT_F32, d.cond_dim, w.c0_w, DT_F32, d.cond_dim, B, D, d.cond_dim); g.tag = "gemm.cond";
     g.act = ACT_SILU; g.ep.bias = w.c0_b; g.ep.out = ws.c_h; g.ep.out2 = ws.c_h_pre; g.ep.ldo = D;
-    V4H_TRY(gemm_simt(g, s));
-    g = linear_fwd(ws.c_h, DT_F32, D, w.c2_w, DT_F32, D, B, D, D);
+    V4H_TRY(run_gemm(p, g, s));
+    g = linear_fwd(ws.c_h, DT_F32, D, w.c2_w, DT_F32, D, B, D, D); g.tag = "gemm.cond";
     g.act = ACT_SILU; g.ep.bias = w.c2_b; g.ep.out = ws.sc; g.ep.out2 = ws.cond; g.ep.ldo = D;
     g.ep.addend = ws.te; g.ep.addend_rows = shared_t ? 1 : 0; g.ep.ld_addend = D;
-    V4H_TRY(gemm_simt(g, s));
+    V4H_TRY(run_gemm(p, g, s));
   }
   // ---- every adaLN modulation of the network in one pass: mod = sc Wada^T + bada   (nn/vit.py:328-330, :348)
   if (p.bf16 && p.use_umma) {
     V4H_TRY(cast_f32_to_bf16(ws.sc, ws.sc_bf16, (int64_t)B * D, s));
     GemmDesc g = linear_fwd(ws.sc_bf16, DT_BF16, D, wa + p.arena_ada, DT_BF16, D, B, p.Nmod, D);
+    g.tag = "gemm.adaln";
     g.ep.bias = reinterpret_cast<const float*>(arena + p.arena_ada_bias_bytes);
     g.ep.out = ws.mod; g.ep.ldo = p.Nmod; g.out_dtype = DT_F32;
     V4H_TRY(run_gemm(p, g, s));
@@ -184,9 +198,10 @@ int forward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const floa
       const bool fin = i == d.depth;
       const int n = fin ? 2 * D : 6 * D;
       GemmDesc g = linear_fwd(ws.sc, DT_F32, D, fin ? w.final_ada_w : w.blocks[i].ada_w, DT_F32, D, B, n, D);
+      g.tag = "gemm.adaln";
       g.ep.bias = fin ? w.final_ada_b : w.blocks[i].ada_b;
       g.ep.out = ws.mod + (size_t)i * 6 * D; g.ep.ldo = p.Nmod;
-      V4H_TRY(gemm_simt(g, s));
+      V4H_TRY(run_gemm(p, g, s));
     }
   }
   // ---- transformer blocks   (nn/vit.py:327-333)
@@ -202,30 +217,34 @@ int forward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const floa
     const void* Wfc1 = p.bf16 ? (const void*)(wa + p.arena_blocks[i].fc1) : (const void*)bw.fc1_w;
     const void* Wfc2 = p.bf16 ? (const void*)(wa + p.arena_blocks[i].fc2) : (const void*)bw.fc2_w;
 
-    V4H_TRY(ln_modulate_fwd<T>(hin, mod + 0 * D, mod + 1 * D, p.Nmod, (T*)bb.a, bb.stats1, M, D, Tn, s));
+    V4H_TRY(prof("ln.fwd", 0, (double)M * D * (4 + sizeof(T)), s, [&] { return ln_modulate_fwd<T>(hin, mod + 0 * D, mod + 1 * D, p.Nmod, (T*)bb.a, bb.stats1, M, D, Tn, s); }));
     {
       GemmDesc g = linear_fwd(bb.a, TA, D, Wqkv, TA, D, M, 3 * D, D);
+      g.tag = "gemm.qkv";
       g.ep.bias = bw.qkv_b; g.ep.out = bb.qkv; g.ep.ldo = 3 * D; g.out_dtype = TA;
       V4H_TRY(run_gemm(p, g, s));
     }
-    V4H_TRY(attention_fwd_simt<T>((const T*)bb.qkv, (T*)bb.o, bb.lse, B, Tn, d.num_heads, D / d.num_heads, s));
+    V4H_TRY(prof("attn.fwd", 4.0 * B * d.num_heads * Tn * Tn * (D / d.num_heads), (double)M * 4 * D * sizeof(T), s, [&] { return attention_fwd_simt<T>((const T*)bb.qkv, (T*)bb.o, bb.lse, B, Tn, d.num_heads, D / d.num_heads, s); }));
     {
       GemmDesc g = linear_fwd(bb.o, TA, D, Wproj, TA, D, M, D, D);
+      g.tag = "gemm.proj";
       g.epi = EPI_GATE_RES; g.out_dtype = TA;
       g.ep.bias = bw.proj_b; g.ep.out2 = bb.y1; g.ep.ldo = D;
       g.ep.gate = mod + 2 * D; g.ep.mod_stride = p.Nmod; g.ep.rows_per_sample = Tn;
       g.ep.res_in = hin; g.ep.res_out = hmid;
       V4H_TRY(run_gemm(p, g, s));
     }
-    V4H_TRY(ln_modulate_fwd<T>(hmid, mod + 3 * D, mod + 4 * D, p.Nmod, (T*)bb.m, bb.stats2, M, D, Tn, s));
+    V4H_TRY(prof("ln.fwd", 0, (double)M * D * (4 + sizeof(T)), s, [&] { return ln_modulate_fwd<T>(hmid, mod + 3 * D, mod + 4 * D, p.Nmod, (T*)bb.m, bb.stats2, M, D, Tn, s); }));
     {
       GemmDesc g = linear_fwd(bb.m, TA, D, Wfc1, TA, D, M, Hm, D);
+      g.tag = "gemm.fc1";
       g.act = ACT_GELU_TANH; g.out_dtype = TA;
       g.ep.bias = bw.fc1_b; g.ep.out = bb.g; g.ep.out2 = bb.u; g.ep.ldo = Hm;
       V4H_TRY(run_gemm(p, g, s));
     }
     {
       GemmDesc g = linear_fwd(bb.g, TA, Hm, Wfc2, TA, Hm, M, D, Hm);
+      g.tag = "gemm.fc2";
       g.epi = EPI_GATE_RES; g.out_dtype = TA;
       g.ep.bias = bw.fc2_b; g.ep.out2 = bb.y2; g.ep.ldo = D;
       g.ep.gate = mod + 5 * D; g.ep.mod_stride = p.Nmod; g.ep.rows_per_sample = Tn;
@@ -237,17 +256,20 @@ int forward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const floa
   {
     const float* mod = ws.mod + (size_t)d.depth * 6 * D;
     float* hl = ws.h[hidx(train, 2 * d.depth)];
-    V4H_TRY(ln_modulate_fwd<T>(hl, mod, mod + D, p.Nmod, (T*)ws.a_f, ws.stats_f, M, D, Tn, s));
+    V4H_TRY(prof("ln.fwd", 0, (double)M * D * (4 + sizeof(T)), s, [&] { return ln_modulate_fwd<T>(hl, mod, mod + D, p.Nmod, (T*)ws.a_f, ws.stats_f, M, D, Tn, s); }));
     GemmDesc g = linear_fwd(ws.a_f, TA, D, w.final_w, DT_F32, D, M, d.out_dim, D);
+    g.tag = "gemm.final";
     g.ep.bias = w.final_b; g.ep.out = out; g.ep.ldo = d.out_dim; g.out_dtype = DT_F32;
-    V4H_TRY(gemm_simt(g, s));
+    V4H_TRY(run_gemm(p, g, s));
   }
   return V4H_OK;
 }
 
 // dX (M x Nin) = dY (M x Nout) W (Nout x Nin)
-GemmDesc dgrad(const void* dY, int dy_dt, int ld_dy, const void* W, int w_dt, int ldw, int M, int Nin, int Nout) {
+GemmDesc dgrad(const void* dY, int dy_dt, int ld_dy, const void* W, int w_dt, int ldw, int M, int Nin, int Nout,
+               const char* tag = "dgrad") {
   GemmDesc g;
+  g.tag = tag;
   g.layout = GEMM_NN; g.A = dY; g.a_dtype = dy_dt; g.lda = ld_dy; g.B = W; g.b_dtype = w_dt; g.ldb = ldw;
   g.M = M; g.N = Nin; g.K = Nout;
   return g;
@@ -269,19 +291,19 @@ int backward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const v4h
       V4H_CUDA(cudaMemsetAsync(ws.dmod, 0, (size_t)B * p.Nmod * sizeof(float), s));
       const size_t offF = (size_t)d.depth * 6 * D;
       V4H_TRY(wgrad(p, dout, DT_F32, d.out_dim, ws.a_f, TA, D, gr.final_w, d.out_dim, D, M, s));
-      V4H_TRY(colsum_add<float>(dout, d.out_dim, gr.final_b, M, d.out_dim, s));
+      V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<float>(dout, d.out_dim, gr.final_b, M, d.out_dim, s); }));
       {
         GemmDesc g = dgrad(dout, DT_F32, d.out_dim, w.final_w, DT_F32, D, M, D, d.out_dim);
         g.ep.out = ws.dm; g.ep.ldo = D; g.out_dtype = TA;
-        V4H_TRY(gemm_simt(g, s));
+        V4H_TRY(run_gemm(p, g, s));
       }
       const int last = d.depth - 1;
       const float* modL = ws.mod + (size_t)last * 6 * D;
       float* dmodL = ws.dmod + (size_t)last * 6 * D;
-      V4H_TRY(ln_modulate_bwd<T>((const T*)ws.dm, ws.h[2 * d.depth], ws.stats_f, ws.mod + offF + D, p.Nmod,
+      V4H_TRY(prof("ln.bwd", 0, (double)M * D * (12 + 3 * sizeof(T)), s, [&] { return ln_modulate_bwd<T>((const T*)ws.dm, ws.h[2 * d.depth], ws.stats_f, ws.mod + offF + D, p.Nmod,
                                  ws.dh, false, ws.dmod + offF, ws.dmod + offF + D, p.Nmod,
                                  (const T*)ws.blk[last].y2, modL + 5 * D, (T*)ws.dy, dmodL + 5 * D,
-                                 gr.blocks[last].fc2_b, M, D, Tn, s));
+                                 gr.blocks[last].fc2_b, M, D, Tn, s); }));
     } else if (stage >= 1) {
       // ---------------- transformer block i
       const int i = stage - 1;
@@ -296,49 +318,49 @@ int backward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const v4h
       const void* Wfc2 = p.bf16 ? (const void*)(wa + p.arena_blocks[i].fc2) : (const void*)bw.fc2_w;
 
       // MLP branch: dy = gate_mlp * dh is ready in ws.dy
-      V4H_TRY(wgrad(p, ws.dy, TA, D, bb.g, TA, Hm, bg.fc2_w, D, Hm, M, s));
+      V4H_TRY(wgrad(p, ws.dy, TA, D, bb.g, TA, Hm, bg.fc2_w, D, Hm, M, s, "wgrad.fc2"));
       {
-        GemmDesc g = dgrad(ws.dy, TA, D, Wfc2, TA, Hm, M, Hm, D);
+        GemmDesc g = dgrad(ws.dy, TA, D, Wfc2, TA, Hm, M, Hm, D, "dgrad.fc2");
         g.epi = EPI_DACT; g.act = ACT_GELU_TANH; g.out_dtype = TA;
         g.ep.out = ws.du; g.ep.ldo = Hm; g.ep.aux = bb.u; g.ep.ld_aux = Hm;
         V4H_TRY(run_gemm(p, g, s));
       }
-      V4H_TRY(colsum_add<T>((const T*)ws.du, Hm, bg.fc1_b, M, Hm, s));
-      V4H_TRY(wgrad(p, ws.du, TA, Hm, bb.m, TA, D, bg.fc1_w, Hm, D, M, s));
+      V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<T>((const T*)ws.du, Hm, bg.fc1_b, M, Hm, s); }));
+      V4H_TRY(wgrad(p, ws.du, TA, Hm, bb.m, TA, D, bg.fc1_w, Hm, D, M, s, "wgrad.fc1"));
       {
-        GemmDesc g = dgrad(ws.du, TA, Hm, Wfc1, TA, D, M, D, Hm);
+        GemmDesc g = dgrad(ws.du, TA, Hm, Wfc1, TA, D, M, D, Hm, "dgrad.fc1");
         g.ep.out = ws.dm; g.ep.ldo = D; g.out_dtype = TA;
         V4H_TRY(run_gemm(p, g, s));
       }
-      V4H_TRY(ln_modulate_bwd<T>((const T*)ws.dm, ws.h[2 * i + 1], bb.stats2, mod + 4 * D, p.Nmod, ws.dh, true,
+      V4H_TRY(prof("ln.bwd", 0, (double)M * D * (12 + 3 * sizeof(T)), s, [&] { return ln_modulate_bwd<T>((const T*)ws.dm, ws.h[2 * i + 1], bb.stats2, mod + 4 * D, p.Nmod, ws.dh, true,
                                  dmod + 3 * D, dmod + 4 * D, p.Nmod, (const T*)bb.y1, mod + 2 * D, (T*)ws.dy,
-                                 dmod + 2 * D, bg.proj_b, M, D, Tn, s));
+                                 dmod + 2 * D, bg.proj_b, M, D, Tn, s); }));
       // attention branch: dy = gate_msa * dh
-      V4H_TRY(wgrad(p, ws.dy, TA, D, bb.o, TA, D, bg.proj_w, D, D, M, s));
+      V4H_TRY(wgrad(p, ws.dy, TA, D, bb.o, TA, D, bg.proj_w, D, D, M, s, "wgrad.proj"));
       {
-        GemmDesc g = dgrad(ws.dy, TA, D, Wproj, TA, D, M, D, D);
+        GemmDesc g = dgrad(ws.dy, TA, D, Wproj, TA, D, M, D, D, "dgrad.proj");
         g.ep.out = ws.dm; g.ep.ldo = D; g.out_dtype = TA;
         V4H_TRY(run_gemm(p, g, s));
       }
-      V4H_TRY(attention_bwd_simt<T>((const T*)bb.qkv, (const T*)bb.o, bb.lse, (const T*)ws.dm, (T*)ws.dqkv, B, Tn,
-                                    H, dh, s));
-      V4H_TRY(colsum_add<T>((const T*)ws.dqkv, 3 * D, bg.qkv_b, M, 3 * D, s));
-      V4H_TRY(wgrad(p, ws.dqkv, TA, 3 * D, bb.a, TA, D, bg.qkv_w, 3 * D, D, M, s));
+      V4H_TRY(prof("attn.bwd", 10.0 * B * H * Tn * Tn * dh, (double)M * 9 * D * sizeof(T), s, [&] { return attention_bwd_simt<T>((const T*)bb.qkv, (const T*)bb.o, bb.lse, (const T*)ws.dm, (T*)ws.dqkv, B, Tn,
+                                    H, dh, s); }));
+      V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<T>((const T*)ws.dqkv, 3 * D, bg.qkv_b, M, 3 * D, s); }));
+      V4H_TRY(wgrad(p, ws.dqkv, TA, 3 * D, bb.a, TA, D, bg.qkv_w, 3 * D, D, M, s, "wgrad.qkv"));
       {
-        GemmDesc g = dgrad(ws.dqkv, TA, 3 * D, Wqkv, TA, D, M, D, 3 * D);
+        GemmDesc g = dgrad(ws.dqkv, TA, 3 * D, Wqkv, TA, D, M, D, 3 * D, "dgrad.qkv");
         g.ep.out = ws.dm; g.ep.ldo = D; g.out_dtype = TA;
         V4H_TRY(run_gemm(p, g, s));
       }
       if (i > 0) {
         const float* modP = ws.mod + (size_t)(i - 1) * 6 * D;
         float* dmodP = ws.dmod + (size_t)(i - 1) * 6 * D;
-        V4H_TRY(ln_modulate_bwd<T>((const T*)ws.dm, ws.h[2 * i], bb.stats1, mod + 1 * D, p.Nmod, ws.dh, true,
+        V4H_TRY(prof("ln.bwd", 0, (double)M * D * (12 + 3 * sizeof(T)), s, [&] { return ln_modulate_bwd<T>((const T*)ws.dm, ws.h[2 * i], bb.stats1, mod + 1 * D, p.Nmod, ws.dh, true,
                                    dmod + 0 * D, dmod + 1 * D, p.Nmod, (const T*)ws.blk[i - 1].y2, modP + 5 * D,
-                                   (T*)ws.dy, dmodP + 5 * D, gr.blocks[i - 1].fc2_b, M, D, Tn, s));
+                                   (T*)ws.dy, dmodP + 5 * D, gr.blocks[i - 1].fc2_b, M, D, Tn, s); }));
       } else {
-        V4H_TRY(ln_modulate_bwd<T>((const T*)ws.dm, ws.h[0], bb.stats1, mod + 1 * D, p.Nmod, ws.dh, true,
+        V4H_TRY(prof("ln.bwd", 0, (double)M * D * (12 + 3 * sizeof(T)), s, [&] { return ln_modulate_bwd<T>((const T*)ws.dm, ws.h[0], bb.stats1, mod + 1 * D, p.Nmod, ws.dh, true,
                                    dmod + 0 * D, dmod + 1 * D, p.Nmod, (const T*)nullptr, nullptr, (T*)nullptr,
-                                   nullptr, nullptr, M, D, Tn, s));
+                                   nullptr, nullptr, M, D, Tn, s); }));
       }
     } else {
       // ---------------- stage 0: embeddings and conditioning.  ws.dh = d loss / d h0
@@ -355,7 +377,7 @@ int backward_stage0(Plan& p, const v4h_vit_params& w, const v4h_vit_params& gr, 
   const v4h_vit_dims& d = p.d;
   const int B = (int)B64, Tn = d.tokens, D = d.hidden_dim, M = B * Tn;
   V4H_TRY(wgrad(p, ws.dh, DT_F32, D, x, DT_F32, d.patch_dim, gr.x_w, D, d.patch_dim, M, s));
-  V4H_TRY(colsum_add<float>(ws.dh, D, gr.x_b, M, D, s));
+  V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<float>(ws.dh, D, gr.x_b, M, D, s); }));
   if (d.learn_pos_embed)
     V4H_TRY(pos_embedding_bwd(ws.dh, w.pos_embed_freqs, w.pos_z, w.pos_y, w.pos_x, gr.pos_embed_freqs, B, Tn,
                               D / 6, s));
@@ -372,13 +394,13 @@ int backward_stage0(Plan& p, const v4h_vit_params& w, const v4h_vit_params& gr, 
       GemmDesc g;
       g.layout = GEMM_TN; g.A = dmod; g.a_dtype = DT_F32; g.lda = p.Nmod; g.B = ws.sc; g.b_dtype = DT_F32;
       g.ldb = D; g.M = n; g.N = D; g.K = B; g.epi = EPI_ATOMIC; g.ep.out = dW; g.ep.ldo = D; g.splitk = 1;
-      V4H_TRY(gemm_simt(g, s));
+      V4H_TRY(run_gemm(p, g, s));
     }
-    V4H_TRY(colsum_add<float>(dmod, p.Nmod, db, B, n, s));
+    V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<float>(dmod, p.Nmod, db, B, n, s); }));
     {
       GemmDesc g = dgrad(dmod, DT_F32, p.Nmod, W, DT_F32, D, B, D, n);
       g.epi = EPI_ATOMIC; g.ep.out = ws.dsc; g.ep.ldo = D; g.splitk = std::max(1, n / 240);
-      V4H_TRY(gemm_simt(g, s));
+      V4H_TRY(run_gemm(p, g, s));
     }
   }
   V4H_TRY(dsilu_mul(ws.dsc, ws.cond, ws.dcond, (int64_t)B * D, s));
@@ -389,12 +411,12 @@ int backward_stage0(Plan& p, const v4h_vit_params& w, const v4h_vit_params& gr, 
       {ws.temb_in, ws.t_h_pre, ws.t_h, d.freq_dim, w.t2_w, gr.t0_w, gr.t0_b, gr.t2_w, gr.t2_b}};
   for (const Mlp& m : mlps) {
     V4H_TRY(wgrad(p, ws.dcond, DT_F32, D, m.h, DT_F32, D, m.dw2, D, D, B, s));
-    V4H_TRY(colsum_add<float>(ws.dcond, D, m.db2, B, D, s));
+    V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<float>(ws.dcond, D, m.db2, B, D, s); }));
     GemmDesc g = dgrad(ws.dcond, DT_F32, D, m.w2, DT_F32, D, B, D, D);
     g.epi = EPI_DACT; g.act = ACT_SILU; g.ep.out = ws.dvec; g.ep.ldo = D; g.ep.aux = m.h_pre; g.ep.ld_aux = D;
-    V4H_TRY(gemm_simt(g, s));
+    V4H_TRY(run_gemm(p, g, s));
     V4H_TRY(wgrad(p, ws.dvec, DT_F32, D, m.in, DT_F32, m.in_dim, m.dw0, D, m.in_dim, B, s));
-    V4H_TRY(colsum_add<float>(ws.dvec, D, m.db0, B, D, s));
+    V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<float>(ws.dvec, D, m.db0, B, D, s); }));
   }
   return V4H_OK;
 }
