@@ -82,7 +82,14 @@ template <> __device__ __forceinline__ float from_f<float>(float v) { return v; 
 template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
 
 // ---------------------------------------------------------------- activations
-enum Act { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU_TANH = 2 };
+// ACT_GELU_TANH_FAST: same function with the hardware tanh.approx (abs. error ~5e-4, below bf16
+// resolution); used by the bf16 tensor-core epilogues only
+enum Act { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU_TANH = 2, ACT_GELU_TANH_FAST = 3 };
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
 __device__ __forceinline__ float dsilu_f(float x) {
@@ -102,12 +109,24 @@ __device__ __forceinline__ float dgelu_tanh_f(float x) {
   float dinner = k0 * (1.f + 3.f * k1 * x2);
   return 0.5f * (1.f + th) + 0.5f * x * (1.f - th * th) * dinner;
 }
+__device__ __forceinline__ float gelu_tanh_fast_f(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  return 0.5f * x * (1.f + tanh_fast(k0 * (x + k1 * x * x * x)));
+}
+__device__ __forceinline__ float dgelu_tanh_fast_f(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float x2 = x * x;
+  const float th = tanh_fast(k0 * (x + k1 * x * x2));
+  return 0.5f * (1.f + th) + 0.5f * x * (1.f - th * th) * k0 * (1.f + 3.f * k1 * x2);
+}
 template <int ACT> __device__ __forceinline__ float act_f(float x) {
+  if (ACT == ACT_GELU_TANH_FAST) return gelu_tanh_fast_f(x);
   if (ACT == ACT_SILU) return silu_f(x);
   if (ACT == ACT_GELU_TANH) return gelu_tanh_f(x);
   return x;
 }
 template <int ACT> __device__ __forceinline__ float dact_f(float x) {
+  if (ACT == ACT_GELU_TANH_FAST) return dgelu_tanh_fast_f(x);
   if (ACT == ACT_SILU) return dsilu_f(x);
   if (ACT == ACT_GELU_TANH) return dgelu_tanh_f(x);
   return 1.f;
@@ -150,55 +169,194 @@ struct EpiParams {
   float* res_out = nullptr;       // fp32 (M, N)
   const void* aux = nullptr;      // TOut (M, ld_aux)
   int ld_aux = 0;
+  bool vec_ok = false;  // set by the launcher (epilogue_vec_ok)
 };
 
+// ---- vector access helpers: NV consecutive values of one row, 16-byte transactions when `vec`
+template <int NV>
+__device__ __forceinline__ void load_row(const float* __restrict__ p, float (&v)[NV], bool vec) {
+  if (vec) {
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i) {
+      const float4 t = *reinterpret_cast<const float4*>(p + 4 * i);
+      v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = p[i];
+  }
+}
+template <int NV>
+__device__ __forceinline__ void load_row(const bf16* __restrict__ p, float (&v)[NV], bool vec) {
+  if (vec) {
+    if (NV % 8 == 0) {
+#pragma unroll
+      for (int i = 0; i < NV / 8; ++i) {
+        const uint4 t = *reinterpret_cast<const uint4*>(p + 8 * i);
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+          v[8 * i + 2 * j] = f.x; v[8 * i + 2 * j + 1] = f.y;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV / 4; ++i) {
+        const uint2 t = *reinterpret_cast<const uint2*>(p + 4 * i);
+        const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+        const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+        v[4 * i] = f0.x; v[4 * i + 1] = f0.y; v[4 * i + 2] = f1.x; v[4 * i + 3] = f1.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = __bfloat162float(p[i]);
+  }
+}
+template <int NV>
+__device__ __forceinline__ void store_row(float* __restrict__ p, const float (&v)[NV], bool vec, int nvalid) {
+  if (vec) {
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i)
+      *reinterpret_cast<float4*>(p + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (i < nvalid) p[i] = v[i];
+  }
+}
+template <int NV>
+__device__ __forceinline__ void store_row(bf16* __restrict__ p, const float (&v)[NV], bool vec, int nvalid) {
+  if (vec) {
+    if (NV % 8 == 0) {
+#pragma unroll
+      for (int i = 0; i < NV / 8; ++i) {
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+          w[j] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(p + 8 * i) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV / 4; ++i) {
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[4 * i], v[4 * i + 1]);
+        const __nv_bfloat162 h1 = __floats2bfloat162_rn(v[4 * i + 2], v[4 * i + 3]);
+        *reinterpret_cast<uint2*>(p + 4 * i) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (i < nvalid) p[i] = __float2bfloat16_rn(v[i]);
+  }
+}
+
+// One run of NV consecutive columns [col0, col0 + NV) of output row `row`; the first `ncols_valid`
+// are inside the matrix.  When the run is complete and p.vec_ok says every row pitch / base pointer
+// involved keeps it 16-byte aligned, all accesses are 128-bit.
 template <int EPI, int ACT, typename TOut, int NV>
 __device__ __forceinline__ void epilogue_run(const EpiParams& p, int row, int col0, int ncols_valid,
                                              const float (&acc)[NV]) {
-  // ncols_valid: number of leading entries of acc that are inside the matrix
+  const bool vec = p.vec_ok && ncols_valid == NV;
   if (EPI == EPI_BIAS_ACT) {
-    TOut* o = reinterpret_cast<TOut*>(p.out) + (size_t)row * p.ldo + col0;
-    TOut* o2 = p.out2 ? reinterpret_cast<TOut*>(p.out2) + (size_t)row * p.ldo + col0 : nullptr;
-    const float* ad = nullptr;
-    if (p.addend) {
-      int ar = p.addend_rows > 0 ? row % p.addend_rows : row;
-      ad = p.addend + (size_t)ar * p.ld_addend + col0;
-    }
+    float pre[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      if (i < ncols_valid) {
-        float pre = acc[i];
-        if (p.bias) pre += p.bias[col0 + i];
-        if (ad) pre += ad[i];
-        if (o2) o2[i] = from_f<TOut>(pre);
-        o[i] = from_f<TOut>(act_f<ACT>(pre));
+    for (int i = 0; i < NV; ++i) pre[i] = acc[i];
+    if (p.bias) {
+      float b[NV];
+      if (vec) load_row<NV>(p.bias + col0, b, true);
+      else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) b[i] = i < ncols_valid ? p.bias[col0 + i] : 0.f;
       }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) pre[i] += b[i];
     }
+    if (p.addend) {
+      const int ar = p.addend_rows > 0 ? row % p.addend_rows : row;
+      const float* ad = p.addend + (size_t)ar * p.ld_addend + col0;
+      float a[NV];
+      if (vec) load_row<NV>(ad, a, true);
+      else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) a[i] = i < ncols_valid ? ad[i] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) pre[i] += a[i];
+    }
+    if (p.out2) store_row<NV>(reinterpret_cast<TOut*>(p.out2) + (size_t)row * p.ldo + col0, pre, vec, ncols_valid);
+    if (ACT != ACT_NONE) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) pre[i] = act_f<ACT>(pre[i]);
+    }
+    store_row<NV>(reinterpret_cast<TOut*>(p.out) + (size_t)row * p.ldo + col0, pre, vec, ncols_valid);
   } else if (EPI == EPI_GATE_RES) {
-    TOut* o2 = p.out2 ? reinterpret_cast<TOut*>(p.out2) + (size_t)row * p.ldo + col0 : nullptr;
     const float* gate = p.gate + (size_t)(row / p.rows_per_sample) * p.mod_stride + col0;
     const float* rin = p.res_in + (size_t)row * p.ldo + col0;
-    float* rout = p.res_out + (size_t)row * p.ldo + col0;
+    float y[NV], gt[NV], r[NV];
+    if (vec) {
+      load_row<NV>(gate, gt, true);
+      load_row<NV>(rin, r, true);
+      if (p.bias) load_row<NV>(p.bias + col0, y, true);
+    } else {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      if (i < ncols_valid) {
-        float y = acc[i] + (p.bias ? p.bias[col0 + i] : 0.f);
-        if (o2) o2[i] = from_f<TOut>(y);
-        rout[i] = rin[i] + gate[i] * y;
+      for (int i = 0; i < NV; ++i) {
+        const bool ok = i < ncols_valid;
+        gt[i] = ok ? gate[i] : 0.f; r[i] = ok ? rin[i] : 0.f; y[i] = (ok && p.bias) ? p.bias[col0 + i] : 0.f;
       }
     }
-  } else if (EPI == EPI_DACT) {
-    TOut* o = reinterpret_cast<TOut*>(p.out) + (size_t)row * p.ldo + col0;
-    const TOut* aux = reinterpret_cast<const TOut*>(p.aux) + (size_t)row * p.ld_aux + col0;
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
-      if (i < ncols_valid) o[i] = from_f<TOut>(acc[i] * dact_f<ACT>(to_f(aux[i])));
+    for (int i = 0; i < NV; ++i) {
+      y[i] = acc[i] + (p.bias ? y[i] : 0.f);
+      r[i] = r[i] + gt[i] * y[i];
+    }
+    if (p.out2) store_row<NV>(reinterpret_cast<TOut*>(p.out2) + (size_t)row * p.ldo + col0, y, vec, ncols_valid);
+    store_row<NV>(p.res_out + (size_t)row * p.ldo + col0, r, vec, ncols_valid);
+  } else if (EPI == EPI_DACT) {
+    const TOut* aux = reinterpret_cast<const TOut*>(p.aux) + (size_t)row * p.ld_aux + col0;
+    float u[NV];
+    if (vec) load_row<NV>(aux, u, true);
+    else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) u[i] = i < ncols_valid ? to_f(aux[i]) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) u[i] = acc[i] * dact_f<ACT>(u[i]);
+    store_row<NV>(reinterpret_cast<TOut*>(p.out) + (size_t)row * p.ldo + col0, u, vec, ncols_valid);
   } else {  // EPI_ATOMIC
     float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0;
+    if (vec) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
-      if (i < ncols_valid) atomicAdd(o + i, acc[i]);
+      for (int i = 0; i < NV / 4; ++i)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * i), "f"(acc[4 * i]),
+                     "f"(acc[4 * i + 1]), "f"(acc[4 * i + 2]), "f"(acc[4 * i + 3])
+                     : "memory");
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (i < ncols_valid) atomicAdd(o + i, acc[i]);
+    }
   }
+}
+
+// host side: can every row run of this epilogue use 128-bit accesses?  (col0 is always a multiple of NV)
+inline bool epilogue_vec_ok(const EpiParams& p, int epi, bool out_bf16) {
+  auto al = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
+  const int unit = out_bf16 ? 8 : 4;  // elements per 16 bytes of TOut
+  if (p.ldo % unit) return false;
+  if (!al(p.out) || !al(p.out2) || !al(p.bias) || !al(p.addend) || !al(p.gate) || !al(p.res_in) || !al(p.res_out) ||
+      !al(p.aux))
+    return false;
+  if (p.addend && p.ld_addend % 4) return false;
+  if (p.gate && p.mod_stride % 4) return false;
+  if (epi == EPI_GATE_RES && p.ldo % 4) return false;
+  if (p.aux && p.ld_aux % unit) return false;
+  return true;
 }
 
 }  // namespace v4h

@@ -108,7 +108,9 @@ int launch(const GemmDesc& d, cudaStream_t s) {
   splits = (int)ceil_div(d.K, kper);
   g.k_per_split = kper;
   dim3 grid((unsigned)ceil_div(d.N, BN), (unsigned)ceil_div(d.M, BM), (unsigned)splits);
-  gemm_simt_kernel<TA, TB, EPI, ACT, TOut><<<grid, NT, 0, s>>>(g, d.ep);
+  EpiParams ep = d.ep;
+  ep.vec_ok = epilogue_vec_ok(ep, EPI, sizeof(TOut) == 2);
+  gemm_simt_kernel<TA, TB, EPI, ACT, TOut><<<grid, NT, 0, s>>>(g, ep);
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }

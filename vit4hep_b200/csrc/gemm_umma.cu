@@ -308,22 +308,24 @@ int gemm_umma(UmmaContext* ctx, const GemmDesc& d, cudaStream_t s) {
   const int total = g.tiles_m * g.tiles_n * g.splits;
   const int grid = total < ctx->num_sms ? total : ctx->num_sms;
   const bool obf = d.out_dtype == DT_BF16;
+  EpiParams ep = d.ep;
+  ep.vec_ok = epilogue_vec_ok(ep, d.epi, d.epi == EPI_ATOMIC ? false : obf);
   switch (d.epi) {
     case EPI_BIAS_ACT:
       if (d.act == ACT_NONE)
-        return obf ? launch<EPI_BIAS_ACT, ACT_NONE, bf16>(ta, tb, g, d.ep, grid, s)
-                   : launch<EPI_BIAS_ACT, ACT_NONE, float>(ta, tb, g, d.ep, grid, s);
-      if (d.act == ACT_GELU_TANH && obf) return launch<EPI_BIAS_ACT, ACT_GELU_TANH, bf16>(ta, tb, g, d.ep, grid, s);
-      if (d.act == ACT_SILU && !obf) return launch<EPI_BIAS_ACT, ACT_SILU, float>(ta, tb, g, d.ep, grid, s);
+        return obf ? launch<EPI_BIAS_ACT, ACT_NONE, bf16>(ta, tb, g, ep, grid, s)
+                   : launch<EPI_BIAS_ACT, ACT_NONE, float>(ta, tb, g, ep, grid, s);
+      if (d.act == ACT_GELU_TANH && obf) return launch<EPI_BIAS_ACT, ACT_GELU_TANH_FAST, bf16>(ta, tb, g, ep, grid, s);
+      if (d.act == ACT_SILU && !obf) return launch<EPI_BIAS_ACT, ACT_SILU, float>(ta, tb, g, ep, grid, s);
       break;
     case EPI_GATE_RES:
-      if (obf) return launch<EPI_GATE_RES, ACT_NONE, bf16>(ta, tb, g, d.ep, grid, s);
+      if (obf) return launch<EPI_GATE_RES, ACT_NONE, bf16>(ta, tb, g, ep, grid, s);
       break;
     case EPI_DACT:
-      if (d.act == ACT_GELU_TANH && obf) return launch<EPI_DACT, ACT_GELU_TANH, bf16>(ta, tb, g, d.ep, grid, s);
+      if (d.act == ACT_GELU_TANH && obf) return launch<EPI_DACT, ACT_GELU_TANH_FAST, bf16>(ta, tb, g, ep, grid, s);
       break;
     case EPI_ATOMIC:
-      return launch<EPI_ATOMIC, ACT_NONE, float>(ta, tb, g, d.ep, grid, s);
+      return launch<EPI_ATOMIC, ACT_NONE, float>(ta, tb, g, ep, grid, s);
   }
   return fail(V4H_ERR_UNSUPPORTED, "gemm_umma: epilogue %d / activation %d / output dtype %d is not instantiated", d.epi,
               d.act, d.out_dtype);
