@@ -64,9 +64,11 @@ def test_simt_gemm_layouts(layout):
         assert vo.rel_l2(got, want) < 1e-6
 
 
-@pytest.mark.parametrize("precision", [0, 1])
-@pytest.mark.parametrize("B,T,H,dh", [(2, 135, 6, 80), (1, 450, 6, 80), (3, 84, 2, 24), (1, 606, 6, 80), (2, 33, 4, 32)])
-def test_attention_fwd_bwd(precision, B, T, H, dh):
+@pytest.mark.parametrize("precision,engine", [(0, 0), (1, 0), (1, 1)])
+@pytest.mark.parametrize("B,T,H,dh", [(2, 135, 6, 80), (1, 450, 6, 80), (3, 84, 2, 24), (1, 606, 6, 80), (2, 33, 4, 32),
+                                      (2, 128, 2, 64), (1, 300, 3, 128), (1, 1, 1, 8), (2, 17, 3, 40)])
+def test_attention_fwd_bwd(precision, engine, B, T, H, dh):
+    """engine 0 = SIMT kernels (fp32 mode arithmetic), 1 = tcgen05 / TMEM kernels (bf16 mode)"""
     from vit4hep_b200 import _cabi
     lib = _cabi.load()
     dev = torch.device("cuda:0")
@@ -78,8 +80,8 @@ def test_attention_fwd_bwd(precision, B, T, H, dh):
     lse = torch.empty(B, H, T, device=dev, dtype=torch.float32)
     dqkv = torch.empty_like(qkv)
     s = torch.cuda.current_stream().cuda_stream
-    _cabi.check(lib.v4h_test_attention_fwd(precision, 0, qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), B, T, H, dh, s))
-    _cabi.check(lib.v4h_test_attention_bwd(precision, 0, qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), d_o.data_ptr(),
+    _cabi.check(lib.v4h_test_attention_fwd(precision, engine, qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), B, T, H, dh, s))
+    _cabi.check(lib.v4h_test_attention_bwd(precision, engine, qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), d_o.data_ptr(),
                                            dqkv.data_ptr(), B, T, H, dh, s))
     ref = qkv.double().requires_grad_(True)
     q, k, v = ref.permute(2, 0, 3, 1, 4)
@@ -88,5 +90,5 @@ def test_attention_fwd_bwd(precision, B, T, H, dh):
     want.backward(d_o.double())
     tol = 2e-2 if precision else 1e-5
     assert vo.rel_l2(o, want) < tol
-    assert vo.rel_l2(lse, torch.logsumexp(sc, -1)) < 1e-5 if not precision else True
+    assert vo.rel_l2(lse, torch.logsumexp(sc, -1)) < (1e-5 if not precision else 2e-3)
     assert vo.rel_l2(dqkv, ref.grad) < tol

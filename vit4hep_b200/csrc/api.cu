@@ -336,7 +336,10 @@ int v4h_test_gemm(int32_t engine, int32_t layout, const void* A, const void* B, 
 int v4h_test_attention_fwd(int32_t precision, int32_t engine, const void* qkv, void* o, float* lse, int32_t batch,
                            int32_t tokens, int32_t heads, int32_t head_dim, v4h_stream_t s) {
   V4H_REQUIRE(qkv && o && lse, "test_attention_fwd: null argument");
-  if (engine != 0) return fail(V4H_ERR_UNSUPPORTED, "test_attention_fwd: tcgen05 attention not built yet");
+  if (engine != 0) {
+    V4H_REQUIRE(precision == V4H_BF16, "test_attention_fwd: the tcgen05 kernels are bf16 only");
+    return attention_fwd_umma((const bf16*)qkv, (bf16*)o, lse, batch, tokens, heads, head_dim, (cudaStream_t)s);
+  }
   if (precision == V4H_BF16)
     return attention_fwd_simt<bf16>((const bf16*)qkv, (bf16*)o, lse, batch, tokens, heads, head_dim, (cudaStream_t)s);
   return attention_fwd_simt<float>((const float*)qkv, (float*)o, lse, batch, tokens, heads, head_dim, (cudaStream_t)s);
@@ -345,7 +348,15 @@ int v4h_test_attention_bwd(int32_t precision, int32_t engine, const void* qkv, c
                            const void* d_o, void* dqkv, int32_t batch, int32_t tokens, int32_t heads,
                            int32_t head_dim, v4h_stream_t s) {
   V4H_REQUIRE(qkv && o && lse && d_o && dqkv, "test_attention_bwd: null argument");
-  if (engine != 0) return fail(V4H_ERR_UNSUPPORTED, "test_attention_bwd: tcgen05 attention not built yet");
+  if (engine != 0) {
+    V4H_REQUIRE(precision == V4H_BF16, "test_attention_bwd: the tcgen05 kernels are bf16 only");
+    float* delta = nullptr;  // test hook only: scratch for rowsum(dO * O)
+    V4H_CUDA(cudaMallocAsync(&delta, sizeof(float) * (size_t)batch * heads * tokens, (cudaStream_t)s));
+    const int rc = attention_bwd_umma((const bf16*)qkv, (const bf16*)o, lse, (const bf16*)d_o, delta, (bf16*)dqkv,
+                                      batch, tokens, heads, head_dim, (cudaStream_t)s);
+    cudaFreeAsync(delta, (cudaStream_t)s);
+    return rc;
+  }
   if (precision == V4H_BF16)
     return attention_bwd_simt<bf16>((const bf16*)qkv, (const bf16*)o, lse, (const bf16*)d_o, (bf16*)dqkv, batch,
                                     tokens, heads, head_dim, (cudaStream_t)s);

@@ -48,6 +48,13 @@ template <typename T>
 int attention_bwd_simt(const T* qkv, const T* o, const float* lse, const T* d_o, T* dqkv, int B, int Tn,
                        int H, int dh, cudaStream_t s);
 
+// attention_umma.cu: the same contraction on tcgen05 / TMEM (bf16 only, head_dim a multiple of 8, <= 128).
+// The backward also writes delta (B, H, T) = rowsum(dO * O) (caller-provided scratch).
+bool attention_umma_supported(int dh);
+int attention_fwd_umma(const bf16* qkv, bf16* o, float* lse, int B, int Tn, int H, int dh, cudaStream_t s);
+int attention_bwd_umma(const bf16* qkv, const bf16* o, const float* lse, const bf16* d_o, float* delta, bf16* dqkv,
+                       int B, int Tn, int H, int dh, cudaStream_t s);
+
 // layernorm.cu
 // a = LN(h) * (1 + scale[b]) + shift[b];  stats[row] = (mean, rstd)
 template <typename T>

@@ -39,6 +39,13 @@ struct BlockBufs {
   float2 *stats1, *stats2;
 };
 
+// attention forward / backward of one block: tcgen05 kernels in bf16 mode, SIMT otherwise
+template <typename T>
+int attn_fwd(const Plan& p, const void* qkv, void* o, float* lse, int B, int Tn, int H, int dh, cudaStream_t s);
+template <typename T>
+int attn_bwd(const Plan& p, const void* qkv, const void* o, const float* lse, const void* d_o, float* delta,
+             void* dqkv, int B, int Tn, int H, int dh, cudaStream_t s);
+
 struct Workspace {
   // conditioning
   float *pe, *temb_in, *t_h_pre, *t_h, *te, *c_h_pre, *c_h, *cond, *sc, *mod;
@@ -49,7 +56,7 @@ struct Workspace {
   void* a_f;
   float2* stats_f;
   // backward scratch
-  float *dh, *dmod, *dsc, *dcond, *dvec;
+  float *dh, *dmod, *dsc, *dcond, *dvec, *attn_delta;
   bf16* dmod_bf16;
   void *dy, *du, *dm, *dqkv;
   size_t bytes = 0;
@@ -95,8 +102,9 @@ struct Workspace {
       dmod_bf16 = (bf16*)take((size_t)B * p.Nmod * 2);
       dsc = (float*)take(B * D * 4); dcond = (float*)take(B * D * 4); dvec = (float*)take(B * D * 4);
       dy = take(M * D * ta); du = take(M * Hm * ta); dm = take(M * D * ta); dqkv = take(M * 3 * D * ta);
+      attn_delta = (float*)take((size_t)B * d.num_heads * d.tokens * 4);
     } else {
-      dh = dmod = dsc = dcond = dvec = nullptr; dmod_bf16 = nullptr;
+      dh = dmod = dsc = dcond = dvec = attn_delta = nullptr; dmod_bf16 = nullptr;
       dy = du = dm = dqkv = nullptr;
     }
     bytes = off;
@@ -104,6 +112,31 @@ struct Workspace {
 };
 
 inline int hidx(bool train, int i) { return train ? i : 0; }
+
+template <>
+int attn_fwd<float>(const Plan&, const void* qkv, void* o, float* lse, int B, int Tn, int H, int dh, cudaStream_t s) {
+  return attention_fwd_simt<float>((const float*)qkv, (float*)o, lse, B, Tn, H, dh, s);
+}
+template <>
+int attn_fwd<bf16>(const Plan& p, const void* qkv, void* o, float* lse, int B, int Tn, int H, int dh, cudaStream_t s) {
+  if (p.use_umma_attn) return attention_fwd_umma((const bf16*)qkv, (bf16*)o, lse, B, Tn, H, dh, s);
+  return attention_fwd_simt<bf16>((const bf16*)qkv, (bf16*)o, lse, B, Tn, H, dh, s);
+}
+template <>
+int attn_bwd<float>(const Plan&, const void* qkv, const void* o, const float* lse, const void* d_o, float*,
+                    void* dqkv, int B, int Tn, int H, int dh, cudaStream_t s) {
+  return attention_bwd_simt<float>((const float*)qkv, (const float*)o, lse, (const float*)d_o, (float*)dqkv, B, Tn, H,
+                                   dh, s);
+}
+template <>
+int attn_bwd<bf16>(const Plan& p, const void* qkv, const void* o, const float* lse, const void* d_o, float* delta,
+                   void* dqkv, int B, int Tn, int H, int dh, cudaStream_t s) {
+  if (p.use_umma_attn)
+    return attention_bwd_umma((const bf16*)qkv, (const bf16*)o, lse, (const bf16*)d_o, delta, (bf16*)dqkv, B, Tn, H,
+                              dh, s);
+  return attention_bwd_simt<bf16>((const bf16*)qkv, (const bf16*)o, lse, (const bf16*)d_o, (bf16*)dqkv, B, Tn, H, dh,
+                                  s);
+}
 
 // run `f` (a launcher) inside a profiling scope
 template <typename F>
@@ -224,7 +257,7 @@ int forward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const floa
       g.ep.bias = bw.qkv_b; g.ep.out = bb.qkv; g.ep.ldo = 3 * D; g.out_dtype = TA;
       V4H_TRY(run_gemm(p, g, s));
     }
-    V4H_TRY(prof("attn.fwd", 4.0 * B * d.num_heads * Tn * Tn * (D / d.num_heads), (double)M * 4 * D * sizeof(T), s, [&] { return attention_fwd_simt<T>((const T*)bb.qkv, (T*)bb.o, bb.lse, B, Tn, d.num_heads, D / d.num_heads, s); }));
+    V4H_TRY(prof("attn.fwd", 4.0 * B * d.num_heads * Tn * Tn * (D / d.num_heads), (double)M * 4 * D * sizeof(T), s, [&] { return attn_fwd<T>(p, bb.qkv, bb.o, bb.lse, B, Tn, d.num_heads, D / d.num_heads, s); }));
     {
       GemmDesc g = linear_fwd(bb.o, TA, D, Wproj, TA, D, M, D, D);
       g.tag = "gemm.proj";
@@ -342,8 +375,7 @@ int backward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const v4h
         g.ep.out = ws.dm; g.ep.ldo = D; g.out_dtype = TA;
         V4H_TRY(run_gemm(p, g, s));
       }
-      V4H_TRY(prof("attn.bwd", 10.0 * B * H * Tn * Tn * dh, (double)M * 9 * D * sizeof(T), s, [&] { return attention_bwd_simt<T>((const T*)bb.qkv, (const T*)bb.o, bb.lse, (const T*)ws.dm, (T*)ws.dqkv, B, Tn,
-                                    H, dh, s); }));
+      V4H_TRY(prof("attn.bwd", 10.0 * B * H * Tn * Tn * dh, (double)M * 9 * D * sizeof(T), s, [&] { return attn_bwd<T>(p, bb.qkv, bb.o, bb.lse, ws.dm, ws.attn_delta, ws.dqkv, B, Tn, H, dh, s); }));
       V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<T>((const T*)ws.dqkv, 3 * D, bg.qkv_b, M, 3 * D, s); }));
       V4H_TRY(wgrad(p, ws.dqkv, TA, 3 * D, bb.a, TA, D, bg.qkv_w, 3 * D, D, M, s, "wgrad.qkv"));
       {
@@ -446,6 +478,9 @@ int plan_create(const v4h_vit_dims* dims, Plan** out) {
   const char* no_umma = getenv("V4H_DISABLE_UMMA");
   p->use_umma = p->bf16 && !(no_umma && no_umma[0] == '1');
   if (p->use_umma) p->umma = umma_context_create();
+  const char* no_umma_attn = getenv("V4H_DISABLE_UMMA_ATTN");
+  p->use_umma_attn = p->use_umma && attention_umma_supported(d.hidden_dim / d.num_heads) &&
+                     !(no_umma_attn && no_umma_attn[0] == '1');
   if (p->bf16) {
     const size_t D = d.hidden_dim, Hm = d.mlp_hidden;
     size_t off = 0;
