@@ -36,6 +36,60 @@ __global__ void colsum_kernel(const T* __restrict__ x, int ld, float* __restrict
   }
 }
 
+
+// vectorised variant: thread = 8 consecutive columns (16-byte loads of bf16, 2 x 16 bytes of fp32),
+// blockDim (32, 8) = 256 columns x 8 row lanes
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+    v[2 * j] = f.x; v[2 * j + 1] = f.y;
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x, int ld, float* __restrict__ out,
+                                                         int M, int N, int rows_per_cta) {
+  __shared__ float red[8][32][9];
+  const int col = (blockIdx.x * 32 + threadIdx.x) * 8;
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int r1 = min(M, r0 + rows_per_cta);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col < N) {
+    int r = r0 + threadIdx.y;
+    for (; r + 8 < r1; r += 16) {  // two rows in flight
+      float a[8], b[8];
+      load8(x + (size_t)r * ld + col, a);
+      load8(x + (size_t)(r + 8) * ld + col, b);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += a[i] + b[i];
+    }
+    for (; r < r1; r += 8) {
+      float a[8];
+      load8(x + (size_t)r * ld + col, a);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += a[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[threadIdx.y][threadIdx.x][i] = acc[i];
+  __syncthreads();
+  // 256 threads -> 256 columns of this CTA
+  const int t = threadIdx.y * 32 + threadIdx.x;
+  const int c = blockIdx.x * 256 + t;
+  if (c < N) {
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += red[i][t >> 3][t & 7];
+    atomicAdd(out + c, sum);
+  }
+}
+
 // ---------------------------------------------------------------- timestep embedding
 // reference nn/vit.py:368-389: cat(cos(t f), sin(t f)), f_i = exp(-ln(1e4) i / half)
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, int shared_t, float* __restrict__ out,
@@ -191,6 +245,13 @@ __global__ void axpy4_kernel(float* __restrict__ out, const float* __restrict__ 
 
 template <typename T>
 int colsum_add(const T* x, int ld, float* out, int M, int N, cudaStream_t s) {
+  if (N % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const int rows = M >= 4096 ? 128 : 64;
+    dim3 vgrid((unsigned)ceil_div(N, 256), (unsigned)ceil_div(M, rows));
+    colsum_vec_kernel<T><<<vgrid, dim3(32, 8), 0, s>>>(x, ld, out, M, N, rows);
+    V4H_LAUNCH_CHECK();
+    return V4H_OK;
+  }
   const int rows_per_cta = 256;
   dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(M, rows_per_cta));
   colsum_kernel<T><<<grid, dim3(32, 8), 0, s>>>(x, ld, out, M, N, rows_per_cta);

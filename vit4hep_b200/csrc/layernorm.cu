@@ -3,6 +3,8 @@
 // Restates: reference nn/vit.py:309-311 (norm1/norm2), :457-458 (modulate), :331-332 (gated residual).
 // One warp per token row; the per-sample reductions (d shift, d scale, d gate) are done per CTA in
 // registers/shared memory and published with one atomicAdd per (CTA, column).
+#include <initializer_list>
+
 #include "kernels.cuh"
 
 namespace v4h {
@@ -146,6 +148,141 @@ __global__ void __launch_bounds__(WARPS * 32) ln_mod_bwd_kernel(
   }
 }
 
+// ---- vectorised variant (D % 4 == 0): thread = 4 consecutive columns, CTA = one slab of rows of ONE
+// sample, RB rows in flight per iteration; the two LayerNorm row sums cross the warps through a
+// double-buffered shared-memory exchange (one __syncthreads per RB rows).  Per-thread state is
+// 4 columns x 4 accumulators, so many CTAs fit per SM and the loads of RB rows overlap.
+constexpr int RB = 4;
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const bf16* p) {
+  const uint2 t = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(bf16* p, float4 v) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+}
+__device__ __forceinline__ void red4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+template <typename T, bool HAS_LN, bool HAS_GATE>
+__global__ void __launch_bounds__(128) ln_mod_bwd_vec_kernel(
+    const T* __restrict__ da, const float* __restrict__ h, const float2* __restrict__ stats,
+    const float* __restrict__ scale, int mod_stride, float* __restrict__ dh, bool dh_accumulate,
+    float* __restrict__ dshift, float* __restrict__ dscale, int dmod_stride, const T* __restrict__ y,
+    const float* __restrict__ gate, T* __restrict__ dy, float* __restrict__ dgate,
+    float* __restrict__ dbias, int D, int rows_per_sample, int rows_per_cta) {
+  __shared__ float2 part[2][RB][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int b = blockIdx.y;
+  const int r_begin = blockIdx.x * rows_per_cta;
+  const int r_end = min(rows_per_sample, r_begin + rows_per_cta);
+  const int col = threadIdx.x * 4;
+  const bool act = col < D;
+  const float inv_d = 1.f / (float)D;
+
+  float4 sc1 = make_float4(0.f, 0.f, 0.f, 0.f), gt = sc1;
+  if (act) {
+    if (HAS_LN) {
+      sc1 = ld4(scale + (size_t)b * mod_stride + col);
+      sc1.x += 1.f; sc1.y += 1.f; sc1.z += 1.f; sc1.w += 1.f;
+    }
+    if (HAS_GATE) gt = ld4(gate + (size_t)b * mod_stride + col);
+  }
+  float4 a_shift = make_float4(0.f, 0.f, 0.f, 0.f), a_scale = a_shift, a_gate = a_shift, a_bias = a_shift;
+
+  int buf = 0;
+  for (int r0 = r_begin; r0 < r_end; r0 += RB, buf ^= 1) {
+    float4 g[RB], xh[RB], dold[RB], yv[RB];
+    float rstd[RB];
+#pragma unroll
+    for (int k = 0; k < RB; ++k) {
+      const bool ok = act && r0 + k < r_end;
+      const size_t off = ((size_t)b * rows_per_sample + min(r0 + k, r_end - 1)) * D + col;
+      g[k] = xh[k] = dold[k] = yv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      rstd[k] = 0.f;
+      if (ok) {
+        if (HAS_LN) {
+          g[k] = ld4(da + off);  // holds da until the accumulators have seen it
+          xh[k] = ld4(h + off);
+          if (dh_accumulate) dold[k] = ld4(dh + off);
+        } else {
+          dold[k] = ld4(dh + off);
+        }
+        if (HAS_GATE) yv[k] = ld4(y + off);
+      }
+    }
+    if (HAS_LN) {
+#pragma unroll
+      for (int k = 0; k < RB; ++k) {
+        const float2 st = stats[(size_t)b * rows_per_sample + min(r0 + k, r_end - 1)];
+        rstd[k] = st.y;
+        const bool ok = act && r0 + k < r_end;
+        float4 x = xh[k], d4 = g[k];
+        x.x = (x.x - st.x) * st.y; x.y = (x.y - st.x) * st.y; x.z = (x.z - st.x) * st.y; x.w = (x.w - st.x) * st.y;
+        if (!ok) x = make_float4(0.f, 0.f, 0.f, 0.f);
+        a_shift.x += d4.x; a_shift.y += d4.y; a_shift.z += d4.z; a_shift.w += d4.w;
+        a_scale.x += d4.x * x.x; a_scale.y += d4.y * x.y; a_scale.z += d4.z * x.z; a_scale.w += d4.w * x.w;
+        d4.x *= sc1.x; d4.y *= sc1.y; d4.z *= sc1.z; d4.w *= sc1.w;
+        xh[k] = x; g[k] = d4;
+        float s1 = d4.x + d4.y + d4.z + d4.w;
+        float s2 = d4.x * x.x + d4.y * x.y + d4.z * x.z + d4.w * x.w;
+        s1 = warp_sum(s1); s2 = warp_sum(s2);
+        if (lane == 0) part[buf][k][warp] = make_float2(s1, s2);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < RB; ++k) {
+      const bool ok = act && r0 + k < r_end;
+      float4 dn = dold[k];
+      if (HAS_LN) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int w = 0; w < nwarps; ++w) { const float2 p2 = part[buf][k][w]; s1 += p2.x; s2 += p2.y; }
+        s1 *= inv_d; s2 *= inv_d;
+        dn.x += rstd[k] * (g[k].x - s1 - xh[k].x * s2);
+        dn.y += rstd[k] * (g[k].y - s1 - xh[k].y * s2);
+        dn.z += rstd[k] * (g[k].z - s1 - xh[k].z * s2);
+        dn.w += rstd[k] * (g[k].w - s1 - xh[k].w * s2);
+      }
+      if (ok) {
+        const size_t off = ((size_t)b * rows_per_sample + r0 + k) * D + col;
+        if (HAS_LN) st4(dh + off, dn);
+        if (HAS_GATE) {
+          const float4 dyv = make_float4(gt.x * dn.x, gt.y * dn.y, gt.z * dn.z, gt.w * dn.w);
+          st4(dy + off, dyv);
+          a_gate.x += dn.x * yv[k].x; a_gate.y += dn.y * yv[k].y; a_gate.z += dn.z * yv[k].z; a_gate.w += dn.w * yv[k].w;
+          a_bias.x += dyv.x; a_bias.y += dyv.y; a_bias.z += dyv.z; a_bias.w += dyv.w;
+        }
+      }
+    }
+  }
+  if (act) {
+    if (HAS_LN) {
+      if (dshift) red4(dshift + (size_t)b * dmod_stride + col, a_shift);
+      if (dscale) red4(dscale + (size_t)b * dmod_stride + col, a_scale);
+    }
+    if (HAS_GATE) {
+      if (dgate) red4(dgate + (size_t)b * dmod_stride + col, a_gate);
+      if (dbias) red4(dbias + col, a_bias);
+    }
+  }
+}
+
+// every pointer the vector kernel touches with 16-byte (fp32) / 8-byte (bf16) accesses
+inline bool ln_vec_ok(int D, int mod_stride, int dmod_stride, std::initializer_list<const void*> ptrs) {
+  if (D % 4 || D > 512 || mod_stride % 4 || dmod_stride % 4) return false;
+  for (const void* q : ptrs)
+    if (reinterpret_cast<uintptr_t>(q) & 15) return false;
+  return true;
+}
+
 }  // namespace
 
 template <typename T>
@@ -165,6 +302,20 @@ int ln_modulate_bwd(const T* da, const float* h, const float2* stats, const floa
                     int rows_per_sample, cudaStream_t s) {
   if (D > MAXV * 32) return fail(V4H_ERR_UNSUPPORTED, "ln_modulate: hidden_dim %d > %d", D, MAXV * 32);
   const int B = M / rows_per_sample;
+  if (ln_vec_ok(D, mod_stride, dmod_stride, {da, h, scale, dh, dshift, dscale, y, gate, dy, dgate, dbias})) {
+    const int rows_per_cta = 16, threads = (int)ceil_div(D / 4, 32) * 32;
+    dim3 vgrid((unsigned)ceil_div(rows_per_sample, rows_per_cta), (unsigned)B);
+    if (gate != nullptr)
+      ln_mod_bwd_vec_kernel<T, true, true><<<vgrid, threads, 0, s>>>(
+          da, h, stats, scale, mod_stride, dh, dh_accumulate, dshift, dscale, dmod_stride, y, gate, dy, dgate,
+          dbias, D, rows_per_sample, rows_per_cta);
+    else
+      ln_mod_bwd_vec_kernel<T, true, false><<<vgrid, threads, 0, s>>>(
+          da, h, stats, scale, mod_stride, dh, dh_accumulate, dshift, dscale, dmod_stride, nullptr, nullptr,
+          nullptr, nullptr, nullptr, D, rows_per_sample, rows_per_cta);
+    V4H_LAUNCH_CHECK();
+    return V4H_OK;
+  }
   const int rows_per_cta = 32;
   dim3 grid((unsigned)ceil_div(rows_per_sample, rows_per_cta), (unsigned)B);
   if (gate != nullptr) {
@@ -185,6 +336,15 @@ int gate_bwd(const float* dh, const T* y, const float* gate, int mod_stride, T* 
              int dmod_stride, float* dbias, int M, int D, int rows_per_sample, cudaStream_t s) {
   if (D > MAXV * 32) return fail(V4H_ERR_UNSUPPORTED, "gate_bwd: hidden_dim %d > %d", D, MAXV * 32);
   const int B = M / rows_per_sample;
+  if (ln_vec_ok(D, mod_stride, dmod_stride, {dh, y, gate, dy, dgate, dbias})) {
+    const int rows_per_cta = 16, threads = (int)ceil_div(D / 4, 32) * 32;
+    dim3 vgrid((unsigned)ceil_div(rows_per_sample, rows_per_cta), (unsigned)B);
+    ln_mod_bwd_vec_kernel<T, false, true><<<vgrid, threads, 0, s>>>(
+        nullptr, nullptr, nullptr, nullptr, mod_stride, const_cast<float*>(dh), false, nullptr, nullptr,
+        dmod_stride, y, gate, dy, dgate, dbias, D, rows_per_sample, rows_per_cta);
+    V4H_LAUNCH_CHECK();
+    return V4H_OK;
+  }
   const int rows_per_cta = 32;
   dim3 grid((unsigned)ceil_div(rows_per_sample, rows_per_cta), (unsigned)B);
   ln_mod_bwd_kernel<T, false, true><<<grid, WARPS * 32, 0, s>>>(
