@@ -341,7 +341,7 @@ def run_b200(args):
             "model_tflops_per_gpu": value * gf / 1e3 / world,
             "frac_of_peak": value * gf / 1e3 / world / peaks["tflops_sustained"],
             "roofline": roofline,
-            "kernels": kernels[:16],
+            "kernels": kernels[:32],
             "sampling": sampling,
             "cpu_baseline": cpu,
         }

@@ -22,6 +22,8 @@
 //   dkv  : CTA per (128 keys, sample-head); S^T = K Q^T and dP^T = V dO^T in TMEM, P^T / dS^T -> smem,
 //          dV += P^T dO, dK += dS^T Q accumulated in TMEM over the query blocks
 // Rows / keys beyond T are zero-filled on load and masked in the softmax.
+#include <cstdlib>
+
 #include "kernels.cuh"
 #include "umma.cuh"
 
@@ -76,12 +78,12 @@ __host__ __device__ constexpr uint32_t g8_bytes(int rows, int cols) { return (ui
 
 // Stage `rows` x DHP (bf16) from global (row pitch `ld` elements) into a G8 tile; rows >= rows_valid
 // and column groups >= dh are zero-filled.
-template <int DHP>
+template <int DHP, int NTHREADS = ATT_THREADS>
 __device__ __forceinline__ void stage_tile(uint32_t dst, int rows, const bf16* __restrict__ src, size_t ld,
                                            int rows_valid, int dh) {
   constexpr int NCG = DHP / 8;
   const uint32_t gs = g8_stride(rows);
-  for (int idx = threadIdx.x; idx < rows * NCG; idx += ATT_THREADS) {
+  for (int idx = threadIdx.x; idx < rows * NCG; idx += NTHREADS) {
     const int row = idx / NCG, cg = idx - row * NCG;
     const bool ok = row < rows_valid && cg * 8 < dh;
     cp_async16(dst + cg * gs + row * 16, ok ? (const void*)(src + (size_t)row * ld + cg * 8) : (const void*)src, ok);
@@ -508,6 +510,233 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_umma_kernel(const At
   attn_epilogue(tmem, a.tmem_cols);
 }
 
+
+// ------------------------------------------------------------------------------------------ fused backward
+// Short sequences (T <= 160: every key fits one MMA N extent): ONE CTA per (sample, head) computes dQ,
+// dK and dV with S and P evaluated once.  256 threads: warps w and w + 4 own the same 32 rows (TMEM lane
+// quadrant w % 4) and split the key columns.  Per 128-query tile:
+//   S = Q K^T -> TMEM          p = exp2(s c - lse) -> bf16 P in smem [q][key]
+//   dP = dO V^T -> TMEM (over S)   dV^T += dO^T P      (A = dO read MN-major, B = P read MN-major)
+//   dS = p (dP - delta) -> over P in smem
+//   dQ = dS K -> TMEM (over dP)    dK^T += Q^T dS      (A = Q read MN-major, B = dS read MN-major)
+// dK^T / dV^T live in TMEM as [d (lane)][key (column)] across the query tiles and are written at the end;
+// the transposed products are what lets one [q][key] tile of P / dS feed both contractions.
+constexpr int FUSED_THREADS = 256;
+
+template <int DHP>
+__global__ void __launch_bounds__(FUSED_THREADS) attn_bwd_fused_umma_kernel(const AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align128(smem_raw);
+  AttnSmem* ctl = reinterpret_cast<AttnSmem*>(smem);
+  float* s_delta = reinterpret_cast<float*>(smem + 128);  // [128]
+  float* s_lse = s_delta + MT;                            // [128], log2 units
+  const int NK = a.BN, T = a.T, H = a.H, dh = a.dh;
+  uint8_t* tiles = smem + 128 + 1024;
+  const uint32_t sQ = smem_u32(tiles);
+  const uint32_t sdO = sQ + g8_bytes(MT, DHP);
+  const uint32_t sK = sdO + g8_bytes(MT, DHP);
+  const uint32_t sV = sK + g8_bytes(NK, DHP);
+  const uint32_t sP = sV + g8_bytes(NK, DHP);
+  uint8_t* sP_ptr = tiles + 2 * g8_bytes(MT, DHP) + 2 * g8_bytes(NK, DHP);
+  const uint32_t gsQ = g8_stride(MT), gsKV = g8_stride(NK), gsP = g8_stride(MT);
+
+  const int bh = blockIdx.x, b = bh / H, hd = bh % H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, half = warp >> 2;
+  const int r = quad * 32 + lane;  // row of the M tile = TMEM lane
+  const size_t ld = (size_t)3 * H * dh, ldo = (size_t)H * dh;
+  const bf16* qbase = a.qkv + (size_t)b * T * ld + (size_t)hd * dh;
+  const bf16* kbase = qbase + (size_t)H * dh;
+  const bf16* vbase = qbase + (size_t)2 * H * dh;
+  const bf16* dobase = a.d_o + (size_t)b * T * ldo + (size_t)hd * dh;
+  const bf16* obase = a.o + (size_t)b * T * ldo + (size_t)hd * dh;
+
+  // prologue (256 threads): barrier + TMEM
+  if (tid == 0) { mbar_init(&ctl->bar, 1); fence_barrier_init(); }
+  if (warp == 1) tmem_alloc_dyn(&ctl->tmem_slot, a.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = ctl->tmem_slot;
+  const int R = NK > DHP ? NK : DHP;  // S / dP / dQ share the first R columns
+  const uint32_t tS = tmem, tdV = tmem + (uint32_t)R, tdK = tdV + (uint32_t)NK;
+  const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+  uint32_t phase = 0;
+
+  // key-column chunks (16 wide) of this warp half
+  const int nchunks = NK / 16;
+  const int ch0 = half == 0 ? 0 : (nchunks + 1) / 2;
+  const int ch1 = half == 0 ? (nchunks + 1) / 2 : nchunks;
+
+  stage_tile<DHP, FUSED_THREADS>(sK, NK, kbase, ld, T, dh);
+  stage_tile<DHP, FUSED_THREADS>(sV, NK, vbase, ld, T, dh);
+
+  const int ntiles = (T + MT - 1) / MT;
+  for (int qt = 0; qt < ntiles; ++qt) {
+    const int q0 = qt * MT;
+    const int nq = min(MT, T - q0);
+    const int kq = (nq + 15) / 16;            // K steps of the contractions over the query rows
+    const bool warp_rows = quad * 32 < kq * 16;  // this warp's rows take part in those contractions
+    stage_tile<DHP, FUSED_THREADS>(sQ, MT, qbase + (size_t)q0 * ld, ld, nq, dh);
+    stage_tile<DHP, FUSED_THREADS>(sdO, MT, dobase + (size_t)q0 * ldo, ldo, nq, dh);
+    if (half == 0) {  // row statistics: delta = sum_d dO * O, lse in log2 units
+      float delta = 0.f, lse2 = 0.f;
+      const int q = q0 + r;
+      if (q < T) {
+        const bf16* dor = dobase + (size_t)q * ldo;
+        const bf16* orow = obase + (size_t)q * ldo;
+        for (int c = 0; c < dh; c += 8) {
+          const uint4 x = *reinterpret_cast<const uint4*>(dor + c);
+          const uint4 y = *reinterpret_cast<const uint4*>(orow + c);
+          const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 fx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xs[i]));
+            const float2 fy = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ys[i]));
+            delta = fmaf(fx.x, fy.x, delta);
+            delta = fmaf(fx.y, fy.y, delta);
+          }
+        }
+        lse2 = a.lse[(size_t)bh * T + q] * 1.4426950408889634f;
+      }
+      s_delta[r] = delta;
+      s_lse[r] = lse2;
+    }
+    cp_async_wait_all();
+    publish_smem_and_sync();
+    if (tid == 0) {
+      issue_mma(tS, sQ, gsQ, sK, gsKV, false, NK, DHP / 16, false);
+      umma_commit(&ctl->bar);
+    }
+    const float delta = s_delta[r], lse2 = s_lse[r];
+    const bool row_ok = q0 + r < T;
+    mbar_wait(&ctl->bar, phase); phase ^= 1;
+    tc_fence_after();
+    // ---- P = exp2(s c - lse) (zero for padded rows / keys) -> smem [q][key]
+    if (warp_rows) {
+      for (int ch = ch0; ch < ch1; ++ch) {
+        const int c0 = ch * 16;
+        float sv[16];
+        tmem_ld16(tS + lane_off + c0, sv);
+        tmem_ld_wait();
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          const float p0 = (row_ok && c0 + i < T) ? exp2_fast(fmaf(sv[i], a.scale_log2, -lse2)) : 0.f;
+          const float p1 = (row_ok && c0 + i + 1 < T) ? exp2_fast(fmaf(sv[i + 1], a.scale_log2, -lse2)) : 0.f;
+          w[i / 2] = pack_bf16(p0, p1);
+        }
+        uint8_t* dst = sP_ptr + (size_t)(c0 / 8) * gsP + r * 16;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(dst + gsP) = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+    }
+    publish_smem_and_sync();
+    if (tid == 0) {
+      issue_mma(tS, sdO, gsQ, sV, gsKV, false, NK, DHP / 16, false);  // dP over S
+      // dV^T[d][key] += sum_q dO[q][d] P[q][key]: both operands MN-major (rows = contraction index q)
+      const uint32_t idesc = make_idesc_bf16(MT, NK, true, true);
+      for (int ks = 0; ks < kq; ++ks)
+        umma_bf16(tdV, desc_ns(sdO + ks * 256, 128, gsQ), desc_ns(sP + ks * 256, 128, gsP), idesc,
+                  (qt > 0 || ks > 0) ? 1u : 0u);
+      umma_commit(&ctl->bar);
+    }
+    mbar_wait(&ctl->bar, phase); phase ^= 1;
+    tc_fence_after();
+    // ---- dS = p (dP - delta), in place over P
+    if (warp_rows) {
+      for (int ch = ch0; ch < ch1; ++ch) {
+        const int c0 = ch * 16;
+        float dp[16];
+        tmem_ld16(tS + lane_off + c0, dp);
+        tmem_ld_wait();
+        uint8_t* dst = sP_ptr + (size_t)(c0 / 8) * gsP + r * 16;
+        const uint4 pa = *reinterpret_cast<const uint4*>(dst), pb = *reinterpret_cast<const uint4*>(dst + gsP);
+        const uint32_t pw[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 pf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pw[i]));
+          w[i] = pack_bf16(pf.x * (dp[2 * i] - delta), pf.y * (dp[2 * i + 1] - delta));
+        }
+        *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(dst + gsP) = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+    } else {
+      tmem_ld_wait();
+    }
+    publish_smem_and_sync();
+    if (tid == 0) {
+      issue_mma(tS, sP, gsP, sK, gsKV, true, DHP, NK / 16, false);  // dQ over dP
+      const uint32_t idesc = make_idesc_bf16(MT, NK, true, true);
+      for (int ks = 0; ks < kq; ++ks)  // dK^T[d][key] += sum_q Q[q][d] dS[q][key]
+        umma_bf16(tdK, desc_ns(sQ + ks * 256, 128, gsQ), desc_ns(sP + ks * 256, 128, gsP), idesc,
+                  (qt > 0 || ks > 0) ? 1u : 0u);
+      umma_commit(&ctl->bar);
+    }
+    mbar_wait(&ctl->bar, phase); phase ^= 1;
+    tc_fence_after();
+    // ---- dQ rows out: the two warp halves split the head dimension in 16-column chunks
+    {
+      constexpr int NDC = DHP / 16;
+      const int d0 = half == 0 ? 0 : (NDC + 1) / 2, d1 = half == 0 ? (NDC + 1) / 2 : NDC;
+      bf16* out = a.dqkv + ((size_t)b * T + min(q0 + r, T - 1)) * ld + (size_t)hd * dh;
+      for (int dc = d0; dc < d1; ++dc) {
+        float v[16];
+        tmem_ld16(tS + lane_off + dc * 16, v);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            if (dc * 16 + 8 * h8 < dh) {
+              uint32_t w[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                w[i] = pack_bf16(v[8 * h8 + 2 * i] * a.scale, v[8 * h8 + 2 * i + 1] * a.scale);
+              *reinterpret_cast<uint4*>(out + dc * 16 + 8 * h8) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+        }
+      }
+    }
+    // the next tile overwrites sQ / sdO / sP and the S region: all MMAs have completed (waited above)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+
+  // ---- dK^T, dV^T out: thread = head dim d (TMEM lane), columns = keys; a warp writes 32 consecutive d
+  // of one key (64 contiguous bytes)
+  if (quad * 32 < dh) {
+    const int dd = r;
+    bf16* base = a.dqkv + (size_t)b * T * ld + (size_t)hd * dh + dd;
+    for (int ch = ch0; ch < ch1; ++ch) {
+      const int c0 = ch * 16;
+      float vk[16], vv[16];
+      tmem_ld16(tdK + lane_off + c0, vk);
+      tmem_ld16(tdV + lane_off + c0, vv);
+      tmem_ld_wait();
+      if (dd < dh) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int key = c0 + i;
+          if (key < T) {
+            bf16* dst = base + (size_t)key * ld + (size_t)H * dh;
+            dst[0] = __float2bfloat16_rn(vk[i] * a.scale);
+            dst[(size_t)H * dh] = __float2bfloat16_rn(vv[i]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_dyn(tmem, a.tmem_cols);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 int pick_dhp(int dh) {
   if (dh <= 32) return 32;
@@ -549,8 +778,29 @@ int fwd_launch(AttnArgs a, int B, cudaStream_t s) {
   return V4H_OK;
 }
 
+bool fused_bwd_enabled() {
+  static const int on = [] { const char* e = getenv("V4H_ATTN_FUSED_BWD"); return (e && e[0] == '0') ? 0 : 1; }();
+  return on != 0;
+}
+
 template <int DHP>
 int bwd_launch(AttnArgs a, int B, cudaStream_t s) {
+  if (a.T <= 160 && fused_bwd_enabled()) {  // one CTA per (sample, head): S and P evaluated once
+    AttnArgs f = a;
+    f.BN = (int)ceil_div(a.T, 16) * 16;
+    f.nblocks = 1;
+    const int R = f.BN > DHP ? f.BN : DHP;
+    f.tmem_cols = pow2_cols(R + 2 * f.BN);
+    // the MN-major reads of Q / dO span 128 "M" columns = 16 column groups even when DHP < 128: the
+    // groups past DHP land in the tiles that follow (garbage rows of dK^T / dV^T that are never stored)
+    const size_t smem = 256 + 1024 + 2 * g8_bytes(MT, DHP) + 2 * g8_bytes(f.BN, DHP) + g8_bytes(MT, f.BN) +
+                        (DHP < 128 ? 16 * g8_stride(MT) : 0);
+    static size_t configured = 0;
+    if (smem > configured) { V4H_TRY(set_smem(attn_bwd_fused_umma_kernel<DHP>, smem)); configured = smem; }
+    attn_bwd_fused_umma_kernel<DHP><<<(unsigned)(B * a.H), FUSED_THREADS, smem, s>>>(f);
+    V4H_LAUNCH_CHECK();
+    return V4H_OK;
+  }
   dim3 grid((unsigned)ceil_div(a.T, MT), (unsigned)(B * a.H));
   {  // dQ + delta
     AttnArgs q = a;

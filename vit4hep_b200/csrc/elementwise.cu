@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x
 // ---------------------------------------------------------------- timestep embedding
 // reference nn/vit.py:368-389: cat(cos(t f), sin(t f)), f_i = exp(-ln(1e4) i / half)
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, int shared_t, float* __restrict__ out,
-                                          int B, int dim) {
+                                          bf16* __restrict__ out_bf, int B, int dim) {
   const int half = dim / 2;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * half) return;
@@ -102,9 +102,15 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, int share
   // match torch: exp(-log(10000) * arange / half) in fp32
   const float f = expf(-9.210340371976184f * (float)i / (float)half);
   const float arg = tv * f;
-  out[(size_t)b * dim + i] = cosf(arg);
-  out[(size_t)b * dim + half + i] = sinf(arg);
+  const float cv = cosf(arg), sv = sinf(arg);
+  out[(size_t)b * dim + i] = cv;
+  out[(size_t)b * dim + half + i] = sv;
   if ((dim & 1) && i == 0) out[(size_t)b * dim + dim - 1] = 0.f;
+  if (out_bf) {  // bf16 copy: the A operand of the first t_embedder Linear on the tensor cores
+    out_bf[(size_t)b * dim + i] = __float2bfloat16_rn(cv);
+    out_bf[(size_t)b * dim + half + i] = __float2bfloat16_rn(sv);
+    if ((dim & 1) && i == 0) out_bf[(size_t)b * dim + dim - 1] = __float2bfloat16_rn(0.f);
+  }
 }
 
 // ---------------------------------------------------------------- learnable positional embedding
@@ -184,9 +190,12 @@ __global__ void cast_many_kernel(const CastJob* __restrict__ jobs) {
 
 // out = x * silu'(pre)   (backward through the SiLU in front of the adaLN Linears)
 __global__ void dsilu_mul_kernel(const float* __restrict__ x, const float* __restrict__ pre,
-                                 float* __restrict__ out, int64_t n) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    out[i] = x[i] * dsilu_f(pre[i]);
+                                 float* __restrict__ out, bf16* __restrict__ out_bf, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[i] * dsilu_f(pre[i]);
+    out[i] = v;
+    if (out_bf) out_bf[i] = __float2bfloat16_rn(v);
+  }
 }
 
 // ---------------------------------------------------------------- CFM
@@ -261,9 +270,9 @@ int colsum_add(const T* x, int ld, float* out, int M, int N, cudaStream_t s) {
 template int colsum_add<float>(const float*, int, float*, int, int, cudaStream_t);
 template int colsum_add<bf16>(const bf16*, int, float*, int, int, cudaStream_t);
 
-int timestep_embedding(const float* t, int shared_t, float* out, int B, int dim, cudaStream_t s) {
+int timestep_embedding(const float* t, int shared_t, float* out, bf16* out_bf, int B, int dim, cudaStream_t s) {
   const int n = B * (dim / 2);
-  timestep_embedding_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, s>>>(t, shared_t, out, B, dim);
+  timestep_embedding_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, s>>>(t, shared_t, out, out_bf, B, dim);
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }
@@ -288,8 +297,8 @@ int silu_to_bf16(const float* x, bf16* out, int64_t n, cudaStream_t s) {
   return V4H_OK;
 }
 
-int dsilu_mul(const float* x, const float* pre, float* out, int64_t n, cudaStream_t s) {
-  dsilu_mul_kernel<<<ew_grid(n, 1), EW_THREADS, 0, s>>>(x, pre, out, n);
+int dsilu_mul(const float* x, const float* pre, float* out, bf16* out_bf, int64_t n, cudaStream_t s) {
+  dsilu_mul_kernel<<<ew_grid(n, 1), EW_THREADS, 0, s>>>(x, pre, out, out_bf, n);
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }

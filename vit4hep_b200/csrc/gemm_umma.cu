@@ -533,11 +533,20 @@ int gemm_umma(UmmaContext* ctx, const GemmDesc& d, cudaStream_t s) {
   g.kblocks = (int)ceil_div(d.K, BK);
   int splits = d.epi == EPI_ATOMIC ? d.splitk : 1;
   if (d.epi == EPI_ATOMIC && splits <= 0) {
-    // auto: enough K ranges to give every SM a work item, at least 4 k-blocks each
+    // auto: the split count whose work items fill whole rounds of the persistent grid.  Cost model in
+    // k-block units: every round of items costs the k-blocks of one item plus a fixed epilogue term
+    // (the fp32 atomics of one output tile), so 150 items on 148 SMs (two rounds) lose to 120 items.
     const int tiles = g.tiles_m * g.tiles_n;
-    splits = (int)ceil_div(ctx->num_sms, tiles);
-    const int cap = g.kblocks / 4 > 0 ? g.kblocks / 4 : 1;
-    if (splits > cap) splits = cap;
+    const int epilogue_cost = 6;
+    long best_cost = -1;
+    splits = 1;
+    for (int sp = 1; sp <= g.kblocks && (long)tiles * sp <= 4L * ctx->num_sms; ++sp) {
+      const int kper = (int)ceil_div(g.kblocks, sp);
+      const int eff = (int)ceil_div(g.kblocks, kper);
+      const long rounds = ceil_div((long)tiles * eff, ctx->num_sms);
+      const long cost = rounds * (kper + epilogue_cost);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; splits = sp; }
+    }
   }
   if (splits < 1) splits = 1;
   if (splits > g.kblocks) splits = g.kblocks;
@@ -596,13 +605,16 @@ int gemm_umma(UmmaContext* ctx, const GemmDesc& d, cudaStream_t s) {
         return obf ? launch2<EPI_BIAS_ACT, ACT_NONE, bf16>(slab, m, g, ep, grid, s)
                    : launch2<EPI_BIAS_ACT, ACT_NONE, float>(slab, m, g, ep, grid, s);
       if (d.act == ACT_GELU_TANH && obf) return launch2<EPI_BIAS_ACT, ACT_GELU_TANH_FAST, bf16>(slab, m, g, ep, grid, s);
-      if (d.act == ACT_SILU && !obf) return launch2<EPI_BIAS_ACT, ACT_SILU, float>(slab, m, g, ep, grid, s);
+      if (d.act == ACT_SILU)
+        return obf ? launch2<EPI_BIAS_ACT, ACT_SILU, bf16>(slab, m, g, ep, grid, s)
+                   : launch2<EPI_BIAS_ACT, ACT_SILU, float>(slab, m, g, ep, grid, s);
       break;
     case EPI_GATE_RES:
       if (obf) return launch2<EPI_GATE_RES, ACT_NONE, bf16>(slab, m, g, ep, grid, s);
       break;
     case EPI_DACT:
       if (d.act == ACT_GELU_TANH && obf) return launch2<EPI_DACT, ACT_GELU_TANH_FAST, bf16>(slab, m, g, ep, grid, s);
+      if (d.act == ACT_SILU && obf) return launch2<EPI_DACT, ACT_SILU, bf16>(slab, m, g, ep, grid, s);
       break;
     case EPI_ATOMIC:
       return launch<EPI_ATOMIC, ACT_NONE, float, false>(m, g, ep, grid, s);

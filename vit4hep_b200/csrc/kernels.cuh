@@ -76,13 +76,14 @@ int gate_bwd(const float* dh, const T* y, const float* gate, int mod_stride, T* 
 
 // elementwise.cu
 template <typename T> int colsum_add(const T* x, int ld, float* out, int M, int N, cudaStream_t s);
-int timestep_embedding(const float* t, int shared_t, float* out, int B, int dim, cudaStream_t s);
+// out_bf / (dsilu_mul) out_bf: optional bf16 copies of the result (tensor-core operands)
+int timestep_embedding(const float* t, int shared_t, float* out, bf16* out_bf, int B, int dim, cudaStream_t s);
 int pos_embedding_fwd(const float* freqs, const float* pz, const float* py, const float* px, float* pe,
                       int Tn, int F, cudaStream_t s);
 // dfreqs[f] += sum over (b, t, part) of dh[b,t,part*F+f] * d pe / d freq
 int pos_embedding_bwd(const float* dh, const float* freqs, const float* pz, const float* py,
                       const float* px, float* dfreqs, int B, int Tn, int F, cudaStream_t s);
-int dsilu_mul(const float* x, const float* pre, float* out, int64_t n, cudaStream_t s);
+int dsilu_mul(const float* x, const float* pre, float* out, bf16* out_bf, int64_t n, cudaStream_t s);
 int silu_to_bf16(const float* x, bf16* out, int64_t n, cudaStream_t s);
 int cast_f32_to_bf16(const float* x, bf16* out, int64_t n, cudaStream_t s);
 struct CastJob { const float* src; bf16* dst; int64_t n; };

@@ -19,6 +19,8 @@ struct Plan {
   // bf16 weight arena layout (element offsets in bf16 units, then the fp32 bias tail in bytes)
   struct BlockArena { size_t qkv, proj, fc1, fc2; } arena_blocks[V4H_MAX_DEPTH];
   size_t arena_ada = 0;           // bf16 (Nmod, D)
+  // bf16 copies of the small Linears so that they run on the tensor cores too
+  size_t arena_final = 0, arena_x = 0, arena_t0 = 0, arena_t2 = 0, arena_c2 = 0;
   size_t arena_bf16_elems = 0;
   size_t arena_ada_bias_bytes = 0;  // byte offset of fp32 (Nmod) concatenated adaLN biases
   size_t arena_bytes = 0;
@@ -50,6 +52,9 @@ struct Workspace {
   // conditioning
   float *pe, *temb_in, *t_h_pre, *t_h, *te, *c_h_pre, *c_h, *cond, *sc, *mod;
   bf16* sc_bf16;
+  // bf16 mode: tensor-core operands of the embedding / conditioning / output Linears
+  bf16 *x_bf, *temb_bf, *t_h_bf, *t_hpre_bf, *c_h_bf, *c_hpre_bf;
+  bf16 *dout_bf, *dh_bf, *dcond_bf, *dvec_bf;  // backward only
   // residual stream (fp32): training keeps 2*depth+1 copies, inference 1
   std::vector<float*> h;
   std::vector<BlockBufs> blk;  // training: depth entries; inference: 1 shared entry
@@ -78,6 +83,14 @@ struct Workspace {
     cond = (float*)take(B * D * 4); sc = (float*)take(B * D * 4);
     sc_bf16 = (bf16*)take(B * D * 2);
     mod = (float*)take((size_t)B * p.Nmod * 4);
+    if (p.bf16) {
+      x_bf = (bf16*)take(M * d.patch_dim * 2);
+      temb_bf = (bf16*)take((size_t)B * d.freq_dim * 2);
+      t_h_bf = (bf16*)take(B * D * 2); t_hpre_bf = (bf16*)take(B * D * 2);
+      c_h_bf = (bf16*)take(B * D * 2); c_hpre_bf = (bf16*)take(B * D * 2);
+    } else {
+      x_bf = temb_bf = t_h_bf = t_hpre_bf = c_h_bf = c_hpre_bf = nullptr;
+    }
     const int nh = train ? 2 * d.depth + 1 : 1;
     h.resize(nh);
     for (int i = 0; i < nh; ++i) h[i] = (float*)take(M * D * 4);
@@ -103,7 +116,14 @@ struct Workspace {
       dsc = (float*)take(B * D * 4); dcond = (float*)take(B * D * 4); dvec = (float*)take(B * D * 4);
       dy = take(M * D * ta); du = take(M * Hm * ta); dm = take(M * D * ta); dqkv = take(M * 3 * D * ta);
       attn_delta = (float*)take((size_t)B * d.num_heads * d.tokens * 4);
+      if (p.bf16) {
+        dout_bf = (bf16*)take(M * d.out_dim * 2); dh_bf = (bf16*)take(M * D * 2);
+        dcond_bf = (bf16*)take(B * D * 2); dvec_bf = (bf16*)take(B * D * 2);
+      } else {
+        dout_bf = dh_bf = dcond_bf = dvec_bf = nullptr;
+      }
     } else {
+      dout_bf = dh_bf = dcond_bf = dvec_bf = nullptr;
       dh = dmod = dsc = dcond = dvec = attn_delta = nullptr; dmod_bf16 = nullptr;
       dy = du = dm = dqkv = nullptr;
     }
@@ -194,16 +214,38 @@ int forward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const floa
     V4H_TRY(pos_embedding_fwd(w.pos_embed_freqs, w.pos_z, w.pos_y, w.pos_x, ws.pe, Tn, D / 6, s));
     pe = ws.pe;
   }
+  const bool fast = p.bf16 && p.use_umma;  // small Linears on the tensor cores with bf16 operand copies
   {
     GemmDesc g = linear_fwd(x, DT_F32, d.patch_dim, w.x_w, DT_F32, d.patch_dim, M, D, d.patch_dim);
+    if (fast) {
+      V4H_TRY(cast_f32_to_bf16(x, ws.x_bf, (int64_t)M * d.patch_dim, s));
+      g = linear_fwd(ws.x_bf, DT_BF16, d.patch_dim, wa + p.arena_x, DT_BF16, d.patch_dim, M, D, d.patch_dim);
+    }
     g.ep.bias = w.x_b; g.ep.out = ws.h[0]; g.ep.ldo = D;
     g.ep.addend = pe; g.ep.addend_rows = Tn; g.ep.ld_addend = D;
     g.tag = "gemm.x_embed";
     V4H_TRY(run_gemm(p, g, s));
   }
   // ---- conditioning: cond = t_embedder(t) + c_embedder(c); sc = SiLU(cond)   (nn/vit.py:197-199)
-  V4H_TRY(timestep_embedding(t, shared_t ? 1 : 0, ws.temb_in, Bt, d.freq_dim, s));
-  {
+  V4H_TRY(timestep_embedding(t, shared_t ? 1 : 0, ws.temb_in, fast ? ws.temb_bf : nullptr, Bt, d.freq_dim, s));
+  if (fast) {
+    // t_embedder.mlp and c_embedder.2 on the tensor cores; hidden activations kept in bf16
+    GemmDesc g = linear_fwd(ws.temb_bf, DT_BF16, d.freq_dim, wa + p.arena_t0, DT_BF16, d.freq_dim, Bt, D, d.freq_dim);
+    g.tag = "gemm.cond"; g.act = ACT_SILU; g.out_dtype = DT_BF16;
+    g.ep.bias = w.t0_b; g.ep.out = ws.t_h_bf; g.ep.out2 = ws.t_hpre_bf; g.ep.ldo = D;
+    V4H_TRY(run_gemm(p, g, s));
+    g = linear_fwd(ws.t_h_bf, DT_BF16, D, wa + p.arena_t2, DT_BF16, D, Bt, D, D); g.tag = "gemm.cond";
+    g.ep.bias = w.t2_b; g.ep.out = ws.te; g.ep.ldo = D;
+    V4H_TRY(run_gemm(p, g, s));
+    g = linear_fwd(c, DT_F32, d.cond_dim, w.c0_w, DT_F32, d.cond_dim, B, D, d.cond_dim); g.tag = "gemm.cond";
+    g.act = ACT_SILU; g.out_dtype = DT_BF16;
+    g.ep.bias = w.c0_b; g.ep.out = ws.c_h_bf; g.ep.out2 = ws.c_hpre_bf; g.ep.ldo = D;
+    V4H_TRY(run_gemm(p, g, s));
+    g = linear_fwd(ws.c_h_bf, DT_BF16, D, wa + p.arena_c2, DT_BF16, D, B, D, D); g.tag = "gemm.cond";
+    g.act = ACT_SILU; g.ep.bias = w.c2_b; g.ep.out = ws.sc; g.ep.out2 = ws.cond; g.ep.ldo = D;
+    g.ep.addend = ws.te; g.ep.addend_rows = shared_t ? 1 : 0; g.ep.ld_addend = D;
+    V4H_TRY(run_gemm(p, g, s));
+  } else {
     GemmDesc g = linear_fwd(ws.temb_in, DT_F32, d.freq_dim, w.t0_w, DT_F32, d.freq_dim, Bt, D, d.freq_dim);
     g.tag = "gemm.cond"; g.act = ACT_SILU; g.ep.bias = w.t0_b; g.ep.out = ws.t_h; g.ep.out2 = ws.t_h_pre; g.ep.ldo = D;
     V4H_TRY(run_gemm(p, g, s));
@@ -290,7 +332,8 @@ int forward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const floa
     const float* mod = ws.mod + (size_t)d.depth * 6 * D;
     float* hl = ws.h[hidx(train, 2 * d.depth)];
     V4H_TRY(prof("ln.fwd", 0, (double)M * D * (4 + sizeof(T)), s, [&] { return ln_modulate_fwd<T>(hl, mod, mod + D, p.Nmod, (T*)ws.a_f, ws.stats_f, M, D, Tn, s); }));
-    GemmDesc g = linear_fwd(ws.a_f, TA, D, w.final_w, DT_F32, D, M, d.out_dim, D);
+    GemmDesc g = fast ? linear_fwd(ws.a_f, TA, D, wa + p.arena_final, DT_BF16, D, M, d.out_dim, D)
+                      : linear_fwd(ws.a_f, TA, D, w.final_w, DT_F32, D, M, d.out_dim, D);
     g.tag = "gemm.final";
     g.ep.bias = w.final_b; g.ep.out = out; g.ep.ldo = d.out_dim; g.out_dtype = DT_F32;
     V4H_TRY(run_gemm(p, g, s));
@@ -323,10 +366,15 @@ int backward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const v4h
       // ---------------- final layer
       V4H_CUDA(cudaMemsetAsync(ws.dmod, 0, (size_t)B * p.Nmod * sizeof(float), s));
       const size_t offF = (size_t)d.depth * 6 * D;
-      V4H_TRY(wgrad(p, dout, DT_F32, d.out_dim, ws.a_f, TA, D, gr.final_w, d.out_dim, D, M, s));
+      const bool fast = p.bf16 && p.use_umma;
+      if (fast) V4H_TRY(cast_f32_to_bf16(dout, ws.dout_bf, (int64_t)M * d.out_dim, s));
+      const void* dY = fast ? (const void*)ws.dout_bf : (const void*)dout;
+      const int dy_dt = fast ? DT_BF16 : DT_F32;
+      V4H_TRY(wgrad(p, dY, dy_dt, d.out_dim, ws.a_f, TA, D, gr.final_w, d.out_dim, D, M, s, "wgrad.final"));
       V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<float>(dout, d.out_dim, gr.final_b, M, d.out_dim, s); }));
       {
-        GemmDesc g = dgrad(dout, DT_F32, d.out_dim, w.final_w, DT_F32, D, M, D, d.out_dim);
+        GemmDesc g = fast ? dgrad(dY, DT_BF16, d.out_dim, wa + p.arena_final, DT_BF16, D, M, D, d.out_dim, "dgrad.final")
+                          : dgrad(dout, DT_F32, d.out_dim, w.final_w, DT_F32, D, M, D, d.out_dim, "dgrad.final");
         g.ep.out = ws.dm; g.ep.ldo = D; g.out_dtype = TA;
         V4H_TRY(run_gemm(p, g, s));
       }
@@ -404,51 +452,95 @@ int backward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const v4h
   return V4H_OK;
 }
 
-int backward_stage0(Plan& p, const v4h_vit_params& w, const v4h_vit_params& gr, const float* x,
+int backward_stage0(Plan& p, const v4h_vit_params& w, const char* arena, const v4h_vit_params& gr, const float* x,
                     const float* c, int64_t B64, Workspace& ws, cudaStream_t s) {
   const v4h_vit_dims& d = p.d;
   const int B = (int)B64, Tn = d.tokens, D = d.hidden_dim, M = B * Tn;
-  V4H_TRY(wgrad(p, ws.dh, DT_F32, D, x, DT_F32, d.patch_dim, gr.x_w, D, d.patch_dim, M, s));
+  const bool fast = p.bf16 && p.use_umma;
+  const bf16* wa = reinterpret_cast<const bf16*>(arena);
+  // x_embedder: dW = dh0^T x (the layer input x is not differentiated), db = colsum(dh0)
+  if (fast) {
+    V4H_TRY(cast_f32_to_bf16(ws.dh, ws.dh_bf, (int64_t)M * D, s));
+    V4H_TRY(wgrad(p, ws.dh_bf, DT_BF16, D, ws.x_bf, DT_BF16, d.patch_dim, gr.x_w, D, d.patch_dim, M, s, "wgrad.x_embed"));
+  } else {
+    V4H_TRY(wgrad(p, ws.dh, DT_F32, D, x, DT_F32, d.patch_dim, gr.x_w, D, d.patch_dim, M, s, "wgrad.x_embed"));
+  }
   V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<float>(ws.dh, D, gr.x_b, M, D, s); }));
   if (d.learn_pos_embed)
     V4H_TRY(pos_embedding_bwd(ws.dh, w.pos_embed_freqs, w.pos_z, w.pos_y, w.pos_x, gr.pos_embed_freqs, B, Tn,
                               D / 6, s));
   // adaLN Linears: d W = dmod^T sc, d b = colsum(dmod), d sc += dmod W
   V4H_CUDA(cudaMemsetAsync(ws.dsc, 0, (size_t)B * D * sizeof(float), s));
-  for (int i = 0; i <= d.depth; ++i) {
-    const bool fin = i == d.depth;
-    const int n = fin ? 2 * D : 6 * D;
-    const float* dmod = ws.dmod + (size_t)i * 6 * D;
-    float* dW = fin ? gr.final_ada_w : gr.blocks[i].ada_w;
-    float* db = fin ? gr.final_ada_b : gr.blocks[i].ada_b;
-    const float* W = fin ? w.final_ada_w : w.blocks[i].ada_w;
-    {
-      GemmDesc g;
-      g.layout = GEMM_TN; g.A = dmod; g.a_dtype = DT_F32; g.lda = p.Nmod; g.B = ws.sc; g.b_dtype = DT_F32;
-      g.ldb = D; g.M = n; g.N = D; g.K = B; g.epi = EPI_ATOMIC; g.ep.out = dW; g.ep.ldo = D; g.splitk = 1;
-      V4H_TRY(run_gemm(p, g, s));
-    }
-    V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<float>(dmod, p.Nmod, db, B, n, s); }));
-    {
-      GemmDesc g = dgrad(dmod, DT_F32, p.Nmod, W, DT_F32, D, B, D, n);
-      g.epi = EPI_ATOMIC; g.ep.out = ws.dsc; g.ep.ldo = D; g.splitk = std::max(1, n / 240);
-      V4H_TRY(run_gemm(p, g, s));
+  // The host lays the adaLN gradients out as ONE (Nmod, D) matrix + ONE (Nmod) vector in block order
+  // (ViT.ordered_parameters): then the whole conditioning backward is two tensor-core GEMMs.
+  bool ada_contig = fast;
+  for (int i = 0; i < d.depth && ada_contig; ++i) {
+    const float* next_w = i + 1 < d.depth ? gr.blocks[i + 1].ada_w : gr.final_ada_w;
+    const float* next_b = i + 1 < d.depth ? gr.blocks[i + 1].ada_b : gr.final_ada_b;
+    ada_contig = next_w == gr.blocks[i].ada_w + (size_t)6 * D * D && next_b == gr.blocks[i].ada_b + (size_t)6 * D;
+  }
+  if (ada_contig) {
+    V4H_TRY(cast_f32_to_bf16(ws.dmod, ws.dmod_bf16, (int64_t)B * p.Nmod, s));
+    V4H_TRY(wgrad(p, ws.dmod_bf16, DT_BF16, p.Nmod, ws.sc_bf16, DT_BF16, D, gr.blocks[0].ada_w, p.Nmod, D, B, s,
+                  "wgrad.adaln"));
+    V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<float>(ws.dmod, p.Nmod, gr.blocks[0].ada_b, B, p.Nmod, s); }));
+    GemmDesc g = dgrad(ws.dmod_bf16, DT_BF16, p.Nmod, wa + p.arena_ada, DT_BF16, D, B, D, p.Nmod, "dgrad.adaln");
+    g.epi = EPI_ATOMIC; g.ep.out = ws.dsc; g.ep.ldo = D; g.splitk = 0;
+    V4H_TRY(run_gemm(p, g, s));
+  } else {
+    for (int i = 0; i <= d.depth; ++i) {
+      const bool fin = i == d.depth;
+      const int n = fin ? 2 * D : 6 * D;
+      const float* dmod = ws.dmod + (size_t)i * 6 * D;
+      float* dW = fin ? gr.final_ada_w : gr.blocks[i].ada_w;
+      float* db = fin ? gr.final_ada_b : gr.blocks[i].ada_b;
+      const float* W = fin ? w.final_ada_w : w.blocks[i].ada_w;
+      {
+        GemmDesc g;
+        g.tag = "wgrad.adaln";
+        g.layout = GEMM_TN; g.A = dmod; g.a_dtype = DT_F32; g.lda = p.Nmod; g.B = ws.sc; g.b_dtype = DT_F32;
+        g.ldb = D; g.M = n; g.N = D; g.K = B; g.epi = EPI_ATOMIC; g.ep.out = dW; g.ep.ldo = D; g.splitk = 1;
+        V4H_TRY(run_gemm(p, g, s));
+      }
+      V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<float>(dmod, p.Nmod, db, B, n, s); }));
+      {
+        GemmDesc g = dgrad(dmod, DT_F32, p.Nmod, W, DT_F32, D, B, D, n, "dgrad.adaln");
+        g.epi = EPI_ATOMIC; g.ep.out = ws.dsc; g.ep.ldo = D; g.splitk = std::max(1, n / 240);
+        V4H_TRY(run_gemm(p, g, s));
+      }
     }
   }
-  V4H_TRY(dsilu_mul(ws.dsc, ws.cond, ws.dcond, (int64_t)B * D, s));
+  V4H_TRY(dsilu_mul(ws.dsc, ws.cond, ws.dcond, fast ? ws.dcond_bf : nullptr, (int64_t)B * D, s));
   // c_embedder (nn/vit.py:77-81) and t_embedder.mlp (nn/vit.py:361-365): Linear -> SiLU -> Linear
-  struct Mlp { const float *in, *h_pre, *h; int in_dim; const float* w2; float *dw0, *db0, *dw2, *db2; };
-  Mlp mlps[2] = {
-      {c, ws.c_h_pre, ws.c_h, d.cond_dim, w.c2_w, gr.c0_w, gr.c0_b, gr.c2_w, gr.c2_b},
-      {ws.temb_in, ws.t_h_pre, ws.t_h, d.freq_dim, w.t2_w, gr.t0_w, gr.t0_b, gr.t2_w, gr.t2_b}};
-  for (const Mlp& m : mlps) {
-    V4H_TRY(wgrad(p, ws.dcond, DT_F32, D, m.h, DT_F32, D, m.dw2, D, D, B, s));
-    V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<float>(ws.dcond, D, m.db2, B, D, s); }));
-    GemmDesc g = dgrad(ws.dcond, DT_F32, D, m.w2, DT_F32, D, B, D, D);
-    g.epi = EPI_DACT; g.act = ACT_SILU; g.ep.out = ws.dvec; g.ep.ldo = D; g.ep.aux = m.h_pre; g.ep.ld_aux = D;
-    V4H_TRY(run_gemm(p, g, s));
-    V4H_TRY(wgrad(p, ws.dvec, DT_F32, D, m.in, DT_F32, m.in_dim, m.dw0, D, m.in_dim, B, s));
-    V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<float>(ws.dvec, D, m.db0, B, D, s); }));
+  if (fast) {
+    struct Mlp { const void* in; int in_dt, in_dim; const bf16 *h_pre, *h; const bf16* w2; float *dw0, *db0, *dw2, *db2; };
+    Mlp mlps[2] = {
+        {c, DT_F32, d.cond_dim, ws.c_hpre_bf, ws.c_h_bf, wa + p.arena_c2, gr.c0_w, gr.c0_b, gr.c2_w, gr.c2_b},
+        {ws.temb_bf, DT_BF16, d.freq_dim, ws.t_hpre_bf, ws.t_h_bf, wa + p.arena_t2, gr.t0_w, gr.t0_b, gr.t2_w, gr.t2_b}};
+    for (const Mlp& m : mlps) {
+      V4H_TRY(wgrad(p, ws.dcond_bf, DT_BF16, D, m.h, DT_BF16, D, m.dw2, D, D, B, s, "wgrad.cond"));
+      V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<float>(ws.dcond, D, m.db2, B, D, s); }));
+      GemmDesc g = dgrad(ws.dcond_bf, DT_BF16, D, m.w2, DT_BF16, D, B, D, D, "dgrad.cond");
+      g.epi = EPI_DACT; g.act = ACT_SILU; g.out_dtype = DT_BF16;
+      g.ep.out = ws.dvec_bf; g.ep.ldo = D; g.ep.aux = m.h_pre; g.ep.ld_aux = D;
+      V4H_TRY(run_gemm(p, g, s));
+      V4H_TRY(wgrad(p, ws.dvec_bf, DT_BF16, D, m.in, m.in_dt, m.in_dim, m.dw0, D, m.in_dim, B, s, "wgrad.cond"));
+      V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<bf16>(ws.dvec_bf, D, m.db0, B, D, s); }));
+    }
+  } else {
+    struct Mlp { const float *in, *h_pre, *h; int in_dim; const float* w2; float *dw0, *db0, *dw2, *db2; };
+    Mlp mlps[2] = {
+        {c, ws.c_h_pre, ws.c_h, d.cond_dim, w.c2_w, gr.c0_w, gr.c0_b, gr.c2_w, gr.c2_b},
+        {ws.temb_in, ws.t_h_pre, ws.t_h, d.freq_dim, w.t2_w, gr.t0_w, gr.t0_b, gr.t2_w, gr.t2_b}};
+    for (const Mlp& m : mlps) {
+      V4H_TRY(wgrad(p, ws.dcond, DT_F32, D, m.h, DT_F32, D, m.dw2, D, D, B, s, "wgrad.cond"));
+      V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<float>(ws.dcond, D, m.db2, B, D, s); }));
+      GemmDesc g = dgrad(ws.dcond, DT_F32, D, m.w2, DT_F32, D, B, D, D, "dgrad.cond");
+      g.epi = EPI_DACT; g.act = ACT_SILU; g.ep.out = ws.dvec; g.ep.ldo = D; g.ep.aux = m.h_pre; g.ep.ld_aux = D;
+      V4H_TRY(run_gemm(p, g, s));
+      V4H_TRY(wgrad(p, ws.dvec, DT_F32, D, m.in, DT_F32, m.in_dim, m.dw0, D, m.in_dim, B, s, "wgrad.cond"));
+      V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<float>(ws.dvec, D, m.db0, B, D, s); }));
+    }
   }
   return V4H_OK;
 }
@@ -492,10 +584,15 @@ int plan_create(const v4h_vit_dims* dims, Plan** out) {
       p->arena_blocks[i].fc2 = take(D * Hm);
     }
     p->arena_ada = take((size_t)p->Nmod * D);
+    p->arena_final = take((size_t)d.out_dim * D);
+    p->arena_x = take(D * (size_t)d.patch_dim);
+    p->arena_t0 = take(D * (size_t)d.freq_dim);
+    p->arena_t2 = take(D * D);
+    p->arena_c2 = take(D * D);
     p->arena_bf16_elems = off;
     p->arena_ada_bias_bytes = align_up(off * 2, 256);
     p->arena_bytes = p->arena_ada_bias_bytes + align_up((size_t)p->Nmod * 4, 256);
-    p->njobs = 4 * d.depth + d.depth + 1;
+    p->njobs = 4 * d.depth + d.depth + 1 + 5;
     if (cudaMalloc(&p->jobs_dev, sizeof(CastJob) * p->njobs) != cudaSuccess ||
         cudaMallocHost(&p->jobs_host, sizeof(CastJob) * p->njobs) != cudaSuccess) {
       delete p;
@@ -545,6 +642,12 @@ int plan_prepare_weights(Plan* p, const v4h_vit_params* w, void* arena, cudaStre
     add(b.ada_w, wa + p->arena_ada + (size_t)i * 6 * D * D, 6 * D * D);
   }
   add(w->final_ada_w, wa + p->arena_ada + (size_t)d.depth * 6 * D * D, 2 * D * D);
+  V4H_REQUIRE(w->final_w && w->x_w && w->t0_w && w->t2_w && w->c2_w, "prepare_weights: null embedding / output weight");
+  add(w->final_w, wa + p->arena_final, (size_t)d.out_dim * D);
+  add(w->x_w, wa + p->arena_x, D * (size_t)d.patch_dim);
+  add(w->t0_w, wa + p->arena_t0, D * (size_t)d.freq_dim);
+  add(w->t2_w, wa + p->arena_t2, D * D);
+  add(w->c2_w, wa + p->arena_c2, D * D);
   if (memcmp(jobs.data(), p->jobs_host, sizeof(CastJob) * jobs.size()) != 0) {
     // parameter storage moved: wait for earlier uses of the staging table, then refresh it
     V4H_CUDA(cudaStreamSynchronize(s));
@@ -592,7 +695,7 @@ int plan_backward(Plan* p, const v4h_vit_params* w, const void* arena, const v4h
   }
   if (stage_end == 0) {
     V4H_REQUIRE(x && c, "vit_backward: stage 0 needs the forward inputs x and c");
-    V4H_TRY(backward_stage0(*p, *w, *grads, x, c, B, ws, s));
+    V4H_TRY(backward_stage0(*p, *w, (const char*)arena, *grads, x, c, B, ws, s));
   }
   return V4H_OK;
 }

@@ -272,11 +272,14 @@ class ViT(nn.Module):
         out += [("x_w", self.x_embedder.weight), ("x_b", self.x_embedder.bias),
                 ("c0_w", c0.weight), ("c0_b", c0.bias), ("c2_w", c2.weight), ("c2_b", c2.bias),
                 ("t0_w", t0.weight), ("t0_b", t0.bias), ("t2_w", t2.weight), ("t2_b", t2.bias)]
-        for i, b in enumerate(self.blocks):
-            ada = b.adaLN_modulation[-1]
-            out += [(f"blocks.{i}.ada_w", ada.weight), (f"blocks.{i}.ada_b", ada.bias)]
-        ada = fl.adaLN_modulation[-1]
-        out += [("final_ada_w", ada.weight), ("final_ada_b", ada.bias)]
+        # every adaLN weight, then every adaLN bias, in block order: their gradients form ONE
+        # (depth*6D + 2D, D) matrix and ONE vector in the flat buffer, which lets the native backward
+        # compute them with a single tensor-core GEMM / column sum (csrc/vit.cu backward_stage0)
+        adas = [b.adaLN_modulation[-1] for b in self.blocks]
+        out += [(f"blocks.{i}.ada_w", a.weight) for i, a in enumerate(adas)]
+        out.append(("final_ada_w", fl.adaLN_modulation[-1].weight))
+        out += [(f"blocks.{i}.ada_b", a.bias) for i, a in enumerate(adas)]
+        out.append(("final_ada_b", fl.adaLN_modulation[-1].bias))
         return out
 
     def stage_boundaries(self) -> List[int]:
