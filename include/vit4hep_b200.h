@@ -162,6 +162,32 @@ int v4h_cfm_loss(const float* v, const float* target, int64_t n, float grad_scal
                  float* loss_out, float* dv, v4h_stream_t s);
 
 /* ------------------------------------------------------------------------------------
+ * Fused tail of the training step (reference experiments/base_experiment.py:573-597:
+ * clip_grad_norm_(parameters, max_grad_norm) then AdamW.step()), one multi-tensor pass that also
+ * refreshes the bf16 operand copy of the GEMM weights.
+ * ------------------------------------------------------------------------------------ */
+typedef struct {
+  float* p;        /* parameter (updated in place) */
+  const float* g;  /* gradient */
+  float* m;        /* exp_avg */
+  float* v;        /* exp_avg_sq */
+  void* bf16_dst;  /* bf16 copy of the updated parameter inside the weight arena, or NULL */
+  float* f32_dst;  /* fp32 copy inside the arena (the concatenated adaLN biases), or NULL */
+  int64_t n;
+} v4h_adamw_job;
+/* out[0] = sum of squares of n fp32 values (the squared global gradient norm when `flat` is the flat
+ * gradient buffer) */
+int v4h_grad_norm_sq(const float* flat, int64_t n, float* out, v4h_stream_t s);
+/* jobs: DEVICE array of njobs entries; max_n = largest jobs[i].n; norm_sq: device scalar from
+ * v4h_grad_norm_sq (NULL = no clipping); step = 1-based step count (bias correction) */
+int v4h_adamw_step(const v4h_adamw_job* jobs, int32_t njobs, int64_t max_n, const float* norm_sq, float max_norm,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, v4h_stream_t s);
+/* byte offset inside the weight arena of the bf16 copy of a parameter, by its v4h_vit_params field
+ * ("final_w", "x_w", "t0_w", "t2_w", "c2_w", "final_ada_w", "blocks.<i>.{qkv_w,proj_w,fc1_w,fc2_w,ada_w}"), or of the fp32 copy of an adaLN bias
+ * ("blocks.<i>.ada_b", "final_ada_b"); -1 when the parameter has no copy */
+int64_t v4h_vit_arena_offset(const v4h_plan* p, const char* field);
+
+/* ------------------------------------------------------------------------------------
  * ODE sampling, torchdiffeq fixed-grid 'rk4' = 3/8 rule (reference
  * calochallenge_cfm/model.py:85-92).  out = y + a0*k0 + a1*k1 + a2*k2 + a3*k3 (null k = skipped):
  * one fused kernel per RK stage/combination.
@@ -195,6 +221,15 @@ int v4h_profile_end(v4h_profile_entry* out, int32_t max, int32_t* n);
  * 1 = tcgen05 bf16 inputs (A, B are bf16 then). */
 int v4h_test_gemm(int32_t engine, int32_t layout, const void* A, const void* B, float* C,
                   int32_t m, int32_t n, int32_t k, v4h_stream_t s);
+/* One tcgen05 GEMM with the epilogue of a model call site, for kernel benchmarking (scripts/gemm_bench.py).
+ * kind: 0 fc1-like (NT, bias + GELU, out and out2), 1 qkv-like (NT, bias), 2 proj/fc2-like (NT, gate +
+ * residual), 3 dgrad through GELU (NN, aux), 4 plain dgrad (NN), 5 wgrad (TN, fp32 atomics into out).
+ * counters: optional device array of 16 int64 cycle counters summed over CTAs: [0,1] producer wait /
+ * issue, [2,3,4] MMA wait accumulator / wait operands / issue, [5..11] epilogue wait accumulator, loads +
+ * TMEM, wait input box, math + staging, barrier, copy-out, tail. */
+int v4h_debug_gemm(int32_t kind, int32_t m, int32_t n, int32_t k, int32_t rows_per_sample, const void* A,
+                   const void* B, const float* bias, void* out, void* out2, const float* res_in,
+                   float* res_out, const float* gate, const void* aux, int64_t* counters, v4h_stream_t s);
 /* qkv (B, T, 3, H, dh) -> o (B, T, H, dh), lse (B, H, T); precision picks fp32 / bf16 buffers */
 int v4h_test_attention_fwd(int32_t precision, int32_t engine, const void* qkv, void* o, float* lse,
                            int32_t batch, int32_t tokens, int32_t heads, int32_t head_dim, v4h_stream_t s);

@@ -208,3 +208,44 @@ def test_linearity_of_the_ode_combination_at_full_size(dev):
     _cabi.check(lib.v4h_axpy4(o1.data_ptr(), y.data_ptr(), k.data_ptr(), 0.5, None, 0, None, 0, None, 0, n, s))
     _cabi.check(lib.v4h_axpy4(o2.data_ptr(), o1.data_ptr(), k.data_ptr(), -0.5, None, 0, None, 0, None, 0, n, s))
     assert vo.rel_l2(o2, y) < 1e-6
+
+
+def test_fused_adamw_matches_torch_adamw_with_clipping(dev):
+    """FusedAdamW (v4h_grad_norm_sq + v4h_adamw_step) against clip_grad_norm_ + torch.optim.AdamW on the same
+    gradients (reference experiments/base_experiment.py:573-592), incl. the refreshed bf16 weight arena."""
+    import copy
+    import vit4hep_b200 as v4
+    cfg = vo.tiny_config("ds2", hidden_dim=96, depth=2, num_heads=2)
+    param = dict(cfg["param"]); param["precision"] = "bf16"
+    torch.manual_seed(0)
+    net = v4.ViT(param).to(dev)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.copy_(torch.randn_like(p) * 0.05)
+    ref = copy.deepcopy(net)
+    g = torch.Generator().manual_seed(5)
+    B, T, P = 4, net.pos_z.numel(), param["patch_dim"]
+    fused = v4.FusedAdamW(net, lr=1e-2, weight_decay=0.1, max_grad_norm=0.5)
+    opt = torch.optim.AdamW(ref.parameters(), lr=1e-2, weight_decay=0.1)
+    for step in range(3):
+        x = torch.randn(B, T, P, generator=g).to(dev)
+        t = torch.rand(B, 1, generator=g).to(dev)
+        c = torch.rand(B, param["condition_dim"], generator=g).to(dev)
+        net(x, t, c).square().mean().backward()
+        for p, q in zip(net.parameters(), ref.parameters()):
+            q.grad = p.grad.clone()
+        want_norm = torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.5)
+        opt.step()
+        fused.step()
+        assert abs(fused.last_grad_norm.item() - want_norm.item()) <= 1e-5 * want_norm.item()
+        for (name, p), q in zip(net.named_parameters(), ref.parameters()):
+            assert vo.rel_l2(p, q) < 1e-6, (step, name)
+        fused.zero_grad(set_to_none=True)
+    # the arena the optimizer refreshed gives the same forward as a freshly cast one
+    x = torch.randn(B, T, P, generator=g).to(dev); t = torch.rand(B, 1, generator=g).to(dev)
+    c = torch.rand(B, param["condition_dim"], generator=g).to(dev)
+    with torch.no_grad():
+        got = net(x, t, c)
+        net._native.arena_key = None  # force the recast path
+        want = net(x, t, c)
+    assert torch.equal(got, want)

@@ -36,6 +36,11 @@ class VitParams(C.Structure):
         "final_w", "final_b", "final_ada_w", "final_ada_b")] + [("blocks", BlockParams * V4H_MAX_DEPTH)]
 
 
+class AdamWJob(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("bf16_dst", C.c_void_p),
+                ("f32_dst", C.c_void_p), ("n", C.c_int64)]
+
+
 class ProfileEntry(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("ms", C.c_double), ("flops", C.c_double),
                 ("bytes", C.c_double)]
@@ -67,10 +72,14 @@ SIGNATURES = {
     "v4h_cfm_prepare": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "v4h_cfm_loss": (C.c_int, [_vp, _vp, _i64, _fl, _vp, _vp, _vp]),
     "v4h_axpy4": (C.c_int, [_vp, _vp, _vp, _fl, _vp, _fl, _vp, _fl, _vp, _fl, _i64, _vp]),
+    "v4h_grad_norm_sq": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "v4h_adamw_step": (C.c_int, [_vp, _i32, _i64, _vp, _fl, _fl, _fl, _fl, _fl, _fl, _i32, _vp]),
+    "v4h_vit_arena_offset": (C.c_int64, [_vp, C.c_char_p]),
     "v4h_launch_count": (C.c_int64, []),
     "v4h_profile_begin": (C.c_int, []),
     "v4h_profile_end": (C.c_int, [C.POINTER(ProfileEntry), _i32, C.POINTER(_i32)]),
     "v4h_test_gemm": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "v4h_debug_gemm": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "v4h_test_attention_fwd": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "v4h_test_attention_bwd": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
 }

@@ -60,6 +60,7 @@ int plan_prepare_weights(Plan* p, const v4h_vit_params* w, void* arena, cudaStre
 int plan_forward(Plan* p, const v4h_vit_params* w, const void* arena, const float* x, const float* t,
                  const float* c, float* out, int64_t B, bool shared_t, bool train, void* workspace,
                  size_t workspace_bytes, cudaStream_t s);
+int64_t plan_arena_offset(const Plan* p, const char* field);
 int plan_backward(Plan* p, const v4h_vit_params* w, const void* arena, const v4h_vit_params* grads,
                   const float* x, const float* c, const float* dout, int64_t B, int stage_begin, int stage_end,
                   void* workspace, size_t workspace_bytes, cudaStream_t s);
@@ -266,6 +267,21 @@ int v4h_axpy4(float* out, const float* y, const float* k0, float a0, const float
   return axpy4(out, y, k0, a0, k1, a1, k2, a2, k3, a3, n, (cudaStream_t)s);
 }
 
+// ------------------------------------------------------------------------------------ optimizer
+int v4h_grad_norm_sq(const float* flat, int64_t n, float* out, v4h_stream_t s) {
+  V4H_REQUIRE(flat && out && n > 0, "grad_norm_sq: bad arguments");
+  return grad_norm_sq(flat, n, out, (cudaStream_t)s);
+}
+int v4h_adamw_step(const v4h_adamw_job* jobs, int32_t njobs, int64_t max_n, const float* norm_sq, float max_norm,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, v4h_stream_t s) {
+  V4H_REQUIRE(jobs && njobs > 0 && njobs <= 65535 && max_n > 0 && step >= 1, "adamw_step: bad arguments");
+  return adamw_step(jobs, njobs, max_n, norm_sq, max_norm, lr, beta1, beta2, eps, weight_decay, step, (cudaStream_t)s);
+}
+int64_t v4h_vit_arena_offset(const v4h_plan* p, const char* field) {
+  if (!p || !field) return -1;
+  return plan_arena_offset(reinterpret_cast<const Plan*>(p), field);
+}
+
 // ------------------------------------------------------------------------------------ measurement
 int64_t v4h_launch_count(void) { return g_launches.load(); }
 
@@ -330,6 +346,36 @@ int v4h_test_gemm(int32_t engine, int32_t layout, const void* A, const void* B, 
     V4H_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)m * n, (cudaStream_t)s));
   }
   if (!gemm_umma_supported(g)) return fail(V4H_ERR_UNSUPPORTED, "test_gemm: shape not supported by the tcgen05 GEMM");
+  return gemm_umma(ctx, g, (cudaStream_t)s);
+}
+
+int v4h_debug_gemm(int32_t kind, int32_t m, int32_t n, int32_t k, int32_t rows_per_sample, const void* A, const void* B,
+                   const float* bias, void* out, void* out2, const float* res_in, float* res_out, const float* gate,
+                   const void* aux, int64_t* counters, v4h_stream_t s) {
+  V4H_REQUIRE(A && B && kind >= 0 && kind <= 5, "debug_gemm: bad arguments");
+  static UmmaContext* ctx = umma_context_create();
+  GemmDesc g;
+  g.A = A; g.B = B; g.M = m; g.N = n; g.K = k; g.a_dtype = g.b_dtype = DT_BF16; g.out_dtype = DT_BF16;
+  g.dbg = reinterpret_cast<long long*>(counters);
+  g.ep.bias = bias; g.ep.ldo = n;
+  switch (kind) {
+    case 0:  // fc1-like: x W^T + b, GELU; both pre-activation and activation stored
+      g.layout = GEMM_NT; g.lda = k; g.ldb = k; g.act = ACT_GELU_TANH; g.ep.out = out; g.ep.out2 = out2; break;
+    case 1:  // qkv-like: x W^T + b
+      g.layout = GEMM_NT; g.lda = k; g.ldb = k; g.ep.out = out; break;
+    case 2:  // proj / fc2-like: gated residual update
+      g.layout = GEMM_NT; g.lda = k; g.ldb = k; g.epi = EPI_GATE_RES; g.ep.out2 = out2; g.ep.gate = gate;
+      g.ep.mod_stride = n; g.ep.rows_per_sample = rows_per_sample; g.ep.res_in = res_in; g.ep.res_out = res_out; break;
+    case 3:  // dgrad through GELU: (dY W) * gelu'(u)
+      g.layout = GEMM_NN; g.lda = k; g.ldb = n; g.epi = EPI_DACT; g.act = ACT_GELU_TANH; g.ep.out = out; g.ep.aux = aux;
+      g.ep.ld_aux = n; g.ep.bias = nullptr; break;
+    case 4:  // plain dgrad
+      g.layout = GEMM_NN; g.lda = k; g.ldb = n; g.ep.out = out; g.ep.bias = nullptr; break;
+    default:  // wgrad: dY^T X with split-K atomics into fp32
+      g.layout = GEMM_TN; g.lda = m; g.ldb = n; g.epi = EPI_ATOMIC; g.out_dtype = DT_F32; g.splitk = 0;
+      g.ep.out = out; g.ep.bias = nullptr; break;
+  }
+  V4H_REQUIRE(gemm_umma_supported(g), "debug_gemm: shape not supported by the tcgen05 GEMM");
   return gemm_umma(ctx, g, (cudaStream_t)s);
 }
 

@@ -11,11 +11,19 @@
 //   warps 4-7 epilogue       (tcgen05.ld 32x32b, one output row per thread, overlaps the next tile's MMAs)
 //
 // Epilogue data movement ("slab" mode): results are produced 32 columns at a time into swizzled
-// shared-memory boxes of [128 rows][32 columns] and written with TMA stores (cp.async.bulk.tensor
-// shared -> global), so every global write is a full row segment and ragged M / N edges are clipped
-// by the tensor map; the residual / pre-activation inputs arrive the same way and are transformed in
-// place.  A 16-column tail (bn % 32 == 16), and every case the slab mode does not cover (split-K
+// shared-memory boxes of [128 rows][32 columns] (row-per-thread writes, conflict-free thanks to the
+// TMA swizzle pattern) and copied out cooperatively, consecutive lanes taking consecutive 16-byte chunks
+// of a row, so every global write is a full 64 / 128-byte row segment; the residual / pre-activation
+// inputs arrive in the same boxes by TMA and are transformed in place.  (TMA stores were tried first:
+// waiting for their shared-memory reads to retire serialised the slabs at about 1 us each.)  A 16-column tail (bn % 32 == 16), and every case the slab mode does not cover (split-K
 // atomics, addends, misaligned buffers), use the direct per-thread path (epilogue_run).
+//
+// CTA pairs (CTAS = 2, used whenever M > 128): the two CTAs of a cluster share one 256-row tile with
+// tcgen05.mma cta_group::2 -- each CTA stages its own 128 rows of A and HALF of the B tile, so the bytes
+// every SM pulls from L2 per flop drop by a third (this GEMM family is bound by the L2 -> shared-memory
+// feed, not by the tensor pipe).  The leader CTA (cluster rank 0) owns the `full` barriers (both
+// producers' TMA transactions are counted there) and issues the MMAs; tcgen05.commit multicasts the
+// `empty` / `acc_full` arrivals to both CTAs; both epilogues arrive on the leader's `acc_empty`.
 //
 // All three layouts of kernels.cuh run on the same kernel: an operand is either K-major (row = M/N
 // index, K contiguous: forward activations and weights) or MN-major (row = K index, M/N contiguous:
@@ -25,6 +33,7 @@
 // Split-K work items (EPI_ATOMIC) cover disjoint K ranges of one output tile.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -41,12 +50,13 @@ namespace {
 constexpr int BM = 128;        // UMMA M
 constexpr int BK = 64;         // bf16 elements per stage along K = one 128-byte swizzle row
 constexpr int MAX_BN = 256;    // UMMA N limit
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 6;
 constexpr int A_BYTES = BM * BK * 2;           // 16 KB
 constexpr int B_BYTES = MAX_BN * BK * 2;       // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES; // 48 KB
 constexpr int CHUNK_BYTES = 64 * BK * 2;       // one [64 k][64 mn] box of an MN-major operand (8 KB)
-constexpr int THREADS = 256;
+constexpr int EG = 2;                          // epilogue groups of 4 warps
+constexpr int THREADS = 128 + 128 * EG;
 constexpr int TMEM_COLS = 512;
 constexpr int SLAB = 32;                       // epilogue slab width in columns
 constexpr int MAX_SLOTS = 6;                   // epilogue-input ring
@@ -55,16 +65,92 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct UmmaArgs {
   int M, N, K;
-  int bn;                 // UMMA N of this launch (multiple of 16)
+  int bn;                 // UMMA N of the full-width column tiles (multiple of 16)
+  int n_pad;              // N rounded up to the tile granularity: the last column tile is n_pad - (tiles_n-1)*bn wide
+  int b_box_rows;         // rows of the K-major B box (TMA always transfers the whole box)
   int tiles_m, tiles_n, splits;
   int kblocks;            // ceil(K / BK)
   int kblocks_per_split;
   int a_mn, b_mn;         // 1 = MN-major operand
   uint32_t idesc;
+  int stage_bytes;        // A tile + this CTA's part of the B tile, 1024-byte multiple
   int stages;             // smem ring depth of the mainloop
   int nslots;             // epilogue-input ring depth (slab mode with a tile-shaped input)
   int has_out2;
+  long long* dbg;         // optional device counters (cycles per role / phase), see v4h_debug_gemm
 };
+
+// cycle accounting for v4h_debug_gemm: T.lap(slot) books the cycles since the previous lap
+struct Lap {
+  long long* dbg;
+  long long t;
+  long long acc[8];
+  __device__ __forceinline__ explicit Lap(long long* d) : dbg(d), t(0) {
+    if (dbg) { t = clock64(); for (int i = 0; i < 8; ++i) acc[i] = 0; }
+  }
+  __device__ __forceinline__ void lap(int i) {
+    if (dbg) { const long long n = clock64(); acc[i] += n - t; t = n; }
+  }
+  __device__ __forceinline__ void flush(int base, int n) {
+    if (dbg) for (int i = 0; i < n; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(dbg + base + i), (unsigned long long)acc[i]);
+  }
+};
+
+// ---- cluster / cta_group::2 primitives
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose mbarrier may live in the peer CTA of the pair (bar = shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at the same shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result) {  // one warp in EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
 
 // byte offset of 16-byte chunk c of row r inside a [128][32]-element box written / read by TMA
 __device__ __forceinline__ uint32_t box_off(int r, int c, int esize) {
@@ -80,7 +166,9 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void group_bar_sync(int grp) {  // the 128 threads of one epilogue group
+  asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+}
 
 __device__ __forceinline__ float4 lds4(const uint8_t* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void sts4(uint8_t* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
@@ -113,6 +201,25 @@ __device__ __forceinline__ void box_write(uint8_t* box, int r, const float (&v)[
   }
 }
 
+// Cooperative copy of one staged box to global memory by the 128 epilogue threads: consecutive lanes
+// take consecutive 16-byte chunks of a row, so every row leaves as one contiguous 64 / 128-byte segment.
+template <int ESIZE>
+__device__ __forceinline__ void box_copy_out(const uint8_t* box, void* gbase, int ld, int m0, int col0, int M, int N,
+                                             int t) {
+  constexpr int CPR = SLAB * ESIZE / 16;  // chunks per row: 4 (bf16) or 8 (fp32)
+  constexpr int EPC = 16 / ESIZE;         // elements per chunk
+  uint8_t* g = reinterpret_cast<uint8_t*>(gbase);
+#pragma unroll
+  for (int i = 0; i < CPR; ++i) {
+    const int idx = t + i * 128;
+    const int row = idx / CPR, c = idx % CPR;
+    if (m0 + row < M && col0 + c * EPC < N) {
+      const uint4 v = *reinterpret_cast<const uint4*>(box + box_off(row, c, ESIZE));
+      *reinterpret_cast<uint4*>(g + ((size_t)(m0 + row) * ld + col0 + c * EPC) * ESIZE) = v;
+    }
+  }
+}
+
 // 32 fp32 values from global (bias, gate); guarded scalar path at the N edge / when not 16-byte aligned
 __device__ __forceinline__ void load32(const float* __restrict__ p, int nvalid, bool vec, float (&v)[SLAB]) {
   if (vec && nvalid >= SLAB) {
@@ -127,11 +234,10 @@ __device__ __forceinline__ void load32(const float* __restrict__ p, int nvalid, 
   }
 }
 
-template <int EPI, int ACT, typename TOut, bool SLABMODE>
+template <int EPI, int ACT, typename TOut, bool SLABMODE, int CTAS>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOut,
-                 const __grid_constant__ CUtensorMap tmOut2, const UmmaArgs g, const EpiParams ep) {
+                 const __grid_constant__ CUtensorMap tmIn, const UmmaArgs g, const EpiParams ep) {
   constexpr bool HAS_IN = SLABMODE && (EPI == EPI_GATE_RES || EPI == EPI_DACT);
   constexpr int IN_ESIZE = EPI == EPI_GATE_RES ? 4 : (int)sizeof(TOut);
   constexpr int IN_BOX = BM * SLAB * IN_ESIZE;
@@ -139,7 +245,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* pool = smem + g.stages * STAGE_BYTES;  // epilogue boxes (1024-byte aligned: STAGE_BYTES is)
+  uint8_t* pool = smem + g.stages * g.stage_bytes;  // epilogue boxes (1024-byte aligned: stage_bytes is)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (SMEM_LIMIT - BAR_BYTES));  // fixed place at the end
   uint64_t* full = bars;                        // [MAX_STAGES]  TMA -> MMA
   uint64_t* empty = full + MAX_STAGES;          // [MAX_STAGES]  MMA -> TMA
@@ -151,104 +257,150 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int STAGES = g.stages;
+  const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;  // CTA of the pair; 0 = leader
+  const int unit = (int)blockIdx.x / CTAS, nunits = (int)gridDim.x / CTAS;  // persistent work index / stride
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
-    if (SLABMODE) {
-      prefetch_tensormap(&tmOut);
-      if (HAS_IN) prefetch_tensormap(&tmIn);
-      if (g.has_out2) prefetch_tensormap(&tmOut2);
-    }
+    if (HAS_IN) prefetch_tensormap(&tmIn);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
-    for (int i = 0; i < MAX_SLOTS; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4 * EG * CTAS); }
+    for (int i = 0; i < MAX_SLOTS; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], 4); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == 2) {
+    if (CTAS == 2) tmem_alloc_pair<TMEM_COLS>(tmem_slot);
+    else tmem_alloc<TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int total_work = g.tiles_m * g.tiles_n * g.splits;
-  const uint32_t b_tile_bytes = g.b_mn ? (uint32_t)((g.bn + 63) / 64) * CHUNK_BYTES : (uint32_t)g.bn * BK * 2;
-  const int nslab = SLABMODE ? g.bn / SLAB : 0;  // full slabs per tile
+  // tile (tm, tn): rows [tm * BM * CTAS, ..), columns [tn * bn, tn * bn + width); the last column tile is
+  // narrower (width a multiple of 16, of 32 in slab mode)
+  auto tile_width = [&](int tn) { return min(g.bn, g.n_pad - tn * g.bn); };
 
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+      Lap T(g.dbg);
+      for (int work = unit; work < total_work; work += nunits) {
         const int split = work % g.splits;
         const int tile = work / g.splits;
-        const int m0 = (tile % g.tiles_m) * BM, n0 = (tile / g.tiles_m) * g.bn;
+        const int tn = tile / g.tiles_m;
+        const int bnh = tile_width(tn) / CTAS;  // B rows / columns staged by this CTA
+        const uint32_t b_part_bytes = g.b_mn ? (uint32_t)((bnh + 63) / 64) * CHUNK_BYTES : (uint32_t)g.b_box_rows * BK * 2;
+        const int m0 = (tile % g.tiles_m) * (BM * CTAS) + (int)rank * BM;
+        const int n0 = tn * g.bn + (int)rank * bnh;
         const int kb0 = split * g.kblocks_per_split;
         const int kb1 = min(g.kblocks, kb0 + g.kblocks_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * STAGE_BYTES;
+          T.lap(0);
+          uint8_t* sa = smem + stage * g.stage_bytes;
           uint8_t* sb = sa + A_BYTES;
-          mbar_expect_tx(&full[stage], A_BYTES + b_tile_bytes);
-          if (!g.a_mn) {
-            tma_load_2d(sa, &tmA, &full[stage], kb * BK, m0);
+          if (CTAS == 1) {
+            mbar_expect_tx(&full[stage], A_BYTES + b_part_bytes);
+            if (!g.a_mn) {
+              tma_load_2d(sa, &tmA, &full[stage], kb * BK, m0);
+            } else {
+              tma_load_2d(sa, &tmA, &full[stage], m0, kb * BK);
+              tma_load_2d(sa + CHUNK_BYTES, &tmA, &full[stage], m0 + 64, kb * BK);
+            }
+            if (!g.b_mn) {
+              tma_load_2d(sb, &tmB, &full[stage], kb * BK, n0);
+            } else {
+              for (int j = 0; j * 64 < bnh; ++j)
+                tma_load_2d(sb + j * CHUNK_BYTES, &tmB, &full[stage], n0 + j * 64, kb * BK);
+            }
           } else {
-            tma_load_2d(sa, &tmA, &full[stage], m0, kb * BK);
-            tma_load_2d(sa + CHUNK_BYTES, &tmA, &full[stage], m0 + 64, kb * BK);
+            // both producers' bytes are counted on the LEADER's full barrier
+            const uint32_t bar = map_to_cta(smem_u32(&full[stage]), 0);
+            if (rank == 0) mbar_expect_tx(&full[stage], 2 * (A_BYTES + b_part_bytes));
+            if (!g.a_mn) {
+              tma_load_2d_pair(sa, &tmA, bar, kb * BK, m0);
+            } else {
+              tma_load_2d_pair(sa, &tmA, bar, m0, kb * BK);
+              tma_load_2d_pair(sa + CHUNK_BYTES, &tmA, bar, m0 + 64, kb * BK);
+            }
+            if (!g.b_mn) {
+              tma_load_2d_pair(sb, &tmB, bar, kb * BK, n0);
+            } else {
+              for (int j = 0; j * 64 < bnh; ++j)
+                tma_load_2d_pair(sb + j * CHUNK_BYTES, &tmB, bar, n0 + j * 64, kb * BK);
+            }
           }
-          if (!g.b_mn) {
-            tma_load_2d(sb, &tmB, &full[stage], kb * BK, n0);
-          } else {
-            for (int j = 0; j * 64 < g.bn; ++j)
-              tma_load_2d(sb + j * CHUNK_BYTES, &tmB, &full[stage], n0 + j * 64, kb * BK);
-          }
+          T.lap(1);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      T.flush(0, 2);
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
-      const int split = work % g.splits;
-      const int kb0 = split * g.kblocks_per_split;
-      const int kb1 = min(g.kblocks, kb0 + g.kblocks_per_split);
-      mbar_wait(&acc_empty[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)acc * MAX_BN;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full[stage], phase);
+    if (rank == 0) {  // pairs: only the leader CTA issues MMAs (for both CTAs)
+      Lap T(lane == 0 ? g.dbg : nullptr);
+      for (int work = unit; work < total_work; work += nunits) {
+        const int split = work % g.splits;
+        const int tile = work / g.splits;
+        const uint32_t idesc = make_idesc_bf16(BM * CTAS, tile_width(tile / g.tiles_m), g.a_mn != 0, g.b_mn != 0);
+        const int kb0 = split * g.kblocks_per_split;
+        const int kb1 = min(g.kblocks, kb0 + g.kblocks_per_split);
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
-          // number of K=16 steps with any in-range data in this block (TMA zero-fills the rest)
-          const int ksteps = min(BK / 16, (g.K - kb * BK + 15) / 16);
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t adesc = g.a_mn ? make_smem_desc(sa + k * 16 * 128, BK * 128, 1024)
-                                          : make_smem_desc(sa + k * 32, 0, 1024);
-            const uint64_t bdesc = g.b_mn ? make_smem_desc(sb + k * 16 * 128, BK * 128, 1024)
-                                          : make_smem_desc(sb + k * 32, 0, 1024);
-            umma_bf16(d_tmem, adesc, bdesc, g.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+        T.lap(0);
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * MAX_BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          T.lap(1);
+          if (lane == 0) {
+            const uint32_t sa = smem_u32(smem + stage * g.stage_bytes);
+            const uint32_t sb = sa + A_BYTES;
+            // number of K=16 steps with any in-range data in this block (TMA zero-fills the rest)
+            const int ksteps = min(BK / 16, (g.K - kb * BK + 15) / 16);
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t adesc = g.a_mn ? make_smem_desc(sa + k * 16 * 128, BK * 128, 1024)
+                                            : make_smem_desc(sa + k * 32, 0, 1024);
+              const uint64_t bdesc = g.b_mn ? make_smem_desc(sb + k * 16 * 128, BK * 128, 1024)
+                                            : make_smem_desc(sb + k * 32, 0, 1024);
+              if (CTAS == 2) umma_bf16_pair(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            if (CTAS == 2) {
+              umma_commit_pair(&empty[stage]);                    // frees the smem slot in both CTAs
+              if (kb == kb1 - 1) umma_commit_pair(&acc_full[acc]);  // accumulator complete, both epilogues
+            } else {
+              umma_commit(&empty[stage]);                    // frees the smem slot when the MMAs have read it
+              if (kb == kb1 - 1) umma_commit(&acc_full[acc]);  // accumulator complete
+            }
           }
-          umma_commit(&empty[stage]);                    // frees the smem slot when the MMAs have read it
-          if (kb == kb1 - 1) umma_commit(&acc_full[acc]);  // accumulator complete
+          __syncwarp();
+          T.lap(2);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      T.flush(2, 3);
     }
   } else if (warp == 3) {
     // ===================================================================== epilogue-input producer
     if (HAS_IN && lane == 0) {
       int slot = 0; uint32_t phase = 0;
-      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+      for (int work = unit; work < total_work; work += nunits) {
         const int tile = work / g.splits;
-        const int m0 = (tile % g.tiles_m) * BM, n0 = (tile / g.tiles_m) * g.bn;
+        const int tn = tile / g.tiles_m;
+        const int m0 = (tile % g.tiles_m) * (BM * CTAS) + (int)rank * BM, n0 = tn * g.bn;
+        const int nslab = tile_width(tn) / SLAB;
         for (int j = 0; j < nslab; ++j) {
           mbar_wait(&in_empty[slot], phase ^ 1);
           mbar_expect_tx(&in_full[slot], IN_BOX);
@@ -258,29 +410,38 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    // ===================================================================== epilogue
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    // ===================================================================== epilogue (EG groups of 4 warps)
+    const int q = warp & 3;            // TMEM lane quadrant this warp may access
+    const int grp = (warp - 4) >> 2;   // epilogue group: takes the slabs j = grp (mod EG) of every tile
     const int r = q * 32 + lane;       // row inside the tile = TMEM lane
-    const bool leader = threadIdx.x == 128;
     int acc = 0; uint32_t acc_phase = 0;
-    int slot = 0; uint32_t in_phase = 0;   // epilogue-input ring position
-    int prev_slot = -1;                    // ring slot whose TMA store was issued last
-    uint32_t it = 0;                       // slab counter: staging buffer = it & 1
-    // pool layout: [ring: nslots x IN_BOX] [staging out: 2 x OUT_BOX] [staging out2: 2 x OUT_BOX]
+    int slab_base = 0;                 // slabs of the tiles this CTA has finished (ring position)
+    uint32_t it = 0;                   // slabs done by this group: staging buffer = it & 1
+    // pool layout: [ring: nslots x IN_BOX] then per group [out: 2 x OUT_BOX] [out2: 2 x OUT_BOX]
     uint8_t* ring = pool;
-    uint8_t* st_out = pool + (HAS_IN ? g.nslots * IN_BOX : 0);
-    uint8_t* st_out2 = st_out + ((EPI == EPI_BIAS_ACT) ? 2 * OUT_BOX : 0);
-    for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+    constexpr int GROUP_STAGING = (EPI == EPI_BIAS_ACT ? 4 : (EPI == EPI_GATE_RES ? 2 : 0)) * OUT_BOX;
+    uint8_t* st_out = pool + (HAS_IN ? g.nslots * IN_BOX : 0) + grp * GROUP_STAGING;
+    uint8_t* st_out2 = st_out + 2 * OUT_BOX;
+    const uint32_t acc_empty_leader[2] = {CTAS == 2 ? map_to_cta(smem_u32(&acc_empty[0]), 0) : 0u,
+                                          CTAS == 2 ? map_to_cta(smem_u32(&acc_empty[1]), 0) : 0u};
+    Lap T(threadIdx.x == 128 ? g.dbg : nullptr);
+    for (int work = unit; work < total_work; work += nunits) {
       const int tile = work / g.splits;
-      const int m0 = (tile % g.tiles_m) * BM, n0 = (tile / g.tiles_m) * g.bn;
+      const int tn = tile / g.tiles_m;
+      const int width = tile_width(tn);
+      const int m0 = (tile % g.tiles_m) * (BM * CTAS) + (int)rank * BM, n0 = tn * g.bn;
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
+      T.lap(0);
       const int row = m0 + r;
       const uint32_t t_row = tmem_base + (uint32_t)acc * MAX_BN + ((uint32_t)(q * 32) << 16);
       if (SLABMODE) {
-        for (int j = 0; j < nslab; ++j, ++it) {
+        const int nslab = width / SLAB;
+        for (int j = grp; j < nslab; j += EG, ++it) {
           const int col0 = n0 + j * SLAB;
-          const int nvalid = g.N - col0;  // > 0 for every launched tile column... may be < SLAB at the N edge
+          const int nvalid = g.N - col0;  // may be < SLAB (even <= 0) at the N edge
+          const int slot = HAS_IN ? (slab_base + j) % g.nslots : 0;
+          const uint32_t in_phase = HAS_IN ? (uint32_t)(((slab_base + j) / g.nslots) & 1) : 0u;
           float b32[SLAB], gt[SLAB];
           if (EPI != EPI_DACT) {
             if (ep.bias) load32(ep.bias + col0, nvalid, ep.vec_ok, b32);
@@ -302,7 +463,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 16; ++i) { v[i] = lo[i]; v[16 + i] = hi[i]; }
           }
+          T.lap(1);
           if (HAS_IN) mbar_wait(&in_full[slot], in_phase);
+          T.lap(2);
           uint8_t* so = st_out + (it & 1) * OUT_BOX;
           if (EPI == EPI_BIAS_ACT) {
 #pragma unroll
@@ -349,51 +512,60 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
           }
-          fence_proxy_async();  // this thread's smem writes -> visible to the TMA store
-          if (leader) {
-            // the stores of the previous slab have finished READING shared memory: its staging buffers
-            // (reused by the next slab) and its ring slot are free after the barrier below
-            tma_store_wait_read0();
-            if (HAS_IN && prev_slot >= 0) mbar_arrive(&in_empty[prev_slot]);
+          // staged boxes complete -> copy out.  Two staging buffers alternate per group; a thread reaches
+          // the group's next barrier only after its reads of this one, so one barrier per slab orders every
+          // reuse.
+          T.lap(3);
+          group_bar_sync(grp);
+          T.lap(4);
+          if (EPI == EPI_BIAS_ACT) {
+            box_copy_out<(int)sizeof(TOut)>(so, ep.out, ep.ldo, m0, col0, g.M, g.N, r);
+            if (g.has_out2) box_copy_out<(int)sizeof(TOut)>(st_out2 + (it & 1) * OUT_BOX, ep.out2, ep.ldo, m0, col0, g.M, g.N, r);
+          } else if (EPI == EPI_GATE_RES) {
+            box_copy_out<4>(ring + slot * IN_BOX, ep.res_out, ep.ldo, m0, col0, g.M, g.N, r);
+            if (g.has_out2) box_copy_out<(int)sizeof(TOut)>(so, ep.out2, ep.ldo, m0, col0, g.M, g.N, r);
+          } else {
+            box_copy_out<(int)sizeof(TOut)>(ring + slot * IN_BOX, ep.out, ep.ldo, m0, col0, g.M, g.N, r);
           }
-          epi_bar_sync();
-          if (leader) {
-            if (EPI == EPI_BIAS_ACT) {
-              tma_store_2d(&tmOut, so, col0, m0);
-              if (g.has_out2) tma_store_2d(&tmOut2, st_out2 + (it & 1) * OUT_BOX, col0, m0);
-            } else if (EPI == EPI_GATE_RES) {
-              tma_store_2d(&tmOut, ring + slot * IN_BOX, col0, m0);   // residual stream out
-              if (g.has_out2) tma_store_2d(&tmOut2, so, col0, m0);    // y
-            } else {
-              tma_store_2d(&tmOut, ring + slot * IN_BOX, col0, m0);
+          if (HAS_IN) {  // this warp has read its part of the ring slot: 4 arrivals hand it back to the producer
+            __syncwarp();
+            if (lane == 0) {
+              fence_proxy_async();  // generic reads of the slot are ordered before its next TMA write
+              mbar_arrive(&in_empty[slot]);
             }
-            tma_store_commit();
-            prev_slot = slot;
           }
-          if (HAS_IN && ++slot == g.nslots) { slot = 0; in_phase ^= 1; }
+          T.lap(5);
+        }
+        slab_base += nslab;
+      } else {
+        // direct path (split-K atomics, addends, misaligned buffers): the groups alternate 16-column chunks
+        for (int c0 = grp * 16; c0 < width; c0 += 16 * EG) {
+          float v[16];
+          tmem_ld16(t_row + c0, v);
+          tmem_ld_wait();
+          const int col0 = n0 + c0;
+          if (row < g.M && col0 < g.N) epilogue_run<EPI, ACT, TOut, 16>(ep, row, col0, min(16, g.N - col0), v);
         }
       }
-      // direct path: everything (no slab mode) or the 16-column tail
-      for (int c0 = nslab * SLAB; c0 < g.bn; c0 += 16) {
-        float v[16];
-        tmem_ld16(t_row + c0, v);
-        tmem_ld_wait();
-        const int col0 = n0 + c0;
-        if (row < g.M && col0 < g.N) epilogue_run<EPI, ACT, TOut, 16>(ep, row, col0, min(16, g.N - col0), v);
-      }
+      T.lap(6);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (lane == 0) {
+        if (CTAS == 2) mbar_arrive_cluster(acc_empty_leader[acc]);
+        else mbar_arrive(&acc_empty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (SLABMODE && leader) tma_store_wait_read0();  // shared memory must outlive the last store's reads
+    T.flush(5, 7);
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();  // the peer may still signal this CTA's barriers / read its tiles
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (CTAS == 2) tmem_dealloc_pair<TMEM_COLS>(tmem_base);
+    else tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
@@ -404,23 +576,44 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-struct Maps { CUtensorMap a, b, in, out, out2; };
+struct Maps { CUtensorMap a, b, in; };
 
-template <int EPI, int ACT, typename TOut, bool SLABMODE>
-int launch(const Maps& m, const UmmaArgs& g, const EpiParams& ep, int grid, cudaStream_t s) {
+template <int EPI, int ACT, typename TOut, bool SLABMODE, int CTAS>
+int launch_k(const Maps& m, const UmmaArgs& g, const EpiParams& ep, int grid, cudaStream_t s) {
+  auto kernel = gemm_umma_kernel<EPI, ACT, TOut, SLABMODE, CTAS>;
   static bool configured = false;  // per instantiation; benign race (idempotent attribute set)
   if (!configured) {
-    V4H_CUDA(cudaFuncSetAttribute(gemm_umma_kernel<EPI, ACT, TOut, SLABMODE>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    V4H_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     configured = true;
   }
-  gemm_umma_kernel<EPI, ACT, TOut, SLABMODE><<<grid, THREADS, SMEM_LIMIT, s>>>(m.a, m.b, m.in, m.out, m.out2, g, ep);
+  if (CTAS == 1) {
+    kernel<<<grid, THREADS, SMEM_LIMIT, s>>>(m.a, m.b, m.in, g, ep);
+  } else {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM_LIMIT;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    V4H_CUDA(cudaLaunchKernelEx(&cfg, kernel, m.a, m.b, m.in, g, ep));
+  }
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }
+template <int EPI, int ACT, typename TOut, bool SLABMODE>
+int launch(const Maps& m, const UmmaArgs& g, const EpiParams& ep, int ctas, int grid, cudaStream_t s) {
+  return ctas == 2 ? launch_k<EPI, ACT, TOut, SLABMODE, 2>(m, g, ep, grid, s)
+                   : launch_k<EPI, ACT, TOut, SLABMODE, 1>(m, g, ep, grid, s);
+}
 template <int EPI, int ACT, typename TOut>
-int launch2(bool slab, const Maps& m, const UmmaArgs& g, const EpiParams& ep, int grid, cudaStream_t s) {
-  return slab ? launch<EPI, ACT, TOut, true>(m, g, ep, grid, s) : launch<EPI, ACT, TOut, false>(m, g, ep, grid, s);
+int launch2(bool slab, const Maps& m, const UmmaArgs& g, const EpiParams& ep, int ctas, int grid, cudaStream_t s) {
+  return slab ? launch<EPI, ACT, TOut, true>(m, g, ep, ctas, grid, s)
+              : launch<EPI, ACT, TOut, false>(m, g, ep, ctas, grid, s);
 }
 
 }  // namespace
@@ -488,25 +681,22 @@ static int get_map(UmmaContext* ctx, const void* base, int inner, int outer, int
   return V4H_OK;
 }
 
-// largest UMMA N (multiple of 16, <= 256) that wastes the fewest columns; ties go to the wider tile
-static int choose_bn(int N) {
-  if (N <= MAX_BN) return (int)ceil_div(N, 16) * 16;
-  int best = MAX_BN; long best_waste = -1;
-  for (int bn = MAX_BN; bn >= 128; bn -= 16) {
-    const long waste = ceil_div(N, bn) * bn - N;
-    if (best_waste < 0 || waste < best_waste) { best = bn; best_waste = waste; }
-  }
-  return best;
+// Column tiling: full tiles of 256 columns plus one narrower last tile, everything a multiple of `gran`
+// (32 in slab mode: whole epilogue slabs; 16 otherwise: the UMMA N granularity at M = 128).
+static void choose_tiling(int N, int gran, int* bn, int* n_pad, int* tiles_n) {
+  *n_pad = (int)ceil_div(N, gran) * gran;
+  *bn = *n_pad < MAX_BN ? *n_pad : MAX_BN;
+  *tiles_n = (int)ceil_div(*n_pad, *bn);
 }
 
 // can the epilogue move its tile-shaped streams with TMA boxes?
-static bool slab_ok(const GemmDesc& d, int bn) {
-  if (d.epi == EPI_ATOMIC || bn < SLAB) return false;
+static bool slab_ok(const GemmDesc& d) {
+  if (d.epi == EPI_ATOMIC) return false;
   const EpiParams& p = d.ep;
   const int esz = d.out_dtype == DT_BF16 ? 2 : 4;
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (p.addend) return false;
-  if ((p.ldo * esz) % 16) return false;
+  if ((p.ldo * esz) % 16 || (d.N * esz) % 16) return false;  // rows leave as whole 16-byte chunks
   switch (d.epi) {
     case EPI_BIAS_ACT:
       return p.out && al(p.out) && al(p.out2);
@@ -527,9 +717,15 @@ int gemm_umma(UmmaContext* ctx, const GemmDesc& d, cudaStream_t s) {
   g.M = d.M; g.N = d.N; g.K = d.K;
   g.a_mn = d.layout == GEMM_TN ? 1 : 0;
   g.b_mn = d.layout == GEMM_NT ? 0 : 1;
-  g.bn = choose_bn(d.N);
-  g.tiles_m = (int)ceil_div(d.M, BM);
-  g.tiles_n = (int)ceil_div(d.N, g.bn);
+  const bool slab = slab_ok(d);
+  choose_tiling(d.N, slab ? SLAB : 16, &g.bn, &g.n_pad, &g.tiles_n);
+  // CTA pairs (cta_group::2, V4H_GEMM_PAIRS=1) when there is more than one 128-row tile of M.  Measured on
+  // the ds2 shapes they are correct but 2-3 % slower than single CTAs (the epilogue, not the L2 -> smem
+  // feed, bounds these K = 480 GEMMs), so they are opt-in.
+  static const int pairs_enabled = [] { const char* e = getenv("V4H_GEMM_PAIRS"); return (e && e[0] == '1') ? 1 : 0; }();
+  const int ctas = (pairs_enabled && d.M > BM && ctx->num_sms % 2 == 0) ? 2 : 1;
+  const int units = ctx->num_sms / ctas;  // persistent CTAs (or CTA pairs)
+  g.tiles_m = (int)ceil_div(d.M, BM * ctas);
   g.kblocks = (int)ceil_div(d.K, BK);
   int splits = d.epi == EPI_ATOMIC ? d.splitk : 1;
   if (d.epi == EPI_ATOMIC && splits <= 0) {
@@ -540,10 +736,10 @@ int gemm_umma(UmmaContext* ctx, const GemmDesc& d, cudaStream_t s) {
     const int epilogue_cost = 6;
     long best_cost = -1;
     splits = 1;
-    for (int sp = 1; sp <= g.kblocks && (long)tiles * sp <= 4L * ctx->num_sms; ++sp) {
+    for (int sp = 1; sp <= g.kblocks && (long)tiles * sp <= 4L * units; ++sp) {
       const int kper = (int)ceil_div(g.kblocks, sp);
       const int eff = (int)ceil_div(g.kblocks, kper);
-      const long rounds = ceil_div((long)tiles * eff, ctx->num_sms);
+      const long rounds = ceil_div((long)tiles * eff, units);
       const long cost = rounds * (kper + epilogue_cost);
       if (best_cost < 0 || cost < best_cost) { best_cost = cost; splits = sp; }
     }
@@ -552,72 +748,71 @@ int gemm_umma(UmmaContext* ctx, const GemmDesc& d, cudaStream_t s) {
   if (splits > g.kblocks) splits = g.kblocks;
   g.kblocks_per_split = (int)ceil_div(g.kblocks, splits);
   g.splits = (int)ceil_div(g.kblocks, g.kblocks_per_split);
-  g.idesc = make_idesc_bf16(BM, g.bn, g.a_mn != 0, g.b_mn != 0);
+  g.idesc = 0;  // built per tile in the kernel (the last column tile is narrower)
+  const int bnh = g.bn / ctas;
+  g.b_box_rows = bnh;
+  const int b_part_bytes = g.b_mn ? (int)ceil_div(bnh, 64) * CHUNK_BYTES : bnh * BK * 2;
+  g.stage_bytes = (int)align_up((size_t)A_BYTES + b_part_bytes, 1024);
 
   Maps m;
   memset(&m, 0, sizeof(m));
   if (!g.a_mn) V4H_TRY(get_map(ctx, d.A, d.K, d.M, d.lda, BK, BM, 2, &m.a));      // A (M, K): box 64 k x 128 rows
   else         V4H_TRY(get_map(ctx, d.A, d.M, d.K, d.lda, 64, BK, 2, &m.a));      // A (K, M): box 64 m x 64 k rows
-  if (!g.b_mn) V4H_TRY(get_map(ctx, d.B, d.K, d.N, d.ldb, BK, g.bn, 2, &m.b));    // B (N, K): box 64 k x bn rows
+  if (!g.b_mn) V4H_TRY(get_map(ctx, d.B, d.K, d.N, d.ldb, BK, bnh, 2, &m.b));     // B (N, K): box 64 k x bn (/2) rows
   else         V4H_TRY(get_map(ctx, d.B, d.N, d.K, d.ldb, 64, BK, 2, &m.b));      // B (K, N): box 64 n x 64 k rows
 
   const bool obf = d.out_dtype == DT_BF16;
   const int osz = obf ? 2 : 4;
   EpiParams ep = d.ep;
   ep.vec_ok = epilogue_vec_ok(ep, d.epi, d.epi == EPI_ATOMIC ? false : obf);
-  const bool slab = slab_ok(d, g.bn);
   // shared-memory budget: [mainloop stages][epilogue pool]; barriers sit in the last BAR_BYTES
   int pool_bytes = 0;
   g.nslots = 0;
   g.has_out2 = ep.out2 != nullptr;
+  g.dbg = d.dbg;
   if (slab) {
     const int out_box = BM * SLAB * osz;
     switch (d.epi) {
       case EPI_BIAS_ACT:
-        pool_bytes = (g.has_out2 ? 4 : 2) * out_box;
-        V4H_TRY(get_map(ctx, ep.out, d.N, d.M, ep.ldo, SLAB, BM, osz, &m.out));
-        if (g.has_out2) V4H_TRY(get_map(ctx, ep.out2, d.N, d.M, ep.ldo, SLAB, BM, osz, &m.out2));
+        pool_bytes = EG * 4 * out_box;
         break;
       case EPI_GATE_RES:
-        g.nslots = 4;
-        pool_bytes = g.nslots * BM * SLAB * 4 + 2 * out_box;
+        g.nslots = ctas == 2 ? 4 : 3;
+        pool_bytes = g.nslots * BM * SLAB * 4 + EG * 2 * out_box;
         V4H_TRY(get_map(ctx, ep.res_in, d.N, d.M, ep.ldo, SLAB, BM, 4, &m.in));
-        V4H_TRY(get_map(ctx, ep.res_out, d.N, d.M, ep.ldo, SLAB, BM, 4, &m.out));
-        if (g.has_out2) V4H_TRY(get_map(ctx, ep.out2, d.N, d.M, ep.ldo, SLAB, BM, 2, &m.out2));
         break;
       case EPI_DACT:
         g.nslots = MAX_SLOTS;
         pool_bytes = g.nslots * out_box;
         V4H_TRY(get_map(ctx, ep.aux, d.N, d.M, ep.ld_aux, SLAB, BM, osz, &m.in));
-        V4H_TRY(get_map(ctx, ep.out, d.N, d.M, ep.ldo, SLAB, BM, osz, &m.out));
         break;
     }
   }
-  g.stages = (SMEM_LIMIT - 1024 - BAR_BYTES - pool_bytes) / STAGE_BYTES;
+  g.stages = (SMEM_LIMIT - 1024 - BAR_BYTES - pool_bytes) / g.stage_bytes;
   if (g.stages > MAX_STAGES) g.stages = MAX_STAGES;
   V4H_REQUIRE(g.stages >= 2, "gemm_umma: internal shared-memory budget error");
 
   const int total = g.tiles_m * g.tiles_n * g.splits;
-  const int grid = total < ctx->num_sms ? total : ctx->num_sms;
+  const int grid = (total < units ? total : units) * ctas;
   switch (d.epi) {
     case EPI_BIAS_ACT:
       if (d.act == ACT_NONE)
-        return obf ? launch2<EPI_BIAS_ACT, ACT_NONE, bf16>(slab, m, g, ep, grid, s)
-                   : launch2<EPI_BIAS_ACT, ACT_NONE, float>(slab, m, g, ep, grid, s);
-      if (d.act == ACT_GELU_TANH && obf) return launch2<EPI_BIAS_ACT, ACT_GELU_TANH_FAST, bf16>(slab, m, g, ep, grid, s);
+        return obf ? launch2<EPI_BIAS_ACT, ACT_NONE, bf16>(slab, m, g, ep, ctas, grid, s)
+                   : launch2<EPI_BIAS_ACT, ACT_NONE, float>(slab, m, g, ep, ctas, grid, s);
+      if (d.act == ACT_GELU_TANH && obf) return launch2<EPI_BIAS_ACT, ACT_GELU_TANH_FAST, bf16>(slab, m, g, ep, ctas, grid, s);
       if (d.act == ACT_SILU)
-        return obf ? launch2<EPI_BIAS_ACT, ACT_SILU, bf16>(slab, m, g, ep, grid, s)
-                   : launch2<EPI_BIAS_ACT, ACT_SILU, float>(slab, m, g, ep, grid, s);
+        return obf ? launch2<EPI_BIAS_ACT, ACT_SILU, bf16>(slab, m, g, ep, ctas, grid, s)
+                   : launch2<EPI_BIAS_ACT, ACT_SILU, float>(slab, m, g, ep, ctas, grid, s);
       break;
     case EPI_GATE_RES:
-      if (obf) return launch2<EPI_GATE_RES, ACT_NONE, bf16>(slab, m, g, ep, grid, s);
+      if (obf) return launch2<EPI_GATE_RES, ACT_NONE, bf16>(slab, m, g, ep, ctas, grid, s);
       break;
     case EPI_DACT:
-      if (d.act == ACT_GELU_TANH && obf) return launch2<EPI_DACT, ACT_GELU_TANH_FAST, bf16>(slab, m, g, ep, grid, s);
-      if (d.act == ACT_SILU && obf) return launch2<EPI_DACT, ACT_SILU, bf16>(slab, m, g, ep, grid, s);
+      if (d.act == ACT_GELU_TANH && obf) return launch2<EPI_DACT, ACT_GELU_TANH_FAST, bf16>(slab, m, g, ep, ctas, grid, s);
+      if (d.act == ACT_SILU && obf) return launch2<EPI_DACT, ACT_SILU, bf16>(slab, m, g, ep, ctas, grid, s);
       break;
     case EPI_ATOMIC:
-      return launch<EPI_ATOMIC, ACT_NONE, float, false>(m, g, ep, grid, s);
+      return launch<EPI_ATOMIC, ACT_NONE, float, false>(m, g, ep, ctas, grid, s);
   }
   return fail(V4H_ERR_UNSUPPORTED, "gemm_umma: epilogue %d / activation %d / output dtype %d is not instantiated", d.epi,
               d.act, d.out_dtype);

@@ -27,6 +27,7 @@ struct GemmDesc {
   int out_dtype = DT_F32;
   const char* tag = "gemm";  // kernel class for v4h_profile_*
   int splitk = 1;  // EPI_ATOMIC only: number of K ranges, 0 = let the engine choose
+  long long* dbg = nullptr;  // tcgen05 engine only: device array of 16 cycle counters (v4h_debug_gemm)
   EpiParams ep;
 };
 
@@ -94,6 +95,11 @@ int cfm_loss(const float* v, const float* target, int64_t n, float grad_scale, f
              cudaStream_t s);
 int axpy4(float* out, const float* y, const float* k0, float a0, const float* k1, float a1,
           const float* k2, float a2, const float* k3, float a3, int64_t n, cudaStream_t s);
+
+// optim.cu: fused gradient clipping + AdamW + bf16 weight refresh
+int grad_norm_sq(const float* flat, int64_t n, float* out, cudaStream_t s);
+int adamw_step(const v4h_adamw_job* jobs_dev, int njobs, int64_t max_n, const float* norm_sq, float max_norm, float lr,
+               float beta1, float beta2, float eps, float weight_decay, int step, cudaStream_t s);
 
 // patchify.cu:  dst[b, j] = src[b, table[j]] staged through shared memory per chunk
 int patch_permute(const float* src, float* dst, const int32_t* table, const int32_t* chunk_bounds,

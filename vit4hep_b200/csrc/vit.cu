@@ -3,6 +3,7 @@
 // kernels in this directory.  Nothing here allocates activations: every buffer is a slice of the
 // caller's workspace, laid out by Workspace::layout().
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "kernels.cuh"
@@ -619,6 +620,38 @@ size_t plan_workspace_bytes(const Plan* p, int64_t B, bool train) {
 }
 
 size_t plan_arena_bytes(const Plan* p) { return p->arena_bytes; }
+
+// byte offset of the bf16 copy of a parameter inside the weight arena (-1: none)
+int64_t plan_arena_offset(const Plan* p, const char* field) {
+  if (!p->bf16) return -1;
+  const size_t D = p->d.hidden_dim;
+  const std::string f(field);
+  size_t elems;
+  if (f == "final_w") elems = p->arena_final;
+  else if (f == "x_w") elems = p->arena_x;
+  else if (f == "t0_w") elems = p->arena_t0;
+  else if (f == "t2_w") elems = p->arena_t2;
+  else if (f == "c2_w") elems = p->arena_c2;
+  else if (f == "final_ada_w") elems = p->arena_ada + (size_t)p->d.depth * 6 * D * D;
+  else if (f == "final_ada_b") return (int64_t)(p->arena_ada_bias_bytes + (size_t)p->d.depth * 6 * D * 4);
+  else if (f.rfind("blocks.", 0) == 0) {
+    const size_t dot = f.find('.', 7);
+    if (dot == std::string::npos) return -1;
+    const int i = atoi(f.substr(7, dot - 7).c_str());
+    if (i < 0 || i >= p->d.depth) return -1;
+    const std::string name = f.substr(dot + 1);
+    if (name == "qkv_w") elems = p->arena_blocks[i].qkv;
+    else if (name == "proj_w") elems = p->arena_blocks[i].proj;
+    else if (name == "fc1_w") elems = p->arena_blocks[i].fc1;
+    else if (name == "fc2_w") elems = p->arena_blocks[i].fc2;
+    else if (name == "ada_w") elems = p->arena_ada + (size_t)i * 6 * D * D;
+    else if (name == "ada_b") return (int64_t)(p->arena_ada_bias_bytes + (size_t)i * 6 * D * 4);
+    else return -1;
+  } else {
+    return -1;
+  }
+  return (int64_t)(elems * 2);
+}
 
 int plan_prepare_weights(Plan* p, const v4h_vit_params* w, void* arena, cudaStream_t s) {
   if (!p->bf16) return V4H_OK;
