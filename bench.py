@@ -31,6 +31,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout and would precede the JSON line
+
 import torch  # noqa: E402
 
 METRIC = "ds2 CFM-ViT train samples/s"

@@ -48,6 +48,16 @@ def run(name, kind, m, n, k, iters=20):
 
 if __name__ == "__main__":
     print("pairs:", os.environ.get("V4H_GEMM_PAIRS", "1"))
+    if "--small" in sys.argv:
+        run("tiny", 1, 128, 256, 64)
+        run("tiny.k480", 1, 128, 256, 480)
+        run("cond.fwd", 1, 64, 480, 480)
+        run("cond.dgrad", 4, 64, 480, 480)
+        run("cond.wgrad", 5, 480, 480, 64)
+        run("adaln.fwd", 1, 64, 18240, 480)
+        run("adaln.dgrad", 4, 64, 480, 18240)
+        run("final", 1, M, 48, 480)
+        sys.exit(0)
     run("fc1", 0, M, H, D)
     run("qkv", 1, M, 3 * D, D)
     run("proj", 2, M, D, D)

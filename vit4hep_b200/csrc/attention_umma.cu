@@ -81,12 +81,16 @@ __host__ __device__ constexpr uint32_t g8_bytes(int rows, int cols) { return (ui
 template <int DHP, int NTHREADS = ATT_THREADS>
 __device__ __forceinline__ void stage_tile(uint32_t dst, int rows, const bf16* __restrict__ src, size_t ld,
                                            int rows_valid, int dh) {
-  constexpr int NCG = DHP / 8;
-  const uint32_t gs = g8_stride(rows);
-  for (int idx = threadIdx.x; idx < rows * NCG; idx += NTHREADS) {
-    const int row = idx / NCG, cg = idx - row * NCG;
-    const bool ok = row < rows_valid && cg * 8 < dh;
-    cp_async16(dst + cg * gs + row * 16, ok ? (const void*)(src + (size_t)row * ld + cg * 8) : (const void*)src, ok);
+  constexpr int NCG = DHP / 8;        // 16-byte column groups per row
+  constexpr int RPI = NTHREADS / NCG;  // rows per sweep: every thread keeps one column group
+  if ((int)threadIdx.x >= RPI * NCG) return;
+  const int r0 = (int)threadIdx.x / NCG, cg = (int)threadIdx.x - r0 * NCG;
+  const bool col_ok = cg * 8 < dh;
+  const bf16* p = src + (size_t)r0 * ld + cg * 8;
+  uint32_t d = dst + cg * g8_stride(rows) + r0 * 16;
+  for (int row = r0; row < rows; row += RPI, p += (size_t)RPI * ld, d += RPI * 16) {
+    const bool ok = col_ok && row < rows_valid;
+    cp_async16(d, ok ? (const void*)p : (const void*)src, ok);
   }
 }
 
@@ -188,6 +192,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_umma_kernel(const AttnAr
 #pragma unroll
   for (int i = 0; i < DHP; ++i) o_acc[i] = 0.f;
   float m_run = -INFINITY, l_run = 0.f;
+  const bool warp_active = q0 + warp * 32 < T;  // any valid query row in this warp
 
   for (int blk = 0; blk < a.nblocks; ++blk) {
     const int n0 = blk * BN;
@@ -203,35 +208,52 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_umma_kernel(const AttnAr
     mbar_wait(&ctl->bar, phase); phase ^= 1;
     tc_fence_after();
 
-    // ---- online softmax on this thread's row: pass 1 = row maximum
-    float mx = -INFINITY;
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      float v[16];
-      tmem_ld16(tS + lane_off + c0, v);
-      tmem_ld_wait();
+    // ---- online softmax on this thread's row (warps whose 32 rows are all beyond T skip the work; their
+    // P rows stay garbage, which only reaches their own, never stored, O rows): pass 1 = row maximum
+    float mx = -INFINITY, corr = 0.f, lsum = 0.f;
+    if (warp_active) {
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        float v[16];
+        tmem_ld16(tS + lane_off + c0, v);
+        tmem_ld_wait();
+        if (c0 + 16 <= nvalid) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) mx = fmaxf(mx, c0 + i < nvalid ? v[i] : -INFINITY);
-    }
-    const float m_new = fmaxf(m_run, mx * a.scale_log2);
-    const float corr = exp2_fast(m_run - m_new);  // first block: exp2(-inf) = 0
-    m_run = m_new;
-    float lsum = 0.f;
-    // pass 2: p = exp2(s * scale_log2 - m), written as the bf16 A operand of P V
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      float v[16];
-      tmem_ld16(tS + lane_off + c0, v);
-      tmem_ld_wait();
-      uint32_t w[8];
+          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, v[i]);
+        } else {
 #pragma unroll
-      for (int i = 0; i < 16; i += 2) {
-        const float p0 = c0 + i < nvalid ? exp2_fast(fmaf(v[i], a.scale_log2, -m_new)) : 0.f;
-        const float p1 = c0 + i + 1 < nvalid ? exp2_fast(fmaf(v[i + 1], a.scale_log2, -m_new)) : 0.f;
-        lsum += p0 + p1;
-        w[i / 2] = pack_bf16(p0, p1);
+          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, c0 + i < nvalid ? v[i] : -INFINITY);
+        }
       }
-      uint8_t* dst = sP_ptr + (size_t)(c0 / 8) * gsP + tid * 16;
-      *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-      *reinterpret_cast<uint4*>(dst + gsP) = make_uint4(w[4], w[5], w[6], w[7]);
+      const float m_new = fmaxf(m_run, mx * a.scale_log2);
+      corr = exp2_fast(m_run - m_new);  // first block: exp2(-inf) = 0
+      m_run = m_new;
+      // pass 2: p = exp2(s * scale_log2 - m), written as the bf16 A operand of P V
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        float v[16];
+        tmem_ld16(tS + lane_off + c0, v);
+        tmem_ld_wait();
+        uint32_t w[8];
+        if (c0 + 16 <= nvalid) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const float p0 = exp2_fast(fmaf(v[i], a.scale_log2, -m_new));
+            const float p1 = exp2_fast(fmaf(v[i + 1], a.scale_log2, -m_new));
+            lsum += p0 + p1;
+            w[i / 2] = pack_bf16(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const float p0 = c0 + i < nvalid ? exp2_fast(fmaf(v[i], a.scale_log2, -m_new)) : 0.f;
+            const float p1 = c0 + i + 1 < nvalid ? exp2_fast(fmaf(v[i + 1], a.scale_log2, -m_new)) : 0.f;
+            lsum += p0 + p1;
+            w[i / 2] = pack_bf16(p0, p1);
+          }
+        }
+        uint8_t* dst = sP_ptr + (size_t)(c0 / 8) * gsP + tid * 16;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(dst + gsP) = make_uint4(w[4], w[5], w[6], w[7]);
+      }
     }
     l_run = l_run * corr + lsum;
     publish_smem_and_sync();
@@ -241,13 +263,15 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_umma_kernel(const AttnAr
     }
     mbar_wait(&ctl->bar, phase); phase ^= 1;
     tc_fence_after();
+    if (warp_active) {
 #pragma unroll
-    for (int c0 = 0; c0 < DHP; c0 += 16) {
-      float v[16];
-      tmem_ld16(tO + lane_off + c0, v);
-      tmem_ld_wait();
+      for (int c0 = 0; c0 < DHP; c0 += 16) {
+        float v[16];
+        tmem_ld16(tO + lane_off + c0, v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 16; ++i) o_acc[c0 + i] = fmaf(o_acc[c0 + i], corr, v[i]);
+        for (int i = 0; i < 16; ++i) o_acc[c0 + i] = fmaf(o_acc[c0 + i], corr, v[i]);
+      }
     }
     // the next iteration overwrites sK / sV / sP and the S / O accumulators: both MMAs have completed
     // (waited above); order this thread's TMEM reads before the next MMA issue
@@ -580,7 +604,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) attn_bwd_fused_umma_kernel(cons
     stage_tile<DHP, FUSED_THREADS>(sQ, MT, qbase + (size_t)q0 * ld, ld, nq, dh);
     stage_tile<DHP, FUSED_THREADS>(sdO, MT, dobase + (size_t)q0 * ldo, ldo, nq, dh);
     if (half == 0) {  // row statistics: delta = sum_d dO * O, lse in log2 units
-      float delta = 0.f, lse2 = 0.f;
+      float delta = 0.f, lse2 = INFINITY;  // padded query row: p = exp2(-inf) = 0
       const int q = q0 + r;
       if (q < T) {
         const bf16* dor = dobase + (size_t)q * ldo;
@@ -620,11 +644,17 @@ __global__ void __launch_bounds__(FUSED_THREADS) attn_bwd_fused_umma_kernel(cons
         tmem_ld16(tS + lane_off + c0, sv);
         tmem_ld_wait();
         uint32_t w[8];
+        if (c0 + 16 <= T) {  // no padded key in this chunk; a padded row has lse2 = +inf -> p = 0
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          const float p0 = (row_ok && c0 + i < T) ? exp2_fast(fmaf(sv[i], a.scale_log2, -lse2)) : 0.f;
-          const float p1 = (row_ok && c0 + i + 1 < T) ? exp2_fast(fmaf(sv[i + 1], a.scale_log2, -lse2)) : 0.f;
-          w[i / 2] = pack_bf16(p0, p1);
+          for (int i = 0; i < 16; i += 2)
+            w[i / 2] = pack_bf16(exp2_fast(fmaf(sv[i], a.scale_log2, -lse2)), exp2_fast(fmaf(sv[i + 1], a.scale_log2, -lse2)));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const float p0 = c0 + i < T ? exp2_fast(fmaf(sv[i], a.scale_log2, -lse2)) : 0.f;
+            const float p1 = c0 + i + 1 < T ? exp2_fast(fmaf(sv[i + 1], a.scale_log2, -lse2)) : 0.f;
+            w[i / 2] = pack_bf16(p0, p1);
+          }
         }
         uint8_t* dst = sP_ptr + (size_t)(c0 / 8) * gsP + r * 16;
         *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
