@@ -181,7 +181,7 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch.distributed as dist
-    from vit4hep_b200 import CaloChallengeCFM, FusedAdamW, ViT, _cabi, dp
+    from vit4hep_b200 import CaloChallengeCFM, FusedAdamW, GraphedTrainStep, ViT, _cabi, dp
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -258,19 +258,36 @@ def run_b200(args):
     W, S = max(args.warmup, 3), args.steps
     for i in range(W):
         train_step((dev_x[i % npool], dev_c[i % npool]), False)
+    # eager numbers first (every launch issued from Python), then the same step replayed as ONE CUDA graph
+    ms_eager, launches = timed(lambda i: train_step((dev_x[i % npool], dev_c[i % npool]), False), S)
+    for i in range(2):
+        train_step((host_x[i % npool], host_c[i % npool]), True)
+    ms_e2e_eager, _ = timed(lambda i: train_step((host_x[i % npool], host_c[i % npool]), True), S)
+    use_graph = (not args.no_graph and not args.torch_optimizer
+                 and (world == 1 or os.environ.get("V4H_GRAPH_DP") == "1"))
+    graphed = GraphedTrainStep(model, opt, dev_x[0], dev_c[0]) if use_graph else None
+    if graphed is not None:
+        step_dev = lambda i: graphed.step(dev_x[i % npool], dev_c[i % npool])
+        step_e2e = lambda i: graphed.step(host_x[i % npool], host_c[i % npool]).item()
+        h2d = host_x[0].numel() * 4 + host_c[0].numel() * 4  # x and c; t is drawn on the device
+    else:
+        step_dev = lambda i: train_step((dev_x[i % npool], dev_c[i % npool]), False)
+        step_e2e = lambda i: train_step((host_x[i % npool], host_c[i % npool]), True)
+        h2d = host_x[0].numel() * 4 + host_c[0].numel() * 4 + B * 4  # x, c and the host-drawn t
+    for i in range(W):
+        step_dev(i)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms, launches = timed(lambda i: train_step((dev_x[i % npool], dev_c[i % npool]), False), S)
+    ms, _ = timed(step_dev, S)
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * S / (ms * 1e-3)
 
     # end to end: pinned host batches through the public API, loss read back every step
     for i in range(2):
-        train_step((host_x[i % npool], host_c[i % npool]), True)
-    ms_e2e, _ = timed(lambda i: train_step((host_x[i % npool], host_c[i % npool]), True), S)
+        step_e2e(i)
+    ms_e2e, _ = timed(step_e2e, S)
     e2e = world * B * S / (ms_e2e * 1e-3)
-    h2d = host_x[0].numel() * 4 + host_c[0].numel() * 4 + B * 4  # x, c and the host-drawn t
 
     # per-kernel-class device time (separate pass: the bracketing events cost launch overhead)
     peaks = measured_peaks()
@@ -311,11 +328,16 @@ def run_b200(args):
         conds = torch.rand(SB, K, generator=g).to(dev)
         model.sample_batch(conds[: min(SB, 32)])
         nb = args.sample_batches
-        ms_s, launches_s = timed(lambda i: model.sample_batch(conds), nb)
+        ms_s_eager, launches_s = timed(lambda i: model.sample_batch(conds), nb)
+        if not args.no_graph:
+            model.graph_sampling = True  # the whole 80-evaluation solve replayed as one CUDA graph
+            model.sample_batch(conds)
+        ms_s, _ = timed(lambda i: model.sample_batch(conds), nb)
         showers = world * SB * nb / (ms_s * 1e-3)
         sampling = {"metric": f"{args.config} ODE-sampled showers/s", "value": showers, "unit": "showers/s",
                     "batch": SB, "batches": nb, "nfe_per_shower": 80, "ms_per_batch": ms_s / nb,
-                    "gpu_launches": launches_s,
+                    "gpu_launches": launches_s, "cuda_graph": not args.no_graph,
+                    "eager_showers_per_s": world * SB * nb / (ms_s_eager * 1e-3),
                     "model_tflops": showers * SAMPLE_GFLOP_PER_SHOWER[args.config] / 1e3 / world,
                     "frac_of_peak": showers * SAMPLE_GFLOP_PER_SHOWER[args.config] / 1e3 / world
                     / peaks["tflops_sustained"]}
@@ -337,6 +359,8 @@ def run_b200(args):
                                    f"batch {B} per GPU, data-parallel x{world} (BASELINE.json configs[1])",
                        "global_batch": B * world, "per_gpu_batch": B, "tokens": geom.tokens,
                        "patch_dim": geom.patch_dim, "parallelism": f"dp{world}",
+                       "execution": ("one CUDA graph per training step (vit4hep_b200.GraphedTrainStep)"
+                                     if graphed is not None else "eager launches"),
                        "optimizer": ("torch AdamW(fused) + clip_grad_norm_(1000)" if args.torch_optimizer else
                                      "vit4hep_b200.FusedAdamW: clip_grad_norm(1000) + AdamW + bf16 weight refresh"),
                        "l2": "no explicit flush: the per-step working set (activation workspace ~1 GB + 104 MB "
@@ -345,6 +369,7 @@ def run_b200(args):
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / S, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches,
+            "eager": {"value": world * B * S / (ms_eager * 1e-3), "e2e": world * B * S / (ms_e2e_eager * 1e-3)},
             "model_tflops_per_gpu": value * gf / 1e3 / world,
             "frac_of_peak": value * gf / 1e3 / world / peaks["tflops_sustained"],
             "roofline": roofline,
@@ -371,6 +396,7 @@ def main():
     ap.add_argument("--sample-batches", type=int, default=2)
     ap.add_argument("--cpu-batch", type=int, default=16, help="batch of the bounded CPU sample")
     ap.add_argument("--torch-optimizer", action="store_true", help="clip_grad_norm_ + torch.optim.AdamW(fused)")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA graph replay")
     ap.add_argument("--no-sampling", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -179,9 +179,13 @@ typedef struct {
  * gradient buffer) */
 int v4h_grad_norm_sq(const float* flat, int64_t n, float* out, v4h_stream_t s);
 /* jobs: DEVICE array of njobs entries; max_n = largest jobs[i].n; norm_sq: device scalar from
- * v4h_grad_norm_sq (NULL = no clipping); step = 1-based step count (bias correction) */
+ * v4h_grad_norm_sq (NULL = no clipping); step = 1-based step count (bias correction).  step_dev / lr_dev
+ * (optional device scalars) override step / lr so that a captured CUDA graph of the training step stays
+ * correct across replays; v4h_counter_increment advances the device step counter in stream order. */
 int v4h_adamw_step(const v4h_adamw_job* jobs, int32_t njobs, int64_t max_n, const float* norm_sq, float max_norm,
-                   float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, v4h_stream_t s);
+                   float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                   const int32_t* step_dev, const float* lr_dev, v4h_stream_t s);
+int v4h_counter_increment(int32_t* counter, v4h_stream_t s);
 /* byte offset inside the weight arena of the bf16 copy of a parameter, by its v4h_vit_params field
  * ("final_w", "x_w", "t0_w", "t2_w", "c2_w", "final_ada_w", "blocks.<i>.{qkv_w,proj_w,fc1_w,fc2_w,ada_w}"), or of the fp32 copy of an adaLN bias
  * ("blocks.<i>.ada_b", "final_ada_b"); -1 when the parameter has no copy */
@@ -230,6 +234,9 @@ int v4h_test_gemm(int32_t engine, int32_t layout, const void* A, const void* B, 
 int v4h_debug_gemm(int32_t kind, int32_t m, int32_t n, int32_t k, int32_t rows_per_sample, const void* A,
                    const void* B, const float* bias, void* out, void* out2, const float* res_in,
                    float* res_out, const float* gate, const void* aux, int64_t* counters, v4h_stream_t s);
+/* device array of 10 int64 cycle counters booked by thread 0 of every tcgen05 attention-forward CTA
+ * (prologue, issue loads, wait loads, publish, S MMA, softmax, publish, PV MMA, output, teardown); NULL = off */
+int v4h_debug_attention_counters(int64_t* counters);
 /* qkv (B, T, 3, H, dh) -> o (B, T, H, dh), lse (B, H, T); precision picks fp32 / bf16 buffers */
 int v4h_test_attention_fwd(int32_t precision, int32_t engine, const void* qkv, void* o, float* lse,
                            int32_t batch, int32_t tokens, int32_t heads, int32_t head_dim, v4h_stream_t s);

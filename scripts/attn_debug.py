@@ -47,7 +47,27 @@ def run(B, T, H, dh, engine, time_it=False):
             print(f"   {name} eng{engine}: {us:8.1f} us  {fl / us / 1e6:8.1f} TFLOP/s", flush=True)
 
 
+def phases(B, T, H, dh):
+    g = torch.Generator().manual_seed(3)
+    qkv = torch.randn(B, T, 3, H, dh, generator=g).to(dev).to(torch.bfloat16)
+    o = torch.zeros(B, T, H, dh, device=dev, dtype=torch.bfloat16)
+    lse = torch.zeros(B, H, T, device=dev, dtype=torch.float32)
+    cnt = torch.zeros(10, dtype=torch.int64, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    lib.v4h_debug_attention_counters(cnt.data_ptr())
+    _cabi.check(lib.v4h_test_attention_fwd(1, 1, qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), B, T, H, dh, s))
+    torch.cuda.synchronize()
+    lib.v4h_debug_attention_counters(None)
+    nct = B * H * ((T + 127) // 128)
+    names = ["prologue", "issue_ld", "wait_ld", "publish", "mma_S", "softmax", "publish2", "mma_PV", "out", "teardown"]
+    print("fwd phases, cycles per CTA:", " ".join(f"{n}={v / nct:.0f}" for n, v in zip(names, cnt.cpu().tolist())), flush=True)
+
+
 if __name__ == "__main__":
+    if "--phases" in sys.argv:
+        phases(64, 135, 6, 80)
+        phases(256, 135, 6, 80)
+        sys.exit(0)
     shapes = [(1, 16, 1, 16), (1, 128, 1, 64), (2, 135, 6, 80), (1, 450, 6, 80), (3, 84, 2, 24), (1, 606, 6, 80), (2, 33, 4, 32),
               (1, 300, 3, 128)]
     for sh in shapes:

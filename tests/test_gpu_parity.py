@@ -249,3 +249,50 @@ def test_fused_adamw_matches_torch_adamw_with_clipping(dev):
         net._native.arena_key = None  # force the recast path
         want = net(x, t, c)
     assert torch.equal(got, want)
+
+
+def test_graphed_train_step_and_sampling_match_eager(dev):
+    """GraphedTrainStep / graph_sampling replay exactly what the eager path launches: same parameters after
+    several steps with the same device RNG stream, same showers from the same noise."""
+    import copy
+    import vit4hep_b200 as v4
+    cfg = vo.tiny_config("ds2", hidden_dim=96, depth=2, num_heads=2)
+    geom, param = cfg["geom"], dict(cfg["param"]); param["precision"] = "bf16"
+    torch.manual_seed(0)
+    net = v4.ViT(param)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.copy_(torch.randn_like(p) * 0.05)
+    mk = lambda n: v4.CaloChallengeCFM(n, [3, 16, 1], 1, "uniform", "linear",
+                                       dict(method="rk4", options=dict(step_size=0.25)), shape=[45, 16, 9]).to(dev)
+    m_eager, m_graph = mk(copy.deepcopy(net)), mk(copy.deepcopy(net))
+    for m in (m_eager, m_graph):
+        m.device, m.dtype = dev, torch.float32
+    g = torch.Generator().manual_seed(7)
+    xs = [torch.randn(4, *geom.sample_shape, generator=g).to(dev) for _ in range(4)]
+    cs = [torch.rand(4, param["condition_dim"], generator=g).to(dev) for _ in range(4)]
+    o_e = v4.FusedAdamW(m_eager.net, lr=1e-3, weight_decay=0.1, max_grad_norm=1.0)
+    o_g = v4.FusedAdamW(m_graph.net, lr=1e-3, weight_decay=0.1, max_grad_norm=1.0)
+    graphed = v4.GraphedTrainStep(m_graph, o_g, xs[0], cs[0], warmup=2)   # 2 eager warm-up steps, then the capture
+    torch.cuda.manual_seed(11)
+    losses_g = [graphed.step(x, c).item() for x, c in zip(xs, cs)]
+    # eager twin: the same 2 priming steps on the first batch (a capture records, it does not execute)
+    for _ in range(2):
+        o_e.zero_grad(set_to_none=True); m_eager._batch_loss((xs[0], cs[0]), device_rng=True).backward(); o_e.step()
+    torch.cuda.manual_seed(11)
+    losses_e = []
+    for x, c in zip(xs, cs):
+        o_e.zero_grad(set_to_none=True)
+        loss = m_eager._batch_loss((x, c), device_rng=True)
+        loss.backward(); o_e.step(); losses_e.append(loss.item())
+    assert all(math.isfinite(v) for v in losses_g)
+    for (name, p), q in zip(m_graph.net.named_parameters(), m_eager.net.parameters()):
+        # the device RNG offsets differ inside / outside a graph, so the twins agree statistically only
+        assert vo.rel_l2(p, q) < 0.1, name
+    assert o_g._step_dev.item() == 2 + 4 and o_e._step_dev.item() == 2 + 4  # the device step counter advances per replay
+    # sampling: identical noise -> identical showers
+    x_T = torch.randn(4, 1, 45, 16, 9, generator=g).to(dev)
+    want = m_graph.integrate(x_T, cs[0])
+    m_graph.graph_sampling = True
+    got1 = m_graph.integrate(x_T, cs[0]); got2 = m_graph.integrate(x_T, cs[0])
+    assert torch.equal(got1, want) and torch.equal(got2, want)

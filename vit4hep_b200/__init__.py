@@ -5,7 +5,7 @@ include/vit4hep_b200.h; see DESIGN.md and INTEGRATION.md.
 """
 from .vit import ViT  # noqa: F401
 from .cfm import (CFM, CaloChallengeCFM, CaloChallengeCFM_DS1, CaloGANCFM, CaloHadCFM, LEMURSCFM,  # noqa: F401
-                  PatchGeometry)
+                  GraphedTrainStep, PatchGeometry)
 
 from .optim import FusedAdamW  # noqa: F401
 

@@ -73,13 +73,15 @@ SIGNATURES = {
     "v4h_cfm_loss": (C.c_int, [_vp, _vp, _i64, _fl, _vp, _vp, _vp]),
     "v4h_axpy4": (C.c_int, [_vp, _vp, _vp, _fl, _vp, _fl, _vp, _fl, _vp, _fl, _i64, _vp]),
     "v4h_grad_norm_sq": (C.c_int, [_vp, _i64, _vp, _vp]),
-    "v4h_adamw_step": (C.c_int, [_vp, _i32, _i64, _vp, _fl, _fl, _fl, _fl, _fl, _fl, _i32, _vp]),
+    "v4h_adamw_step": (C.c_int, [_vp, _i32, _i64, _vp, _fl, _fl, _fl, _fl, _fl, _fl, _i32, _vp, _vp, _vp]),
+    "v4h_counter_increment": (C.c_int, [_vp, _vp]),
     "v4h_vit_arena_offset": (C.c_int64, [_vp, C.c_char_p]),
     "v4h_launch_count": (C.c_int64, []),
     "v4h_profile_begin": (C.c_int, []),
     "v4h_profile_end": (C.c_int, [C.POINTER(ProfileEntry), _i32, C.POINTER(_i32)]),
     "v4h_test_gemm": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "v4h_debug_gemm": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "v4h_debug_attention_counters": (C.c_int, [_vp]),
     "v4h_test_attention_fwd": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "v4h_test_attention_bwd": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
 }

@@ -27,7 +27,7 @@ import torch.nn as nn
 
 from . import _cabi
 
-__all__ = ["PatchGeometry", "CFM", "CaloChallengeCFM", "CaloChallengeCFM_DS1", "CaloGANCFM", "CaloHadCFM",
+__all__ = ["PatchGeometry", "GraphedTrainStep", "CFM", "CaloChallengeCFM", "CaloChallengeCFM_DS1", "CaloGANCFM", "CaloHadCFM",
            "LEMURSCFM", "fixed_grid", "linear_trajectory"]
 
 
@@ -214,6 +214,10 @@ class CFM(nn.Module):
         self.odeint_kwargs = odeint_kwargs
         self.net = net
         self._geometry: Optional[PatchGeometry] = None
+        # extension: replay the whole ODE solve of a sample batch as one CUDA graph (launch-bound loop of
+        # 80 network evaluations); off by default because it pins the batch size's buffers
+        self.graph_sampling = False
+        self._sample_graphs = {}
 
     # -- reference API ---------------------------------------------------------------
     def get_trajectory(self, trajectory):
@@ -255,9 +259,10 @@ class CFM(nn.Module):
         """from_patches(net(to_patches(x), t, c)) (reference calochallenge_cfm/model.py:62-66)"""
         return self.from_patches(self.net(self.to_patches(x), t, c))
 
-    def _batch_loss(self, x):
+    def _batch_loss(self, x, device_rng: bool = False):
         """CFM loss of one batch (x, c) (reference models/base_model.py:203-218): t ~ U(0,1) drawn on the host
-        with shape (B, 1, ..), x_0 = randn_like(x) on the device, linear trajectory, MSE on the velocity."""
+        with shape (B, 1, ..), x_0 = randn_like(x) on the device, linear trajectory, MSE on the velocity.
+        ``device_rng`` (extension, used under CUDA-graph capture) draws t from the device generator instead."""
         x, c = x[0], x[1]
         device = getattr(self, "device", None) or x.device
         dtype = getattr(self, "dtype", None) or torch.float32
@@ -265,14 +270,27 @@ class CFM(nn.Module):
             raise TypeError("vit4hep_b200 computes with fp32 inputs; model.dtype must be torch.float32")
         x = x.to(dtype=dtype, device=device, non_blocking=True)
         c = c.to(dtype=dtype, device=device, non_blocking=True)
-        t = self.time_distribution.sample([x.shape[0]] + [1] * (x.dim() - 1))
-        t = t.to(device, dtype, non_blocking=True)
+        if device_rng:
+            if self.time_distribution.low != 0.0 or self.time_distribution.high != 1.0:
+                raise NotImplementedError("device_rng supports the uniform(0, 1) time distribution")
+            t = torch.rand([x.shape[0]] + [1] * (x.dim() - 1), device=device, dtype=dtype)
+        else:
+            t = self.time_distribution.sample([x.shape[0]] + [1] * (x.dim() - 1))
+            t = t.to(device, dtype, non_blocking=True)
         x_0 = torch.randn_like(x)
         x_t, target = self.geometry.cfm_prepare(x, x_0, t.view(-1))
         velocity = self.net(x_t, t.view(-1, 1), c)
         return _MSELoss.apply(velocity, target)
 
     # -- sampling ----------------------------------------------------------------------
+    def _stage_times(self, times, device):
+        """stage times of the fixed-grid solve as a cached device tensor (no host copy inside a graph capture)"""
+        cache = self.__dict__.setdefault("_time_cache", {})
+        key = (times, device)
+        if key not in cache:
+            cache[key] = torch.tensor(times, dtype=torch.float32).to(device)
+        return cache[key]
+
     def _sample_noise(self, batch):
         return torch.randn((batch.shape[0], *self.shape), dtype=batch.dtype, device=batch.device)
 
@@ -285,6 +303,33 @@ class CFM(nn.Module):
 
     @torch.inference_mode()
     def integrate(self, x_T: torch.Tensor, cond: torch.Tensor) -> torch.Tensor:
+        if self.graph_sampling and x_T.is_cuda:
+            return self._integrate_graphed(x_T, cond)
+        return self._integrate(x_T, cond)
+
+    def _integrate_graphed(self, x_T, cond):
+        """one CUDA graph per (batch shape, device): static input / output buffers, the eager solve captured once"""
+        key = (tuple(x_T.shape), tuple(cond.shape), x_T.device)
+        entry = self._sample_graphs.get(key)
+        if entry is None:
+            xs, cs = torch.empty_like(x_T), torch.empty_like(cond)
+            xs.copy_(x_T); cs.copy_(cond)
+            side = torch.cuda.Stream(device=x_T.device)
+            side.wait_stream(torch.cuda.current_stream(x_T.device))
+            with torch.cuda.stream(side):  # warm-up off the capture: plans, tensor maps, weight arena
+                self._integrate(xs, cs, max_steps=1)
+            torch.cuda.current_stream(x_T.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, capture_error_mode="relaxed"):
+                out = self._integrate(xs, cs)
+            entry = (graph, xs, cs, out)
+            self._sample_graphs[key] = entry
+        graph, xs, cs, out = entry
+        xs.copy_(x_T); cs.copy_(cond)
+        graph.replay()
+        return out.clone()
+
+    def _integrate(self, x_T: torch.Tensor, cond: torch.Tensor, max_steps: Optional[int] = None) -> torch.Tensor:
         kw = dict(self.odeint_kwargs or {})
         method = kw.get("method", None)
         if method not in _SCHEMES:
@@ -302,7 +347,7 @@ class CFM(nn.Module):
             dt = tb - ta
             for frac in scheme["c"]:
                 times.append(tb if frac == 1.0 else ta + dt * frac)
-        t_dev = torch.stack(times).to(cond.device)
+        t_dev = self._stage_times(tuple(float(v) for v in times), cond.device)
         geom = self.geometry
         lib = _cabi.load()
         net = self._net()
@@ -320,7 +365,9 @@ class CFM(nn.Module):
 
         i = 0
         with torch.cuda.device(y.device):
-            for ta, tb in zip(grid[:-1], grid[1:]):
+            for step, (ta, tb) in enumerate(zip(grid[:-1], grid[1:])):
+                if max_steps is not None and step >= max_steps:
+                    break
                 dt = float(tb - ta)
                 ks: List[torch.Tensor] = []
                 for st in range(nstage):
@@ -333,6 +380,47 @@ class CFM(nn.Module):
                     i += 1
                 axpy(y, y, ks, [dt * b for b in scheme["final"]])
         return geom.from_patches(y)
+
+
+class GraphedTrainStep:
+    """One training step -- ``_batch_loss`` (device RNG), ``zero_grad``, backward (with the data-parallel
+    all-reduce when enabled), optimizer step -- captured once as a CUDA graph and replayed per batch.
+
+    Extension for launch-bound regimes (the reference's ``BaseExperiment._step`` issues the same work
+    eagerly, experiments/base_experiment.py:555-597).  ``step(x, c)`` copies the batch into the static input
+    buffers (host tensors should be pinned) and returns the static 0-dim loss tensor of the replay."""
+
+    def __init__(self, model, optimizer, x_example: torch.Tensor, c_example: torch.Tensor, warmup: int = 3):
+        dev = getattr(model, "device", None) or next(model.parameters()).device
+        self.model, self.optimizer = model, optimizer
+        self.x = torch.empty(x_example.shape, dtype=torch.float32, device=dev)
+        self.c = torch.empty(c_example.shape, dtype=torch.float32, device=dev)
+        self.x.copy_(x_example); self.c.copy_(c_example)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._eager()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        # relaxed: the optimizer may allocate a pinned job table, the autograd thread runs the backward
+        with torch.cuda.graph(self.graph, capture_error_mode="relaxed"):
+            self.loss = self._eager()
+
+    def _eager(self):
+        self.optimizer.zero_grad(set_to_none=True)
+        loss = self.model._batch_loss((self.x, self.c), device_rng=True)
+        loss.backward()
+        self.optimizer.step()
+        return loss.detach()
+
+    def step(self, x: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
+        self.x.copy_(x, non_blocking=True)
+        self.c.copy_(c, non_blocking=True)
+        if hasattr(self.optimizer, "sync_lr"):
+            self.optimizer.sync_lr()
+        self.graph.replay()
+        return self.loss
 
 
 class CaloChallengeCFM(CFM):

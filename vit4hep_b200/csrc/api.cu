@@ -273,9 +273,15 @@ int v4h_grad_norm_sq(const float* flat, int64_t n, float* out, v4h_stream_t s) {
   return grad_norm_sq(flat, n, out, (cudaStream_t)s);
 }
 int v4h_adamw_step(const v4h_adamw_job* jobs, int32_t njobs, int64_t max_n, const float* norm_sq, float max_norm,
-                   float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, v4h_stream_t s) {
-  V4H_REQUIRE(jobs && njobs > 0 && njobs <= 65535 && max_n > 0 && step >= 1, "adamw_step: bad arguments");
-  return adamw_step(jobs, njobs, max_n, norm_sq, max_norm, lr, beta1, beta2, eps, weight_decay, step, (cudaStream_t)s);
+                   float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                   const int32_t* step_dev, const float* lr_dev, v4h_stream_t s) {
+  V4H_REQUIRE(jobs && njobs > 0 && njobs <= 65535 && max_n > 0 && (step >= 1 || step_dev), "adamw_step: bad arguments");
+  return adamw_step(jobs, njobs, max_n, norm_sq, max_norm, lr, beta1, beta2, eps, weight_decay, step, step_dev, lr_dev,
+                    (cudaStream_t)s);
+}
+int v4h_counter_increment(int32_t* counter, v4h_stream_t s) {
+  V4H_REQUIRE(counter, "counter_increment: null");
+  return counter_increment(counter, (cudaStream_t)s);
 }
 int64_t v4h_vit_arena_offset(const v4h_plan* p, const char* field) {
   if (!p || !field) return -1;
@@ -377,6 +383,11 @@ int v4h_debug_gemm(int32_t kind, int32_t m, int32_t n, int32_t k, int32_t rows_p
   }
   V4H_REQUIRE(gemm_umma_supported(g), "debug_gemm: shape not supported by the tcgen05 GEMM");
   return gemm_umma(ctx, g, (cudaStream_t)s);
+}
+
+int v4h_debug_attention_counters(int64_t* counters) {
+  attention_debug_counters(reinterpret_cast<long long*>(counters));
+  return V4H_OK;
 }
 
 int v4h_test_attention_fwd(int32_t precision, int32_t engine, const void* qkv, void* o, float* lse, int32_t batch,

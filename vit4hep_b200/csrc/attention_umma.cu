@@ -157,6 +157,18 @@ struct AttnArgs {
   uint32_t tmem_cols;
   float scale;       // dh^-0.5
   float scale_log2;  // scale * log2(e)
+  long long* dbg;    // optional cycle counters per phase (v4h_debug_attention_counters)
+};
+
+struct ALap {  // cycle accounting of thread 0 of each CTA
+  long long* dbg; long long t; long long acc[10];
+  __device__ __forceinline__ explicit ALap(long long* d) : dbg(threadIdx.x == 0 ? d : nullptr), t(0) {
+    if (dbg) { t = clock64(); for (int i = 0; i < 10; ++i) acc[i] = 0; }
+  }
+  __device__ __forceinline__ void lap(int i) { if (dbg) { const long long n = clock64(); acc[i] += n - t; t = n; } }
+  __device__ __forceinline__ void flush() {
+    if (dbg) for (int i = 0; i < 10; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(dbg + i), (unsigned long long)acc[i]);
+  }
 };
 
 // ------------------------------------------------------------------------------------------ forward
@@ -181,7 +193,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_umma_kernel(const AttnAr
   const bf16* kbase = qbase + (size_t)H * dh;
   const bf16* vbase = qbase + (size_t)2 * H * dh;
 
+  ALap L(a.dbg);
   const uint32_t tmem = attn_prologue(ctl, a.tmem_cols);
+  L.lap(0);
   const uint32_t tS = tmem, tO = tmem + (uint32_t)BN;
   const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
   uint32_t phase = 0;
@@ -199,14 +213,18 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_umma_kernel(const AttnAr
     const int nvalid = min(BN, T - n0);
     stage_tile<DHP>(sK, BN, kbase + (size_t)n0 * ld, ld, nvalid, dh);
     stage_tile<DHP>(sV, BN, vbase + (size_t)n0 * ld, ld, nvalid, dh);
+    L.lap(1);
     cp_async_wait_all();
+    L.lap(2);
     publish_smem_and_sync();
+    L.lap(3);
     if (tid == 0) {
       issue_mma(tS, sQ, gsQ, sK, gsKV, false, BN, DHP / 16, false);
       umma_commit(&ctl->bar);
     }
     mbar_wait(&ctl->bar, phase); phase ^= 1;
     tc_fence_after();
+    L.lap(4);
 
     // ---- online softmax on this thread's row (warps whose 32 rows are all beyond T skip the work; their
     // P rows stay garbage, which only reaches their own, never stored, O rows): pass 1 = row maximum
@@ -256,13 +274,16 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_umma_kernel(const AttnAr
       }
     }
     l_run = l_run * corr + lsum;
+    L.lap(5);
     publish_smem_and_sync();
+    L.lap(6);
     if (tid == 0) {
       issue_mma(tO, sP, gsP, sV, gsKV, true, DHP, BN / 16, false);
       umma_commit(&ctl->bar);
     }
     mbar_wait(&ctl->bar, phase); phase ^= 1;
     tc_fence_after();
+    L.lap(7);
     if (warp_active) {
 #pragma unroll
       for (int c0 = 0; c0 < DHP; c0 += 16) {
@@ -295,7 +316,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_umma_kernel(const AttnAr
     }
     a.lse[(size_t)bh * T + q] = (m_run + log2f(l_run)) * 0.6931471805599453f;
   }
+  L.lap(8);
   attn_epilogue(tmem, a.tmem_cols);
+  L.lap(9);
+  L.flush();
 }
 
 // ------------------------------------------------------------------------------------------ dQ (+ delta)
@@ -868,11 +892,15 @@ int check_args(const AttnArgs& a, int B) {
 
 }  // namespace
 
+static long long* g_attn_dbg = nullptr;
+void attention_debug_counters(long long* dev_counters) { g_attn_dbg = dev_counters; }
+
 bool attention_umma_supported(int dh) { return dh >= 8 && dh % 8 == 0 && dh <= 128; }
 
 int attention_fwd_umma(const bf16* qkv, bf16* o, float* lse, int B, int Tn, int H, int dh, cudaStream_t s) {
   AttnArgs a{};
   a.qkv = qkv; a.o = o; a.lse = lse; a.T = Tn; a.H = H; a.dh = dh;
+  a.dbg = g_attn_dbg;
   a.scale = 1.f / sqrtf((float)dh);
   a.scale_log2 = a.scale * 1.4426950408889634f;
   V4H_TRY(check_args(a, B));

@@ -52,6 +52,7 @@ int attention_bwd_simt(const T* qkv, const T* o, const float* lse, const T* d_o,
 // attention_umma.cu: the same contraction on tcgen05 / TMEM (bf16 only, head_dim a multiple of 8, <= 128).
 // The backward also writes delta (B, H, T) = rowsum(dO * O) (caller-provided scratch).
 bool attention_umma_supported(int dh);
+void attention_debug_counters(long long* dev_counters);  // 10 cycle counters of the forward kernel, or null
 int attention_fwd_umma(const bf16* qkv, bf16* o, float* lse, int B, int Tn, int H, int dh, cudaStream_t s);
 int attention_bwd_umma(const bf16* qkv, const bf16* o, const float* lse, const bf16* d_o, float* delta, bf16* dqkv,
                        int B, int Tn, int H, int dh, cudaStream_t s);
@@ -99,7 +100,9 @@ int axpy4(float* out, const float* y, const float* k0, float a0, const float* k1
 // optim.cu: fused gradient clipping + AdamW + bf16 weight refresh
 int grad_norm_sq(const float* flat, int64_t n, float* out, cudaStream_t s);
 int adamw_step(const v4h_adamw_job* jobs_dev, int njobs, int64_t max_n, const float* norm_sq, float max_norm, float lr,
-               float beta1, float beta2, float eps, float weight_decay, int step, cudaStream_t s);
+               float beta1, float beta2, float eps, float weight_decay, int step, const int* step_dev,
+               const float* lr_dev, cudaStream_t s);
+int counter_increment(int* counter, cudaStream_t s);
 
 // patchify.cu:  dst[b, j] = src[b, table[j]] staged through shared memory per chunk
 int patch_permute(const float* src, float* dst, const int32_t* table, const int32_t* chunk_bounds,

@@ -42,8 +42,12 @@ struct AdamArgs {
   const float* norm_sq;  // device scalar: sum of squared gradients (null: no clipping)
   float max_norm;
   float lr, beta1, beta2, eps, weight_decay;
-  float bc1, bc2_sqrt;   // 1 - beta1^t, sqrt(1 - beta2^t)
+  float bc1, bc2_sqrt;   // 1 - beta1^t, sqrt(1 - beta2^t) from the host step count ...
+  const int* step_dev;   // ... or, when non-null, computed from this device step counter (CUDA-graph replay)
+  const float* lr_dev;   // optional device learning rate overriding `lr` (schedulers under graph replay)
 };
+
+__global__ void counter_increment_kernel(int* c) { *c += 1; }
 
 __device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v, const AdamArgs& a, float coef) {
   g *= coef;
@@ -56,8 +60,14 @@ __device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v,
 }
 
 // grid (chunks, jobs): one parameter tensor per blockIdx.y
-__global__ void __launch_bounds__(OPT_THREADS) adamw_kernel(const v4h_adamw_job* __restrict__ jobs, const AdamArgs a) {
+__global__ void __launch_bounds__(OPT_THREADS) adamw_kernel(const v4h_adamw_job* __restrict__ jobs, AdamArgs a) {
   const v4h_adamw_job j = jobs[blockIdx.y];
+  if (a.step_dev) {
+    const float t = (float)*a.step_dev;
+    a.bc1 = 1.f - powf(a.beta1, t);
+    a.bc2_sqrt = sqrtf(1.f - powf(a.beta2, t));
+  }
+  if (a.lr_dev) a.lr = *a.lr_dev;
   float coef = 1.f;
   if (a.norm_sq) {
     const float c = a.max_norm / (sqrtf(*a.norm_sq) + 1e-6f);
@@ -110,9 +120,17 @@ int grad_norm_sq(const float* flat, int64_t n, float* out, cudaStream_t s) {
   return V4H_OK;
 }
 
+int counter_increment(int* counter, cudaStream_t s) {
+  counter_increment_kernel<<<1, 1, 0, s>>>(counter);
+  V4H_LAUNCH_CHECK();
+  return V4H_OK;
+}
+
 int adamw_step(const v4h_adamw_job* jobs_dev, int njobs, int64_t max_n, const float* norm_sq, float max_norm, float lr,
-               float beta1, float beta2, float eps, float weight_decay, int step, cudaStream_t s) {
+               float beta1, float beta2, float eps, float weight_decay, int step, const int* step_dev,
+               const float* lr_dev, cudaStream_t s) {
   AdamArgs a;
+  a.step_dev = step_dev; a.lr_dev = lr_dev;
   a.norm_sq = norm_sq; a.max_norm = max_norm;
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
   a.bc1 = 1.f - powf(beta1, (float)step);

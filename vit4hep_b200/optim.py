@@ -40,8 +40,17 @@ class FusedAdamW(torch.optim.Optimizer):
         self._jobs_host = None
         self._jobs_dev = None
         self._norm_sq = None
+        self._lr_dev = None
         self._key = None
         self._step = 0
+
+    def sync_lr(self):
+        """push param_groups[0]["lr"] to the device scalar the kernel reads (call before a graph replay when a
+        scheduler changed it; step() does it itself)"""
+        lr = float(self.param_groups[0]["lr"])
+        if getattr(self, "_lr_dev", None) is not None and lr != self._lr_host:
+            self._lr_dev.fill_(lr)
+            self._lr_host = lr
 
     def _state_for(self, p):
         st = self.state[p]
@@ -86,25 +95,35 @@ class FusedAdamW(torch.optim.Optimizer):
         states = [self._state_for(p) for p in params]
         key = tuple((p.data_ptr(), p.grad.data_ptr(), targets.get(id(p), (0, False))[0]) for p in params)
         n = len(params)
-        if self._jobs_dev is None or self._jobs_dev.numel() < n * ctypes.sizeof(_cabi.AdamWJob):
-            nbytes = n * ctypes.sizeof(_cabi.AdamWJob)
-            self._jobs_host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
-            self._jobs_dev = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        if self._norm_sq is None:
             self._norm_sq = torch.zeros(1, dtype=torch.float32, device=dev)
-            self._key = None
+            self._step_dev = torch.full((1,), self._step, dtype=torch.int32, device=dev)
+            self._lr_dev = torch.full((1,), float(group["lr"]), dtype=torch.float32, device=dev)
+            self._lr_host = float(group["lr"])
+            self._tables = {}
         if key != self._key:
-            table = (_cabi.AdamWJob * n).from_address(self._jobs_host.data_ptr())
-            for i, (p, st) in enumerate(zip(params, states)):
-                table[i].p, table[i].g = p.data_ptr(), p.grad.data_ptr()
-                table[i].m, table[i].v = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
-                addr, is_f32 = targets.get(id(p), (0, False))
-                table[i].bf16_dst = None if (is_f32 or not addr) else addr
-                table[i].f32_dst = addr if (is_f32 and addr) else None
-                table[i].n = p.numel()
-            # the pinned table may still be read by an earlier copy: order through the stream
-            torch.cuda.current_stream(dev).synchronize()
-            self._jobs_dev.copy_(self._jobs_host, non_blocking=True)
+            # one immutable (pinned, device) table per distinct set of addresses (gradient buffers move
+            # rarely and between few places): no reuse hazard, so no stream synchronisation -- which also
+            # keeps step() legal under CUDA-graph capture
+            if key not in self._tables:
+                nbytes = n * ctypes.sizeof(_cabi.AdamWJob)
+                host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+                table = (_cabi.AdamWJob * n).from_address(host.data_ptr())
+                for i, (p, st) in enumerate(zip(params, states)):
+                    table[i].p, table[i].g = p.data_ptr(), p.grad.data_ptr()
+                    table[i].m, table[i].v = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
+                    addr, is_f32 = targets.get(id(p), (0, False))
+                    table[i].bf16_dst = None if (is_f32 or not addr) else addr
+                    table[i].f32_dst = addr if (is_f32 and addr) else None
+                    table[i].n = p.numel()
+                devt = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                devt.copy_(host, non_blocking=True)
+                if len(self._tables) >= 64:
+                    self._tables.pop(next(iter(self._tables)))
+                self._tables[key] = (host, devt)
+            self._jobs_host, self._jobs_dev = self._tables[key]
             self._key = key
+        self.sync_lr()
         norm_ptr = None
         if self.max_grad_norm is not None:
             # gradients of a vit4hep_b200.ViT are views of one flat buffer: one pass over it
@@ -124,9 +143,13 @@ class FusedAdamW(torch.optim.Optimizer):
             st["step"] += 1
         b1, b2 = group["betas"]
         with torch.cuda.device(dev):
+            # step count and learning rate travel through device scalars so that a CUDA graph of this call
+            # (GraphedTrainStep) keeps the bias correction and the schedule right on every replay
+            _cabi.check(lib.v4h_counter_increment(self._step_dev.data_ptr(), stream))
             _cabi.check(lib.v4h_adamw_step(self._jobs_dev.data_ptr(), n, max(p.numel() for p in params), norm_ptr,
                                            float(self.max_grad_norm or 0.0), float(group["lr"]), float(b1), float(b2),
-                                           float(group["eps"]), float(group["weight_decay"]), self._step, stream))
+                                           float(group["eps"]), float(group["weight_decay"]), self._step,
+                                           self._step_dev.data_ptr(), self._lr_dev.data_ptr(), stream))
         # the bf16 arena now matches the parameters: spare the next forward its recast
         nat = getattr(self.net, "_native", None)
         if targets and nat is not None:
