@@ -264,7 +264,7 @@ def run_b200(args):
         train_step((host_x[i % npool], host_c[i % npool]), True)
     ms_e2e_eager, _ = timed(lambda i: train_step((host_x[i % npool], host_c[i % npool]), True), S)
     use_graph = (not args.no_graph and not args.torch_optimizer
-                 and (world == 1 or os.environ.get("V4H_GRAPH_DP") == "1"))
+                 and (world == 1 or os.environ.get("V4H_GRAPH_DP", "1") == "1"))
     graphed = GraphedTrainStep(model, opt, dev_x[0], dev_c[0]) if use_graph else None
     if graphed is not None:
         step_dev = lambda i: graphed.step(dev_x[i % npool], dev_c[i % npool])
@@ -379,8 +379,13 @@ def run_b200(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # every collective of this run has completed on every rank (the last one is the max-over-ranks of a
+        # timed region).  Tearing NCCL down after CUDA-graph captures that contain collectives can hang, so
+        # leave without the process-group destructor.
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
