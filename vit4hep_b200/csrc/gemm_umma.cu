@@ -59,7 +59,7 @@ constexpr int EG = 2;                          // epilogue groups of 4 warps
 constexpr int THREADS = 128 + 128 * EG;
 constexpr int TMEM_COLS = 512;
 constexpr int SLAB = 32;                       // epilogue slab width in columns
-constexpr int MAX_SLOTS = 6;                   // epilogue-input ring
+constexpr int MAX_SLOTS = 8;                   // epilogue-input ring
 constexpr int BAR_BYTES = 512;
 constexpr int SMEM_LIMIT = 227 * 1024;
 
@@ -77,6 +77,8 @@ struct UmmaArgs {
   int stages;             // smem ring depth of the mainloop
   int nslots;             // epilogue-input ring depth (slab mode with a tile-shaped input)
   int has_out2;
+  int tma_store;          // slab mode: results leave through TMA stores (bias / activation / act' epilogues)
+  int nbuf;               // staging buffers (or in-flight ring slots) per epilogue group in that mode
   long long* dbg;         // optional device counters (cycles per role / phase), see v4h_debug_gemm
 };
 
@@ -166,6 +168,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void group_bar_sync(int grp) {  // the 128 threads of one epilogue group
   asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
 }
@@ -237,7 +240,8 @@ __device__ __forceinline__ void load32(const float* __restrict__ p, int nvalid, 
 template <int EPI, int ACT, typename TOut, bool SLABMODE, int CTAS>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmIn, const UmmaArgs g, const EpiParams ep) {
+                 const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOut,
+                 const __grid_constant__ CUtensorMap tmOut2, const UmmaArgs g, const EpiParams ep) {
   constexpr bool HAS_IN = SLABMODE && (EPI == EPI_GATE_RES || EPI == EPI_DACT);
   constexpr int IN_ESIZE = EPI == EPI_GATE_RES ? 4 : (int)sizeof(TOut);
   constexpr int IN_BOX = BM * SLAB * IN_ESIZE;
@@ -264,11 +268,15 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
     if (HAS_IN) prefetch_tensormap(&tmIn);
+    if (SLABMODE && g.tma_store) {
+      prefetch_tensormap(&tmOut);
+      if (g.has_out2) prefetch_tensormap(&tmOut2);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4 * EG * CTAS); }
-    for (int i = 0; i < MAX_SLOTS; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], 4); }
+    for (int i = 0; i < MAX_SLOTS; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], g.tma_store ? 1 : 4); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -419,9 +427,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t it = 0;                   // slabs done by this group: staging buffer = it & 1
     // pool layout: [ring: nslots x IN_BOX] then per group [out: 2 x OUT_BOX] [out2: 2 x OUT_BOX]
     uint8_t* ring = pool;
-    constexpr int GROUP_STAGING = (EPI == EPI_BIAS_ACT ? 4 : (EPI == EPI_GATE_RES ? 2 : 0)) * OUT_BOX;
-    uint8_t* st_out = pool + (HAS_IN ? g.nslots * IN_BOX : 0) + grp * GROUP_STAGING;
-    uint8_t* st_out2 = st_out + 2 * OUT_BOX;
+    const int NB = g.tma_store ? g.nbuf : 2;  // staging buffers per output and group
+    const int group_staging = (EPI == EPI_BIAS_ACT ? (g.has_out2 ? 2 : 1) * NB : (EPI == EPI_GATE_RES ? 2 : 0)) * OUT_BOX;
+    uint8_t* st_out = pool + (HAS_IN ? g.nslots * IN_BOX : 0) + grp * group_staging;
+    uint8_t* st_out2 = st_out + NB * OUT_BOX;
+    const bool leader = (threadIdx.x & 127) == 0;  // first thread of the group: issues its TMA stores
+    int hist[2] = {-1, -1};                        // ring slots of the group's previous two slabs
     const uint32_t acc_empty_leader[2] = {CTAS == 2 ? map_to_cta(smem_u32(&acc_empty[0]), 0) : 0u,
                                           CTAS == 2 ? map_to_cta(smem_u32(&acc_empty[1]), 0) : 0u};
     Lap T(threadIdx.x == 128 ? g.dbg : nullptr);
@@ -466,11 +477,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           T.lap(1);
           if (HAS_IN) mbar_wait(&in_full[slot], in_phase);
           T.lap(2);
-          uint8_t* so = st_out + (it & 1) * OUT_BOX;
+          const int sbuf = (int)(it % (uint32_t)NB);
+          uint8_t* so = st_out + sbuf * OUT_BOX;
           if (EPI == EPI_BIAS_ACT) {
 #pragma unroll
             for (int i = 0; i < SLAB; ++i) v[i] += b32[i];
-            if (g.has_out2) box_write<TOut>(st_out2 + (it & 1) * OUT_BOX, r, v);
+            if (g.has_out2) box_write<TOut>(st_out2 + sbuf * OUT_BOX, r, v);
             if (ACT != ACT_NONE) {
 #pragma unroll
               for (int i = 0; i < SLAB; ++i) v[i] = act_f<ACT>(v[i]);
@@ -512,26 +524,51 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
           }
-          // staged boxes complete -> copy out.  Two staging buffers alternate per group; a thread reaches
-          // the group's next barrier only after its reads of this one, so one barrier per slab orders every
-          // reuse.
           T.lap(3);
-          group_bar_sync(grp);
-          T.lap(4);
-          if (EPI == EPI_BIAS_ACT) {
-            box_copy_out<(int)sizeof(TOut)>(so, ep.out, ep.ldo, m0, col0, g.M, g.N, r);
-            if (g.has_out2) box_copy_out<(int)sizeof(TOut)>(st_out2 + (it & 1) * OUT_BOX, ep.out2, ep.ldo, m0, col0, g.M, g.N, r);
-          } else if (EPI == EPI_GATE_RES) {
-            box_copy_out<4>(ring + slot * IN_BOX, ep.res_out, ep.ldo, m0, col0, g.M, g.N, r);
-            if (g.has_out2) box_copy_out<(int)sizeof(TOut)>(so, ep.out2, ep.ldo, m0, col0, g.M, g.N, r);
+          if (EPI != EPI_GATE_RES && g.tma_store) {
+            // staged boxes complete -> TMA stores, asynchronous: the group goes on with the next slab while
+            // they drain.  Before the barrier the leader makes sure the stores of NB - 1 slabs ago have
+            // finished reading shared memory: their staging buffer is the one the NEXT slab writes, and
+            // their ring slot (act' epilogue, transformed in place) goes back to its producer.
+            fence_proxy_async();  // this thread's smem writes -> visible to the TMA store
+            if (leader) {
+              if (NB >= 3) tma_store_wait_read1(); else tma_store_wait_read0();
+              const int done = NB >= 3 ? hist[1] : hist[0];
+              if (HAS_IN && done >= 0) mbar_arrive(&in_empty[done]);
+            }
+            group_bar_sync(grp);
+            T.lap(4);
+            if (leader) {
+              if (EPI == EPI_BIAS_ACT) {
+                tma_store_2d(&tmOut, so, col0, m0);
+                if (g.has_out2) tma_store_2d(&tmOut2, st_out2 + sbuf * OUT_BOX, col0, m0);
+              } else {
+                tma_store_2d(&tmOut, ring + slot * IN_BOX, col0, m0);
+              }
+              tma_store_commit();
+            }
+            hist[1] = hist[0]; hist[0] = slot;
           } else {
-            box_copy_out<(int)sizeof(TOut)>(ring + slot * IN_BOX, ep.out, ep.ldo, m0, col0, g.M, g.N, r);
-          }
-          if (HAS_IN) {  // this warp has read its part of the ring slot: 4 arrivals hand it back to the producer
-            __syncwarp();
-            if (lane == 0) {
-              fence_proxy_async();  // generic reads of the slot are ordered before its next TMA write
-              mbar_arrive(&in_empty[slot]);
+            // staged boxes complete -> cooperative copy out.  Two staging buffers alternate per group; a
+            // thread reaches the group's next barrier only after its reads of this one, so one barrier per
+            // slab orders every reuse.
+            group_bar_sync(grp);
+            T.lap(4);
+            if (EPI == EPI_BIAS_ACT) {
+              box_copy_out<(int)sizeof(TOut)>(so, ep.out, ep.ldo, m0, col0, g.M, g.N, r);
+              if (g.has_out2) box_copy_out<(int)sizeof(TOut)>(st_out2 + sbuf * OUT_BOX, ep.out2, ep.ldo, m0, col0, g.M, g.N, r);
+            } else if (EPI == EPI_GATE_RES) {
+              box_copy_out<4>(ring + slot * IN_BOX, ep.res_out, ep.ldo, m0, col0, g.M, g.N, r);
+              if (g.has_out2) box_copy_out<(int)sizeof(TOut)>(so, ep.out2, ep.ldo, m0, col0, g.M, g.N, r);
+            } else {
+              box_copy_out<(int)sizeof(TOut)>(ring + slot * IN_BOX, ep.out, ep.ldo, m0, col0, g.M, g.N, r);
+            }
+            if (HAS_IN) {  // this warp has read its part of the ring slot: 4 arrivals hand it back to the producer
+              __syncwarp();
+              if (lane == 0) {
+                fence_proxy_async();  // generic reads of the slot are ordered before its next TMA write
+                mbar_arrive(&in_empty[slot]);
+              }
             }
           }
           T.lap(5);
@@ -556,6 +593,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (SLABMODE && g.tma_store && leader) tma_store_wait_read0();  // smem must outlive the last stores' reads
     T.flush(5, 7);
   }
 
@@ -576,7 +614,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-struct Maps { CUtensorMap a, b, in; };
+struct Maps { CUtensorMap a, b, in, out, out2; };
 
 template <int EPI, int ACT, typename TOut, bool SLABMODE, int CTAS>
 int launch_k(const Maps& m, const UmmaArgs& g, const EpiParams& ep, int grid, cudaStream_t s) {
@@ -587,7 +625,7 @@ int launch_k(const Maps& m, const UmmaArgs& g, const EpiParams& ep, int grid, cu
     configured = true;
   }
   if (CTAS == 1) {
-    kernel<<<grid, THREADS, SMEM_LIMIT, s>>>(m.a, m.b, m.in, g, ep);
+    kernel<<<grid, THREADS, SMEM_LIMIT, s>>>(m.a, m.b, m.in, m.out, m.out2, g, ep);
   } else {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -600,7 +638,7 @@ int launch_k(const Maps& m, const UmmaArgs& g, const EpiParams& ep, int grid, cu
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    V4H_CUDA(cudaLaunchKernelEx(&cfg, kernel, m.a, m.b, m.in, g, ep));
+    V4H_CUDA(cudaLaunchKernelEx(&cfg, kernel, m.a, m.b, m.in, m.out, m.out2, g, ep));
   }
   V4H_LAUNCH_CHECK();
   return V4H_OK;
@@ -732,6 +770,8 @@ int gemm_umma(UmmaContext* ctx, const GemmDesc& d, cudaStream_t s) {
     // auto: the split count whose work items fill whole rounds of the persistent grid.  Cost model in
     // k-block units: every round of items costs the k-blocks of one item plus a fixed epilogue term
     // (the fp32 atomics of one output tile), so 150 items on 148 SMs (two rounds) lose to 120 items.
+    // (Measured: two rounds of half-length items with overlapped epilogues are NOT faster, the atomics
+    // of the extra items cost what the overlap saves.)
     const int tiles = g.tiles_m * g.tiles_n;
     const int epilogue_cost = 6;
     long best_cost = -1;
@@ -768,13 +808,22 @@ int gemm_umma(UmmaContext* ctx, const GemmDesc& d, cudaStream_t s) {
   // shared-memory budget: [mainloop stages][epilogue pool]; barriers sit in the last BAR_BYTES
   int pool_bytes = 0;
   g.nslots = 0;
+  g.tma_store = 0;
+  g.nbuf = 2;
+  static const int tma_store_enabled = [] { const char* e = getenv("V4H_GEMM_TMA_STORE"); return (e && e[0] == '0') ? 0 : 1; }();
   g.has_out2 = ep.out2 != nullptr;
   g.dbg = d.dbg;
   if (slab) {
     const int out_box = BM * SLAB * osz;
     switch (d.epi) {
       case EPI_BIAS_ACT:
-        pool_bytes = EG * 4 * out_box;
+        g.tma_store = tma_store_enabled;
+        g.nbuf = (g.has_out2 && ctas == 1) ? 2 : 3;  // out + out2 at 3 buffers would starve the mainloop ring
+        pool_bytes = EG * (g.has_out2 ? 2 : 1) * (g.tma_store ? g.nbuf : 2) * out_box;
+        if (g.tma_store) {
+          V4H_TRY(get_map(ctx, ep.out, d.N, d.M, ep.ldo, SLAB, BM, osz, &m.out));
+          if (g.has_out2) V4H_TRY(get_map(ctx, ep.out2, d.N, d.M, ep.ldo, SLAB, BM, osz, &m.out2));
+        }
         break;
       case EPI_GATE_RES:
         g.nslots = ctas == 2 ? 4 : 3;
@@ -782,9 +831,12 @@ int gemm_umma(UmmaContext* ctx, const GemmDesc& d, cudaStream_t s) {
         V4H_TRY(get_map(ctx, ep.res_in, d.N, d.M, ep.ldo, SLAB, BM, 4, &m.in));
         break;
       case EPI_DACT:
-        g.nslots = MAX_SLOTS;
+        g.tma_store = tma_store_enabled;
+        g.nbuf = 3;
+        g.nslots = g.tma_store ? MAX_SLOTS : 6;  // with in-flight stores each group holds up to 3 slots
         pool_bytes = g.nslots * out_box;
         V4H_TRY(get_map(ctx, ep.aux, d.N, d.M, ep.ld_aux, SLAB, BM, osz, &m.in));
+        if (g.tma_store) V4H_TRY(get_map(ctx, ep.out, d.N, d.M, ep.ldo, SLAB, BM, osz, &m.out));
         break;
     }
   }

@@ -467,9 +467,14 @@ int backward_stage0(Plan& p, const v4h_vit_params& w, const char* arena, const v
     V4H_TRY(wgrad(p, ws.dh, DT_F32, D, x, DT_F32, d.patch_dim, gr.x_w, D, d.patch_dim, M, s, "wgrad.x_embed"));
   }
   V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<float>(ws.dh, D, gr.x_b, M, D, s); }));
-  if (d.learn_pos_embed)
-    V4H_TRY(pos_embedding_bwd(ws.dh, w.pos_embed_freqs, w.pos_z, w.pos_y, w.pos_x, gr.pos_embed_freqs, B, Tn,
+  if (d.learn_pos_embed) {
+    // sum d h0 over the batch first (a column sum of the (B, T*D) view, into the now idle PE buffer), then
+    // one pass over (T, D) applies d PE / d freq
+    V4H_CUDA(cudaMemsetAsync(ws.pe, 0, (size_t)Tn * D * sizeof(float), s));
+    V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<float>(ws.dh, Tn * D, ws.pe, B, Tn * D, s); }));
+    V4H_TRY(pos_embedding_bwd(ws.pe, w.pos_embed_freqs, w.pos_z, w.pos_y, w.pos_x, gr.pos_embed_freqs, 1, Tn,
                               D / 6, s));
+  }
   // adaLN Linears: d W = dmod^T sc, d b = colsum(dmod), d sc += dmod W
   V4H_CUDA(cudaMemsetAsync(ws.dsc, 0, (size_t)B * D * sizeof(float), s));
   // The host lays the adaLN gradients out as ONE (Nmod, D) matrix + ONE (Nmod) vector in block order
