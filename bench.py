@@ -306,20 +306,29 @@ def run_b200(args):
                         "share": e["ms"] / total_ms, "avg_ms": per,
                         "tflops": e["flops"] / (e["ms"] * 1e-3) / 1e12 if e["ms"] > 0 else 0.0,
                         "gbs": e["bytes"] / (e["ms"] * 1e-3) / 1e9 if e["ms"] > 0 else 0.0})
-    # roofline of the dominant kernel (by time): all tcgen05 GEMM classes are one kernel template, so take
-    # the class with the largest time share
+    # roofline of the dominant kernel: every gemm.* / dgrad.* / wgrad.* class is ONE kernel template
+    # (gemm_umma_kernel, csrc/gemm_umma.cu), which together takes the largest share of the step.
+    # achieved = algorithmic flops of those launches (2 M N K each) / their summed device time;
+    # traffic = DRAM bytes per launch of the same kernel from the committed ncu capture (profiles/traffic.json)
     if kernels:
-        top = kernels[0]
-        if top["tflops"] > 0 and (top["name"].startswith(("gemm", "wgrad", "dgrad", "attn"))):
-            roofline = {"kernel": top["name"], "bound": "tensor", "achieved": top["tflops"],
-                        "peak": peaks["tflops_sustained"] / 1.0, "unit": "TFLOP/s",
-                        "frac": top["tflops"] / peaks["tflops_sustained"], "traffic": None,
+        fam = [k for k in kernels if k["name"].startswith(("gemm", "wgrad", "dgrad"))]
+        fam_ms = sum(k["ms_per_step"] for k in fam)
+        fam_flops = sum(k["tflops"] * 1e12 * k["ms_per_step"] * 1e-3 for k in fam)
+        fam_launches = sum(k["launches_per_step"] for k in fam)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.isfile(tpath):
+            with open(tpath) as fh:
+                traffic = json.load(fh).get("gemm_umma_kernel", {}).get("dram_bytes_per_launch")
+        if fam_ms > 0:
+            ach = fam_flops / (fam_ms * 1e-3) / 1e12
+            roofline = {"kernel": "gemm_umma_kernel (tcgen05 GEMM: all gemm.* / dgrad.* / wgrad.* classes)",
+                        "bound": "tensor", "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                        "frac": ach / peaks["tflops_sustained"], "traffic": traffic,
+                        "flops_per_launch": fam_flops / max(fam_launches, 1),
+                        "avg_launch_ms": fam_ms / max(fam_launches, 1), "launches_per_step": fam_launches,
                         "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
-                        "share_of_step": top["share"]}
-        else:
-            roofline = {"kernel": top["name"], "bound": "hbm", "achieved": top["gbs"], "peak": peaks["hbm_gbs"],
-                        "unit": "GB/s", "frac": top["gbs"] / peaks["hbm_gbs"], "traffic": None,
-                        "peak_source": f"{peaks['source']} hbm_gbs", "share_of_step": top["share"]}
+                        "share_of_step": fam_ms / (total_ms / psteps)}
 
     # ODE sampling: 20 RK4 (3/8) steps = 80 network evaluations per shower, batches sharded over ranks
     sampling = None
