@@ -169,6 +169,10 @@ struct EpiParams {
   float* res_out = nullptr;       // fp32 (M, N)
   const void* aux = nullptr;      // TOut (M, ld_aux)
   int ld_aux = 0;
+  // EPI_ATOMIC only: output column `extra_col` (an appended "ones" column of the B operand, i.e. the
+  // column sums of A^T) is accumulated into extra_out[row] instead of out[row, extra_col]
+  float* extra_out = nullptr;
+  int extra_col = -1;
   bool vec_ok = false;  // set by the launcher (epilogue_vec_ok)
 };
 
@@ -339,7 +343,10 @@ __device__ __forceinline__ void epilogue_run(const EpiParams& p, int row, int co
     } else {
 #pragma unroll
       for (int i = 0; i < NV; ++i)
-        if (i < ncols_valid) atomicAdd(o + i, acc[i]);
+        if (i < ncols_valid) {
+          if (p.extra_out != nullptr && col0 + i == p.extra_col) atomicAdd(p.extra_out + row, acc[i]);
+          else atomicAdd(o + i, acc[i]);
+        }
     }
   }
 }

@@ -2,9 +2,9 @@
 // shared epilogues of common.cuh applied straight out of TMEM.
 //
 // One persistent CTA per SM, warp-specialised:
-//   warp 0    TMA producer   (cp.async.bulk.tensor, 128B-swizzled tiles, mbarrier ring of 3-4 stages)
+//   warp 0    TMA producer of A (cp.async.bulk.tensor, 128B-swizzled tiles, mbarrier ring of 3-4 stages)
 //   warp 1    MMA issuer     (one elected thread, tcgen05.mma cta_group::1, M = 128, N = bn <= 256, K = 16)
-//   warp 2    TMEM allocator (512 columns = two accumulator stages of up to 256 columns)
+//   warp 2    TMEM allocator (512 columns = two accumulator stages of up to 256 columns), then TMA producer of B
 //   warp 3    epilogue-input producer: TMA loads of the tile-shaped epilogue operand (the fp32 residual
 //             stream of EPI_GATE_RES, the saved pre-activation of EPI_DACT) into a ring of 32-column
 //             slabs, running ahead of the epilogue
@@ -294,11 +294,14 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // narrower (width a multiple of 16, of 32 in slab mode)
   auto tile_width = [&](int tn) { return min(g.bn, g.n_pad - tn * g.bn); };
 
-  if (warp == 0) {
-    // ===================================================================== TMA producer
+  if (warp == 0 || warp == 2) {
+    // ===================================================================== TMA producers
+    // warp 0 stages A (and arms the stage's transaction count), warp 2 -- idle once TMEM is allocated --
+    // stages B: issuing a TMA box costs ~100 cycles, and an MN-major B tile is up to four boxes per k-block
+    const bool load_a = warp == 0;
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      Lap T(g.dbg);
+      Lap T(load_a ? g.dbg : nullptr);
       for (int work = unit; work < total_work; work += nunits) {
         const int split = work % g.splits;
         const int tile = work / g.splits;
@@ -315,30 +318,32 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* sa = smem + stage * g.stage_bytes;
           uint8_t* sb = sa + A_BYTES;
           if (CTAS == 1) {
-            mbar_expect_tx(&full[stage], A_BYTES + b_part_bytes);
-            if (!g.a_mn) {
-              tma_load_2d(sa, &tmA, &full[stage], kb * BK, m0);
-            } else {
-              tma_load_2d(sa, &tmA, &full[stage], m0, kb * BK);
-              tma_load_2d(sa + CHUNK_BYTES, &tmA, &full[stage], m0 + 64, kb * BK);
-            }
-            if (!g.b_mn) {
+            if (load_a) {
+              mbar_expect_tx(&full[stage], A_BYTES + b_part_bytes);
+              if (!g.a_mn) {
+                tma_load_2d(sa, &tmA, &full[stage], kb * BK, m0);
+              } else {
+                tma_load_2d(sa, &tmA, &full[stage], m0, kb * BK);
+                tma_load_2d(sa + CHUNK_BYTES, &tmA, &full[stage], m0 + 64, kb * BK);
+              }
+            } else if (!g.b_mn) {
               tma_load_2d(sb, &tmB, &full[stage], kb * BK, n0);
             } else {
               for (int j = 0; j * 64 < bnh; ++j)
                 tma_load_2d(sb + j * CHUNK_BYTES, &tmB, &full[stage], n0 + j * 64, kb * BK);
             }
           } else {
-            // both producers' bytes are counted on the LEADER's full barrier
+            // both CTAs' bytes are counted on the LEADER's full barrier
             const uint32_t bar = map_to_cta(smem_u32(&full[stage]), 0);
-            if (rank == 0) mbar_expect_tx(&full[stage], 2 * (A_BYTES + b_part_bytes));
-            if (!g.a_mn) {
-              tma_load_2d_pair(sa, &tmA, bar, kb * BK, m0);
-            } else {
-              tma_load_2d_pair(sa, &tmA, bar, m0, kb * BK);
-              tma_load_2d_pair(sa + CHUNK_BYTES, &tmA, bar, m0 + 64, kb * BK);
-            }
-            if (!g.b_mn) {
+            if (load_a) {
+              if (rank == 0) mbar_expect_tx(&full[stage], 2 * (A_BYTES + b_part_bytes));
+              if (!g.a_mn) {
+                tma_load_2d_pair(sa, &tmA, bar, kb * BK, m0);
+              } else {
+                tma_load_2d_pair(sa, &tmA, bar, m0, kb * BK);
+                tma_load_2d_pair(sa + CHUNK_BYTES, &tmA, bar, m0 + 64, kb * BK);
+              }
+            } else if (!g.b_mn) {
               tma_load_2d_pair(sb, &tmB, bar, kb * BK, n0);
             } else {
               for (int j = 0; j * 64 < bnh; ++j)

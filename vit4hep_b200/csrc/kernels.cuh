@@ -58,9 +58,11 @@ int attention_bwd_umma(const bf16* qkv, const bf16* o, const float* lse, const b
                        int B, int Tn, int H, int dh, cudaStream_t s);
 
 // layernorm.cu
-// a = LN(h) * (1 + scale[b]) + shift[b];  stats[row] = (mean, rstd)
+// a = LN(h) * (1 + scale[b]) + shift[b];  stats[row] = (mean, rstd).  ld_a >= D is the row pitch of a; when
+// ld_a > D the kernel also writes a[row][D] = 1 and zeros up to the pitch: that "ones" column turns the
+// weight-gradient GEMM dY^T a into [dW | column sums of dY], i.e. the bias gradient comes for free.
 template <typename T>
-int ln_modulate_fwd(const float* h, const float* shift, const float* scale, int mod_stride, T* a,
+int ln_modulate_fwd(const float* h, const float* shift, const float* scale, int mod_stride, T* a, int ld_a,
                     float2* stats, int M, int D, int rows_per_sample, cudaStream_t s);
 // dh (+)= LNbwd(da * (1 + scale));  dshift[b] += sum_t da;  dscale[b] += sum_t da * xhat
 // optionally fused gate backward of the branch that follows in the backward chain:

@@ -18,7 +18,7 @@ constexpr int WARPS = 8;
 template <typename T>
 __global__ void __launch_bounds__(WARPS * 32) ln_mod_fwd_kernel(
     const float* __restrict__ h, const float* __restrict__ shift, const float* __restrict__ scale,
-    int mod_stride, T* __restrict__ a, float2* __restrict__ stats, int M, int D, int rows_per_sample) {
+    int mod_stride, T* __restrict__ a, int ld_a, float2* __restrict__ stats, int M, int D, int rows_per_sample) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -44,12 +44,13 @@ __global__ void __launch_bounds__(WARPS * 32) ln_mod_fwd_kernel(
   const int b = row / rows_per_sample;
   const float* sh = shift + (size_t)b * mod_stride;
   const float* sc = scale + (size_t)b * mod_stride;
-  T* ar = a + (size_t)row * D;
+  T* ar = a + (size_t)row * ld_a;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     int d = lane + i * 32;
     if (d < D) ar[d] = from_f<T>((v[i] - mean) * rstd * (1.f + sc[d]) + sh[d]);
   }
+  if (lane < ld_a - D) ar[D + lane] = from_f<T>(lane == 0 ? 1.f : 0.f);  // "ones" column, see ln_modulate_fwd
 }
 
 // grid (chunks, B); each CTA owns rows [chunk*rows_per_cta, ...) of ONE sample.
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(128) ln_mod_bwd_vec_kernel(
 template <typename T>
 __global__ void __launch_bounds__(256) ln_mod_fwd_vec_kernel(
     const float* __restrict__ h, const float* __restrict__ shift, const float* __restrict__ scale,
-    int mod_stride, T* __restrict__ a, float2* __restrict__ stats, int M, int D, int rows_per_sample) {
+    int mod_stride, T* __restrict__ a, int ld_a, float2* __restrict__ stats, int M, int D, int rows_per_sample) {
   const int lane = threadIdx.x & 31;
   const int warp = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int nv = D >> 2;  // float4 per row
@@ -313,7 +314,8 @@ __global__ void __launch_bounds__(256) ln_mod_fwd_vec_kernel(
     const int b = row / rows_per_sample;
     const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)b * mod_stride);
     const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)b * mod_stride);
-    T* ar = a + (size_t)row * D;
+    T* ar = a + (size_t)row * ld_a;
+    if (lane < ld_a - D) ar[D + lane] = from_f<T>(lane == 0 ? 1.f : 0.f);  // "ones" column
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int c = lane + 32 * i;
@@ -341,16 +343,17 @@ inline bool ln_vec_ok(int D, int mod_stride, int dmod_stride, std::initializer_l
 }  // namespace
 
 template <typename T>
-int ln_modulate_fwd(const float* h, const float* shift, const float* scale, int mod_stride, T* a,
+int ln_modulate_fwd(const float* h, const float* shift, const float* scale, int mod_stride, T* a, int ld_a,
                     float2* stats, int M, int D, int rows_per_sample, cudaStream_t s) {
   if (D > MAXV * 32) return fail(V4H_ERR_UNSUPPORTED, "ln_modulate: hidden_dim %d > %d", D, MAXV * 32);
-  if (ln_vec_ok(D, mod_stride, 0, {h, shift, scale, a})) {
-    ln_mod_fwd_vec_kernel<T><<<(unsigned)ceil_div(M, 16), 256, 0, s>>>(h, shift, scale, mod_stride, a, stats, M, D,
+  if (ld_a < D || ld_a - D > 32) return fail(V4H_ERR_INVALID, "ln_modulate: bad output pitch %d for %d columns", ld_a, D);
+  if (ld_a % 4 == 0 && ln_vec_ok(D, mod_stride, 0, {h, shift, scale, a})) {
+    ln_mod_fwd_vec_kernel<T><<<(unsigned)ceil_div(M, 16), 256, 0, s>>>(h, shift, scale, mod_stride, a, ld_a, stats, M, D,
                                                                       rows_per_sample);
     V4H_LAUNCH_CHECK();
     return V4H_OK;
   }
-  ln_mod_fwd_kernel<T><<<(unsigned)ceil_div(M, WARPS), WARPS * 32, 0, s>>>(h, shift, scale, mod_stride, a,
+  ln_mod_fwd_kernel<T><<<(unsigned)ceil_div(M, WARPS), WARPS * 32, 0, s>>>(h, shift, scale, mod_stride, a, ld_a,
                                                                           stats, M, D, rows_per_sample);
   V4H_LAUNCH_CHECK();
   return V4H_OK;
@@ -416,7 +419,7 @@ int gate_bwd(const float* dh, const T* y, const float* gate, int mod_stride, T* 
 }
 
 #define INST(T)                                                                                          \
-  template int ln_modulate_fwd<T>(const float*, const float*, const float*, int, T*, float2*, int, int, \
+  template int ln_modulate_fwd<T>(const float*, const float*, const float*, int, T*, int, float2*, int, int, \
                                   int, cudaStream_t);                                                    \
   template int ln_modulate_bwd<T>(const T*, const float*, const float2*, const float*, int, float*,    \
                                   bool, float*, float*, int, const T*, const float*, T*, float*,        \

@@ -16,6 +16,7 @@ struct Plan {
   bool bf16 = false;
   bool use_umma = false;  // tcgen05 GEMMs (bf16 precision only)
   bool use_umma_attn = false;
+  int ldx = 0;  // row pitch of the LN-modulated activations a / m: D, or D + 8 with the "ones" column
   UmmaContext* umma = nullptr;
   // bf16 weight arena layout (element offsets in bf16 units, then the fp32 bias tail in bytes)
   struct BlockArena { size_t qkv, proj, fc1, fc2; } arena_blocks[V4H_MAX_DEPTH];
@@ -99,9 +100,9 @@ struct Workspace {
     blk.resize(nb);
     for (int i = 0; i < nb; ++i) {
       BlockBufs& b = blk[i];
-      b.a = take(M * D * ta); b.qkv = take(M * 3 * D * ta); b.o = take(M * D * ta);
+      b.a = take(M * p.ldx * ta); b.qkv = take(M * 3 * D * ta); b.o = take(M * D * ta);
       b.y1 = train ? take(M * D * ta) : nullptr;
-      b.m = take(M * D * ta);
+      b.m = take(M * p.ldx * ta);
       b.u = train ? take(M * Hm * ta) : nullptr;
       b.g = take(M * Hm * ta);
       b.y2 = train ? take(M * D * ta) : nullptr;
@@ -187,13 +188,16 @@ GemmDesc linear_fwd(const void* A, int a_dt, int lda, const void* W, int w_dt, i
 }
 
 // dW (M_out x N_out) += A^T B with A (K, M_out), B (K, N_out)
+// bias_out (optional): B carries a "ones" column at index N_out (ldb > N_out): the extra output column, the
+// column sums of A = the bias gradient, is accumulated into bias_out (M_out)
 int wgrad(const Plan& p, const void* A, int a_dt, int lda, const void* B, int b_dt, int ldb, float* dW,
-          int M_out, int N_out, int K, cudaStream_t s, const char* tag = "wgrad") {
+          int M_out, int N_out, int K, cudaStream_t s, const char* tag = "wgrad", float* bias_out = nullptr) {
   GemmDesc g;
   g.tag = tag;
   g.layout = GEMM_TN; g.A = A; g.a_dtype = a_dt; g.lda = lda; g.B = B; g.b_dtype = b_dt; g.ldb = ldb;
-  g.M = M_out; g.N = N_out; g.K = K;
+  g.M = M_out; g.N = bias_out ? N_out + 1 : N_out; g.K = K;
   g.epi = EPI_ATOMIC; g.out_dtype = DT_F32;
+  g.ep.extra_out = bias_out; g.ep.extra_col = bias_out ? N_out : -1;
   g.ep.out = dW; g.ep.ldo = N_out;
   g.splitk = 0;  // auto
   return run_gemm(p, g, s);
@@ -293,9 +297,9 @@ int forward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const floa
     const void* Wfc1 = p.bf16 ? (const void*)(wa + p.arena_blocks[i].fc1) : (const void*)bw.fc1_w;
     const void* Wfc2 = p.bf16 ? (const void*)(wa + p.arena_blocks[i].fc2) : (const void*)bw.fc2_w;
 
-    V4H_TRY(prof("ln.fwd", 0, (double)M * D * (4 + sizeof(T)), s, [&] { return ln_modulate_fwd<T>(hin, mod + 0 * D, mod + 1 * D, p.Nmod, (T*)bb.a, bb.stats1, M, D, Tn, s); }));
+    V4H_TRY(prof("ln.fwd", 0, (double)M * D * (4 + sizeof(T)), s, [&] { return ln_modulate_fwd<T>(hin, mod + 0 * D, mod + 1 * D, p.Nmod, (T*)bb.a, p.ldx, bb.stats1, M, D, Tn, s); }));
     {
-      GemmDesc g = linear_fwd(bb.a, TA, D, Wqkv, TA, D, M, 3 * D, D);
+      GemmDesc g = linear_fwd(bb.a, TA, p.ldx, Wqkv, TA, D, M, 3 * D, D);
       g.tag = "gemm.qkv";
       g.ep.bias = bw.qkv_b; g.ep.out = bb.qkv; g.ep.ldo = 3 * D; g.out_dtype = TA;
       V4H_TRY(run_gemm(p, g, s));
@@ -310,9 +314,9 @@ int forward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const floa
       g.ep.res_in = hin; g.ep.res_out = hmid;
       V4H_TRY(run_gemm(p, g, s));
     }
-    V4H_TRY(prof("ln.fwd", 0, (double)M * D * (4 + sizeof(T)), s, [&] { return ln_modulate_fwd<T>(hmid, mod + 3 * D, mod + 4 * D, p.Nmod, (T*)bb.m, bb.stats2, M, D, Tn, s); }));
+    V4H_TRY(prof("ln.fwd", 0, (double)M * D * (4 + sizeof(T)), s, [&] { return ln_modulate_fwd<T>(hmid, mod + 3 * D, mod + 4 * D, p.Nmod, (T*)bb.m, p.ldx, bb.stats2, M, D, Tn, s); }));
     {
-      GemmDesc g = linear_fwd(bb.m, TA, D, Wfc1, TA, D, M, Hm, D);
+      GemmDesc g = linear_fwd(bb.m, TA, p.ldx, Wfc1, TA, D, M, Hm, D);
       g.tag = "gemm.fc1";
       g.act = ACT_GELU_TANH; g.out_dtype = TA;
       g.ep.bias = bw.fc1_b; g.ep.out = bb.g; g.ep.out2 = bb.u; g.ep.ldo = Hm;
@@ -332,7 +336,7 @@ int forward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const floa
   {
     const float* mod = ws.mod + (size_t)d.depth * 6 * D;
     float* hl = ws.h[hidx(train, 2 * d.depth)];
-    V4H_TRY(prof("ln.fwd", 0, (double)M * D * (4 + sizeof(T)), s, [&] { return ln_modulate_fwd<T>(hl, mod, mod + D, p.Nmod, (T*)ws.a_f, ws.stats_f, M, D, Tn, s); }));
+    V4H_TRY(prof("ln.fwd", 0, (double)M * D * (4 + sizeof(T)), s, [&] { return ln_modulate_fwd<T>(hl, mod, mod + D, p.Nmod, (T*)ws.a_f, D, ws.stats_f, M, D, Tn, s); }));
     GemmDesc g = fast ? linear_fwd(ws.a_f, TA, D, wa + p.arena_final, DT_BF16, D, M, d.out_dim, D)
                       : linear_fwd(ws.a_f, TA, D, w.final_w, DT_F32, D, M, d.out_dim, D);
     g.tag = "gemm.final";
@@ -407,8 +411,12 @@ int backward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const v4h
         g.ep.out = ws.du; g.ep.ldo = Hm; g.ep.aux = bb.u; g.ep.ld_aux = Hm;
         V4H_TRY(run_gemm(p, g, s));
       }
-      V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<T>((const T*)ws.du, Hm, bg.fc1_b, M, Hm, s); }));
-      V4H_TRY(wgrad(p, ws.du, TA, Hm, bb.m, TA, D, bg.fc1_w, Hm, D, M, s, "wgrad.fc1"));
+      if (p.ldx > D) {  // the ones column of m: fc1 bias gradient out of the same GEMM
+        V4H_TRY(wgrad(p, ws.du, TA, Hm, bb.m, TA, p.ldx, bg.fc1_w, Hm, D, M, s, "wgrad.fc1", bg.fc1_b));
+      } else {
+        V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<T>((const T*)ws.du, Hm, bg.fc1_b, M, Hm, s); }));
+        V4H_TRY(wgrad(p, ws.du, TA, Hm, bb.m, TA, D, bg.fc1_w, Hm, D, M, s, "wgrad.fc1"));
+      }
       {
         GemmDesc g = dgrad(ws.du, TA, Hm, Wfc1, TA, D, M, D, Hm, "dgrad.fc1");
         g.ep.out = ws.dm; g.ep.ldo = D; g.out_dtype = TA;
@@ -425,8 +433,12 @@ int backward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const v4h
         V4H_TRY(run_gemm(p, g, s));
       }
       V4H_TRY(prof("attn.bwd", 10.0 * B * H * Tn * Tn * dh, (double)M * 9 * D * sizeof(T), s, [&] { return attn_bwd<T>(p, bb.qkv, bb.o, bb.lse, ws.dm, ws.attn_delta, ws.dqkv, B, Tn, H, dh, s); }));
-      V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<T>((const T*)ws.dqkv, 3 * D, bg.qkv_b, M, 3 * D, s); }));
-      V4H_TRY(wgrad(p, ws.dqkv, TA, 3 * D, bb.a, TA, D, bg.qkv_w, 3 * D, D, M, s, "wgrad.qkv"));
+      if (p.ldx > D) {
+        V4H_TRY(wgrad(p, ws.dqkv, TA, 3 * D, bb.a, TA, p.ldx, bg.qkv_w, 3 * D, D, M, s, "wgrad.qkv", bg.qkv_b));
+      } else {
+        V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<T>((const T*)ws.dqkv, 3 * D, bg.qkv_b, M, 3 * D, s); }));
+        V4H_TRY(wgrad(p, ws.dqkv, TA, 3 * D, bb.a, TA, D, bg.qkv_w, 3 * D, D, M, s, "wgrad.qkv"));
+      }
       {
         GemmDesc g = dgrad(ws.dqkv, TA, 3 * D, Wqkv, TA, D, M, D, 3 * D, "dgrad.qkv");
         g.ep.out = ws.dm; g.ep.ldo = D; g.out_dtype = TA;
@@ -576,6 +588,7 @@ int plan_create(const v4h_vit_dims* dims, Plan** out) {
   const char* no_umma = getenv("V4H_DISABLE_UMMA");
   p->use_umma = p->bf16 && !(no_umma && no_umma[0] == '1');
   if (p->use_umma) p->umma = umma_context_create();
+  p->ldx = (p->use_umma && d.hidden_dim % 8 == 0) ? d.hidden_dim + 8 : d.hidden_dim;
   const char* no_umma_attn = getenv("V4H_DISABLE_UMMA_ATTN");
   p->use_umma_attn = p->use_umma && attention_umma_supported(d.hidden_dim / d.num_heads) &&
                      !(no_umma_attn && no_umma_attn[0] == '1');
