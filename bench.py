@@ -35,7 +35,7 @@ os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout and wo
 
 import torch  # noqa: E402
 
-METRIC = "ds2 CFM-ViT train samples/s"
+METRIC = "ds2 CFM-ViT train samples/s"  # --config ds3 reports the same metric on the ds3 shape (secondary)
 UNIT = "samples/s"
 TRAIN_GFLOP_PER_SAMPLE = {"ds2": 14.160, "ds3": 52.078}   # 3 x forward
 SAMPLE_GFLOP_PER_SHOWER = {"ds2": 377.6, "ds3": 1388.7}    # 80 NFE
@@ -160,7 +160,8 @@ def run_reference(args):
     if rank != 0:
         return
     batch = args.cpu_batch
-    value, ms, threads = cpu_train_samples_per_s(args.config, batch, args.steps, args.warmup)
+    steps, warmup = min(args.steps, 40), min(args.warmup, 3)  # bounded sample: about a second per step
+    value, ms, threads = cpu_train_samples_per_s(args.config, batch, steps, warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -168,8 +169,8 @@ def run_reference(args):
         "config": {"workload": f"CaloChallenge {args.config} shape CFM-ViT training step (CPU oracle port of the "
                                f"reference path, batch {batch} per step)", "batch_per_step": batch},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} training steps of batch {batch} (fwd+bwd+clip+AdamW), "
-                                   f"{args.warmup} warm-up"},
+                         "sample": f"{steps} training steps of batch {batch} (fwd+bwd+clip+AdamW) of the CPU oracle "
+                                   f"port, {warmup} warm-up (bounded: --steps {args.steps} --warmup {args.warmup})"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -353,15 +354,15 @@ def run_b200(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cms, threads = cpu_train_samples_per_s(args.config, args.cpu_batch, 3, 1)
+        v, cms, threads = cpu_train_samples_per_s(args.config, args.cpu_batch, args.cpu_steps, 2)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"3 training steps of batch {args.cpu_batch} (fwd+bwd+clip+AdamW) of the CPU oracle port, "
-                         f"1 warm-up, {cms:.0f} ms/step"}
+               "sample": f"{args.cpu_steps} training steps of batch {args.cpu_batch} (fwd+bwd+clip+AdamW) of the CPU "
+                         f"oracle port of the reference path, 2 warm-up, {cms:.0f} ms/step"}
 
     if rank == 0:
         gf = TRAIN_GFLOP_PER_SAMPLE[args.config]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": S, "warmup": W,
+            "metric": METRIC.replace("ds2", args.config), "value": value, "unit": UNIT, "n_gpus": world, "steps": S, "warmup": W,
             "ms_per_step": ms / S, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
             "config": {"workload": f"CaloChallenge {args.config} shape CFM-ViT {args.precision} training, "
@@ -400,15 +401,16 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="ds2", choices=["ds2", "ds3"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=64, help="training batch per GPU")
     ap.add_argument("--sample-batch", type=int, default=256)
     ap.add_argument("--sample-batches", type=int, default=2)
-    ap.add_argument("--cpu-batch", type=int, default=16, help="batch of the bounded CPU sample")
+    ap.add_argument("--cpu-batch", type=int, default=64, help="batch of the bounded CPU sample")
+    ap.add_argument("--cpu-steps", type=int, default=12, help="timed steps of the cpu_baseline leg (2 warm-up)")
     ap.add_argument("--torch-optimizer", action="store_true", help="clip_grad_norm_ + torch.optim.AdamW(fused)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA graph replay")
     ap.add_argument("--no-sampling", action="store_true")

@@ -227,7 +227,8 @@ int v4h_test_gemm(int32_t engine, int32_t layout, const void* A, const void* B, 
                   int32_t m, int32_t n, int32_t k, v4h_stream_t s);
 /* One tcgen05 GEMM with the epilogue of a model call site, for kernel benchmarking (scripts/gemm_bench.py).
  * kind: 0 fc1-like (NT, bias + GELU, out and out2), 1 qkv-like (NT, bias), 2 proj/fc2-like (NT, gate +
- * residual), 3 dgrad through GELU (NN, aux), 4 plain dgrad (NN), 5 wgrad (TN, fp32 atomics into out).
+ * residual), 3 dgrad through GELU (NN, aux), 4 plain dgrad (NN), 5 wgrad (TN, fp32 atomics into out),
+ * 6 final-layer-like (NT, bias, fp32 out).
  * counters: optional device array of 16 int64 cycle counters summed over CTAs: [0,1] producer wait /
  * issue, [2,3,4] MMA wait accumulator / wait operands / issue, [5..11] epilogue wait accumulator, loads +
  * TMEM, wait input box, math + staging, barrier, copy-out, tail. */

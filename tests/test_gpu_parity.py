@@ -296,3 +296,21 @@ def test_graphed_train_step_and_sampling_match_eager(dev):
     m_graph.graph_sampling = True
     got1 = m_graph.integrate(x_T, cs[0]); got2 = m_graph.integrate(x_T, cs[0])
     assert torch.equal(got1, want) and torch.equal(got2, want)
+
+
+def test_ds3_sampling_at_changing_batch_sizes(dev):
+    """Full-size ds3 network (T = 450: multi-block attention, multi-tile GEMMs, patch_dim 90 on the direct
+    epilogue path), forward-only, at two batch sizes in a row; the solve is deterministic for a fixed x_T."""
+    cfg = vo.CONFIGS["ds3"]
+    geom, param = cfg["geom"], cfg["param"]
+    model = build_model("ds3", param, "bf16", dev)
+    model.odeint_kwargs = dict(method="rk4", options=dict(step_size=0.25))
+    model.net.load_state_dict(vo.init_state_dict(param, seed=3))
+    g = torch.Generator().manual_seed(5)
+    for B in (32, 64):
+        x_T = torch.randn(B, 1, *geom.segments[0].shape, generator=g).to(dev)
+        c = torch.rand(B, param["condition_dim"], generator=g).to(dev)
+        a = model.integrate(x_T, c)
+        b = model.integrate(x_T, c)
+        torch.cuda.synchronize()
+        assert torch.isfinite(a).all() and torch.equal(a, b)

@@ -78,9 +78,14 @@ def test_state_dict_names_and_shapes_match_the_reference(name):
     assert {id(p) for _, p in ordered} == {id(p) for p in net.parameters()}
     assert len(ordered) == len(list(net.parameters()))
     bounds = net.stage_boundaries()
-    assert len(bounds) == len(net.blocks) + 2 and bounds[-1] == sum(p.numel() for p in net.parameters())
+    offs, total = net.flat_layout(ordered)
+    nparams = sum(p.numel() for p in net.parameters())
+    # gradients start 16-byte aligned in the flat buffer: at most 3 padding elements per parameter
+    assert len(bounds) == len(net.blocks) + 2 and bounds[-1] == total and nparams <= total <= nparams + 3 * len(ordered)
+    assert all(o % 4 == 0 for o in offs) and bounds == sorted(bounds)
+    assert all(b in set(offs) | {total} for b in bounds)  # stage boundaries fall between parameters
     if name == "ds2":
-        assert bounds[-1] == 26_042_528  # parameter count of the ds2 network
+        assert nparams == 26_042_528 == total  # parameter count of the ds2 network
 
 
 def test_reference_state_dict_loads(golden_dir):

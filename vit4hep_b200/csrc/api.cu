@@ -1,5 +1,6 @@
 // extern "C" surface of libvit4hep_b200.so (declared in include/vit4hep_b200.h).
 #include <algorithm>
+#include <cstdlib>
 #include <atomic>
 #include <map>
 #include <mutex>
@@ -18,6 +19,10 @@ char* last_error_buffer() {
 // ---------------------------------------------------------------- launch counter / profiler
 static std::atomic<int64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+bool launch_sync_enabled() {
+  static const bool on = [] { const char* e = getenv("V4H_LAUNCH_SYNC"); return e && e[0] == '1'; }();
+  return on;
+}
 
 namespace {
 struct ProfRecord { std::string tag; double flops, bytes; cudaEvent_t e0, e1; };
@@ -358,7 +363,7 @@ int v4h_test_gemm(int32_t engine, int32_t layout, const void* A, const void* B, 
 int v4h_debug_gemm(int32_t kind, int32_t m, int32_t n, int32_t k, int32_t rows_per_sample, const void* A, const void* B,
                    const float* bias, void* out, void* out2, const float* res_in, float* res_out, const float* gate,
                    const void* aux, int64_t* counters, v4h_stream_t s) {
-  V4H_REQUIRE(A && B && kind >= 0 && kind <= 5, "debug_gemm: bad arguments");
+  V4H_REQUIRE(A && B && kind >= 0 && kind <= 6, "debug_gemm: bad arguments");
   static UmmaContext* ctx = umma_context_create();
   GemmDesc g;
   g.A = A; g.B = B; g.M = m; g.N = n; g.K = k; g.a_dtype = g.b_dtype = DT_BF16; g.out_dtype = DT_BF16;
@@ -377,6 +382,8 @@ int v4h_debug_gemm(int32_t kind, int32_t m, int32_t n, int32_t k, int32_t rows_p
       g.ep.ld_aux = n; g.ep.bias = nullptr; break;
     case 4:  // plain dgrad
       g.layout = GEMM_NN; g.lda = k; g.ldb = n; g.ep.out = out; g.ep.bias = nullptr; break;
+    case 6:  // final-layer-like: x W^T + b into fp32
+      g.layout = GEMM_NT; g.lda = k; g.ldb = k; g.ep.out = out; g.out_dtype = DT_F32; break;
     default:  // wgrad: dY^T X with split-K atomics into fp32
       g.layout = GEMM_TN; g.lda = m; g.ldb = n; g.epi = EPI_ATOMIC; g.out_dtype = DT_F32; g.splitk = 0;
       g.ep.out = out; g.ep.bias = nullptr; break;

@@ -37,10 +37,14 @@ inline int fail(int code, const char* fmt, ...) {
 // every kernel launch in the library is followed by this: counts the launch (v4h_launch_count) and
 // surfaces launch errors
 void count_launch();  // api.cu
-#define V4H_LAUNCH_CHECK()       \
-  do {                           \
-    ::v4h::count_launch();       \
-    V4H_CUDA(cudaGetLastError()); \
+// V4H_LAUNCH_SYNC=1 (debug): synchronise after every launch so that a device fault is reported at the
+// launch that caused it
+bool launch_sync_enabled();  // api.cu
+#define V4H_LAUNCH_CHECK()                                              \
+  do {                                                                  \
+    ::v4h::count_launch();                                              \
+    V4H_CUDA(cudaGetLastError());                                       \
+    if (::v4h::launch_sync_enabled()) V4H_CUDA(cudaDeviceSynchronize()); \
   } while (0)
 
 // Optional per-kernel-class timing (v4h_profile_begin / v4h_profile_end): when enabled, a ProfScope

@@ -846,11 +846,16 @@ int gemm_umma(UmmaContext* ctx, const GemmDesc& d, cudaStream_t s) {
     }
   }
   g.stages = (SMEM_LIMIT - 1024 - BAR_BYTES - pool_bytes) / g.stage_bytes;
-  if (g.stages > MAX_STAGES) g.stages = MAX_STAGES;
+  static const int max_stages = [] { const char* e = getenv("V4H_GEMM_MAX_STAGES"); const int v = e ? atoi(e) : MAX_STAGES; return v >= 2 && v <= MAX_STAGES ? v : MAX_STAGES; }();
+  if (g.stages > max_stages) g.stages = max_stages;
   V4H_REQUIRE(g.stages >= 2, "gemm_umma: internal shared-memory budget error");
 
   const int total = g.tiles_m * g.tiles_n * g.splits;
   const int grid = (total < units ? total : units) * ctas;
+  if (launch_sync_enabled())
+    fprintf(stderr, "[v4h] gemm %s layout=%d epi=%d act=%d M=%d N=%d K=%d obf=%d slab=%d ctas=%d bn=%d n_pad=%d tiles=%dx%d splits=%d stages=%d nslots=%d nbuf=%d tma_store=%d out2=%d grid=%d\n",
+            d.tag, d.layout, d.epi, d.act, d.M, d.N, d.K, (int)obf, (int)slab, ctas, g.bn, g.n_pad, g.tiles_m, g.tiles_n,
+            g.splits, g.stages, g.nslots, g.nbuf, g.tma_store, g.has_out2, grid);
   switch (d.epi) {
     case EPI_BIAS_ACT:
       if (d.act == ACT_NONE)

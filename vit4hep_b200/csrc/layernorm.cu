@@ -3,6 +3,7 @@
 // Restates: reference nn/vit.py:309-311 (norm1/norm2), :457-458 (modulate), :331-332 (gated residual).
 // One warp per token row; the per-sample reductions (d shift, d scale, d gate) are done per CTA in
 // registers/shared memory and published with one atomicAdd per (CTA, column).
+#include <cstdlib>
 #include <initializer_list>
 
 #include "kernels.cuh"
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(WARPS * 32) ln_mod_bwd_kernel(
 // sample, RB rows in flight per iteration; the two LayerNorm row sums cross the warps through a
 // double-buffered shared-memory exchange (one __syncthreads per RB rows).  Per-thread state is
 // 4 columns x 4 accumulators, so many CTAs fit per SM and the loads of RB rows overlap.
-constexpr int RB = 4;
+constexpr int RB = 2;
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float4 ld4(const bf16* p) {
@@ -173,12 +174,12 @@ __device__ __forceinline__ void red4(float* p, float4 v) {
 }
 
 template <typename T, bool HAS_LN, bool HAS_GATE>
-__global__ void __launch_bounds__(128) ln_mod_bwd_vec_kernel(
+__global__ void __launch_bounds__(128, 6) ln_mod_bwd_vec_kernel(
     const T* __restrict__ da, const float* __restrict__ h, const float2* __restrict__ stats,
     const float* __restrict__ scale, int mod_stride, float* __restrict__ dh, bool dh_accumulate,
     float* __restrict__ dshift, float* __restrict__ dscale, int dmod_stride, const T* __restrict__ y,
     const float* __restrict__ gate, T* __restrict__ dy, float* __restrict__ dgate,
-    float* __restrict__ dbias, int D, int rows_per_sample, int rows_per_cta) {
+    float* __restrict__ dbias, int D, int rows_per_sample, int rows_per_cta, int DBG_SKIP) {
   __shared__ float2 part[2][RB][4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int b = blockIdx.y;
@@ -266,12 +267,12 @@ __global__ void __launch_bounds__(128) ln_mod_bwd_vec_kernel(
   }
   if (act) {
     if (HAS_LN) {
-      if (dshift) red4(dshift + (size_t)b * dmod_stride + col, a_shift);
-      if (dscale) red4(dscale + (size_t)b * dmod_stride + col, a_scale);
+      if (dshift && !(DBG_SKIP & 2)) red4(dshift + (size_t)b * dmod_stride + col, a_shift);
+      if (dscale && !(DBG_SKIP & 2)) red4(dscale + (size_t)b * dmod_stride + col, a_scale);
     }
     if (HAS_GATE) {
-      if (dgate) red4(dgate + (size_t)b * dmod_stride + col, a_gate);
-      if (dbias) red4(dbias + col, a_bias);
+      if (dgate && !(DBG_SKIP & 2)) red4(dgate + (size_t)b * dmod_stride + col, a_gate);
+      if (dbias && !(DBG_SKIP & 1)) red4(dbias + col, a_bias);
     }
   }
 }
@@ -369,14 +370,15 @@ int ln_modulate_bwd(const T* da, const float* h, const float2* stats, const floa
   if (ln_vec_ok(D, mod_stride, dmod_stride, {da, h, scale, dh, dshift, dscale, y, gate, dy, dgate, dbias})) {
     const int rows_per_cta = 16, threads = (int)ceil_div(D / 4, 32) * 32;
     dim3 vgrid((unsigned)ceil_div(rows_per_sample, rows_per_cta), (unsigned)B);
+    static const int dbg_skip = [] { const char* e = getenv("V4H_LN_DBG_SKIP"); return e ? atoi(e) : 0; }();
     if (gate != nullptr)
       ln_mod_bwd_vec_kernel<T, true, true><<<vgrid, threads, 0, s>>>(
           da, h, stats, scale, mod_stride, dh, dh_accumulate, dshift, dscale, dmod_stride, y, gate, dy, dgate,
-          dbias, D, rows_per_sample, rows_per_cta);
+          dbias, D, rows_per_sample, rows_per_cta, dbg_skip);
     else
       ln_mod_bwd_vec_kernel<T, true, false><<<vgrid, threads, 0, s>>>(
           da, h, stats, scale, mod_stride, dh, dh_accumulate, dshift, dscale, dmod_stride, nullptr, nullptr,
-          nullptr, nullptr, nullptr, D, rows_per_sample, rows_per_cta);
+          nullptr, nullptr, nullptr, D, rows_per_sample, rows_per_cta, dbg_skip);
     V4H_LAUNCH_CHECK();
     return V4H_OK;
   }
@@ -405,7 +407,7 @@ int gate_bwd(const float* dh, const T* y, const float* gate, int mod_stride, T* 
     dim3 vgrid((unsigned)ceil_div(rows_per_sample, rows_per_cta), (unsigned)B);
     ln_mod_bwd_vec_kernel<T, false, true><<<vgrid, threads, 0, s>>>(
         nullptr, nullptr, nullptr, nullptr, mod_stride, const_cast<float*>(dh), false, nullptr, nullptr,
-        dmod_stride, y, gate, dy, dgate, dbias, D, rows_per_sample, rows_per_cta);
+        dmod_stride, y, gate, dy, dgate, dbias, D, rows_per_sample, rows_per_cta, 0);
     V4H_LAUNCH_CHECK();
     return V4H_OK;
   }

@@ -57,11 +57,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
-// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.  The
+// bound is wall-clock (2 s on %globaltimer, sampled every 4096 polls): a spin count alone can expire
+// spuriously when the SM is stalled for reasons outside the kernel.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) __trap();
+    if ((++spins & 4095u) == 0) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) __trap();
+    }
   }
 }
 

@@ -127,13 +127,14 @@ class FusedAdamW(torch.optim.Optimizer):
         norm_ptr = None
         if self.max_grad_norm is not None:
             # gradients of a vit4hep_b200.ViT are views of one flat buffer: one pass over it
-            first = min(params, key=lambda p: p.grad.data_ptr())
-            total = sum(p.numel() for p in params)
-            lo = first.grad.data_ptr()
+            lo = min(p.grad.data_ptr() for p in params)
             hi = max(p.grad.data_ptr() + 4 * p.numel() for p in params)
+            store = params[0].grad.untyped_storage()
+            one_buffer = all(p.grad.untyped_storage().data_ptr() == store.data_ptr() for p in params) and \
+                hi - lo <= store.nbytes() and sum(p.numel() for p in params) * 4 >= (hi - lo) - 16 * len(params)
             with torch.cuda.device(dev):
-                if hi - lo == 4 * total:
-                    _cabi.check(lib.v4h_grad_norm_sq(lo, total, self._norm_sq.data_ptr(), stream))
+                if one_buffer:  # alignment padding between the views is zero: it does not change the norm
+                    _cabi.check(lib.v4h_grad_norm_sq(lo, (hi - lo) // 4, self._norm_sq.data_ptr(), stream))
                 else:  # gradients live in separate allocations (not produced by the fused backward)
                     self._norm_sq.copy_(torch.stack([p.grad.square().sum() for p in params]).sum().reshape(1))
             norm_ptr = self._norm_sq.data_ptr()

@@ -282,19 +282,32 @@ class ViT(nn.Module):
         out.append(("final_ada_b", fl.adaLN_modulation[-1].bias))
         return out
 
+    FLAT_ALIGN = 4  # elements: every gradient starts on a 16-byte boundary of the flat buffer
+
+    @classmethod
+    def flat_layout(cls, ordered) -> Tuple[List[int], int]:
+        """Offsets (in elements) of every parameter's gradient inside the flat gradient buffer, and its
+        total length.  Each gradient starts 16-byte aligned so the native kernels (vector atomics of the
+        LayerNorm backward, the fused optimizer) keep their 128-bit paths for any patch_dim / cond_dim."""
+        offs, off = [], 0
+        a = cls.FLAT_ALIGN
+        for _, p in ordered:
+            offs.append(off)
+            off += (p.numel() + a - 1) // a * a
+        return offs, off
+
     def stage_boundaries(self) -> List[int]:
         """Element offsets into the flat gradient buffer at which each backward stage's parameters
         end: [after final layer, after block depth-1, ..., after block 0, after stage 0]."""
-        bounds, off = [], 0
         names = self.ordered_parameters()
-        idx = 0
-        off += sum(p.numel() for _, p in names[idx:idx + 2]); idx += 2
-        bounds.append(off)
+        offs, total = self.flat_layout(names)
+        ends = offs[1:] + [total]
+        bounds = [ends[1]]                       # final_w, final_b
+        idx = 2
         for _ in range(len(self.blocks)):
-            off += sum(p.numel() for _, p in names[idx:idx + 8]); idx += 8
-            bounds.append(off)
-        off += sum(p.numel() for _, p in names[idx:])
-        bounds.append(off)
+            idx += 8
+            bounds.append(ends[idx - 1])
+        bounds.append(total)
         return bounds
 
     @staticmethod
@@ -406,10 +419,9 @@ class ViT(nn.Module):
         stream = torch.cuda.current_stream(x.device).cuda_stream
         w = self._weights_struct(ordered)
         g = _cabi.VitParams()
-        off = 0
-        for field, p in ordered:
+        offs, _ = self.flat_layout(ordered)
+        for (field, p), off in zip(ordered, offs):
             self._fill(g, field, flat_grad.data_ptr() + 4 * off)
-            off += p.numel()
         arena = None if self._native.arena is None else self._native.arena.data_ptr()
         _cabi.check(lib.v4h_vit_backward(plan, ctypes.byref(w), arena, ctypes.byref(g), x.data_ptr(), c.data_ptr(),
                                          dout.data_ptr(), x.shape[0], stage_begin, stage_end, ws.data_ptr(),
@@ -436,7 +448,7 @@ class _ViTFunction(torch.autograd.Function):
         module: ViT = ctx.module
         x, c = ctx.saved_tensors
         ordered = module.ordered_parameters()
-        total = sum(p.numel() for _, p in ordered)
+        offs, total = module.flat_layout(ordered)
         flat = torch.zeros(total, dtype=torch.float32, device=x.device)
         dout = dout.contiguous()
         depth = len(module.blocks)
@@ -445,9 +457,7 @@ class _ViTFunction(torch.autograd.Function):
         else:
             module._dp.backward(module, x, c, dout, ctx.ws, ordered, flat)
         ctx.ws = None
-        grads, off = [], 0
-        for _, p in ordered:
-            n = p.numel()
-            grads.append(flat[off:off + n].view(p.shape) if p.requires_grad else None)
-            off += n
+        grads = []
+        for (_, p), off in zip(ordered, offs):
+            grads.append(flat[off:off + p.numel()].view(p.shape) if p.requires_grad else None)
         return (None, None, None, None, None, *grads)
