@@ -22,7 +22,12 @@
 //   dkv  : CTA per (128 keys, sample-head); S^T = K Q^T and dP^T = V dO^T in TMEM, P^T / dS^T -> smem,
 //          dV += P^T dO, dK += dS^T Q accumulated in TMEM over the query blocks
 // Rows / keys beyond T are zero-filled on load and masked in the softmax.
+#include <cuda.h>
+
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <tuple>
 
 #include "kernels.cuh"
 #include "umma.cuh"
@@ -75,6 +80,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // G8 tile geometry
 __host__ __device__ constexpr uint32_t g8_stride(int rows) { return (uint32_t)(rows + 1) * 16u; }
 __host__ __device__ constexpr uint32_t g8_bytes(int rows, int cols) { return (uint32_t)(cols / 8) * g8_stride(rows); }
+// allocation of a tile that TMA may write: 128-byte aligned extents
+__host__ __device__ constexpr uint32_t g8_alloc(int rows, int cols) { return (g8_bytes(rows, cols) + 127u) & ~127u; }
 
 // Stage `rows` x DHP (bf16) from global (row pitch `ld` elements) into a G8 tile; rows >= rows_valid
 // and column groups >= dh are zero-filled.
@@ -107,7 +114,8 @@ __device__ __forceinline__ void issue_mma(uint32_t d_tmem, uint32_t a_base, uint
 }
 
 struct AttnSmem {
-  uint64_t bar;
+  uint64_t bar;      // MMA completion
+  uint64_t ld_bar;   // TMA operand loads
   uint32_t tmem_slot;
 };
 
@@ -120,6 +128,7 @@ __device__ __forceinline__ uint32_t attn_prologue(AttnSmem* ctl, uint32_t tmem_c
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     mbar_init(&ctl->bar, 1);
+    mbar_init(&ctl->ld_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_dyn(&ctl->tmem_slot, tmem_cols);
@@ -158,6 +167,7 @@ struct AttnArgs {
   float scale;       // dh^-0.5
   float scale_log2;  // scale * log2(e)
   long long* dbg;    // optional cycle counters per phase (v4h_debug_attention_counters)
+  int use_tma;       // operand tiles staged by TMA (5-d tensor maps writing the G8 layout) instead of cp.async
 };
 
 struct ALap {  // cycle accounting of thread 0 of each CTA
@@ -172,18 +182,24 @@ struct ALap {  // cycle accounting of thread 0 of each CTA
 };
 
 // ------------------------------------------------------------------------------------------ forward
+// tmQ / tmKV: 5-d views (8 elements, T rows, dh/8 column groups, 3H, B) of qkv with boxes of 128 / BN rows: one
+// TMA load writes a whole operand tile in the G8 layout (group stride rows * 16, no pad)
 template <int DHP>
-__global__ void __launch_bounds__(ATT_THREADS) attn_fwd_umma_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(ATT_THREADS) attn_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                    const __grid_constant__ CUtensorMap tmKV,
+                                                                    const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align128(smem_raw);
   AttnSmem* ctl = reinterpret_cast<AttnSmem*>(smem);
   const int BN = a.BN, T = a.T, H = a.H, dh = a.dh;
   const uint32_t sQ = smem_u32(smem + 128);
-  const uint32_t sK = sQ + g8_bytes(MT, DHP);
-  const uint32_t sV = sK + g8_bytes(BN, DHP);
-  const uint32_t sP = sV + g8_bytes(BN, DHP);
-  uint8_t* sP_ptr = smem + 128 + g8_bytes(MT, DHP) + 2 * g8_bytes(BN, DHP);
-  const uint32_t gsQ = g8_stride(MT), gsKV = g8_stride(BN), gsP = g8_stride(MT);
+  const uint32_t sK = sQ + g8_alloc(MT, DHP);
+  const uint32_t sV = sK + g8_alloc(BN, DHP);
+  const uint32_t sP = sV + g8_alloc(BN, DHP);
+  uint8_t* sP_ptr = smem + 128 + g8_alloc(MT, DHP) + 2 * g8_alloc(BN, DHP);
+  const bool tma = a.use_tma != 0;
+  const uint32_t gsQ = tma ? MT * 16u : g8_stride(MT), gsKV = tma ? (uint32_t)BN * 16u : g8_stride(BN), gsP = g8_stride(MT);
+  uint32_t ld_phase = 0;
 
   const int bh = blockIdx.y, b = bh / H, hd = bh % H;
   const int q0 = blockIdx.x * MT;
@@ -200,7 +216,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_umma_kernel(const AttnAr
   const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
   uint32_t phase = 0;
 
-  stage_tile<DHP>(sQ, MT, qbase + (size_t)q0 * ld, ld, T - q0, dh);
+  if (!tma) stage_tile<DHP>(sQ, MT, qbase + (size_t)q0 * ld, ld, T - q0, dh);
 
   float o_acc[DHP];
 #pragma unroll
@@ -211,10 +227,22 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_umma_kernel(const AttnAr
   for (int blk = 0; blk < a.nblocks; ++blk) {
     const int n0 = blk * BN;
     const int nvalid = min(BN, T - n0);
-    stage_tile<DHP>(sK, BN, kbase + (size_t)n0 * ld, ld, nvalid, dh);
-    stage_tile<DHP>(sV, BN, vbase + (size_t)n0 * ld, ld, nvalid, dh);
-    L.lap(1);
-    cp_async_wait_all();
+    if (tma) {
+      if (tid == 0) {
+        const uint32_t kv_bytes = (uint32_t)BN * DHP * 2;
+        mbar_expect_tx(&ctl->ld_bar, 2 * kv_bytes + (blk == 0 ? (uint32_t)MT * DHP * 2 : 0u));
+        if (blk == 0) tma_load_5d(smem + 128, &tmQ, &ctl->ld_bar, 0, q0, 0, hd, b);
+        tma_load_5d(smem + 128 + g8_alloc(MT, DHP), &tmKV, &ctl->ld_bar, 0, n0, 0, H + hd, b);
+        tma_load_5d(smem + 128 + g8_alloc(MT, DHP) + g8_alloc(BN, DHP), &tmKV, &ctl->ld_bar, 0, n0, 0, 2 * H + hd, b);
+      }
+      L.lap(1);
+      mbar_wait(&ctl->ld_bar, ld_phase); ld_phase ^= 1;
+    } else {
+      stage_tile<DHP>(sK, BN, kbase + (size_t)n0 * ld, ld, nvalid, dh);
+      stage_tile<DHP>(sV, BN, vbase + (size_t)n0 * ld, ld, nvalid, dh);
+      L.lap(1);
+      cp_async_wait_all();
+    }
     L.lap(2);
     publish_smem_and_sync();
     L.lap(3);
@@ -818,16 +846,64 @@ int set_smem(K kernel, size_t bytes) {
   return V4H_OK;
 }
 
+// 5-d tensor map over a (B, T, nh, dh) bf16 tensor with row pitch `ld` elements between tokens: dims
+// (8, T, dh/8, nh, B), box (8, rows, dh/8, 1, 1): the box lands in shared memory as [dh/8][rows][8] = G8.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int make_g8_map(const void* base, int B, int T, int nh, int dh, size_t ld, int rows, CUtensorMap* out) {
+  static EncodeTiledFn encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(fn);
+  }();
+  if (!encode) return fail(V4H_ERR_CUDA, "attention: cuTensorMapEncodeTiled is not available from the driver");
+  static std::mutex mu;
+  static std::map<std::tuple<const void*, int, int, int, int, size_t, int>, CUtensorMap> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  const auto key = std::make_tuple(base, B, T, nh, dh, ld, rows);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return V4H_OK; }
+  cuuint64_t dims[5] = {8, (cuuint64_t)T, (cuuint64_t)(dh / 8), (cuuint64_t)nh, (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)ld * 2, 16, (cuuint64_t)dh * 2, (cuuint64_t)T * ld * 2};
+  cuuint32_t box[5] = {8, (cuuint32_t)rows, (cuuint32_t)(dh / 8), 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUtensorMap m;
+  const CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(V4H_ERR_CUDA, "attention: cuTensorMapEncodeTiled (5-d G8 view) failed (%d)", (int)r);
+  if (cache.size() > 1024) cache.clear();
+  cache[key] = m;
+  *out = m;
+  return V4H_OK;
+}
+bool attn_tma_enabled() {
+  static const int on = [] { const char* e = getenv("V4H_ATTN_TMA"); return (e && e[0] == '0') ? 0 : 1; }();
+  return on != 0;
+}
+
 template <int DHP>
 int fwd_launch(AttnArgs a, int B, cudaStream_t s) {
   const int cap = std::min(160, 512 - DHP) / 16 * 16;
   pick_block(a.T, cap, &a.BN, &a.nblocks);
   a.tmem_cols = pow2_cols(a.BN + DHP);
-  const size_t smem = 256 + g8_bytes(MT, DHP) + 2 * g8_bytes(a.BN, DHP) + g8_bytes(MT, a.BN);
+  const size_t smem = 256 + g8_alloc(MT, DHP) + 2 * g8_alloc(a.BN, DHP) + g8_alloc(MT, a.BN);
   static size_t configured = 0;
   if (smem > configured) { V4H_TRY(set_smem(attn_fwd_umma_kernel<DHP>, smem)); configured = smem; }
+  CUtensorMap mq, mkv;
+  memset(&mq, 0, sizeof(mq)); memset(&mkv, 0, sizeof(mkv));
+  a.use_tma = (attn_tma_enabled() && a.dh == DHP) ? 1 : 0;  // the box must cover the padded head dim exactly
+  if (a.use_tma) {
+    const size_t ld = (size_t)3 * a.H * a.dh;
+    V4H_TRY(make_g8_map(a.qkv, B, a.T, 3 * a.H, a.dh, ld, MT, &mq));
+    V4H_TRY(make_g8_map(a.qkv, B, a.T, 3 * a.H, a.dh, ld, a.BN, &mkv));
+  }
   dim3 grid((unsigned)ceil_div(a.T, MT), (unsigned)(B * a.H));
-  attn_fwd_umma_kernel<DHP><<<grid, ATT_THREADS, smem, s>>>(a);
+  attn_fwd_umma_kernel<DHP><<<grid, ATT_THREADS, smem, s>>>(mq, mkv, a);
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }

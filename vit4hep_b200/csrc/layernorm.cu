@@ -284,29 +284,37 @@ template <typename T>
 __global__ void __launch_bounds__(256) ln_mod_fwd_vec_kernel(
     const float* __restrict__ h, const float* __restrict__ shift, const float* __restrict__ scale,
     int mod_stride, T* __restrict__ a, int ld_a, float2* __restrict__ stats, int M, int D, int rows_per_sample) {
+  constexpr int RW = 4;  // rows per warp, all loads issued before the first reduction
   const int lane = threadIdx.x & 31;
   const int warp = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int nv = D >> 2;  // float4 per row
   const float inv_d = 1.f / (float)D;
+  const int row0 = warp * RW;
+  if (row0 >= M) return;
+  float4 v[RW][4];
 #pragma unroll
-  for (int rr = 0; rr < 2; ++rr) {
-    const int row = warp * 2 + rr;
-    if (row >= M) return;
+  for (int rr = 0; rr < RW; ++rr) {
+    const int row = min(row0 + rr, M - 1);
     const float4* hr = reinterpret_cast<const float4*>(h + (size_t)row * D);
-    float4 v[4];
-    float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int c = lane + 32 * i;
-      v[i] = c < nv ? hr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
-      sum += v[i].x + v[i].y + v[i].z + v[i].w;
+      v[rr][i] = c < nv ? hr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  }
+#pragma unroll
+  for (int rr = 0; rr < RW; ++rr) {
+    const int row = row0 + rr;
+    if (row >= M) break;
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sum += v[rr][i].x + v[rr][i].y + v[rr][i].z + v[rr][i].w;
     const float mean = warp_sum(sum) * inv_d;
     float sq = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       if (lane + 32 * i < nv) {
-        const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+        const float a0 = v[rr][i].x - mean, a1 = v[rr][i].y - mean, a2 = v[rr][i].z - mean, a3 = v[rr][i].w - mean;
         sq += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
       }
     }
@@ -323,10 +331,10 @@ __global__ void __launch_bounds__(256) ln_mod_fwd_vec_kernel(
       if (c < nv) {
         const float4 s4 = __ldg(sc + c), t4 = __ldg(sh + c);
         float4 o;
-        o.x = (v[i].x - mean) * rstd * (1.f + s4.x) + t4.x;
-        o.y = (v[i].y - mean) * rstd * (1.f + s4.y) + t4.y;
-        o.z = (v[i].z - mean) * rstd * (1.f + s4.z) + t4.z;
-        o.w = (v[i].w - mean) * rstd * (1.f + s4.w) + t4.w;
+        o.x = (v[rr][i].x - mean) * rstd * (1.f + s4.x) + t4.x;
+        o.y = (v[rr][i].y - mean) * rstd * (1.f + s4.y) + t4.y;
+        o.z = (v[rr][i].z - mean) * rstd * (1.f + s4.z) + t4.z;
+        o.w = (v[rr][i].w - mean) * rstd * (1.f + s4.w) + t4.w;
         st4(ar + 4 * c, o);
       }
     }
@@ -349,7 +357,7 @@ int ln_modulate_fwd(const float* h, const float* shift, const float* scale, int 
   if (D > MAXV * 32) return fail(V4H_ERR_UNSUPPORTED, "ln_modulate: hidden_dim %d > %d", D, MAXV * 32);
   if (ld_a < D || ld_a - D > 32) return fail(V4H_ERR_INVALID, "ln_modulate: bad output pitch %d for %d columns", ld_a, D);
   if (ld_a % 4 == 0 && ln_vec_ok(D, mod_stride, 0, {h, shift, scale, a})) {
-    ln_mod_fwd_vec_kernel<T><<<(unsigned)ceil_div(M, 16), 256, 0, s>>>(h, shift, scale, mod_stride, a, ld_a, stats, M, D,
+    ln_mod_fwd_vec_kernel<T><<<(unsigned)ceil_div(M, 32), 256, 0, s>>>(h, shift, scale, mod_stride, a, ld_a, stats, M, D,
                                                                       rows_per_sample);
     V4H_LAUNCH_CHECK();
     return V4H_OK;
