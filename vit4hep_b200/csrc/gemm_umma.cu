@@ -726,9 +726,9 @@ static int get_map(UmmaContext* ctx, const void* base, int inner, int outer, int
 
 // Column tiling: full tiles of 256 columns plus one narrower last tile, everything a multiple of `gran`
 // (32 in slab mode: whole epilogue slabs; 16 otherwise: the UMMA N granularity at M = 128).
-static void choose_tiling(int N, int gran, int* bn, int* n_pad, int* tiles_n) {
+static void choose_tiling(int N, int gran, int max_bn, int* bn, int* n_pad, int* tiles_n) {
   *n_pad = (int)ceil_div(N, gran) * gran;
-  *bn = *n_pad < MAX_BN ? *n_pad : MAX_BN;
+  *bn = *n_pad < max_bn ? *n_pad : max_bn;
   *tiles_n = (int)ceil_div(*n_pad, *bn);
 }
 
@@ -761,7 +761,9 @@ int gemm_umma(UmmaContext* ctx, const GemmDesc& d, cudaStream_t s) {
   g.a_mn = d.layout == GEMM_TN ? 1 : 0;
   g.b_mn = d.layout == GEMM_NT ? 0 : 1;
   const bool slab = slab_ok(d);
-  choose_tiling(d.N, slab ? SLAB : 16, &g.bn, &g.n_pad, &g.tiles_n);
+  choose_tiling(d.N, slab ? SLAB : 16, MAX_BN, &g.bn, &g.n_pad, &g.tiles_n);
+  // (Measured: halving the tile width of the one-round N = 480 GEMMs so that epilogues overlap the next
+  // tile's MMAs is slower -- fc2 40 us vs 29 us -- the extra A traffic and N = 128 MMAs cost more.)
   // CTA pairs (cta_group::2, V4H_GEMM_PAIRS=1) when there is more than one 128-row tile of M.  Measured on
   // the ds2 shapes they are correct but 2-3 % slower than single CTAs (the epilogue, not the L2 -> smem
   // feed, bounds these K = 480 GEMMs), so they are opt-in.
