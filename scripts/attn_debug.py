@@ -61,6 +61,16 @@ def phases(B, T, H, dh):
     nct = B * H * ((T + 127) // 128)
     names = ["prologue", "issue_ld", "wait_ld", "publish", "mma_S", "softmax", "publish2", "mma_PV", "out", "teardown"]
     print("fwd phases, cycles per CTA:", " ".join(f"{n}={v / nct:.0f}" for n, v in zip(names, cnt.cpu().tolist())), flush=True)
+    if T <= 160:
+        d_o = torch.randn(B, T, H, dh, generator=g).to(dev).to(torch.bfloat16)
+        dqkv = torch.zeros_like(qkv)
+        cnt.zero_()
+        lib.v4h_debug_attention_counters(cnt.data_ptr())
+        _cabi.check(lib.v4h_test_attention_bwd(1, 1, qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), d_o.data_ptr(), dqkv.data_ptr(), B, T, H, dh, s))
+        torch.cuda.synchronize()
+        lib.v4h_debug_attention_counters(None)
+        names = ["stage+stats", "wait_ld", "mma_S", "P", "mma_dP_dV", "dS", "mma_dQ_dK", "dQ_out", "dKdV_out", "teardown"]
+        print("fused bwd phases, cycles per CTA:", " ".join(f"{n}={v / (B * H):.0f}" for n, v in zip(names, cnt.cpu().tolist())), flush=True)
 
 
 if __name__ == "__main__":

@@ -85,9 +85,11 @@ __host__ __device__ constexpr uint32_t g8_alloc(int rows, int cols) { return (g8
 
 // Stage `rows` x DHP (bf16) from global (row pitch `ld` elements) into a G8 tile; rows >= rows_valid
 // and column groups >= dh are zero-filled.
+// Only the first `load_rows` rows are touched (the rest of the tile keeps whatever it held: rows that no
+// stored result depends on).
 template <int DHP, int NTHREADS = ATT_THREADS>
 __device__ __forceinline__ void stage_tile(uint32_t dst, int rows, const bf16* __restrict__ src, size_t ld,
-                                           int rows_valid, int dh) {
+                                           int rows_valid, int dh, int load_rows = -1) {
   constexpr int NCG = DHP / 8;        // 16-byte column groups per row
   constexpr int RPI = NTHREADS / NCG;  // rows per sweep: every thread keeps one column group
   if ((int)threadIdx.x >= RPI * NCG) return;
@@ -95,7 +97,8 @@ __device__ __forceinline__ void stage_tile(uint32_t dst, int rows, const bf16* _
   const bool col_ok = cg * 8 < dh;
   const bf16* p = src + (size_t)r0 * ld + cg * 8;
   uint32_t d = dst + cg * g8_stride(rows) + r0 * 16;
-  for (int row = r0; row < rows; row += RPI, p += (size_t)RPI * ld, d += RPI * 16) {
+  const int nload = load_rows < 0 ? rows : load_rows;
+  for (int row = r0; row < nload; row += RPI, p += (size_t)RPI * ld, d += RPI * 16) {
     const bool ok = col_ok && row < rows_valid;
     cp_async16(d, ok ? (const void*)p : (const void*)src, ok);
   }
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_umma_kernel(const __grid
   const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
   uint32_t phase = 0;
 
-  if (!tma) stage_tile<DHP>(sQ, MT, qbase + (size_t)q0 * ld, ld, T - q0, dh);
+  if (!tma) stage_tile<DHP>(sQ, MT, qbase + (size_t)q0 * ld, ld, T - q0, dh, min(MT, (T - q0 + 15) / 16 * 16));
 
   float o_acc[DHP];
 #pragma unroll
@@ -389,10 +392,16 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_umma_kernel(const Att
   if (q < T) {
     const bf16* dor = dobase + (size_t)q * ldo;
     const bf16* orow = obase + (size_t)q * ldo;
-    for (int c = 0; c < dh; c += 8) {
-      const uint4 x = *reinterpret_cast<const uint4*>(dor + c);
-      const uint4 y = *reinterpret_cast<const uint4*>(orow + c);
-      const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+    uint4 xv[DHP / 8], yv[DHP / 8];  // all loads of the row in flight before the first use
+#pragma unroll
+    for (int c = 0; c < DHP / 8; ++c) {
+      const bool in = c * 8 < dh;
+      xv[c] = in ? *reinterpret_cast<const uint4*>(dor + c * 8) : make_uint4(0, 0, 0, 0);
+      yv[c] = in ? *reinterpret_cast<const uint4*>(orow + c * 8) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int c = 0; c < DHP / 8; ++c) {
+      const uint32_t xs[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w}, ys[4] = {yv[c].x, yv[c].y, yv[c].z, yv[c].w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float2 fx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xs[i]));
@@ -600,7 +609,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_umma_kernel(const At
 constexpr int FUSED_THREADS = 256;
 
 template <int DHP>
-__global__ void __launch_bounds__(FUSED_THREADS) attn_bwd_fused_umma_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(FUSED_THREADS) attn_bwd_fused_umma_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                          const __grid_constant__ CUtensorMap tmKV,
+                                                                          const __grid_constant__ CUtensorMap tmdO,
+                                                                          const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align128(smem_raw);
   AttnSmem* ctl = reinterpret_cast<AttnSmem*>(smem);
@@ -609,12 +621,15 @@ __global__ void __launch_bounds__(FUSED_THREADS) attn_bwd_fused_umma_kernel(cons
   const int NK = a.BN, T = a.T, H = a.H, dh = a.dh;
   uint8_t* tiles = smem + 128 + 1024;
   const uint32_t sQ = smem_u32(tiles);
-  const uint32_t sdO = sQ + g8_bytes(MT, DHP);
-  const uint32_t sK = sdO + g8_bytes(MT, DHP);
-  const uint32_t sV = sK + g8_bytes(NK, DHP);
-  const uint32_t sP = sV + g8_bytes(NK, DHP);
-  uint8_t* sP_ptr = tiles + 2 * g8_bytes(MT, DHP) + 2 * g8_bytes(NK, DHP);
-  const uint32_t gsQ = g8_stride(MT), gsKV = g8_stride(NK), gsP = g8_stride(MT);
+  const uint32_t sdO = sQ + g8_alloc(MT, DHP);
+  const uint32_t sK = sdO + g8_alloc(MT, DHP);
+  const uint32_t sV = sK + g8_alloc(NK, DHP);
+  const uint32_t sP = sV + g8_alloc(NK, DHP);
+  uint8_t* sP_ptr = tiles + 2 * g8_alloc(MT, DHP) + 2 * g8_alloc(NK, DHP);
+  const bool tma = a.use_tma != 0;
+  // TMA writes tiles densely (group stride rows * 16); the cp.async path pads the stride by 16 bytes
+  const uint32_t gsKV = tma ? (uint32_t)NK * 16u : g8_stride(NK), gsP = g8_stride(MT);
+  uint32_t ld_phase = 0;
 
   const int bh = blockIdx.x, b = bh / H, hd = bh % H;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -628,7 +643,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) attn_bwd_fused_umma_kernel(cons
   const bf16* obase = a.o + (size_t)b * T * ldo + (size_t)hd * dh;
 
   // prologue (256 threads): barrier + TMEM
-  if (tid == 0) { mbar_init(&ctl->bar, 1); fence_barrier_init(); }
+  if (tid == 0) { mbar_init(&ctl->bar, 1); mbar_init(&ctl->ld_bar, 1); fence_barrier_init(); }
   if (warp == 1) tmem_alloc_dyn(&ctl->tmem_slot, a.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -644,8 +659,11 @@ __global__ void __launch_bounds__(FUSED_THREADS) attn_bwd_fused_umma_kernel(cons
   const int ch0 = half == 0 ? 0 : (nchunks + 1) / 2;
   const int ch1 = half == 0 ? (nchunks + 1) / 2 : nchunks;
 
-  stage_tile<DHP, FUSED_THREADS>(sK, NK, kbase, ld, T, dh);
-  stage_tile<DHP, FUSED_THREADS>(sV, NK, vbase, ld, T, dh);
+  ALap L(a.dbg);
+  if (!tma) {
+    stage_tile<DHP, FUSED_THREADS>(sK, NK, kbase, ld, T, dh);
+    stage_tile<DHP, FUSED_THREADS>(sV, NK, vbase, ld, T, dh);
+  }
 
   const int ntiles = (T + MT - 1) / MT;
   for (int qt = 0; qt < ntiles; ++qt) {
@@ -653,18 +671,44 @@ __global__ void __launch_bounds__(FUSED_THREADS) attn_bwd_fused_umma_kernel(cons
     const int nq = min(MT, T - q0);
     const int kq = (nq + 15) / 16;            // K steps of the contractions over the query rows
     const bool warp_rows = quad * 32 < kq * 16;  // this warp's rows take part in those contractions
-    stage_tile<DHP, FUSED_THREADS>(sQ, MT, qbase + (size_t)q0 * ld, ld, nq, dh);
-    stage_tile<DHP, FUSED_THREADS>(sdO, MT, dobase + (size_t)q0 * ldo, ldo, nq, dh);
+    // full tiles (and K / V, once) arrive by TMA; a short tail tile is staged by cp.async, only the rows of
+    // its K steps
+    const bool tile_tma = tma && nq == MT;
+    const uint32_t gsQ = tile_tma ? MT * 16u : g8_stride(MT);
+    if (tid == 0 && (tile_tma || (tma && qt == 0))) {
+      const uint32_t q_bytes = (uint32_t)MT * DHP * 2, kv_bytes = (uint32_t)NK * DHP * 2;
+      mbar_expect_tx(&ctl->ld_bar, (tile_tma ? 2 * q_bytes : 0u) + (qt == 0 ? 2 * kv_bytes : 0u));
+      if (qt == 0) {
+        tma_load_5d(tiles + 2 * g8_alloc(MT, DHP), &tmKV, &ctl->ld_bar, 0, 0, 0, H + hd, b);
+        tma_load_5d(tiles + 2 * g8_alloc(MT, DHP) + g8_alloc(NK, DHP), &tmKV, &ctl->ld_bar, 0, 0, 0, 2 * H + hd, b);
+      }
+      if (tile_tma) {
+        tma_load_5d(tiles, &tmQ, &ctl->ld_bar, 0, q0, 0, hd, b);
+        tma_load_5d(tiles + g8_alloc(MT, DHP), &tmdO, &ctl->ld_bar, 0, q0, 0, hd, b);
+      }
+    }
+    if (!tile_tma) {
+      stage_tile<DHP, FUSED_THREADS>(sQ, MT, qbase + (size_t)q0 * ld, ld, nq, dh, kq * 16);
+      stage_tile<DHP, FUSED_THREADS>(sdO, MT, dobase + (size_t)q0 * ldo, ldo, nq, dh, kq * 16);
+    }
     if (half == 0) {  // row statistics: delta = sum_d dO * O, lse in log2 units
       float delta = 0.f, lse2 = INFINITY;  // padded query row: p = exp2(-inf) = 0
       const int q = q0 + r;
       if (q < T) {
         const bf16* dor = dobase + (size_t)q * ldo;
         const bf16* orow = obase + (size_t)q * ldo;
-        for (int c = 0; c < dh; c += 8) {
-          const uint4 x = *reinterpret_cast<const uint4*>(dor + c);
-          const uint4 y = *reinterpret_cast<const uint4*>(orow + c);
-          const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+        // every load of the row issued before the first use (the loop would otherwise serialise 2 * dh / 8
+        // L2 round trips)
+        uint4 xv[DHP / 8], yv[DHP / 8];
+#pragma unroll
+        for (int c = 0; c < DHP / 8; ++c) {
+          const bool in = c * 8 < dh;
+          xv[c] = in ? *reinterpret_cast<const uint4*>(dor + c * 8) : make_uint4(0, 0, 0, 0);
+          yv[c] = in ? *reinterpret_cast<const uint4*>(orow + c * 8) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int c = 0; c < DHP / 8; ++c) {
+          const uint32_t xs[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w}, ys[4] = {yv[c].x, yv[c].y, yv[c].z, yv[c].w};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float2 fx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xs[i]));
@@ -678,8 +722,11 @@ __global__ void __launch_bounds__(FUSED_THREADS) attn_bwd_fused_umma_kernel(cons
       s_delta[r] = delta;
       s_lse[r] = lse2;
     }
+    L.lap(0);
     cp_async_wait_all();
+    if (tile_tma || (tma && qt == 0)) { mbar_wait(&ctl->ld_bar, ld_phase); ld_phase ^= 1; }
     publish_smem_and_sync();
+    L.lap(1);
     if (tid == 0) {
       issue_mma(tS, sQ, gsQ, sK, gsKV, false, NK, DHP / 16, false);
       umma_commit(&ctl->bar);
@@ -688,6 +735,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) attn_bwd_fused_umma_kernel(cons
     const bool row_ok = q0 + r < T;
     mbar_wait(&ctl->bar, phase); phase ^= 1;
     tc_fence_after();
+    L.lap(2);
     // ---- P = exp2(s c - lse) (zero for padded rows / keys) -> smem [q][key]
     if (warp_rows) {
       for (int ch = ch0; ch < ch1; ++ch) {
@@ -713,6 +761,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) attn_bwd_fused_umma_kernel(cons
         *reinterpret_cast<uint4*>(dst + gsP) = make_uint4(w[4], w[5], w[6], w[7]);
       }
     }
+    L.lap(3);
     publish_smem_and_sync();
     if (tid == 0) {
       issue_mma(tS, sdO, gsQ, sV, gsKV, false, NK, DHP / 16, false);  // dP over S
@@ -725,6 +774,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) attn_bwd_fused_umma_kernel(cons
     }
     mbar_wait(&ctl->bar, phase); phase ^= 1;
     tc_fence_after();
+    L.lap(4);
     // ---- dS = p (dP - delta), in place over P
     if (warp_rows) {
       for (int ch = ch0; ch < ch1; ++ch) {
@@ -747,6 +797,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) attn_bwd_fused_umma_kernel(cons
     } else {
       tmem_ld_wait();
     }
+    L.lap(5);
     publish_smem_and_sync();
     if (tid == 0) {
       issue_mma(tS, sP, gsP, sK, gsKV, true, DHP, NK / 16, false);  // dQ over dP
@@ -758,6 +809,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) attn_bwd_fused_umma_kernel(cons
     }
     mbar_wait(&ctl->bar, phase); phase ^= 1;
     tc_fence_after();
+    L.lap(6);
     // ---- dQ rows out: the two warp halves split the head dimension in 16-column chunks
     {
       constexpr int NDC = DHP / 16;
@@ -785,38 +837,48 @@ __global__ void __launch_bounds__(FUSED_THREADS) attn_bwd_fused_umma_kernel(cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    L.lap(7);
   }
 
   // ---- dK^T, dV^T out: thread = head dim d (TMEM lane), columns = keys; a warp writes 32 consecutive d
   // of one key (64 contiguous bytes)
   if (quad * 32 < dh) {
+    // lane pairs exchange one value per key pair so that every lane stores two consecutive head dims of ONE
+    // key as a 4-byte word: even lane -> (d, d+1) of the even key, odd lane -> (d-1, d) of the odd key
     const int dd = r;
-    bf16* base = a.dqkv + (size_t)b * T * ld + (size_t)hd * dh + dd;
+    const bool odd = (lane & 1) != 0;
+    const int dcol = odd ? dd - 1 : dd;
+    bf16* base = a.dqkv + (size_t)b * T * ld + (size_t)hd * dh + dcol;
     for (int ch = ch0; ch < ch1; ++ch) {
       const int c0 = ch * 16;
       float vk[16], vv[16];
       tmem_ld16(tdK + lane_off + c0, vk);
       tmem_ld16(tdV + lane_off + c0, vv);
       tmem_ld_wait();
-      if (dd < dh) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int key = c0 + i;
-          if (key < T) {
-            bf16* dst = base + (size_t)key * ld + (size_t)H * dh;
-            dst[0] = __float2bfloat16_rn(vk[i] * a.scale);
-            dst[(size_t)H * dh] = __float2bfloat16_rn(vv[i]);
-          }
+      for (int i = 0; i < 16; i += 2) {
+        const float rk = __shfl_xor_sync(0xffffffffu, odd ? vk[i] : vk[i + 1], 1);
+        const float rv = __shfl_xor_sync(0xffffffffu, odd ? vv[i] : vv[i + 1], 1);
+        const int key = c0 + i + (odd ? 1 : 0);
+        if (dcol + 1 < dh + 1 && dcol < dh && key < T) {
+          const float k_lo = odd ? rk : vk[i], k_hi = odd ? vk[i + 1] : rk;
+          const float v_lo = odd ? rv : vv[i], v_hi = odd ? vv[i + 1] : rv;
+          bf16* dst = base + (size_t)key * ld + (size_t)H * dh;
+          *reinterpret_cast<uint32_t*>(dst) = pack_bf16(k_lo * a.scale, k_hi * a.scale);
+          *reinterpret_cast<uint32_t*>(dst + (size_t)H * dh) = pack_bf16(v_lo, v_hi);
         }
       }
     }
   }
+  L.lap(8);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_dyn(tmem, a.tmem_cols);
   }
+  L.lap(9);
+  L.flush();
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -923,11 +985,20 @@ int bwd_launch(AttnArgs a, int B, cudaStream_t s) {
     f.tmem_cols = pow2_cols(R + 2 * f.BN);
     // the MN-major reads of Q / dO span 128 "M" columns = 16 column groups even when DHP < 128: the
     // groups past DHP land in the tiles that follow (garbage rows of dK^T / dV^T that are never stored)
-    const size_t smem = 256 + 1024 + 2 * g8_bytes(MT, DHP) + 2 * g8_bytes(f.BN, DHP) + g8_bytes(MT, f.BN) +
+    const size_t smem = 256 + 1024 + 2 * g8_alloc(MT, DHP) + 2 * g8_alloc(f.BN, DHP) + g8_alloc(MT, f.BN) +
                         (DHP < 128 ? 16 * g8_stride(MT) : 0);
     static size_t configured = 0;
     if (smem > configured) { V4H_TRY(set_smem(attn_bwd_fused_umma_kernel<DHP>, smem)); configured = smem; }
-    attn_bwd_fused_umma_kernel<DHP><<<(unsigned)(B * a.H), FUSED_THREADS, smem, s>>>(f);
+    CUtensorMap mq, mkv, mdo;
+    memset(&mq, 0, sizeof(mq)); memset(&mkv, 0, sizeof(mkv)); memset(&mdo, 0, sizeof(mdo));
+    f.use_tma = (attn_tma_enabled() && a.dh == DHP) ? 1 : 0;
+    if (f.use_tma) {
+      const size_t ldq = (size_t)3 * a.H * a.dh;
+      V4H_TRY(make_g8_map(a.qkv, B, a.T, 3 * a.H, a.dh, ldq, MT, &mq));
+      V4H_TRY(make_g8_map(a.qkv, B, a.T, 3 * a.H, a.dh, ldq, f.BN, &mkv));
+      V4H_TRY(make_g8_map(a.d_o, B, a.T, a.H, a.dh, (size_t)a.H * a.dh, MT, &mdo));
+    }
+    attn_bwd_fused_umma_kernel<DHP><<<(unsigned)(B * a.H), FUSED_THREADS, smem, s>>>(mq, mkv, mdo, f);
     V4H_LAUNCH_CHECK();
     return V4H_OK;
   }
@@ -993,6 +1064,7 @@ int attention_bwd_umma(const bf16* qkv, const bf16* o, const float* lse, const b
   AttnArgs a{};
   a.qkv = qkv; a.o = const_cast<bf16*>(o); a.lse = const_cast<float*>(lse); a.d_o = d_o; a.delta = delta;
   a.dqkv = dqkv; a.T = Tn; a.H = H; a.dh = dh;
+  a.dbg = g_attn_dbg;
   a.scale = 1.f / sqrtf((float)dh);
   a.scale_log2 = a.scale * 1.4426950408889634f;
   V4H_TRY(check_args(a, B));
