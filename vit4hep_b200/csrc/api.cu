@@ -19,6 +19,10 @@ char* last_error_buffer() {
 // ---------------------------------------------------------------- launch counter / profiler
 static std::atomic<int64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("V4H_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
 bool launch_sync_enabled() {
   static const bool on = [] { const char* e = getenv("V4H_LAUNCH_SYNC"); return e && e[0] == '1'; }();
   return on;

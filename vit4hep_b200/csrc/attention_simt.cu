@@ -38,6 +38,7 @@ template <typename T, int DPT>
 __global__ void __launch_bounds__(ATHREADS) attn_fwd_kernel(const T* __restrict__ qkv, T* __restrict__ o,
                                                             float* __restrict__ lse, int Tn, int H, int dh,
                                                             float scale) {
+  pdl_wait();
   __shared__ float Ks[TILE][4 * (DPT + 1)];
   __shared__ float Vs[TILE][4 * (DPT + 1)];
   const int bh = blockIdx.y, b = bh / H, hd = bh % H;
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(ATHREADS) attn_bwd_dq_kernel(const T* __restri
                                                                const float* __restrict__ lse,
                                                                const T* __restrict__ d_o, T* __restrict__ dqkv,
                                                                int Tn, int H, int dh, float scale) {
+  pdl_wait();
   __shared__ float Ks[TILE][4 * (DPT + 1)];
   __shared__ float Vs[TILE][4 * (DPT + 1)];
   const int bh = blockIdx.y, b = bh / H, hd = bh % H;
@@ -172,6 +174,7 @@ __global__ void __launch_bounds__(ATHREADS) attn_bwd_dkv_kernel(const T* __restr
                                                                 const float* __restrict__ lse,
                                                                 const T* __restrict__ d_o, T* __restrict__ dqkv,
                                                                 int Tn, int H, int dh, float scale) {
+  pdl_wait();
   __shared__ float Qs[TILE][4 * (DPT + 1)];
   __shared__ float Ds[TILE][4 * (DPT + 1)];
   __shared__ float lse_s[TILE], delta_s[TILE];
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(ATHREADS) attn_bwd_dkv_kernel(const T* __restr
 template <typename T, int DPT>
 int launch_fwd(const T* qkv, T* o, float* lse, int B, int Tn, int H, int dh, cudaStream_t s) {
   dim3 grid((unsigned)ceil_div(Tn, ROWS), (unsigned)(B * H));
-  attn_fwd_kernel<T, DPT><<<grid, ATHREADS, 0, s>>>(qkv, o, lse, Tn, H, dh, 1.f / sqrtf((float)dh));
+  V4H_CUDA(launch_pdl(attn_fwd_kernel<T, DPT>, dim3(grid), dim3(ATHREADS), 0, s, qkv, o, lse, Tn, H, dh, 1.f / sqrtf((float)dh)));
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }
@@ -259,9 +262,9 @@ int launch_bwd(const T* qkv, const T* o, const float* lse, const T* d_o, T* dqkv
                cudaStream_t s) {
   dim3 grid((unsigned)ceil_div(Tn, ROWS), (unsigned)(B * H));
   const float scale = 1.f / sqrtf((float)dh);
-  attn_bwd_dq_kernel<T, DPT><<<grid, ATHREADS, 0, s>>>(qkv, o, lse, d_o, dqkv, Tn, H, dh, scale);
+  V4H_CUDA(launch_pdl(attn_bwd_dq_kernel<T, DPT>, dim3(grid), dim3(ATHREADS), 0, s, qkv, o, lse, d_o, dqkv, Tn, H, dh, scale));
   V4H_LAUNCH_CHECK();
-  attn_bwd_dkv_kernel<T, DPT><<<grid, ATHREADS, 0, s>>>(qkv, o, lse, d_o, dqkv, Tn, H, dh, scale);
+  V4H_CUDA(launch_pdl(attn_bwd_dkv_kernel<T, DPT>, dim3(grid), dim3(ATHREADS), 0, s, qkv, o, lse, d_o, dqkv, Tn, H, dh, scale));
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }

@@ -138,6 +138,9 @@ __device__ __forceinline__ uint32_t attn_prologue(AttnSmem* ctl, uint32_t tmem_c
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // only now may dependents start: this CTA already holds its TMEM columns, so a dependent CTA that lands on
+  // the same SM and allocates TMEM in its own prologue can never starve it
+  pdl_wait();
   return ctl->tmem_slot;
 }
 __device__ __forceinline__ void attn_epilogue(uint32_t tmem_base, uint32_t tmem_cols) {
@@ -648,6 +651,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) attn_bwd_fused_umma_kernel(cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem = ctl->tmem_slot;
   const int R = NK > DHP ? NK : DHP;  // S / dP / dQ share the first R columns
   const uint32_t tS = tmem, tdV = tmem + (uint32_t)R, tdK = tdV + (uint32_t)NK;
@@ -965,7 +969,7 @@ int fwd_launch(AttnArgs a, int B, cudaStream_t s) {
     V4H_TRY(make_g8_map(a.qkv, B, a.T, 3 * a.H, a.dh, ld, a.BN, &mkv));
   }
   dim3 grid((unsigned)ceil_div(a.T, MT), (unsigned)(B * a.H));
-  attn_fwd_umma_kernel<DHP><<<grid, ATT_THREADS, smem, s>>>(mq, mkv, a);
+  V4H_CUDA(launch_pdl(attn_fwd_umma_kernel<DHP>, dim3(grid), dim3(ATT_THREADS), smem, s, mq, mkv, a));
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }
@@ -998,7 +1002,7 @@ int bwd_launch(AttnArgs a, int B, cudaStream_t s) {
       V4H_TRY(make_g8_map(a.qkv, B, a.T, 3 * a.H, a.dh, ldq, f.BN, &mkv));
       V4H_TRY(make_g8_map(a.d_o, B, a.T, a.H, a.dh, (size_t)a.H * a.dh, MT, &mdo));
     }
-    attn_bwd_fused_umma_kernel<DHP><<<(unsigned)(B * a.H), FUSED_THREADS, smem, s>>>(mq, mkv, mdo, f);
+    V4H_CUDA(launch_pdl(attn_bwd_fused_umma_kernel<DHP>, dim3((unsigned)(B * a.H)), dim3(FUSED_THREADS), smem, s, mq, mkv, mdo, f));
     V4H_LAUNCH_CHECK();
     return V4H_OK;
   }
@@ -1011,7 +1015,7 @@ int bwd_launch(AttnArgs a, int B, cudaStream_t s) {
     const size_t smem = 256 + 2 * g8_bytes(MT, DHP) + 2 * g8_bytes(q.BN, DHP) + g8_bytes(MT, q.BN);
     static size_t configured = 0;
     if (smem > configured) { V4H_TRY(set_smem(attn_bwd_dq_umma_kernel<DHP>, smem)); configured = smem; }
-    attn_bwd_dq_umma_kernel<DHP><<<grid, ATT_THREADS, smem, s>>>(q);
+    V4H_CUDA(launch_pdl(attn_bwd_dq_umma_kernel<DHP>, dim3(grid), dim3(ATT_THREADS), smem, s, q));
     V4H_LAUNCH_CHECK();
   }
   {  // dK, dV
@@ -1022,7 +1026,7 @@ int bwd_launch(AttnArgs a, int B, cudaStream_t s) {
     const size_t smem = 256 + 2048 + 2 * g8_bytes(MT, DHP) + 2 * g8_bytes(k.BN, DHP) + 2 * g8_bytes(MT, k.BN);
     static size_t configured = 0;
     if (smem > configured) { V4H_TRY(set_smem(attn_bwd_dkv_umma_kernel<DHP>, smem)); configured = smem; }
-    attn_bwd_dkv_umma_kernel<DHP><<<grid, ATT_THREADS, smem, s>>>(k);
+    V4H_CUDA(launch_pdl(attn_bwd_dkv_umma_kernel<DHP>, dim3(grid), dim3(ATT_THREADS), smem, s, k));
     V4H_LAUNCH_CHECK();
   }
   return V4H_OK;

@@ -18,6 +18,7 @@ inline unsigned ew_grid(int64_t n, int per_thread = 4) {
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ x, int ld, float* __restrict__ out, int M, int N,
                               int rows_per_cta) {
+  pdl_wait();
   // blockDim = (32, 8): 32 consecutive columns x 8 row lanes
   __shared__ float red[8][33];
   const int col = blockIdx.x * 32 + threadIdx.x;
@@ -55,6 +56,7 @@ __device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x, int ld, float* __restrict__ out,
                                                          int M, int N, int rows_per_cta) {
+  pdl_wait();
   __shared__ float red[8][32][9];
   const int col = (blockIdx.x * 32 + threadIdx.x) * 8;
   const int r0 = blockIdx.y * rows_per_cta;
@@ -94,6 +96,7 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x
 // reference nn/vit.py:368-389: cat(cos(t f), sin(t f)), f_i = exp(-ln(1e4) i / half)
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, int shared_t, float* __restrict__ out,
                                           bf16* __restrict__ out_bf, int B, int dim) {
+  pdl_wait();
   const int half = dim / 2;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * half) return;
@@ -118,6 +121,7 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, int share
 __global__ void pos_embed_fwd_kernel(const float* __restrict__ freqs, const float* __restrict__ pz,
                                      const float* __restrict__ py, const float* __restrict__ px,
                                      float* __restrict__ pe, int Tn, int F) {
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Tn * F) return;
   const int t = idx / F, f = idx % F;
@@ -135,6 +139,7 @@ __global__ void pos_embed_bwd_kernel(const float* __restrict__ dh, const float* 
                                      const float* __restrict__ pz, const float* __restrict__ py,
                                      const float* __restrict__ px, float* __restrict__ dfreqs, int B,
                                      int Tn, int F) {
+  pdl_wait();
   const int t = blockIdx.x;
   const int D = 6 * F;
   const float two_pi = 2.f * 3.14159265358979323846f;
@@ -152,6 +157,7 @@ __global__ void pos_embed_bwd_kernel(const float* __restrict__ dh, const float* 
 
 // ---------------------------------------------------------------- casts
 __global__ void silu_to_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ out, int64_t n) {
+  pdl_wait();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = __float2bfloat16_rn(silu_f(x[i]));
 }
@@ -178,11 +184,13 @@ __device__ __forceinline__ void cast_span(const float* __restrict__ src, bf16* _
 }
 
 __global__ void cast_kernel(const float* __restrict__ x, bf16* __restrict__ out, int64_t n) {
+  pdl_wait();
   cast_span(x, out, n, blockIdx.x * (int64_t)blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
 }
 
 // one launch for every weight tensor: blockIdx.y = job
 __global__ void cast_many_kernel(const CastJob* __restrict__ jobs) {
+  pdl_wait();
   const CastJob j = jobs[blockIdx.y];
   cast_span(j.src, j.dst, j.n, blockIdx.x * (int64_t)blockDim.x + threadIdx.x,
             (int64_t)gridDim.x * blockDim.x);
@@ -191,6 +199,7 @@ __global__ void cast_many_kernel(const CastJob* __restrict__ jobs) {
 // out = x * silu'(pre)   (backward through the SiLU in front of the adaLN Linears)
 __global__ void dsilu_mul_kernel(const float* __restrict__ x, const float* __restrict__ pre,
                                  float* __restrict__ out, bf16* __restrict__ out_bf, int64_t n) {
+  pdl_wait();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float v = x[i] * dsilu_f(pre[i]);
     out[i] = v;
@@ -204,6 +213,7 @@ __global__ void dsilu_mul_kernel(const float* __restrict__ x, const float* __res
 __global__ void cfm_prepare_kernel(const float* __restrict__ x1, const float* __restrict__ x0,
                                    const float* __restrict__ t, const int32_t* __restrict__ table,
                                    float* __restrict__ xt, float* __restrict__ target, int per_sample) {
+  pdl_wait();
   const int b = blockIdx.y;
   const float tv = t[b];
   const size_t base = (size_t)b * per_sample;
@@ -219,6 +229,7 @@ __global__ void cfm_prepare_kernel(const float* __restrict__ x1, const float* __
 __global__ void cfm_loss_kernel(const float* __restrict__ v, const float* __restrict__ target, int64_t n,
                                 float inv_n, float grad_scale, float* __restrict__ loss_out,
                                 float* __restrict__ dv) {
+  pdl_wait();
   __shared__ float red[EW_THREADS / 32];
   float acc = 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -240,6 +251,7 @@ __global__ void cfm_loss_kernel(const float* __restrict__ v, const float* __rest
 __global__ void axpy4_kernel(float* __restrict__ out, const float* __restrict__ y, const float* __restrict__ k0,
                              float a0, const float* __restrict__ k1, float a1, const float* __restrict__ k2,
                              float a2, const float* __restrict__ k3, float a3, int64_t n) {
+  pdl_wait();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float r = y[i];
     if (k0) r = fmaf(a0, k0[i], r);
@@ -257,13 +269,13 @@ int colsum_add(const T* x, int ld, float* out, int M, int N, cudaStream_t s) {
   if (N % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
     const int rows = M >= 4096 ? 128 : 64;
     dim3 vgrid((unsigned)ceil_div(N, 256), (unsigned)ceil_div(M, rows));
-    colsum_vec_kernel<T><<<vgrid, dim3(32, 8), 0, s>>>(x, ld, out, M, N, rows);
+    V4H_CUDA(launch_pdl(colsum_vec_kernel<T>, dim3(vgrid), dim3(dim3(32, 8)), 0, s, x, ld, out, M, N, rows));
     V4H_LAUNCH_CHECK();
     return V4H_OK;
   }
   const int rows_per_cta = 256;
   dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(M, rows_per_cta));
-  colsum_kernel<T><<<grid, dim3(32, 8), 0, s>>>(x, ld, out, M, N, rows_per_cta);
+  V4H_CUDA(launch_pdl(colsum_kernel<T>, dim3(grid), dim3(dim3(32, 8)), 0, s, x, ld, out, M, N, rows_per_cta));
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }
@@ -272,39 +284,39 @@ template int colsum_add<bf16>(const bf16*, int, float*, int, int, cudaStream_t);
 
 int timestep_embedding(const float* t, int shared_t, float* out, bf16* out_bf, int B, int dim, cudaStream_t s) {
   const int n = B * (dim / 2);
-  timestep_embedding_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, s>>>(t, shared_t, out, out_bf, B, dim);
+  V4H_CUDA(launch_pdl(timestep_embedding_kernel, dim3((unsigned)ceil_div(n, 128)), dim3(128), 0, s, t, shared_t, out, out_bf, B, dim));
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }
 
 int pos_embedding_fwd(const float* freqs, const float* pz, const float* py, const float* px, float* pe,
                       int Tn, int F, cudaStream_t s) {
-  pos_embed_fwd_kernel<<<(unsigned)ceil_div((int64_t)Tn * F, 128), 128, 0, s>>>(freqs, pz, py, px, pe, Tn, F);
+  V4H_CUDA(launch_pdl(pos_embed_fwd_kernel, dim3((unsigned)ceil_div((int64_t)Tn * F, 128)), dim3(128), 0, s, freqs, pz, py, px, pe, Tn, F));
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }
 
 int pos_embedding_bwd(const float* dh, const float* freqs, const float* pz, const float* py, const float* px,
                       float* dfreqs, int B, int Tn, int F, cudaStream_t s) {
-  pos_embed_bwd_kernel<<<(unsigned)Tn, 128, 0, s>>>(dh, freqs, pz, py, px, dfreqs, B, Tn, F);
+  V4H_CUDA(launch_pdl(pos_embed_bwd_kernel, dim3((unsigned)Tn), dim3(128), 0, s, dh, freqs, pz, py, px, dfreqs, B, Tn, F));
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }
 
 int silu_to_bf16(const float* x, bf16* out, int64_t n, cudaStream_t s) {
-  silu_to_bf16_kernel<<<ew_grid(n, 1), EW_THREADS, 0, s>>>(x, out, n);
+  V4H_CUDA(launch_pdl(silu_to_bf16_kernel, dim3(ew_grid(n, 1)), dim3(EW_THREADS), 0, s, x, out, n));
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }
 
 int dsilu_mul(const float* x, const float* pre, float* out, bf16* out_bf, int64_t n, cudaStream_t s) {
-  dsilu_mul_kernel<<<ew_grid(n, 1), EW_THREADS, 0, s>>>(x, pre, out, out_bf, n);
+  V4H_CUDA(launch_pdl(dsilu_mul_kernel, dim3(ew_grid(n, 1)), dim3(EW_THREADS), 0, s, x, pre, out, out_bf, n));
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }
 
 int cast_f32_to_bf16(const float* x, bf16* out, int64_t n, cudaStream_t s) {
-  cast_kernel<<<ew_grid(n, 8), EW_THREADS, 0, s>>>(x, out, n);
+  V4H_CUDA(launch_pdl(cast_kernel, dim3(ew_grid(n, 8)), dim3(EW_THREADS), 0, s, x, out, n));
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }
@@ -313,7 +325,7 @@ int cast_many_f32_to_bf16(const CastJob* jobs_dev, int njobs, int64_t max_n, cud
   unsigned gx = (unsigned)ceil_div(max_n, (int64_t)EW_THREADS * 8 * 4);
   if (gx < 1) gx = 1;
   if (gx > 64) gx = 64;
-  cast_many_kernel<<<dim3(gx, (unsigned)njobs), EW_THREADS, 0, s>>>(jobs_dev);
+  V4H_CUDA(launch_pdl(cast_many_kernel, dim3(dim3(gx, (unsigned)njobs)), dim3(EW_THREADS), 0, s, jobs_dev));
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }
@@ -321,7 +333,7 @@ int cast_many_f32_to_bf16(const CastJob* jobs_dev, int njobs, int64_t max_n, cud
 int cfm_prepare(const float* x1, const float* x0, const float* t, const int32_t* table, float* xt_tok,
                 float* target_tok, int64_t B, int per_sample, cudaStream_t s) {
   unsigned gx = (unsigned)ceil_div(per_sample, EW_THREADS * 4);
-  cfm_prepare_kernel<<<dim3(gx, (unsigned)B), EW_THREADS, 0, s>>>(x1, x0, t, table, xt_tok, target_tok, per_sample);
+  V4H_CUDA(launch_pdl(cfm_prepare_kernel, dim3(dim3(gx, (unsigned)B)), dim3(EW_THREADS), 0, s, x1, x0, t, table, xt_tok, target_tok, per_sample));
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }
@@ -329,14 +341,14 @@ int cfm_prepare(const float* x1, const float* x0, const float* t, const int32_t*
 int cfm_loss(const float* v, const float* target, int64_t n, float grad_scale, float* loss_out, float* dv,
              cudaStream_t s) {
   V4H_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), s));
-  cfm_loss_kernel<<<ew_grid(n, 4), EW_THREADS, 0, s>>>(v, target, n, 1.f / (float)n, grad_scale, loss_out, dv);
+  V4H_CUDA(launch_pdl(cfm_loss_kernel, dim3(ew_grid(n, 4)), dim3(EW_THREADS), 0, s, v, target, n, 1.f / (float)n, grad_scale, loss_out, dv));
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }
 
 int axpy4(float* out, const float* y, const float* k0, float a0, const float* k1, float a1, const float* k2,
           float a2, const float* k3, float a3, int64_t n, cudaStream_t s) {
-  axpy4_kernel<<<ew_grid(n, 4), EW_THREADS, 0, s>>>(out, y, k0, a0, k1, a1, k2, a2, k3, a3, n);
+  V4H_CUDA(launch_pdl(axpy4_kernel, dim3(ew_grid(n, 4)), dim3(EW_THREADS), 0, s, out, y, k0, a0, k1, a1, k2, a2, k3, a3, n));
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }

@@ -20,6 +20,7 @@ struct SimtArgs {
 
 template <typename TA, typename TB, int EPI, int ACT, typename TOut>
 __global__ void __launch_bounds__(NT) gemm_simt_kernel(SimtArgs g, EpiParams p) {
+  pdl_wait();
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
   const TA* __restrict__ A = reinterpret_cast<const TA*>(g.A);
@@ -110,7 +111,7 @@ int launch(const GemmDesc& d, cudaStream_t s) {
   dim3 grid((unsigned)ceil_div(d.N, BN), (unsigned)ceil_div(d.M, BM), (unsigned)splits);
   EpiParams ep = d.ep;
   ep.vec_ok = epilogue_vec_ok(ep, EPI, sizeof(TOut) == 2);
-  gemm_simt_kernel<TA, TB, EPI, ACT, TOut><<<grid, NT, 0, s>>>(g, ep);
+  V4H_CUDA(launch_pdl(gemm_simt_kernel<TA, TB, EPI, ACT, TOut>, dim3(grid), dim3(NT), 0, s, g, ep));
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }

@@ -288,6 +288,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (CTAS == 2) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // barriers, TMEM and tensor-map prefetch above overlap the previous kernel's tail
 
   const int total_work = g.tiles_m * g.tiles_n * g.splits;
   // tile (tm, tn): rows [tm * BM * CTAS, ..), columns [tn * bn, tn * bn + width); the last column tile is
@@ -630,7 +631,7 @@ int launch_k(const Maps& m, const UmmaArgs& g, const EpiParams& ep, int grid, cu
     configured = true;
   }
   if (CTAS == 1) {
-    kernel<<<grid, THREADS, SMEM_LIMIT, s>>>(m.a, m.b, m.in, m.out, m.out2, g, ep);
+    V4H_CUDA(launch_pdl(kernel, dim3(grid), dim3(THREADS), SMEM_LIMIT, s, m.a, m.b, m.in, m.out, m.out2, g, ep));
   } else {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -638,11 +639,13 @@ int launch_k(const Maps& m, const UmmaArgs& g, const EpiParams& ep, int grid, cu
     cfg.blockDim = dim3(THREADS);
     cfg.dynamicSmemBytes = SMEM_LIMIT;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     V4H_CUDA(cudaLaunchKernelEx(&cfg, kernel, m.a, m.b, m.in, m.out, m.out2, g, ep));
   }
   V4H_LAUNCH_CHECK();

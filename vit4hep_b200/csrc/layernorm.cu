@@ -20,6 +20,7 @@ template <typename T>
 __global__ void __launch_bounds__(WARPS * 32) ln_mod_fwd_kernel(
     const float* __restrict__ h, const float* __restrict__ shift, const float* __restrict__ scale,
     int mod_stride, T* __restrict__ a, int ld_a, float2* __restrict__ stats, int M, int D, int rows_per_sample) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -62,6 +63,7 @@ __global__ void __launch_bounds__(WARPS * 32) ln_mod_bwd_kernel(
     float* __restrict__ dshift, float* __restrict__ dscale, int dmod_stride, const T* __restrict__ y,
     const float* __restrict__ gate, T* __restrict__ dy, float* __restrict__ dgate,
     float* __restrict__ dbias, int D, int rows_per_sample, int rows_per_cta) {
+  pdl_wait();
   __shared__ float red[WARPS][MAXV * 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
@@ -180,6 +182,7 @@ __global__ void __launch_bounds__(128, 6) ln_mod_bwd_vec_kernel(
     float* __restrict__ dshift, float* __restrict__ dscale, int dmod_stride, const T* __restrict__ y,
     const float* __restrict__ gate, T* __restrict__ dy, float* __restrict__ dgate,
     float* __restrict__ dbias, int D, int rows_per_sample, int rows_per_cta, int DBG_SKIP) {
+  pdl_wait();
   __shared__ float2 part[2][RB][4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int b = blockIdx.y;
@@ -284,6 +287,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) ln_mod_fwd_vec_kernel(
     const float* __restrict__ h, const float* __restrict__ shift, const float* __restrict__ scale,
     int mod_stride, T* __restrict__ a, int ld_a, float2* __restrict__ stats, int M, int D, int rows_per_sample) {
+  pdl_wait();
   constexpr int RW = 4;  // rows per warp, all loads issued before the first reduction
   const int lane = threadIdx.x & 31;
   const int warp = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -357,13 +361,11 @@ int ln_modulate_fwd(const float* h, const float* shift, const float* scale, int 
   if (D > MAXV * 32) return fail(V4H_ERR_UNSUPPORTED, "ln_modulate: hidden_dim %d > %d", D, MAXV * 32);
   if (ld_a < D || ld_a - D > 32) return fail(V4H_ERR_INVALID, "ln_modulate: bad output pitch %d for %d columns", ld_a, D);
   if (ld_a % 4 == 0 && ln_vec_ok(D, mod_stride, 0, {h, shift, scale, a})) {
-    ln_mod_fwd_vec_kernel<T><<<(unsigned)ceil_div(M, 32), 256, 0, s>>>(h, shift, scale, mod_stride, a, ld_a, stats, M, D,
-                                                                      rows_per_sample);
+    V4H_CUDA(launch_pdl(ln_mod_fwd_vec_kernel<T>, dim3((unsigned)ceil_div(M, 32)), dim3(256), 0, s, h, shift, scale, mod_stride, a, ld_a, stats, M, D, rows_per_sample));
     V4H_LAUNCH_CHECK();
     return V4H_OK;
   }
-  ln_mod_fwd_kernel<T><<<(unsigned)ceil_div(M, WARPS), WARPS * 32, 0, s>>>(h, shift, scale, mod_stride, a, ld_a,
-                                                                          stats, M, D, rows_per_sample);
+  V4H_CUDA(launch_pdl(ln_mod_fwd_kernel<T>, dim3((unsigned)ceil_div(M, WARPS)), dim3(WARPS * 32), 0, s, h, shift, scale, mod_stride, a, ld_a, stats, M, D, rows_per_sample));
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }
@@ -380,26 +382,18 @@ int ln_modulate_bwd(const T* da, const float* h, const float2* stats, const floa
     dim3 vgrid((unsigned)ceil_div(rows_per_sample, rows_per_cta), (unsigned)B);
     static const int dbg_skip = [] { const char* e = getenv("V4H_LN_DBG_SKIP"); return e ? atoi(e) : 0; }();
     if (gate != nullptr)
-      ln_mod_bwd_vec_kernel<T, true, true><<<vgrid, threads, 0, s>>>(
-          da, h, stats, scale, mod_stride, dh, dh_accumulate, dshift, dscale, dmod_stride, y, gate, dy, dgate,
-          dbias, D, rows_per_sample, rows_per_cta, dbg_skip);
+      V4H_CUDA(launch_pdl(ln_mod_bwd_vec_kernel<T, true, true>, dim3(vgrid), dim3(threads), 0, s,  da, h, stats, scale, mod_stride, dh, dh_accumulate, dshift, dscale, dmod_stride, y, gate, dy, dgate, dbias, D, rows_per_sample, rows_per_cta, dbg_skip));
     else
-      ln_mod_bwd_vec_kernel<T, true, false><<<vgrid, threads, 0, s>>>(
-          da, h, stats, scale, mod_stride, dh, dh_accumulate, dshift, dscale, dmod_stride, nullptr, nullptr,
-          nullptr, nullptr, nullptr, D, rows_per_sample, rows_per_cta, dbg_skip);
+      V4H_CUDA(launch_pdl(ln_mod_bwd_vec_kernel<T, true, false>, dim3(vgrid), dim3(threads), 0, s,  da, h, stats, scale, mod_stride, dh, dh_accumulate, dshift, dscale, dmod_stride, nullptr, nullptr, nullptr, nullptr, nullptr, D, rows_per_sample, rows_per_cta, dbg_skip));
     V4H_LAUNCH_CHECK();
     return V4H_OK;
   }
   const int rows_per_cta = 32;
   dim3 grid((unsigned)ceil_div(rows_per_sample, rows_per_cta), (unsigned)B);
   if (gate != nullptr) {
-    ln_mod_bwd_kernel<T, true, true><<<grid, WARPS * 32, 0, s>>>(
-        da, h, stats, scale, mod_stride, dh, dh_accumulate, dshift, dscale, dmod_stride, y, gate, dy, dgate,
-        dbias, D, rows_per_sample, rows_per_cta);
+    V4H_CUDA(launch_pdl(ln_mod_bwd_kernel<T, true, true>, dim3(grid), dim3(WARPS * 32), 0, s,  da, h, stats, scale, mod_stride, dh, dh_accumulate, dshift, dscale, dmod_stride, y, gate, dy, dgate, dbias, D, rows_per_sample, rows_per_cta));
   } else {
-    ln_mod_bwd_kernel<T, true, false><<<grid, WARPS * 32, 0, s>>>(
-        da, h, stats, scale, mod_stride, dh, dh_accumulate, dshift, dscale, dmod_stride, nullptr, nullptr,
-        nullptr, nullptr, nullptr, D, rows_per_sample, rows_per_cta);
+    V4H_CUDA(launch_pdl(ln_mod_bwd_kernel<T, true, false>, dim3(grid), dim3(WARPS * 32), 0, s,  da, h, stats, scale, mod_stride, dh, dh_accumulate, dshift, dscale, dmod_stride, nullptr, nullptr, nullptr, nullptr, nullptr, D, rows_per_sample, rows_per_cta));
   }
   V4H_LAUNCH_CHECK();
   return V4H_OK;
@@ -413,17 +407,13 @@ int gate_bwd(const float* dh, const T* y, const float* gate, int mod_stride, T* 
   if (ln_vec_ok(D, mod_stride, dmod_stride, {dh, y, gate, dy, dgate, dbias})) {
     const int rows_per_cta = 16, threads = (int)ceil_div(D / 4, 32) * 32;
     dim3 vgrid((unsigned)ceil_div(rows_per_sample, rows_per_cta), (unsigned)B);
-    ln_mod_bwd_vec_kernel<T, false, true><<<vgrid, threads, 0, s>>>(
-        nullptr, nullptr, nullptr, nullptr, mod_stride, const_cast<float*>(dh), false, nullptr, nullptr,
-        dmod_stride, y, gate, dy, dgate, dbias, D, rows_per_sample, rows_per_cta, 0);
+    V4H_CUDA(launch_pdl(ln_mod_bwd_vec_kernel<T, false, true>, dim3(vgrid), dim3(threads), 0, s,  nullptr, nullptr, nullptr, nullptr, mod_stride, const_cast<float*>(dh), false, nullptr, nullptr, dmod_stride, y, gate, dy, dgate, dbias, D, rows_per_sample, rows_per_cta, 0));
     V4H_LAUNCH_CHECK();
     return V4H_OK;
   }
   const int rows_per_cta = 32;
   dim3 grid((unsigned)ceil_div(rows_per_sample, rows_per_cta), (unsigned)B);
-  ln_mod_bwd_kernel<T, false, true><<<grid, WARPS * 32, 0, s>>>(
-      nullptr, nullptr, nullptr, nullptr, mod_stride, const_cast<float*>(dh), false, nullptr, nullptr,
-      dmod_stride, y, gate, dy, dgate, dbias, D, rows_per_sample, rows_per_cta);
+  V4H_CUDA(launch_pdl(ln_mod_bwd_kernel<T, false, true>, dim3(grid), dim3(WARPS * 32), 0, s,  nullptr, nullptr, nullptr, nullptr, mod_stride, const_cast<float*>(dh), false, nullptr, nullptr, dmod_stride, y, gate, dy, dgate, dbias, D, rows_per_sample, rows_per_cta));
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }

@@ -13,6 +13,7 @@ namespace {
 constexpr int OPT_THREADS = 256;
 
 __global__ void __launch_bounds__(OPT_THREADS) sumsq_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+  pdl_wait();
   __shared__ float red[OPT_THREADS / 32];
   float acc = 0.f;
   const int64_t n4 = n / 4;
@@ -47,7 +48,8 @@ struct AdamArgs {
   const float* lr_dev;   // optional device learning rate overriding `lr` (schedulers under graph replay)
 };
 
-__global__ void counter_increment_kernel(int* c) { *c += 1; }
+__global__ void counter_increment_kernel(int* c) {
+  pdl_wait(); *c += 1; }
 
 __device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v, const AdamArgs& a, float coef) {
   g *= coef;
@@ -61,6 +63,7 @@ __device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v,
 
 // grid (chunks, jobs): one parameter tensor per blockIdx.y
 __global__ void __launch_bounds__(OPT_THREADS) adamw_kernel(const v4h_adamw_job* __restrict__ jobs, AdamArgs a) {
+  pdl_wait();
   const v4h_adamw_job j = jobs[blockIdx.y];
   if (a.step_dev) {
     const float t = (float)*a.step_dev;
@@ -115,13 +118,13 @@ int grad_norm_sq(const float* flat, int64_t n, float* out, cudaStream_t s) {
   int64_t blocks = ceil_div(n, (int64_t)OPT_THREADS * 16);
   if (blocks < 1) blocks = 1;
   if (blocks > 1184) blocks = 1184;
-  sumsq_kernel<<<(unsigned)blocks, OPT_THREADS, 0, s>>>(flat, n, out);
+  V4H_CUDA(launch_pdl(sumsq_kernel, dim3((unsigned)blocks), dim3(OPT_THREADS), 0, s, flat, n, out));
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }
 
 int counter_increment(int* counter, cudaStream_t s) {
-  counter_increment_kernel<<<1, 1, 0, s>>>(counter);
+  V4H_CUDA(launch_pdl(counter_increment_kernel, dim3(1), dim3(1), 0, s, counter));
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }
@@ -138,7 +141,7 @@ int adamw_step(const v4h_adamw_job* jobs_dev, int njobs, int64_t max_n, const fl
   int64_t gx = ceil_div(max_n, (int64_t)OPT_THREADS * 4 * 4);
   if (gx < 1) gx = 1;
   if (gx > 128) gx = 128;
-  adamw_kernel<<<dim3((unsigned)gx, (unsigned)njobs), OPT_THREADS, 0, s>>>(jobs_dev, a);
+  V4H_CUDA(launch_pdl(adamw_kernel, dim3(dim3((unsigned)gx, (unsigned)njobs)), dim3(OPT_THREADS), 0, s, jobs_dev, a));
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }

@@ -23,6 +23,7 @@ constexpr int PP_THREADS = 256;
 __global__ void __launch_bounds__(PP_THREADS) patch_permute_smem_kernel(
     const float* __restrict__ src, float* __restrict__ dst, const int32_t* __restrict__ table,
     const int32_t* __restrict__ chunk_bounds, int per_sample) {
+  pdl_wait();
   extern __shared__ float stage[];
   const int c0 = chunk_bounds[blockIdx.x], c1 = chunk_bounds[blockIdx.x + 1];
   const int n = c1 - c0;
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(PP_THREADS) patch_permute_smem_kernel(
 // generic fallback (multi-channel geometries, or a slab larger than shared memory): plain gather
 __global__ void patch_permute_gather_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                             const int32_t* __restrict__ table, int per_sample) {
+  pdl_wait();
   const size_t base = (size_t)blockIdx.y * per_sample;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < per_sample; j += gridDim.x * blockDim.x)
     dst[base + j] = src[base + table[j]];
@@ -68,12 +70,10 @@ int patch_permute(const float* src, float* dst, const int32_t* table, const int3
   if (B == 0) return V4H_OK;
   V4H_REQUIRE(B <= 65535, "patch_permute: batch %lld exceeds 65535 per call", (long long)B);
   if (num_chunks > 0) {
-    patch_permute_smem_kernel<<<dim3((unsigned)num_chunks, (unsigned)B), PP_THREADS,
-                                (size_t)max_chunk * sizeof(float), s>>>(src, dst, table, chunk_bounds,
-                                                                         per_sample);
+    V4H_CUDA(launch_pdl(patch_permute_smem_kernel, dim3(dim3((unsigned)num_chunks, (unsigned)B)), dim3(PP_THREADS), (size_t)max_chunk * sizeof(float), s, src, dst, table, chunk_bounds, per_sample));
   } else {
     unsigned gx = (unsigned)ceil_div(per_sample, 256 * 4);
-    patch_permute_gather_kernel<<<dim3(gx, (unsigned)B), 256, 0, s>>>(src, dst, table, per_sample);
+    V4H_CUDA(launch_pdl(patch_permute_gather_kernel, dim3(dim3(gx, (unsigned)B)), dim3(256), 0, s, src, dst, table, per_sample));
   }
   V4H_LAUNCH_CHECK();
   return V4H_OK;
