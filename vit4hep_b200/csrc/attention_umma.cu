@@ -119,8 +119,101 @@ __device__ __forceinline__ void issue_mma(uint32_t d_tmem, uint32_t a_base, uint
 struct AttnSmem {
   uint64_t bar;      // MMA completion
   uint64_t ld_bar;   // TMA operand loads
+  uint64_t v_bar;    // forward: the V tile (second TMA barrier)
   uint32_t tmem_slot;
 };
+
+// ---- "W" tiles: what TMA writes with the 128-byte swizzle.  A ROWS x DHP bf16 tile is ceil(DHP / 64) boxes
+// of [ROWS][64] (128-byte rows; the 16-byte chunk c of row r sits at chunk (c ^ (r & 7))), ROWS * 128 bytes
+// apart, 1024-byte aligned.  One box row is one TMA "piece", so a tile moves in 2 pieces per row where the
+// G8 view needs dh / 8 -- the 16-byte pieces of the G8 loads ran at 12-14 B/clk/SM and dominated the forward
+// and the fused backward.  The same bytes serve as
+//   - K-major operand  (rows = M/N index, K step ks = columns [16 ks, 16 ks + 16)): box ks / 4, +32 bytes per step
+//   - MN-major operand (rows = K index, 16 per step; columns = M/N index in 64-wide chunks): LBO = box stride
+// The tiles P / dS that threads write stay G8 (row per thread, conflict-free 16-byte stores).
+__host__ __device__ constexpr int w_boxes(int dhp) { return (dhp + 63) / 64; }
+__host__ __device__ constexpr uint32_t w_box(int rows) { return (uint32_t)rows * 128u; }
+__host__ __device__ constexpr uint32_t w_bytes(int rows, int dhp) { return (uint32_t)w_boxes(dhp) * w_box(rows); }
+
+struct Opnd {       // one shared-memory operand tile
+  uint32_t base;    // shared address
+  uint32_t stride;  // W: box stride (rows * 128); G8: group stride
+  bool w;
+};
+__device__ __forceinline__ Opnd opnd_w(uint32_t base, int rows) { return Opnd{base, w_box(rows), true}; }
+__device__ __forceinline__ Opnd opnd_g8(uint32_t base, uint32_t gstride) { return Opnd{base, gstride, false}; }
+// descriptor of K step `ks` when the tile's COLUMNS are the contraction index
+__device__ __forceinline__ uint64_t desc_kmajor(const Opnd& o, int ks) {
+  return o.w ? make_smem_desc(o.base + (uint32_t)(ks >> 2) * o.stride + (uint32_t)(ks & 3) * 32u, 0, 1024)
+             : desc_ns(o.base + 2u * ks * o.stride, o.stride, 128);
+}
+// descriptor of K step `ks` when the tile's ROWS are the contraction index
+__device__ __forceinline__ uint64_t desc_mnmajor(const Opnd& o, int ks) {
+  return o.w ? make_smem_desc(o.base + (uint32_t)ks * 2048u, o.stride, 1024) : desc_ns(o.base + (uint32_t)ks * 256u, 128, o.stride);
+}
+// D[tmem 128 x n] (+)= A B over `ksteps` steps of 16; *_mn: that operand is read MN-major.  One thread.
+__device__ __forceinline__ void issue_mma_x(uint32_t d_tmem, const Opnd& A, bool a_mn, const Opnd& B, bool b_mn, int n,
+                                            int ksteps, bool accumulate_first) {
+  const uint32_t idesc = make_idesc_bf16(MT, n, a_mn, b_mn);
+  for (int ks = 0; ks < ksteps; ++ks)
+    umma_bf16(d_tmem, a_mn ? desc_mnmajor(A, ks) : desc_kmajor(A, ks), b_mn ? desc_mnmajor(B, ks) : desc_kmajor(B, ks),
+              idesc, (accumulate_first || ks > 0) ? 1u : 0u);
+}
+
+// explicit shared-window accesses: the tile pointers come out of an integer round trip (alignment), so plain
+// dereferences compile to generic ST.E / LD.E with 64-bit address arithmetic per access
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts16(uint32_t addr, uint32_t v) {
+  asm volatile("{ .reg .b16 h; cvt.u16.u32 h, %1; st.shared.b16 [%0], h; }" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// cp.async fallback of the TMA load of a W tile (head dims the box cannot cover, TMA switched off): rows >=
+// rows_valid and columns >= dh are zero-filled; only the first `load_rows` rows are touched
+template <int DHP, int NTHREADS>
+__device__ __forceinline__ void stage_tile_w(uint32_t dst, int rows, const bf16* __restrict__ src, size_t ld,
+                                             int rows_valid, int dh, int load_rows) {
+  constexpr int NCG = DHP / 8;
+  constexpr int RPI = NTHREADS / NCG;
+  if ((int)threadIdx.x >= RPI * NCG) return;
+  const int r0 = (int)threadIdx.x / NCG, cg = (int)threadIdx.x - r0 * NCG;
+  const bool col_ok = cg * 8 < dh;
+  const bf16* p = src + (size_t)r0 * ld + cg * 8;
+  const uint32_t d = dst + (uint32_t)(cg >> 3) * w_box(rows);
+  for (int row = r0; row < load_rows; row += RPI, p += (size_t)RPI * ld) {
+    const bool ok = col_ok && row < rows_valid;
+    cp_async16(d + (uint32_t)row * 128u + (uint32_t)(((cg & 7) ^ (row & 7)) << 4), ok ? (const void*)p : (const void*)src, ok);
+  }
+}
+// TMA load of a W tile: box b covers columns [col0 + 64 b, +64) of rows [row0, row0 + rows) of sample `batch`
+template <int DHP>
+__device__ __forceinline__ void tma_load_w(uint8_t* dst, int rows, const CUtensorMap* map, uint64_t* bar, int col0,
+                                           int row0, int batch) {
+#pragma unroll
+  for (int b = 0; b < w_boxes(DHP); ++b) tma_load_3d(dst + b * w_box(rows), map, bar, col0 + 64 * b, row0, batch);
+}
+// the same boxes, only as far as L2
+template <int DHP>
+__device__ __forceinline__ void tma_prefetch_w(const CUtensorMap* map, int col0, int row0, int batch) {
+#pragma unroll
+  for (int b = 0; b < w_boxes(DHP); ++b)
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(col0 + 64 * b), "r"(row0), "r"(batch)
+                 : "memory");
+}
+__device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
+}
+
 
 __device__ __forceinline__ uint8_t* align128(uint8_t* p) {
   return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 127) & ~uintptr_t(127));
@@ -132,6 +225,7 @@ __device__ __forceinline__ uint32_t attn_prologue(AttnSmem* ctl, uint32_t tmem_c
   if (threadIdx.x == 0) {
     mbar_init(&ctl->bar, 1);
     mbar_init(&ctl->ld_bar, 1);
+    mbar_init(&ctl->v_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_dyn(&ctl->tmem_slot, tmem_cols);
@@ -173,7 +267,13 @@ struct AttnArgs {
   float scale;       // dh^-0.5
   float scale_log2;  // scale * log2(e)
   long long* dbg;    // optional cycle counters per phase (v4h_debug_attention_counters)
-  int use_tma;       // operand tiles staged by TMA (5-d tensor maps writing the G8 layout) instead of cp.async
+  int use_tma;       // operand tiles staged by TMA instead of cp.async
+  int p_off;         // forward: byte offset of the P tile from the first operand tile
+  // fused backward: byte offsets of the tiles (Q, dO, K, V, P, tail Q, tail dO, tail P) and the TMEM column of
+  // the tail tile's dQ accumulator
+  int off[8];
+  uint32_t dq2_col;
+  int pf_stride;     // CTAs resident at a time (L2 prefetch distance); 0 = no prefetch
 };
 
 struct ALap {  // cycle accounting of thread 0 of each CTA
@@ -188,23 +288,26 @@ struct ALap {  // cycle accounting of thread 0 of each CTA
 };
 
 // ------------------------------------------------------------------------------------------ forward
-// tmQ / tmKV: 5-d views (8 elements, T rows, dh/8 column groups, 3H, B) of qkv with boxes of 128 / BN rows: one
-// TMA load writes a whole operand tile in the G8 layout (group stride rows * 16, no pad)
-template <int DHP>
+// tmQ / tmKV: 3-d views (3 H dh columns, T rows, B) of qkv with 128-byte-swizzled boxes of [128 | BN rows][64
+// columns].  ONE = every key fits one block (T <= 160): the score row stays in registers between the
+// maximum and the exponentials (one TMEM read), O is read once at the end and P may overlay Q / K.
+template <int DHP, bool ONE>
 __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                     const __grid_constant__ CUtensorMap tmKV,
                                                                     const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = align128(smem_raw);
+  uint8_t* smem = align1024(smem_raw);
   AttnSmem* ctl = reinterpret_cast<AttnSmem*>(smem);
+  uint8_t* tiles = smem + 1024;
   const int BN = a.BN, T = a.T, H = a.H, dh = a.dh;
-  const uint32_t sQ = smem_u32(smem + 128);
-  const uint32_t sK = sQ + g8_alloc(MT, DHP);
-  const uint32_t sV = sK + g8_alloc(BN, DHP);
-  const uint32_t sP = sV + g8_alloc(BN, DHP);
-  uint8_t* sP_ptr = smem + 128 + g8_alloc(MT, DHP) + 2 * g8_alloc(BN, DHP);
+  uint8_t* pQ = tiles;
+  uint8_t* pK = pQ + w_bytes(MT, DHP);
+  uint8_t* pV = pK + w_bytes(BN, DHP);
+  uint8_t* sP_ptr = tiles + a.p_off;
+  const uint32_t gsP = g8_stride(MT);
+  const Opnd oQ = opnd_w(smem_u32(pQ), MT), oK = opnd_w(smem_u32(pK), BN), oV = opnd_w(smem_u32(pV), BN);
+  const Opnd oP = opnd_g8(smem_u32(sP_ptr), gsP);
   const bool tma = a.use_tma != 0;
-  const uint32_t gsQ = tma ? MT * 16u : g8_stride(MT), gsKV = tma ? (uint32_t)BN * 16u : g8_stride(BN), gsP = g8_stride(MT);
   uint32_t ld_phase = 0;
 
   const int bh = blockIdx.y, b = bh / H, hd = bh % H;
@@ -221,122 +324,199 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_umma_kernel(const __grid
   const uint32_t tS = tmem, tO = tmem + (uint32_t)BN;
   const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
   uint32_t phase = 0;
+  const int q_rows = min(MT, (T - q0 + 15) / 16 * 16);  // rows of the Q tile any stored result depends on
 
-  if (!tma) stage_tile<DHP>(sQ, MT, qbase + (size_t)q0 * ld, ld, T - q0, dh, min(MT, (T - q0 + 15) / 16 * 16));
-
-  float o_acc[DHP];
+  float o_acc[ONE ? 1 : DHP];
 #pragma unroll
-  for (int i = 0; i < DHP; ++i) o_acc[i] = 0.f;
+  for (int i = 0; i < (ONE ? 1 : DHP); ++i) o_acc[i] = 0.f;
   float m_run = -INFINITY, l_run = 0.f;
   const bool warp_active = q0 + warp * 32 < T;  // any valid query row in this warp
 
   for (int blk = 0; blk < a.nblocks; ++blk) {
     const int n0 = blk * BN;
     const int nvalid = min(BN, T - n0);
+    // Q and K arrive on one barrier, V on a second one: S = Q K^T and the softmax run under the V load
     if (tma) {
       if (tid == 0) {
-        const uint32_t kv_bytes = (uint32_t)BN * DHP * 2;
-        mbar_expect_tx(&ctl->ld_bar, 2 * kv_bytes + (blk == 0 ? (uint32_t)MT * DHP * 2 : 0u));
-        if (blk == 0) tma_load_5d(smem + 128, &tmQ, &ctl->ld_bar, 0, q0, 0, hd, b);
-        tma_load_5d(smem + 128 + g8_alloc(MT, DHP), &tmKV, &ctl->ld_bar, 0, n0, 0, H + hd, b);
-        tma_load_5d(smem + 128 + g8_alloc(MT, DHP) + g8_alloc(BN, DHP), &tmKV, &ctl->ld_bar, 0, n0, 0, 2 * H + hd, b);
+        mbar_expect_tx(&ctl->ld_bar, w_bytes(BN, DHP) + (blk == 0 ? w_bytes(MT, DHP) : 0u));
+        if (blk == 0) tma_load_w<DHP>(pQ, MT, &tmQ, &ctl->ld_bar, hd * dh, q0, b);
+        tma_load_w<DHP>(pK, BN, &tmKV, &ctl->ld_bar, (H + hd) * dh, n0, b);
+        mbar_expect_tx(&ctl->v_bar, w_bytes(BN, DHP));
+        tma_load_w<DHP>(pV, BN, &tmKV, &ctl->v_bar, (2 * H + hd) * dh, n0, b);
       }
       L.lap(1);
-      mbar_wait(&ctl->ld_bar, ld_phase); ld_phase ^= 1;
+      mbar_wait(&ctl->ld_bar, ld_phase);
     } else {
-      stage_tile<DHP>(sK, BN, kbase + (size_t)n0 * ld, ld, nvalid, dh);
-      stage_tile<DHP>(sV, BN, vbase + (size_t)n0 * ld, ld, nvalid, dh);
+      if (blk == 0) stage_tile_w<DHP, ATT_THREADS>(oQ.base, MT, qbase + (size_t)q0 * ld, ld, T - q0, dh, q_rows);
+      stage_tile_w<DHP, ATT_THREADS>(oK.base, BN, kbase + (size_t)n0 * ld, ld, nvalid, dh, BN);
+      cp_async_commit();
+      stage_tile_w<DHP, ATT_THREADS>(oV.base, BN, vbase + (size_t)n0 * ld, ld, nvalid, dh, BN);
+      cp_async_commit();
       L.lap(1);
-      cp_async_wait_all();
+      cp_async_wait_group<1>();
     }
     L.lap(2);
     publish_smem_and_sync();
     L.lap(3);
     if (tid == 0) {
-      issue_mma(tS, sQ, gsQ, sK, gsKV, false, BN, DHP / 16, false);
+      issue_mma_x(tS, oQ, false, oK, false, BN, DHP / 16, false);
       umma_commit(&ctl->bar);
     }
     mbar_wait(&ctl->bar, phase); phase ^= 1;
     tc_fence_after();
     L.lap(4);
 
-    // ---- online softmax on this thread's row (warps whose 32 rows are all beyond T skip the work; their
-    // P rows stay garbage, which only reaches their own, never stored, O rows): pass 1 = row maximum
-    float mx = -INFINITY, corr = 0.f, lsum = 0.f;
+    // ---- softmax on this thread's row (warps whose 32 rows are all beyond T skip the work; their P rows
+    // stay garbage, which only reaches their own, never stored, O rows)
+    float corr = 0.f, lsum = 0.f;
     if (warp_active) {
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        float v[16];
-        tmem_ld16(tS + lane_off + c0, v);
+      if (ONE) {
+        constexpr int MAXCH = 10;  // BN <= 160
+        float sv[MAXCH][16];
+        const int nch = BN / 16;
+#pragma unroll
+        for (int c = 0; c < MAXCH; ++c)
+          if (c < nch) tmem_ld16(tS + lane_off + c * 16, sv[c]);
         tmem_ld_wait();
-        if (c0 + 16 <= nvalid) {
+        // padded keys (only in the last chunk) are pushed to -inf once: exp2 then gives their p = 0
+        const int lastc = nch - 1;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, v[i]);
-        } else {
+        for (int c = 0; c < MAXCH; ++c) {
+          if (c == lastc) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, c0 + i < nvalid ? v[i] : -INFINITY);
-        }
-      }
-      const float m_new = fmaxf(m_run, mx * a.scale_log2);
-      corr = exp2_fast(m_run - m_new);  // first block: exp2(-inf) = 0
-      m_run = m_new;
-      // pass 2: p = exp2(s * scale_log2 - m), written as the bf16 A operand of P V
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        float v[16];
-        tmem_ld16(tS + lane_off + c0, v);
-        tmem_ld_wait();
-        uint32_t w[8];
-        if (c0 + 16 <= nvalid) {
-#pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            const float p0 = exp2_fast(fmaf(v[i], a.scale_log2, -m_new));
-            const float p1 = exp2_fast(fmaf(v[i + 1], a.scale_log2, -m_new));
-            lsum += p0 + p1;
-            w[i / 2] = pack_bf16(p0, p1);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            const float p0 = c0 + i < nvalid ? exp2_fast(fmaf(v[i], a.scale_log2, -m_new)) : 0.f;
-            const float p1 = c0 + i + 1 < nvalid ? exp2_fast(fmaf(v[i + 1], a.scale_log2, -m_new)) : 0.f;
-            lsum += p0 + p1;
-            w[i / 2] = pack_bf16(p0, p1);
+            for (int i = 0; i < 16; ++i) sv[c][i] = c * 16 + i < nvalid ? sv[c][i] : -INFINITY;
           }
         }
-        uint8_t* dst = sP_ptr + (size_t)(c0 / 8) * gsP + tid * 16;
-        *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-        *reinterpret_cast<uint4*>(dst + gsP) = make_uint4(w[4], w[5], w[6], w[7]);
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < MAXCH; ++c) {
+          if (c < nch) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], sv[c][i]);
+          }
+        }
+        const float m_new = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * a.scale_log2;
+        m_run = m_new;
+        float ls4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < MAXCH; ++c) {
+          if (c < nch) {
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              const float p0 = exp2_fast(fmaf(sv[c][i], a.scale_log2, -m_new));
+              const float p1 = exp2_fast(fmaf(sv[c][i + 1], a.scale_log2, -m_new));
+              ls4[(i >> 1) & 3] += p0 + p1;
+              w[i / 2] = pack_bf16(p0, p1);
+            }
+            const uint32_t dst = oP.base + (uint32_t)(2 * c) * gsP + (uint32_t)tid * 16u;
+            sts128(dst, w[0], w[1], w[2], w[3]);
+            sts128(dst + gsP, w[4], w[5], w[6], w[7]);
+          }
+        }
+        lsum = (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
+      } else {
+        // online softmax, pass 1 = row maximum
+        float mx = -INFINITY;
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          float v[16];
+          tmem_ld16(tS + lane_off + c0, v);
+          tmem_ld_wait();
+          if (c0 + 16 <= nvalid) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) mx = fmaxf(mx, v[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) mx = fmaxf(mx, c0 + i < nvalid ? v[i] : -INFINITY);
+          }
+        }
+        const float m_new = fmaxf(m_run, mx * a.scale_log2);
+        corr = exp2_fast(m_run - m_new);  // first block: exp2(-inf) = 0
+        m_run = m_new;
+        // pass 2: p = exp2(s * scale_log2 - m), written as the bf16 A operand of P V
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          float v[16];
+          tmem_ld16(tS + lane_off + c0, v);
+          tmem_ld_wait();
+          uint32_t w[8];
+          if (c0 + 16 <= nvalid) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              const float p0 = exp2_fast(fmaf(v[i], a.scale_log2, -m_new));
+              const float p1 = exp2_fast(fmaf(v[i + 1], a.scale_log2, -m_new));
+              lsum += p0 + p1;
+              w[i / 2] = pack_bf16(p0, p1);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              const float p0 = c0 + i < nvalid ? exp2_fast(fmaf(v[i], a.scale_log2, -m_new)) : 0.f;
+              const float p1 = c0 + i + 1 < nvalid ? exp2_fast(fmaf(v[i + 1], a.scale_log2, -m_new)) : 0.f;
+              lsum += p0 + p1;
+              w[i / 2] = pack_bf16(p0, p1);
+            }
+          }
+          const uint32_t dst = oP.base + (uint32_t)(c0 / 8) * gsP + (uint32_t)tid * 16u;
+          sts128(dst, w[0], w[1], w[2], w[3]);
+          sts128(dst + gsP, w[4], w[5], w[6], w[7]);
+        }
       }
     }
     l_run = l_run * corr + lsum;
     L.lap(5);
+    if (tma) { mbar_wait(&ctl->v_bar, ld_phase); ld_phase ^= 1; }
+    else cp_async_wait_group<0>();
     publish_smem_and_sync();
     L.lap(6);
     if (tid == 0) {
-      issue_mma(tO, sP, gsP, sV, gsKV, true, DHP, BN / 16, false);
+      issue_mma_x(tO, oP, false, oV, true, DHP, BN / 16, false);
       umma_commit(&ctl->bar);
     }
     mbar_wait(&ctl->bar, phase); phase ^= 1;
     tc_fence_after();
     L.lap(7);
-    if (warp_active) {
+    if (!ONE) {
+      if (warp_active) {
 #pragma unroll
-      for (int c0 = 0; c0 < DHP; c0 += 16) {
-        float v[16];
-        tmem_ld16(tO + lane_off + c0, v);
-        tmem_ld_wait();
+        for (int c0 = 0; c0 < DHP; c0 += 16) {
+          float v[16];
+          tmem_ld16(tO + lane_off + c0, v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) o_acc[c0 + i] = fmaf(o_acc[c0 + i], corr, v[i]);
+          for (int i = 0; i < 16; ++i) o_acc[ONE ? 0 : c0 + i] = fmaf(o_acc[ONE ? 0 : c0 + i], corr, v[i]);
+        }
       }
+      // the next iteration overwrites sK / sV / sP and the S / O accumulators: both MMAs have completed
+      // (waited above); order this thread's TMEM reads before the next MMA issue
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
     }
-    // the next iteration overwrites sK / sV / sP and the S / O accumulators: both MMAs have completed
-    // (waited above); order this thread's TMEM reads before the next MMA issue
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
   }
 
   const int q = q0 + tid;
-  if (q < T) {
+  if (ONE) {
+    if (warp_active) {
+      const float inv = 1.f / l_run;
+      bf16* orow = a.o + ((size_t)b * T + min(q, T - 1)) * H * dh + (size_t)hd * dh;
+      float v[DHP / 16][16];
+#pragma unroll
+      for (int c = 0; c < DHP / 16; ++c) tmem_ld16(tO + lane_off + c * 16, v[c]);
+      tmem_ld_wait();
+      if (q < T) {
+#pragma unroll
+        for (int c = 0; c < DHP / 8; ++c) {
+          if (c * 8 < dh) {
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              w[i] = pack_bf16(v[c / 2][(c & 1) * 8 + 2 * i] * inv, v[c / 2][(c & 1) * 8 + 2 * i + 1] * inv);
+            *reinterpret_cast<uint4*>(orow + c * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+    }
+  } else if (q < T) {
     const float inv = 1.f / l_run;
     bf16* orow = a.o + ((size_t)b * T + q) * H * dh + (size_t)hd * dh;
 #pragma unroll
@@ -344,12 +524,13 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_umma_kernel(const __grid
       if (c < dh) {
         uint32_t w[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) w[i] = pack_bf16(o_acc[c + 2 * i] * inv, o_acc[c + 2 * i + 1] * inv);
+        for (int i = 0; i < 4; ++i)
+          w[i] = pack_bf16(o_acc[ONE ? 0 : c + 2 * i] * inv, o_acc[ONE ? 0 : c + 2 * i + 1] * inv);
         *reinterpret_cast<uint4*>(orow + c) = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
-    a.lse[(size_t)bh * T + q] = (m_run + log2f(l_run)) * 0.6931471805599453f;
   }
+  if (q < T) a.lse[(size_t)bh * T + q] = (m_run + log2f(l_run)) * 0.6931471805599453f;
   L.lap(8);
   attn_epilogue(tmem, a.tmem_cols);
   L.lap(9);
@@ -601,43 +782,72 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_umma_kernel(const At
 
 // ------------------------------------------------------------------------------------------ fused backward
 // Short sequences (T <= 160: every key fits one MMA N extent): ONE CTA per (sample, head) computes dQ,
-// dK and dV with S and P evaluated once.  256 threads: warps w and w + 4 own the same 32 rows (TMEM lane
-// quadrant w % 4) and split the key columns.  Per 128-query tile:
+// dK and dV with S and P evaluated once, in ONE pass over the query rows: rows [0, 128) are the main M
+// tile, rows [128, T) a 32-row tail tile whose products are issued in the same MMA batches into their own
+// TMEM columns (the tail would otherwise repeat the whole dependent chain for a handful of rows).
+// 256 threads: warps w and w + 4 own the same 32 rows (TMEM lane quadrant w % 4) and split the key columns;
+// the tail rows belong to the two quadrant-0 warps.
 //   S = Q K^T -> TMEM          p = exp2(s c - lse) -> bf16 P in smem [q][key]
 //   dP = dO V^T -> TMEM (over S)   dV^T += dO^T P      (A = dO read MN-major, B = P read MN-major)
 //   dS = p (dP - delta) -> over P in smem
 //   dQ = dS K -> TMEM (over dP)    dK^T += Q^T dS      (A = Q read MN-major, B = dS read MN-major)
-// dK^T / dV^T live in TMEM as [d (lane)][key (column)] across the query tiles and are written at the end;
-// the transposed products are what lets one [q][key] tile of P / dS feed both contractions.
+// dK^T / dV^T live in TMEM as [d (lane)][key (column)] and leave through a [key][d] staging tile in shared
+// memory (coalesced 16-byte rows); the transposed products are what lets one [q][key] tile of P / dS feed
+// both contractions.  TMEM columns: [0, R) S / dP / dQ, [R, R + NK) dV^T, [R + NK, R + 2 NK) dK^T -- which
+// first holds the tail's S / dP -- and the tail's dQ at dq2_col.  delta = rowsum(dO * O) is taken from the
+// staged dO and O tiles (O lands where P goes later).
 constexpr int FUSED_THREADS = 256;
+constexpr int TAILR = 32;  // rows of the tail query tile
+enum { OQ = 0, ODO, OK_, OV, OP, OQ2, ODO2, OP2 };
+
+// sum_d x[r][d] * y[r][d] over the valid head dims of row r of two W tiles
+__device__ __forceinline__ float row_dot_w(uint32_t x, uint32_t y, int rows, int r, int dh) {
+  float acc = 0.f;
+  for (int c = 0; c < dh / 8; ++c) {
+    const uint32_t off = (uint32_t)(c >> 3) * w_box(rows) + (uint32_t)r * 128u + (uint32_t)(((c & 7) ^ (r & 7)) << 4);
+    const uint4 xv = lds128(x + off), yv = lds128(y + off);
+    const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 fx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xs[i]));
+      const float2 fy = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ys[i]));
+      acc = fmaf(fx.x, fy.x, acc);
+      acc = fmaf(fx.y, fy.y, acc);
+    }
+  }
+  return acc;
+}
+
+struct FusedMaps { CUtensorMap q, kv, q2, d_o, d_o2, o, o2; };
 
 template <int DHP>
-__global__ void __launch_bounds__(FUSED_THREADS) attn_bwd_fused_umma_kernel(const __grid_constant__ CUtensorMap tmQ,
-                                                                          const __grid_constant__ CUtensorMap tmKV,
-                                                                          const __grid_constant__ CUtensorMap tmdO,
+__global__ void __launch_bounds__(FUSED_THREADS) attn_bwd_fused_umma_kernel(const __grid_constant__ FusedMaps tm,
                                                                           const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = align128(smem_raw);
+  uint8_t* smem = align1024(smem_raw);
   AttnSmem* ctl = reinterpret_cast<AttnSmem*>(smem);
-  float* s_delta = reinterpret_cast<float*>(smem + 128);  // [128]
-  float* s_lse = s_delta + MT;                            // [128], log2 units
+  float* s_delta = reinterpret_cast<float*>(smem + 128);  // [128 + 32]: main rows, tail rows
+  float* s_lse = s_delta + MT + TAILR;                    // [128 + 32], log2 units
   const int NK = a.BN, T = a.T, H = a.H, dh = a.dh;
-  uint8_t* tiles = smem + 128 + 1024;
-  const uint32_t sQ = smem_u32(tiles);
-  const uint32_t sdO = sQ + g8_alloc(MT, DHP);
-  const uint32_t sK = sdO + g8_alloc(MT, DHP);
-  const uint32_t sV = sK + g8_alloc(NK, DHP);
-  const uint32_t sP = sV + g8_alloc(NK, DHP);
-  uint8_t* sP_ptr = tiles + 2 * g8_alloc(MT, DHP) + 2 * g8_alloc(NK, DHP);
+  uint8_t* tiles = smem + 2048;
+  uint8_t* pQ = tiles + a.off[OQ];
+  uint8_t* pdO = tiles + a.off[ODO];
+  uint8_t* pK = tiles + a.off[OK_];
+  uint8_t* pV = tiles + a.off[OV];
+  uint8_t* pP = tiles + a.off[OP];
+  uint8_t* pQ2 = tiles + a.off[OQ2];
+  uint8_t* pdO2 = tiles + a.off[ODO2];
+  uint8_t* pP2 = tiles + a.off[OP2];
+  const uint32_t gsP = g8_stride(MT), gsP2 = g8_stride(TAILR);
+  const Opnd oQ = opnd_w(smem_u32(pQ), MT), odO = opnd_w(smem_u32(pdO), MT), oK = opnd_w(smem_u32(pK), NK),
+             oV = opnd_w(smem_u32(pV), NK), oP = opnd_g8(smem_u32(pP), gsP);
+  const Opnd oQ2 = opnd_w(smem_u32(pQ2), TAILR), odO2 = opnd_w(smem_u32(pdO2), TAILR), oP2 = opnd_g8(smem_u32(pP2), gsP2);
   const bool tma = a.use_tma != 0;
-  // TMA writes tiles densely (group stride rows * 16); the cp.async path pads the stride by 16 bytes
-  const uint32_t gsKV = tma ? (uint32_t)NK * 16u : g8_stride(NK), gsP = g8_stride(MT);
-  uint32_t ld_phase = 0;
 
   const int bh = blockIdx.x, b = bh / H, hd = bh % H;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quad = warp & 3, half = warp >> 2;
-  const int r = quad * 32 + lane;  // row of the M tile = TMEM lane
+  const int r = quad * 32 + lane;  // row of the main tile = TMEM lane
   const size_t ld = (size_t)3 * H * dh, ldo = (size_t)H * dh;
   const bf16* qbase = a.qkv + (size_t)b * T * ld + (size_t)hd * dh;
   const bf16* kbase = qbase + (size_t)H * dh;
@@ -645,8 +855,15 @@ __global__ void __launch_bounds__(FUSED_THREADS) attn_bwd_fused_umma_kernel(cons
   const bf16* dobase = a.d_o + (size_t)b * T * ldo + (size_t)hd * dh;
   const bf16* obase = a.o + (size_t)b * T * ldo + (size_t)hd * dh;
 
-  // prologue (256 threads): barrier + TMEM
-  if (tid == 0) { mbar_init(&ctl->bar, 1); mbar_init(&ctl->ld_bar, 1); fence_barrier_init(); }
+  const bool tail = T > MT;
+  const int n1 = min(T, MT);                     // valid rows of the main tile
+  const int kq1 = (n1 + 15) / 16;                // K steps of the contractions over its rows
+  const int kq2 = tail ? (T - MT + 15) / 16 : 0;  // ... over the tail rows
+  const bool warp_rows = quad * 32 < kq1 * 16;   // this warp's main rows take part in those contractions
+  const bool tail_warp = tail && quad == 0;      // warps 0 and 4: tail row = lane
+
+  // prologue (256 threads): barriers + TMEM
+  if (tid == 0) { mbar_init(&ctl->bar, 1); mbar_init(&ctl->ld_bar, 1); mbar_init(&ctl->v_bar, 1); fence_barrier_init(); }
   if (warp == 1) tmem_alloc_dyn(&ctl->tmem_slot, a.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -654,7 +871,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) attn_bwd_fused_umma_kernel(cons
   pdl_wait();
   const uint32_t tmem = ctl->tmem_slot;
   const int R = NK > DHP ? NK : DHP;  // S / dP / dQ share the first R columns
-  const uint32_t tS = tmem, tdV = tmem + (uint32_t)R, tdK = tdV + (uint32_t)NK;
+  const uint32_t tS = tmem, tdV = tmem + (uint32_t)R, tdK = tdV + (uint32_t)NK, tdQ2 = tmem + a.dq2_col;
   const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
   uint32_t phase = 0;
 
@@ -664,214 +881,250 @@ __global__ void __launch_bounds__(FUSED_THREADS) attn_bwd_fused_umma_kernel(cons
   const int ch1 = half == 0 ? (nchunks + 1) / 2 : nchunks;
 
   ALap L(a.dbg);
-  if (!tma) {
-    stage_tile<DHP, FUSED_THREADS>(sK, NK, kbase, ld, T, dh);
-    stage_tile<DHP, FUSED_THREADS>(sV, NK, vbase, ld, T, dh);
+  // ---- operand tiles: Q, K (and the tail Q) on the first barrier -- S starts as soon as they are in -- dO, O, V
+  // on the second
+  if (tma) {
+    if (tid == 0) {
+      mbar_expect_tx(&ctl->ld_bar, w_bytes(MT, DHP) + w_bytes(NK, DHP) + (tail ? w_bytes(TAILR, DHP) : 0u));
+      tma_load_w<DHP>(pK, NK, &tm.kv, &ctl->ld_bar, (H + hd) * dh, 0, b);
+      tma_load_w<DHP>(pQ, MT, &tm.q, &ctl->ld_bar, hd * dh, 0, b);
+      if (tail) tma_load_w<DHP>(pQ2, TAILR, &tm.q2, &ctl->ld_bar, hd * dh, MT, b);
+      mbar_expect_tx(&ctl->v_bar, 2 * w_bytes(MT, DHP) + w_bytes(NK, DHP) + (tail ? 2 * w_bytes(TAILR, DHP) : 0u));
+      tma_load_w<DHP>(pdO, MT, &tm.d_o, &ctl->v_bar, hd * dh, 0, b);
+      tma_load_w<DHP>(pP, MT, &tm.o, &ctl->v_bar, hd * dh, 0, b);
+      if (tail) {
+        tma_load_w<DHP>(pdO2, TAILR, &tm.d_o2, &ctl->v_bar, hd * dh, MT, b);
+        tma_load_w<DHP>(pP2, TAILR, &tm.o2, &ctl->v_bar, hd * dh, MT, b);
+      }
+      tma_load_w<DHP>(pV, NK, &tm.kv, &ctl->v_bar, (2 * H + hd) * dh, 0, b);
+    }
+    // one CTA per SM and nothing to overlap its loads with: pull the tiles of the CTA that will follow on this
+    // SM (same index + number of SMs) into L2 while this one computes
+    const int nbh = bh + a.pf_stride;
+    if (warp == 2 && lane == 0 && a.pf_stride > 0 && nbh < (int)gridDim.x) {
+      const int nb = nbh / H, nh = nbh % H;
+      tma_prefetch_w<DHP>(&tm.kv, (H + nh) * dh, 0, nb);
+      tma_prefetch_w<DHP>(&tm.q, nh * dh, 0, nb);
+      tma_prefetch_w<DHP>(&tm.d_o, nh * dh, 0, nb);
+      tma_prefetch_w<DHP>(&tm.o, nh * dh, 0, nb);
+      tma_prefetch_w<DHP>(&tm.kv, (2 * H + nh) * dh, 0, nb);
+      if (tail) {
+        tma_prefetch_w<DHP>(&tm.q2, nh * dh, MT, nb);
+        tma_prefetch_w<DHP>(&tm.d_o2, nh * dh, MT, nb);
+        tma_prefetch_w<DHP>(&tm.o2, nh * dh, MT, nb);
+      }
+    }
+  } else {
+    stage_tile_w<DHP, FUSED_THREADS>(oK.base, NK, kbase, ld, T, dh, NK);
+    stage_tile_w<DHP, FUSED_THREADS>(oQ.base, MT, qbase, ld, T, dh, kq1 * 16);
+    stage_tile_w<DHP, FUSED_THREADS>(odO.base, MT, dobase, ldo, T, dh, kq1 * 16);
+    stage_tile_w<DHP, FUSED_THREADS>(smem_u32(pP), MT, obase, ldo, T, dh, kq1 * 16);
+    stage_tile_w<DHP, FUSED_THREADS>(oV.base, NK, vbase, ld, T, dh, NK);
+    if (tail) {
+      stage_tile_w<DHP, FUSED_THREADS>(oQ2.base, TAILR, qbase + (size_t)MT * ld, ld, T - MT, dh, TAILR);
+      stage_tile_w<DHP, FUSED_THREADS>(odO2.base, TAILR, dobase + (size_t)MT * ldo, ldo, T - MT, dh, TAILR);
+      stage_tile_w<DHP, FUSED_THREADS>(smem_u32(pP2), TAILR, obase + (size_t)MT * ldo, ldo, T - MT, dh, TAILR);
+    }
   }
-
-  const int ntiles = (T + MT - 1) / MT;
-  for (int qt = 0; qt < ntiles; ++qt) {
-    const int q0 = qt * MT;
-    const int nq = min(MT, T - q0);
-    const int kq = (nq + 15) / 16;            // K steps of the contractions over the query rows
-    const bool warp_rows = quad * 32 < kq * 16;  // this warp's rows take part in those contractions
-    // full tiles (and K / V, once) arrive by TMA; a short tail tile is staged by cp.async, only the rows of
-    // its K steps
-    const bool tile_tma = tma && nq == MT;
-    const uint32_t gsQ = tile_tma ? MT * 16u : g8_stride(MT);
-    if (tid == 0 && (tile_tma || (tma && qt == 0))) {
-      const uint32_t q_bytes = (uint32_t)MT * DHP * 2, kv_bytes = (uint32_t)NK * DHP * 2;
-      mbar_expect_tx(&ctl->ld_bar, (tile_tma ? 2 * q_bytes : 0u) + (qt == 0 ? 2 * kv_bytes : 0u));
-      if (qt == 0) {
-        tma_load_5d(tiles + 2 * g8_alloc(MT, DHP), &tmKV, &ctl->ld_bar, 0, 0, 0, H + hd, b);
-        tma_load_5d(tiles + 2 * g8_alloc(MT, DHP) + g8_alloc(NK, DHP), &tmKV, &ctl->ld_bar, 0, 0, 0, 2 * H + hd, b);
-      }
-      if (tile_tma) {
-        tma_load_5d(tiles, &tmQ, &ctl->ld_bar, 0, q0, 0, hd, b);
-        tma_load_5d(tiles + g8_alloc(MT, DHP), &tmdO, &ctl->ld_bar, 0, q0, 0, hd, b);
-      }
+  // lse of the rows whose statistics this thread produces: half 0 -> main row r, warp 4 -> tail row `lane`
+  const bool stat_main = half == 0, stat_tail = tail && warp == 4;
+  float my_lse2 = INFINITY;  // padded query row: p = exp2(-inf) = 0
+  {
+    const int q = stat_main ? r : MT + lane;
+    if ((stat_main || stat_tail) && q < T) my_lse2 = a.lse[(size_t)bh * T + q] * 1.4426950408889634f;
+  }
+  auto issue_S = [&]() {
+    issue_mma_x(tS, oQ, false, oK, false, NK, DHP / 16, false);
+    if (tail) issue_mma_x(tdK, oQ2, false, oK, false, NK, DHP / 16, false);
+    umma_commit(&ctl->bar);
+  };
+  L.lap(0);
+  if (tma) {
+    if (tid == 0) {
+      mbar_wait(&ctl->ld_bar, 0);
+      tc_fence_after();
+      issue_S();
     }
-    if (!tile_tma) {
-      stage_tile<DHP, FUSED_THREADS>(sQ, MT, qbase + (size_t)q0 * ld, ld, nq, dh, kq * 16);
-      stage_tile<DHP, FUSED_THREADS>(sdO, MT, dobase + (size_t)q0 * ldo, ldo, nq, dh, kq * 16);
-    }
-    if (half == 0) {  // row statistics: delta = sum_d dO * O, lse in log2 units
-      float delta = 0.f, lse2 = INFINITY;  // padded query row: p = exp2(-inf) = 0
-      const int q = q0 + r;
-      if (q < T) {
-        const bf16* dor = dobase + (size_t)q * ldo;
-        const bf16* orow = obase + (size_t)q * ldo;
-        // every load of the row issued before the first use (the loop would otherwise serialise 2 * dh / 8
-        // L2 round trips)
-        uint4 xv[DHP / 8], yv[DHP / 8];
-#pragma unroll
-        for (int c = 0; c < DHP / 8; ++c) {
-          const bool in = c * 8 < dh;
-          xv[c] = in ? *reinterpret_cast<const uint4*>(dor + c * 8) : make_uint4(0, 0, 0, 0);
-          yv[c] = in ? *reinterpret_cast<const uint4*>(orow + c * 8) : make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int c = 0; c < DHP / 8; ++c) {
-          const uint32_t xs[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w}, ys[4] = {yv[c].x, yv[c].y, yv[c].z, yv[c].w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 fx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xs[i]));
-            const float2 fy = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ys[i]));
-            delta = fmaf(fx.x, fy.x, delta);
-            delta = fmaf(fx.y, fy.y, delta);
-          }
-        }
-        lse2 = a.lse[(size_t)bh * T + q] * 1.4426950408889634f;
-      }
-      s_delta[r] = delta;
-      s_lse[r] = lse2;
-    }
-    L.lap(0);
+    __syncwarp();
+    mbar_wait(&ctl->v_bar, 0);
+  } else {
     cp_async_wait_all();
-    if (tile_tma || (tma && qt == 0)) { mbar_wait(&ctl->ld_bar, ld_phase); ld_phase ^= 1; }
     publish_smem_and_sync();
-    L.lap(1);
-    if (tid == 0) {
-      issue_mma(tS, sQ, gsQ, sK, gsKV, false, NK, DHP / 16, false);
-      umma_commit(&ctl->bar);
-    }
-    const float delta = s_delta[r], lse2 = s_lse[r];
-    const bool row_ok = q0 + r < T;
-    mbar_wait(&ctl->bar, phase); phase ^= 1;
-    tc_fence_after();
-    L.lap(2);
-    // ---- P = exp2(s c - lse) (zero for padded rows / keys) -> smem [q][key]
-    if (warp_rows) {
-      for (int ch = ch0; ch < ch1; ++ch) {
-        const int c0 = ch * 16;
-        float sv[16];
-        tmem_ld16(tS + lane_off + c0, sv);
-        tmem_ld_wait();
-        uint32_t w[8];
-        if (c0 + 16 <= T) {  // no padded key in this chunk; a padded row has lse2 = +inf -> p = 0
+    if (tid == 0) issue_S();
+  }
+  L.lap(1);
+  // ---- row statistics from the staged tiles: delta = sum_d dO * O
+  if (stat_main) {
+    s_delta[r] = r < T ? row_dot_w(odO.base, oP.base, MT, r, dh) : 0.f;
+    s_lse[r] = my_lse2;
+  } else if (stat_tail) {
+    s_delta[MT + lane] = MT + lane < T ? row_dot_w(odO2.base, oP2.base, TAILR, lane, dh) : 0.f;
+    s_lse[MT + lane] = my_lse2;
+  }
+  __syncthreads();  // statistics visible; every read of the O tiles is done before P overwrites them
+  const float delta = s_delta[r], lse2 = s_lse[r];
+  const float delta_t = tail_warp ? s_delta[MT + lane] : 0.f, lse2_t = tail_warp ? s_lse[MT + lane] : INFINITY;
+  mbar_wait(&ctl->bar, phase); phase ^= 1;
+  tc_fence_after();
+  L.lap(2);
+
+  // ---- P = exp2(s c - lse) (zero for padded rows / keys) -> smem [q][key].  Row set 0 = main rows, 1 = tail
+  // rows; the loops stay rolled: the kernel runs once per CTA, straight-line code would only cost
+  // instruction fetches
+  const int nsets = tail ? 2 : 1;
+#pragma unroll 1
+  for (int set = 0; set < nsets; ++set) {
+    if (!(set == 0 ? warp_rows : tail_warp)) continue;  // warp-uniform
+    const uint32_t t_src = set == 0 ? tS + lane_off : tdK;
+    const uint32_t gs = set == 0 ? gsP : gsP2;
+    const uint32_t tile = (set == 0 ? oP.base : oP2.base) + (uint32_t)(set == 0 ? r : lane) * 16u;
+    const float lse = set == 0 ? lse2 : lse2_t;
+#pragma unroll 1
+    for (int ch = ch0; ch < ch1; ++ch) {
+      const int c0 = ch * 16;
+      float sv[16];
+      tmem_ld16(t_src + (uint32_t)c0, sv);
+      tmem_ld_wait();
+      uint32_t w[8];
 #pragma unroll
-          for (int i = 0; i < 16; i += 2)
-            w[i / 2] = pack_bf16(exp2_fast(fmaf(sv[i], a.scale_log2, -lse2)), exp2_fast(fmaf(sv[i + 1], a.scale_log2, -lse2)));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            const float p0 = c0 + i < T ? exp2_fast(fmaf(sv[i], a.scale_log2, -lse2)) : 0.f;
-            const float p1 = c0 + i + 1 < T ? exp2_fast(fmaf(sv[i + 1], a.scale_log2, -lse2)) : 0.f;
-            w[i / 2] = pack_bf16(p0, p1);
-          }
-        }
-        uint8_t* dst = sP_ptr + (size_t)(c0 / 8) * gsP + r * 16;
-        *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-        *reinterpret_cast<uint4*>(dst + gsP) = make_uint4(w[4], w[5], w[6], w[7]);
+      for (int i = 0; i < 16; i += 2) {
+        // a padded row has lse = +inf -> p = 0; padded keys (last chunk only) are zeroed below
+        w[i / 2] = pack_bf16(exp2_fast(fmaf(sv[i], a.scale_log2, -lse)), exp2_fast(fmaf(sv[i + 1], a.scale_log2, -lse)));
       }
-    }
-    L.lap(3);
-    publish_smem_and_sync();
-    if (tid == 0) {
-      issue_mma(tS, sdO, gsQ, sV, gsKV, false, NK, DHP / 16, false);  // dP over S
-      // dV^T[d][key] += sum_q dO[q][d] P[q][key]: both operands MN-major (rows = contraction index q)
-      const uint32_t idesc = make_idesc_bf16(MT, NK, true, true);
-      for (int ks = 0; ks < kq; ++ks)
-        umma_bf16(tdV, desc_ns(sdO + ks * 256, 128, gsQ), desc_ns(sP + ks * 256, 128, gsP), idesc,
-                  (qt > 0 || ks > 0) ? 1u : 0u);
-      umma_commit(&ctl->bar);
-    }
-    mbar_wait(&ctl->bar, phase); phase ^= 1;
-    tc_fence_after();
-    L.lap(4);
-    // ---- dS = p (dP - delta), in place over P
-    if (warp_rows) {
-      for (int ch = ch0; ch < ch1; ++ch) {
-        const int c0 = ch * 16;
-        float dp[16];
-        tmem_ld16(tS + lane_off + c0, dp);
-        tmem_ld_wait();
-        uint8_t* dst = sP_ptr + (size_t)(c0 / 8) * gsP + r * 16;
-        const uint4 pa = *reinterpret_cast<const uint4*>(dst), pb = *reinterpret_cast<const uint4*>(dst + gsP);
-        const uint32_t pw[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
-        uint32_t w[8];
+      if (c0 + 16 > T) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float2 pf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pw[i]));
-          w[i] = pack_bf16(pf.x * (dp[2 * i] - delta), pf.y * (dp[2 * i + 1] - delta));
+          if (c0 + 2 * i >= T) w[i] = 0u;
+          else if (c0 + 2 * i + 1 >= T) w[i] &= 0xFFFFu;
         }
-        *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-        *reinterpret_cast<uint4*>(dst + gsP) = make_uint4(w[4], w[5], w[6], w[7]);
       }
-    } else {
+      const uint32_t dst = tile + (uint32_t)(c0 / 8) * gs;
+      sts128(dst, w[0], w[1], w[2], w[3]);
+      sts128(dst + gs, w[4], w[5], w[6], w[7]);
+    }
+  }
+  L.lap(3);
+  publish_smem_and_sync();
+  if (tid == 0) {
+    issue_mma_x(tS, odO, false, oV, false, NK, DHP / 16, false);  // dP over S
+    if (tail) issue_mma_x(tdK, odO2, false, oV, false, NK, DHP / 16, false);
+    // dV^T[d][key] = sum_q dO[q][d] P[q][key]: both operands MN-major (rows = contraction index q)
+    issue_mma_x(tdV, odO, true, oP, true, NK, kq1, false);
+    if (tail) issue_mma_x(tdV, odO2, true, oP2, true, NK, kq2, true);
+    umma_commit(&ctl->bar);
+  }
+  mbar_wait(&ctl->bar, phase); phase ^= 1;
+  tc_fence_after();
+  L.lap(4);
+
+  // ---- dS = p (dP - delta), in place over P
+#pragma unroll 1
+  for (int set = 0; set < nsets; ++set) {
+    if (!(set == 0 ? warp_rows : tail_warp)) continue;
+    const uint32_t t_src = set == 0 ? tS + lane_off : tdK;
+    const uint32_t gs = set == 0 ? gsP : gsP2;
+    const uint32_t tile = (set == 0 ? oP.base : oP2.base) + (uint32_t)(set == 0 ? r : lane) * 16u;
+    const float dl = set == 0 ? delta : delta_t;
+#pragma unroll 1
+    for (int ch = ch0; ch < ch1; ++ch) {
+      float dp[16];
+      tmem_ld16(t_src + (uint32_t)ch * 16u, dp);
+      const uint32_t dst = tile + (uint32_t)(ch * 2) * gs;
+      const uint4 pa = lds128(dst), pb = lds128(dst + gs);
       tmem_ld_wait();
+      const uint32_t pw[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+      uint32_t w[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 pf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pw[i]));
+        w[i] = pack_bf16(pf.x * (dp[2 * i] - dl), pf.y * (dp[2 * i + 1] - dl));
+      }
+      sts128(dst, w[0], w[1], w[2], w[3]);
+      sts128(dst + gs, w[4], w[5], w[6], w[7]);
     }
-    L.lap(5);
-    publish_smem_and_sync();
-    if (tid == 0) {
-      issue_mma(tS, sP, gsP, sK, gsKV, true, DHP, NK / 16, false);  // dQ over dP
-      const uint32_t idesc = make_idesc_bf16(MT, NK, true, true);
-      for (int ks = 0; ks < kq; ++ks)  // dK^T[d][key] += sum_q Q[q][d] dS[q][key]
-        umma_bf16(tdK, desc_ns(sQ + ks * 256, 128, gsQ), desc_ns(sP + ks * 256, 128, gsP), idesc,
-                  (qt > 0 || ks > 0) ? 1u : 0u);
-      umma_commit(&ctl->bar);
-    }
-    mbar_wait(&ctl->bar, phase); phase ^= 1;
-    tc_fence_after();
-    L.lap(6);
-    // ---- dQ rows out: the two warp halves split the head dimension in 16-column chunks
-    {
-      constexpr int NDC = DHP / 16;
-      const int d0 = half == 0 ? 0 : (NDC + 1) / 2, d1 = half == 0 ? (NDC + 1) / 2 : NDC;
-      bf16* out = a.dqkv + ((size_t)b * T + min(q0 + r, T - 1)) * ld + (size_t)hd * dh;
+  }
+  L.lap(5);
+  publish_smem_and_sync();
+  if (tid == 0) {
+    issue_mma_x(tS, oP, false, oK, true, DHP, NK / 16, false);  // dQ over dP
+    if (tail) issue_mma_x(tdQ2, oP2, false, oK, true, DHP, NK / 16, false);
+    // dK^T[d][key] = sum_q Q[q][d] dS[q][key], over the tail's (consumed) dP
+    issue_mma_x(tdK, oQ, true, oP, true, NK, kq1, false);
+    if (tail) issue_mma_x(tdK, oQ2, true, oP2, true, NK, kq2, true);
+    umma_commit(&ctl->bar);
+  }
+  mbar_wait(&ctl->bar, phase); phase ^= 1;
+  tc_fence_after();
+  L.lap(6);
+
+  // ---- dQ rows out: the two warp halves split the head dimension in 16-column chunks
+  {
+    constexpr int NDC = DHP / 16;
+    const int d0 = half == 0 ? 0 : (NDC + 1) / 2, d1 = half == 0 ? (NDC + 1) / 2 : NDC;
+#pragma unroll 1
+    for (int set = 0; set < nsets; ++set) {
+      if (set == 1 && !tail_warp) continue;
+      const uint32_t t_src = set == 0 ? tS + lane_off : tdQ2;
+      const int q = set == 0 ? r : MT + lane;
+      bf16* out = a.dqkv + ((size_t)b * T + min(q, T - 1)) * ld + (size_t)hd * dh;
+#pragma unroll 1
       for (int dc = d0; dc < d1; ++dc) {
         float v[16];
-        tmem_ld16(tS + lane_off + dc * 16, v);
+        tmem_ld16(t_src + (uint32_t)dc * 16u, v);
         tmem_ld_wait();
-        if (row_ok) {
+        if (q < T) {
 #pragma unroll
           for (int h8 = 0; h8 < 2; ++h8) {
             if (dc * 16 + 8 * h8 < dh) {
               uint32_t w[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                w[i] = pack_bf16(v[8 * h8 + 2 * i] * a.scale, v[8 * h8 + 2 * i + 1] * a.scale);
+              for (int i = 0; i < 4; ++i) w[i] = pack_bf16(v[8 * h8 + 2 * i] * a.scale, v[8 * h8 + 2 * i + 1] * a.scale);
               *reinterpret_cast<uint4*>(out + dc * 16 + 8 * h8) = make_uint4(w[0], w[1], w[2], w[3]);
             }
           }
         }
       }
     }
-    // the next tile overwrites sQ / sdO / sP and the S region: all MMAs have completed (waited above)
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    L.lap(7);
   }
+  L.lap(7);
 
-  // ---- dK^T, dV^T out: thread = head dim d (TMEM lane), columns = keys; a warp writes 32 consecutive d
-  // of one key (64 contiguous bytes)
-  if (quad * 32 < dh) {
-    // lane pairs exchange one value per key pair so that every lane stores two consecutive head dims of ONE
-    // key as a 4-byte word: even lane -> (d, d+1) of the even key, odd lane -> (d-1, d) of the odd key
-    const int dd = r;
-    const bool odd = (lane & 1) != 0;
-    const int dcol = odd ? dd - 1 : dd;
-    bf16* base = a.dqkv + (size_t)b * T * ld + (size_t)hd * dh + dcol;
+  // ---- dK^T, dV^T out: thread = head dim d (TMEM lane), columns = keys.  The values go through [key][d]
+  // staging tiles (the dead Q / dO and K / V regions; every MMA has completed) and leave as 16-byte pieces
+  // of contiguous rows
+  const uint32_t pitch = (uint32_t)dh * 2u + 16u;
+  const uint32_t stK = oQ.base, stV = oK.base;  // rows [0, NK): padded keys are staged too, never copied out
+  if (quad * 32 < dh) {  // warp-uniform: tcgen05.ld is a whole-warp instruction
+#pragma unroll 1
     for (int ch = ch0; ch < ch1; ++ch) {
-      const int c0 = ch * 16;
-      float vk[16], vv[16];
-      tmem_ld16(tdK + lane_off + c0, vk);
-      tmem_ld16(tdV + lane_off + c0, vv);
-      tmem_ld_wait();
+      {
+        const int c0 = ch * 16;
+        float vk[16], vv[16];
+        tmem_ld16(tdK + lane_off + c0, vk);
+        tmem_ld16(tdV + lane_off + c0, vv);
+        tmem_ld_wait();
+        if (r < dh) {
+          uint32_t ak = stK + (uint32_t)c0 * pitch + (uint32_t)r * 2u, av = stV + (uint32_t)c0 * pitch + (uint32_t)r * 2u;
 #pragma unroll
-      for (int i = 0; i < 16; i += 2) {
-        const float rk = __shfl_xor_sync(0xffffffffu, odd ? vk[i] : vk[i + 1], 1);
-        const float rv = __shfl_xor_sync(0xffffffffu, odd ? vv[i] : vv[i + 1], 1);
-        const int key = c0 + i + (odd ? 1 : 0);
-        if (dcol + 1 < dh + 1 && dcol < dh && key < T) {
-          const float k_lo = odd ? rk : vk[i], k_hi = odd ? vk[i + 1] : rk;
-          const float v_lo = odd ? rv : vv[i], v_hi = odd ? vv[i + 1] : rv;
-          bf16* dst = base + (size_t)key * ld + (size_t)H * dh;
-          *reinterpret_cast<uint32_t*>(dst) = pack_bf16(k_lo * a.scale, k_hi * a.scale);
-          *reinterpret_cast<uint32_t*>(dst + (size_t)H * dh) = pack_bf16(v_lo, v_hi);
+          for (int i = 0; i < 16; i += 2) {
+            const uint32_t wk = pack_bf16(vk[i] * a.scale, vk[i + 1] * a.scale), wv = pack_bf16(vv[i], vv[i + 1]);
+            sts16(ak, wk); sts16(ak + pitch, wk >> 16);
+            sts16(av, wv); sts16(av + pitch, wv >> 16);
+            ak += 2 * pitch; av += 2 * pitch;
+          }
         }
       }
+    }
+  }
+  __syncthreads();
+  {
+    const int ppr = dh / 8;  // 16-byte pieces per row
+    bf16* kout = a.dqkv + (size_t)b * T * ld + (size_t)(H + hd) * dh;
+    bf16* vout = kout + (size_t)H * dh;
+    for (int idx = tid; idx < T * ppr; idx += FUSED_THREADS) {
+      const int key = idx / ppr, c = idx - key * ppr;
+      const uint32_t so = (uint32_t)key * pitch + (uint32_t)c * 16u;
+      *reinterpret_cast<uint4*>(kout + (size_t)key * ld + c * 8) = lds128(stK + so);
+      *reinterpret_cast<uint4*>(vout + (size_t)key * ld + c * 8) = lds128(stV + so);
     }
   }
   L.lap(8);
@@ -952,57 +1205,146 @@ bool attn_tma_enabled() {
   return on != 0;
 }
 
+// 3-d tensor map over a (B, T, cols) bf16 tensor with row pitch `ld` elements: box = [rows][64 columns],
+// 128-byte swizzle -- one box of a W tile; columns past `cols` and rows past T read as zero
+int make_w_map(const void* base, int B, int T, int cols, size_t ld, int rows, CUtensorMap* out) {
+  static EncodeTiledFn encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(fn);
+  }();
+  if (!encode) return fail(V4H_ERR_CUDA, "attention: cuTensorMapEncodeTiled is not available from the driver");
+  static std::mutex mu;
+  static std::map<std::tuple<const void*, int, int, int, size_t, int>, CUtensorMap> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  const auto key = std::make_tuple(base, B, T, cols, ld, rows);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return V4H_OK; }
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)T * ld * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  const CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(V4H_ERR_CUDA, "attention: cuTensorMapEncodeTiled (swizzled tile view) failed (%d)", (int)r);
+  if (cache.size() > 1024) cache.clear();
+  cache[key] = m;
+  *out = m;
+  return V4H_OK;
+}
+
+template <int DHP, bool ONE>
+int fwd_launch_one(AttnArgs a, int B, cudaStream_t s) {
+  const uint32_t qkv_bytes = w_bytes(MT, DHP) + 2 * w_bytes(a.BN, DHP), p_bytes = g8_bytes(MT, a.BN) + 16;
+  // one key block: P may overlay Q and K (both dead once S is complete)
+  const bool overlay = ONE && p_bytes <= w_bytes(MT, DHP) + w_bytes(a.BN, DHP);
+  a.p_off = overlay ? 0 : (int)qkv_bytes;
+  const size_t smem = 2048 + qkv_bytes + (overlay ? 0 : p_bytes);
+  static size_t configured = 0;
+  if (smem > configured) { V4H_TRY((set_smem(attn_fwd_umma_kernel<DHP, ONE>, smem))); configured = smem; }
+  CUtensorMap mq, mkv;
+  memset(&mq, 0, sizeof(mq)); memset(&mkv, 0, sizeof(mkv));
+  a.use_tma = (attn_tma_enabled() && a.dh == DHP) ? 1 : 0;  // columns past dh must read as zero otherwise
+  if (a.use_tma) {
+    const size_t ld = (size_t)3 * a.H * a.dh;
+    V4H_TRY(make_w_map(a.qkv, B, a.T, 3 * a.H * a.dh, ld, MT, &mq));
+    V4H_TRY(make_w_map(a.qkv, B, a.T, 3 * a.H * a.dh, ld, a.BN, &mkv));
+  }
+  dim3 grid((unsigned)ceil_div(a.T, MT), (unsigned)(B * a.H));
+  V4H_CUDA(launch_pdl(attn_fwd_umma_kernel<DHP, ONE>, dim3(grid), dim3(ATT_THREADS), smem, s, mq, mkv, a));
+  V4H_LAUNCH_CHECK();
+  return V4H_OK;
+}
 template <int DHP>
 int fwd_launch(AttnArgs a, int B, cudaStream_t s) {
   const int cap = std::min(160, 512 - DHP) / 16 * 16;
   pick_block(a.T, cap, &a.BN, &a.nblocks);
   a.tmem_cols = pow2_cols(a.BN + DHP);
-  const size_t smem = 256 + g8_alloc(MT, DHP) + 2 * g8_alloc(a.BN, DHP) + g8_alloc(MT, a.BN);
-  static size_t configured = 0;
-  if (smem > configured) { V4H_TRY(set_smem(attn_fwd_umma_kernel<DHP>, smem)); configured = smem; }
-  CUtensorMap mq, mkv;
-  memset(&mq, 0, sizeof(mq)); memset(&mkv, 0, sizeof(mkv));
-  a.use_tma = (attn_tma_enabled() && a.dh == DHP) ? 1 : 0;  // the box must cover the padded head dim exactly
-  if (a.use_tma) {
-    const size_t ld = (size_t)3 * a.H * a.dh;
-    V4H_TRY(make_g8_map(a.qkv, B, a.T, 3 * a.H, a.dh, ld, MT, &mq));
-    V4H_TRY(make_g8_map(a.qkv, B, a.T, 3 * a.H, a.dh, ld, a.BN, &mkv));
-  }
-  dim3 grid((unsigned)ceil_div(a.T, MT), (unsigned)(B * a.H));
-  V4H_CUDA(launch_pdl(attn_fwd_umma_kernel<DHP>, dim3(grid), dim3(ATT_THREADS), smem, s, mq, mkv, a));
-  V4H_LAUNCH_CHECK();
-  return V4H_OK;
+  return a.nblocks == 1 ? fwd_launch_one<DHP, true>(a, B, s) : fwd_launch_one<DHP, false>(a, B, s);
 }
 
+int sm_count() {
+  static const int n = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) v = 0;
+    return v;
+  }();
+  return n;
+}
 bool fused_bwd_enabled() {
   static const int on = [] { const char* e = getenv("V4H_ATTN_FUSED_BWD"); return (e && e[0] == '0') ? 0 : 1; }();
   return on != 0;
 }
 
+// fused backward: tile offsets, TMEM columns; false when the shape does not fit one CTA
+template <int DHP>
+bool fused_plan(AttnArgs& f, size_t* smem_bytes) {
+  auto up = [](uint32_t x) { return (x + 1023u) & ~1023u; };
+  f.BN = (int)ceil_div(f.T, 16) * 16;
+  f.nblocks = 1;
+  const int NK = f.BN;
+  const bool tail = f.T > MT;
+  if (f.T > MT + TAILR) return false;
+  const int R = NK > DHP ? NK : DHP;
+  int cols = R + 2 * NK;
+  f.dq2_col = 0;
+  if (tail) {
+    if (2 * DHP <= R) f.dq2_col = (uint32_t)DHP;  // next to the main dQ inside the S region
+    else if (cols + DHP <= 512) { f.dq2_col = (uint32_t)cols; cols += DHP; }
+    else return false;
+  }
+  if (cols > 512) return false;
+  f.tmem_cols = pow2_cols(cols);
+  const uint32_t W1 = w_bytes(MT, DHP), WK = w_bytes(NK, DHP), W2 = w_bytes(TAILR, DHP);
+  // the P tiles first receive the O tiles (row statistics)
+  const uint32_t P1 = up(std::max(g8_bytes(MT, NK) + 16u, W1)), P2 = up(std::max(g8_bytes(TAILR, NK) + 16u, W2));
+  f.off[OQ] = 0; f.off[ODO] = (int)W1; f.off[OK_] = (int)(2 * W1); f.off[OV] = (int)(2 * W1 + WK);
+  f.off[OP] = (int)(2 * W1 + 2 * WK);
+  uint32_t end = (uint32_t)f.off[OP] + P1;
+  f.off[OQ2] = f.off[ODO2] = f.off[OP2] = (int)end;
+  if (tail) {
+    f.off[OQ2] = (int)end; f.off[ODO2] = (int)(end + W2); f.off[OP2] = (int)(end + 2 * W2);
+    end += 2 * W2 + P2;
+    // K-major A reads span 128 rows: the 32-row tail tiles are over-read into what follows (garbage rows of
+    // the accumulators that are never stored); keep those reads inside the allocation
+    end = std::max(end, (uint32_t)f.off[ODO2] + W2 + 128u * 128u);
+    end = std::max(end, (uint32_t)f.off[OP2] + (uint32_t)(NK / 8) * g8_stride(TAILR) + 128u * 16u);
+  }
+  // MN-major A reads span two 64-column chunks even when DHP <= 64; the dK / dV staging tiles ([key][dh + 8])
+  // reuse Q + dO and K + V
+  end = std::max(end, (uint32_t)f.off[OP] + 2 * w_box(MT));
+  if ((uint32_t)f.T * ((uint32_t)f.dh * 2u + 16u) > 2 * std::min(W1, WK)) return false;
+  *smem_bytes = 3072 + end;
+  return *smem_bytes <= 227 * 1024;
+}
+
 template <int DHP>
 int bwd_launch(AttnArgs a, int B, cudaStream_t s) {
-  if (a.T <= 160 && fused_bwd_enabled()) {  // one CTA per (sample, head): S and P evaluated once
-    AttnArgs f = a;
-    f.BN = (int)ceil_div(a.T, 16) * 16;
-    f.nblocks = 1;
-    const int R = f.BN > DHP ? f.BN : DHP;
-    f.tmem_cols = pow2_cols(R + 2 * f.BN);
-    // the MN-major reads of Q / dO span 128 "M" columns = 16 column groups even when DHP < 128: the
-    // groups past DHP land in the tiles that follow (garbage rows of dK^T / dV^T that are never stored)
-    const size_t smem = 256 + 1024 + 2 * g8_alloc(MT, DHP) + 2 * g8_alloc(f.BN, DHP) + g8_alloc(MT, f.BN) +
-                        (DHP < 128 ? 16 * g8_stride(MT) : 0);
+  AttnArgs f = a;
+  size_t fsmem = 0;
+  if (a.T <= 160 && fused_bwd_enabled() && fused_plan<DHP>(f, &fsmem)) {  // one CTA per (sample, head)
     static size_t configured = 0;
-    if (smem > configured) { V4H_TRY(set_smem(attn_bwd_fused_umma_kernel<DHP>, smem)); configured = smem; }
-    CUtensorMap mq, mkv, mdo;
-    memset(&mq, 0, sizeof(mq)); memset(&mkv, 0, sizeof(mkv)); memset(&mdo, 0, sizeof(mdo));
+    if (fsmem > configured) { V4H_TRY(set_smem(attn_bwd_fused_umma_kernel<DHP>, fsmem)); configured = fsmem; }
+    FusedMaps tm;
+    memset(&tm, 0, sizeof(tm));
     f.use_tma = (attn_tma_enabled() && a.dh == DHP) ? 1 : 0;
+    f.pf_stride = sm_count();
     if (f.use_tma) {
-      const size_t ldq = (size_t)3 * a.H * a.dh;
-      V4H_TRY(make_g8_map(a.qkv, B, a.T, 3 * a.H, a.dh, ldq, MT, &mq));
-      V4H_TRY(make_g8_map(a.qkv, B, a.T, 3 * a.H, a.dh, ldq, f.BN, &mkv));
-      V4H_TRY(make_g8_map(a.d_o, B, a.T, a.H, a.dh, (size_t)a.H * a.dh, MT, &mdo));
+      const size_t ldq = (size_t)3 * a.H * a.dh, ldo = (size_t)a.H * a.dh;
+      V4H_TRY(make_w_map(a.qkv, B, a.T, 3 * a.H * a.dh, ldq, MT, &tm.q));
+      V4H_TRY(make_w_map(a.qkv, B, a.T, 3 * a.H * a.dh, ldq, f.BN, &tm.kv));
+      V4H_TRY(make_w_map(a.qkv, B, a.T, 3 * a.H * a.dh, ldq, TAILR, &tm.q2));
+      V4H_TRY(make_w_map(a.d_o, B, a.T, a.H * a.dh, ldo, MT, &tm.d_o));
+      V4H_TRY(make_w_map(a.d_o, B, a.T, a.H * a.dh, ldo, TAILR, &tm.d_o2));
+      V4H_TRY(make_w_map(a.o, B, a.T, a.H * a.dh, ldo, MT, &tm.o));
+      V4H_TRY(make_w_map(a.o, B, a.T, a.H * a.dh, ldo, TAILR, &tm.o2));
     }
-    V4H_CUDA(launch_pdl(attn_bwd_fused_umma_kernel<DHP>, dim3((unsigned)(B * a.H)), dim3(FUSED_THREADS), smem, s, mq, mkv, mdo, f));
+    V4H_CUDA(launch_pdl(attn_bwd_fused_umma_kernel<DHP>, dim3((unsigned)(B * a.H)), dim3(FUSED_THREADS), fsmem, s, tm, f));
     V4H_LAUNCH_CHECK();
     return V4H_OK;
   }
