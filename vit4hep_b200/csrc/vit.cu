@@ -30,6 +30,10 @@ struct Plan {
   CastJob* jobs_dev = nullptr;
   CastJob* jobs_host = nullptr;
   int njobs = 0;
+  // weight-gradient GEMMs run on a side stream, off the dgrad -> LayerNorm -> attention chain: their CTAs fill
+  // the SMs that the chain's kernels leave idle in their ragged tails (V4H_WGRAD_STREAM=0: same stream)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace {
@@ -65,7 +69,7 @@ struct Workspace {
   // backward scratch
   float *dh, *dmod, *dsc, *dcond, *dvec, *attn_delta;
   bf16* dmod_bf16;
-  void *dy, *du, *dm, *dqkv;
+  void *dy_mlp[2], *dy_attn, *du, *dm, *dqkv;  // dy: gate * dh of the MLP branch (by block parity) / attention branch
   size_t bytes = 0;
 
   void layout(const Plan& p, char* base, int64_t B, bool train) {
@@ -116,7 +120,7 @@ struct Workspace {
       dmod = (float*)take((size_t)B * p.Nmod * 4);
       dmod_bf16 = (bf16*)take((size_t)B * p.Nmod * 2);
       dsc = (float*)take(B * D * 4); dcond = (float*)take(B * D * 4); dvec = (float*)take(B * D * 4);
-      dy = take(M * D * ta); du = take(M * Hm * ta); dm = take(M * D * ta); dqkv = take(M * 3 * D * ta);
+      dy_mlp[0] = take(M * D * ta); dy_mlp[1] = take(M * D * ta); dy_attn = take(M * D * ta); du = take(M * Hm * ta); dm = take(M * D * ta); dqkv = take(M * 3 * D * ta);
       attn_delta = (float*)take((size_t)B * d.num_heads * d.tokens * 4);
       if (p.bf16) {
         dout_bf = (bf16*)take(M * d.out_dim * 2); dh_bf = (bf16*)take(M * D * 2);
@@ -127,7 +131,7 @@ struct Workspace {
     } else {
       dout_bf = dh_bf = dcond_bf = dvec_bf = nullptr;
       dh = dmod = dsc = dcond = dvec = attn_delta = nullptr; dmod_bf16 = nullptr;
-      dy = du = dm = dqkv = nullptr;
+      dy_mlp[0] = dy_mlp[1] = dy_attn = du = dm = dqkv = nullptr;
     }
     bytes = off;
   }
@@ -366,7 +370,26 @@ int backward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const v4h
   const bf16* wa = reinterpret_cast<const bf16*>(arena);
   const int H = d.num_heads, dh = D / H;
 
+  // side-stream weight gradients: fork after the kernel that produced dY, join before the buffers a block's
+  // wgrads read are written again (start of the next block) and before returning
+  bool side_busy = false;
+  auto on_side = [&](auto&& launch) -> int {
+    if (!p.side || profiling_enabled()) return launch(s);  // per-kernel timing wants launches that do not overlap
+    V4H_CUDA(cudaEventRecord(p.ev_fork, s));
+    V4H_CUDA(cudaStreamWaitEvent(p.side, p.ev_fork, 0));
+    side_busy = true;
+    return launch(p.side);
+  };
+  auto join_side = [&]() -> int {
+    if (!side_busy) return V4H_OK;
+    V4H_CUDA(cudaEventRecord(p.ev_join, p.side));
+    V4H_CUDA(cudaStreamWaitEvent(s, p.ev_join, 0));
+    side_busy = false;
+    return V4H_OK;
+  };
+
   for (int stage = stage_begin; stage >= stage_end; --stage) {
+    V4H_TRY(join_side());
     if (stage == d.depth + 1) {
       // ---------------- final layer
       V4H_CUDA(cudaMemsetAsync(ws.dmod, 0, (size_t)B * p.Nmod * sizeof(float), s));
@@ -375,7 +398,7 @@ int backward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const v4h
       if (fast) V4H_TRY(cast_f32_to_bf16(dout, ws.dout_bf, (int64_t)M * d.out_dim, s));
       const void* dY = fast ? (const void*)ws.dout_bf : (const void*)dout;
       const int dy_dt = fast ? DT_BF16 : DT_F32;
-      V4H_TRY(wgrad(p, dY, dy_dt, d.out_dim, ws.a_f, TA, D, gr.final_w, d.out_dim, D, M, s, "wgrad.final"));
+      V4H_TRY(on_side([&](cudaStream_t q) { return wgrad(p, dY, dy_dt, d.out_dim, ws.a_f, TA, D, gr.final_w, d.out_dim, D, M, q, "wgrad.final"); }));
       V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<float>(dout, d.out_dim, gr.final_b, M, d.out_dim, s); }));
       {
         GemmDesc g = fast ? dgrad(dY, DT_BF16, d.out_dim, wa + p.arena_final, DT_BF16, D, M, D, d.out_dim, "dgrad.final")
@@ -388,7 +411,7 @@ int backward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const v4h
       float* dmodL = ws.dmod + (size_t)last * 6 * D;
       V4H_TRY(prof("ln.bwd", 0, (double)M * D * (12 + 3 * sizeof(T)), s, [&] { return ln_modulate_bwd<T>((const T*)ws.dm, ws.h[2 * d.depth], ws.stats_f, ws.mod + offF + D, p.Nmod,
                                  ws.dh, false, ws.dmod + offF, ws.dmod + offF + D, p.Nmod,
-                                 (const T*)ws.blk[last].y2, modL + 5 * D, (T*)ws.dy, dmodL + 5 * D,
+                                 (const T*)ws.blk[last].y2, modL + 5 * D, (T*)ws.dy_mlp[last & 1], dmodL + 5 * D,
                                  gr.blocks[last].fc2_b, M, D, Tn, s); }));
     } else if (stage >= 1) {
       // ---------------- transformer block i
@@ -403,19 +426,23 @@ int backward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const v4h
       const void* Wfc1 = p.bf16 ? (const void*)(wa + p.arena_blocks[i].fc1) : (const void*)bw.fc1_w;
       const void* Wfc2 = p.bf16 ? (const void*)(wa + p.arena_blocks[i].fc2) : (const void*)bw.fc2_w;
 
-      // MLP branch: dy = gate_mlp * dh is ready in ws.dy
-      V4H_TRY(wgrad(p, ws.dy, TA, D, bb.g, TA, Hm, bg.fc2_w, D, Hm, M, s, "wgrad.fc2"));
+      // MLP branch: dy = gate_mlp * dh is ready in dy_mlp[i & 1]; the attention branch uses dy_attn, and the
+      // LayerNorm backward that closes this block writes dy_mlp[(i - 1) & 1]: no buffer a side-stream wgrad of
+      // this block reads is rewritten before the join at the start of the next block
+      void* dy1 = ws.dy_mlp[i & 1];
+      void* dy2 = ws.dy_attn;
+      V4H_TRY(on_side([&](cudaStream_t q) { return wgrad(p, dy1, TA, D, bb.g, TA, Hm, bg.fc2_w, D, Hm, M, q, "wgrad.fc2"); }));
       {
-        GemmDesc g = dgrad(ws.dy, TA, D, Wfc2, TA, Hm, M, Hm, D, "dgrad.fc2");
+        GemmDesc g = dgrad(dy1, TA, D, Wfc2, TA, Hm, M, Hm, D, "dgrad.fc2");
         g.epi = EPI_DACT; g.act = ACT_GELU_TANH; g.out_dtype = TA;
         g.ep.out = ws.du; g.ep.ldo = Hm; g.ep.aux = bb.u; g.ep.ld_aux = Hm;
         V4H_TRY(run_gemm(p, g, s));
       }
       if (p.ldx > D) {  // the ones column of m: fc1 bias gradient out of the same GEMM
-        V4H_TRY(wgrad(p, ws.du, TA, Hm, bb.m, TA, p.ldx, bg.fc1_w, Hm, D, M, s, "wgrad.fc1", bg.fc1_b));
+        V4H_TRY(on_side([&](cudaStream_t q) { return wgrad(p, ws.du, TA, Hm, bb.m, TA, p.ldx, bg.fc1_w, Hm, D, M, q, "wgrad.fc1", bg.fc1_b); }));
       } else {
         V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<T>((const T*)ws.du, Hm, bg.fc1_b, M, Hm, s); }));
-        V4H_TRY(wgrad(p, ws.du, TA, Hm, bb.m, TA, D, bg.fc1_w, Hm, D, M, s, "wgrad.fc1"));
+        V4H_TRY(on_side([&](cudaStream_t q) { return wgrad(p, ws.du, TA, Hm, bb.m, TA, D, bg.fc1_w, Hm, D, M, q, "wgrad.fc1"); }));
       }
       {
         GemmDesc g = dgrad(ws.du, TA, Hm, Wfc1, TA, D, M, D, Hm, "dgrad.fc1");
@@ -423,21 +450,21 @@ int backward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const v4h
         V4H_TRY(run_gemm(p, g, s));
       }
       V4H_TRY(prof("ln.bwd", 0, (double)M * D * (12 + 3 * sizeof(T)), s, [&] { return ln_modulate_bwd<T>((const T*)ws.dm, ws.h[2 * i + 1], bb.stats2, mod + 4 * D, p.Nmod, ws.dh, true,
-                                 dmod + 3 * D, dmod + 4 * D, p.Nmod, (const T*)bb.y1, mod + 2 * D, (T*)ws.dy,
+                                 dmod + 3 * D, dmod + 4 * D, p.Nmod, (const T*)bb.y1, mod + 2 * D, (T*)dy2,
                                  dmod + 2 * D, bg.proj_b, M, D, Tn, s); }));
       // attention branch: dy = gate_msa * dh
-      V4H_TRY(wgrad(p, ws.dy, TA, D, bb.o, TA, D, bg.proj_w, D, D, M, s, "wgrad.proj"));
+      V4H_TRY(on_side([&](cudaStream_t q) { return wgrad(p, dy2, TA, D, bb.o, TA, D, bg.proj_w, D, D, M, q, "wgrad.proj"); }));
       {
-        GemmDesc g = dgrad(ws.dy, TA, D, Wproj, TA, D, M, D, D, "dgrad.proj");
+        GemmDesc g = dgrad(dy2, TA, D, Wproj, TA, D, M, D, D, "dgrad.proj");
         g.ep.out = ws.dm; g.ep.ldo = D; g.out_dtype = TA;
         V4H_TRY(run_gemm(p, g, s));
       }
       V4H_TRY(prof("attn.bwd", 10.0 * B * H * Tn * Tn * dh, (double)M * 9 * D * sizeof(T), s, [&] { return attn_bwd<T>(p, bb.qkv, bb.o, bb.lse, ws.dm, ws.attn_delta, ws.dqkv, B, Tn, H, dh, s); }));
       if (p.ldx > D) {
-        V4H_TRY(wgrad(p, ws.dqkv, TA, 3 * D, bb.a, TA, p.ldx, bg.qkv_w, 3 * D, D, M, s, "wgrad.qkv", bg.qkv_b));
+        V4H_TRY(on_side([&](cudaStream_t q) { return wgrad(p, ws.dqkv, TA, 3 * D, bb.a, TA, p.ldx, bg.qkv_w, 3 * D, D, M, q, "wgrad.qkv", bg.qkv_b); }));
       } else {
         V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<T>((const T*)ws.dqkv, 3 * D, bg.qkv_b, M, 3 * D, s); }));
-        V4H_TRY(wgrad(p, ws.dqkv, TA, 3 * D, bb.a, TA, D, bg.qkv_w, 3 * D, D, M, s, "wgrad.qkv"));
+        V4H_TRY(on_side([&](cudaStream_t q) { return wgrad(p, ws.dqkv, TA, 3 * D, bb.a, TA, D, bg.qkv_w, 3 * D, D, M, q, "wgrad.qkv"); }));
       }
       {
         GemmDesc g = dgrad(ws.dqkv, TA, 3 * D, Wqkv, TA, D, M, D, 3 * D, "dgrad.qkv");
@@ -449,7 +476,7 @@ int backward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const v4h
         float* dmodP = ws.dmod + (size_t)(i - 1) * 6 * D;
         V4H_TRY(prof("ln.bwd", 0, (double)M * D * (12 + 3 * sizeof(T)), s, [&] { return ln_modulate_bwd<T>((const T*)ws.dm, ws.h[2 * i], bb.stats1, mod + 1 * D, p.Nmod, ws.dh, true,
                                    dmod + 0 * D, dmod + 1 * D, p.Nmod, (const T*)ws.blk[i - 1].y2, modP + 5 * D,
-                                   (T*)ws.dy, dmodP + 5 * D, gr.blocks[i - 1].fc2_b, M, D, Tn, s); }));
+                                   (T*)ws.dy_mlp[(i - 1) & 1], dmodP + 5 * D, gr.blocks[i - 1].fc2_b, M, D, Tn, s); }));
       } else {
         V4H_TRY(prof("ln.bwd", 0, (double)M * D * (12 + 3 * sizeof(T)), s, [&] { return ln_modulate_bwd<T>((const T*)ws.dm, ws.h[0], bb.stats1, mod + 1 * D, p.Nmod, ws.dh, true,
                                    dmod + 0 * D, dmod + 1 * D, p.Nmod, (const T*)nullptr, nullptr, (T*)nullptr,
@@ -462,6 +489,7 @@ int backward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const v4h
       return fail(V4H_ERR_INVALID, "internal: stage 0 must be run through backward_stage0");
     }
   }
+  V4H_TRY(join_side());
   return V4H_OK;
 }
 
@@ -588,6 +616,17 @@ int plan_create(const v4h_vit_dims* dims, Plan** out) {
   const char* no_umma = getenv("V4H_DISABLE_UMMA");
   p->use_umma = p->bf16 && !(no_umma && no_umma[0] == '1');
   if (p->use_umma) p->umma = umma_context_create();
+  {
+    const char* e = getenv("V4H_WGRAD_STREAM");
+    if (p->use_umma && !(e && e[0] == '0')) {
+      if (cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        p->side = nullptr;  // no side stream: the weight gradients stay on the caller's stream
+      }
+    }
+  }
   p->ldx = (p->use_umma && d.hidden_dim % 8 == 0) ? d.hidden_dim + 8 : d.hidden_dim;
   const char* no_umma_attn = getenv("V4H_DISABLE_UMMA_ATTN");
   p->use_umma_attn = p->use_umma && attention_umma_supported(d.hidden_dim / d.num_heads) &&
@@ -628,6 +667,9 @@ void plan_destroy(Plan* p) {
   if (p->jobs_dev) cudaFree(p->jobs_dev);
   if (p->jobs_host) cudaFreeHost(p->jobs_host);
   if (p->umma) umma_context_destroy(p->umma);
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->ev_join) cudaEventDestroy(p->ev_join);
+  if (p->side) cudaStreamDestroy(p->side);
   delete p;
 }
 
