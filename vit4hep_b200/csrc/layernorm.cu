@@ -545,6 +545,113 @@ __global__ void __launch_bounds__(256) ln_mod_fwd_vec_kernel(
   }
 }
 
+// streaming forward: same ring as the streaming backward (rows of h bulk-copied SF stages ahead, warp per row);
+// (1 + scale) and shift of the current sample stay in registers and are reloaded when the sample changes
+constexpr int SF = 4;  // stages
+template <typename T>
+__global__ void __launch_bounds__(SW * 32, 3) ln_mod_fwd_stream_kernel(
+    const float* __restrict__ h, const float* __restrict__ shift, const float* __restrict__ scale,
+    int mod_stride, T* __restrict__ a, int ld_a, float2* __restrict__ stats, int M, int D, int rows_per_sample,
+    int rows_per_cta) {
+  using namespace sm100;
+  extern __shared__ uint8_t ln_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ln_smem_raw) + 127) & ~uintptr_t(127));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [SF]
+  uint64_t* empty = full + SF;                         // [SF], SW arrivals
+  uint8_t* ring = smem + 128;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r_begin = blockIdx.x * rows_per_cta;
+  const int r_end = min(M, r_begin + rows_per_cta);
+  const int nv = D >> 2;
+  const float inv_d = 1.f / (float)D;
+  const uint32_t row_f = (uint32_t)D * 4u, stage_bytes = SR * row_f;
+  const int nchunks = (r_end - r_begin + SR - 1) / SR;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SF; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], SW); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  pdl_wait();
+  if (nchunks <= 0) return;
+
+  auto issue = [&](int c) {
+    const int stage = c % SF;
+    if (c >= SF) mbar_wait(&empty[stage], (uint32_t)((c / SF) - 1) & 1u);
+    const int r0 = r_begin + c * SR, rows = min(SR, r_end - r0);
+    mbar_expect_tx(&full[stage], (uint32_t)rows * row_f);
+    bulk_load(ring + (size_t)stage * stage_bytes, h + (size_t)r0 * D, (uint32_t)rows * row_f, &full[stage]);
+  };
+  if (threadIdx.x == 0)
+    for (int c = 0; c < SF - 1 && c < nchunks; ++c) issue(c);
+
+  float4 sc1[SV], sh[SV];
+  int cur_b = -1;
+  for (int c = 0; c < nchunks; ++c) {
+    const int stage = c % SF;
+    if (threadIdx.x == 0 && c + SF - 1 < nchunks) issue(c + SF - 1);
+    __syncwarp();
+    const int row = r_begin + c * SR + warp;
+    const bool row_ok = row < r_end;
+    if (row_ok) {
+      const int b = row / rows_per_sample;
+      if (b != cur_b) {  // warp-uniform
+        cur_b = b;
+#pragma unroll
+        for (int i = 0; i < SV; ++i) {
+          const int cv = lane + 32 * i;
+          sc1[i] = sh[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (cv < nv) {
+            sc1[i] = ld4(scale + (size_t)b * mod_stride + 4 * cv);
+            sc1[i].x += 1.f; sc1[i].y += 1.f; sc1[i].z += 1.f; sc1[i].w += 1.f;
+            sh[i] = ld4(shift + (size_t)b * mod_stride + 4 * cv);
+          }
+        }
+      }
+    }
+    mbar_wait(&full[stage], (uint32_t)(c / SF) & 1u);
+    float4 v[SV];
+#pragma unroll
+    for (int i = 0; i < SV; ++i) {
+      const int cv = lane + 32 * i;
+      v[i] = (row_ok && cv < nv) ? ld4(reinterpret_cast<const float*>(ring + (size_t)stage * stage_bytes) + warp * D + 4 * cv)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[stage]);
+    if (!row_ok) continue;
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < SV; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(sum) * inv_d;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < SV; ++i) {
+      if (lane + 32 * i < nv) {
+        const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+        sq += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * inv_d + LN_EPS);
+    if (lane == 0 && stats) stats[row] = make_float2(mean, rstd);
+    T* ar = a + (size_t)row * ld_a;
+    if (lane < ld_a - D) ar[D + lane] = from_f<T>(lane == 0 ? 1.f : 0.f);  // "ones" column
+#pragma unroll
+    for (int i = 0; i < SV; ++i) {
+      const int cv = lane + 32 * i;
+      if (cv < nv) {
+        float4 o;
+        o.x = (v[i].x - mean) * rstd * sc1[i].x + sh[i].x;
+        o.y = (v[i].y - mean) * rstd * sc1[i].y + sh[i].y;
+        o.z = (v[i].z - mean) * rstd * sc1[i].z + sh[i].z;
+        o.w = (v[i].w - mean) * rstd * sc1[i].w + sh[i].w;
+        st4(ar + 4 * cv, o);
+      }
+    }
+  }
+}
+
+
 // every pointer the vector kernel touches with 16-byte (fp32) / 8-byte (bf16) accesses
 inline bool ln_vec_ok(int D, int mod_stride, int dmod_stride, std::initializer_list<const void*> ptrs) {
   if (D % 4 || D > 512 || mod_stride % 4 || dmod_stride % 4) return false;
@@ -592,6 +699,21 @@ int ln_modulate_fwd(const float* h, const float* shift, const float* scale, int 
                     float2* stats, int M, int D, int rows_per_sample, cudaStream_t s) {
   if (D > MAXV * 32) return fail(V4H_ERR_UNSUPPORTED, "ln_modulate: hidden_dim %d > %d", D, MAXV * 32);
   if (ld_a < D || ld_a - D > 32) return fail(V4H_ERR_INVALID, "ln_modulate: bad output pitch %d for %d columns", ld_a, D);
+  if (ld_a % 4 == 0 && ln_vec_ok(D, mod_stride, 0, {h, shift, scale, a}) && ln_stream_enabled()) {
+    const size_t smem = 256 + (size_t)SF * SR * D * 4;
+    static size_t configured = 0;
+    if (smem > configured) {
+      V4H_CUDA(cudaFuncSetAttribute(ln_mod_fwd_stream_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    // three CTAs per SM (shared memory) in one wave, slabs a multiple of the stage rows
+    const int nslab = std::max(1, std::min((int)ceil_div(M, SR), 3 * sm_count_ln()));
+    const int rows_per_cta = (int)ceil_div(ceil_div(M, nslab), SR) * SR;
+    V4H_CUDA(launch_pdl(ln_mod_fwd_stream_kernel<T>, dim3((unsigned)ceil_div(M, rows_per_cta)), dim3(SW * 32), smem, s, h, shift,
+                        scale, mod_stride, a, ld_a, stats, M, D, rows_per_sample, rows_per_cta));
+    V4H_LAUNCH_CHECK();
+    return V4H_OK;
+  }
   if (ld_a % 4 == 0 && ln_vec_ok(D, mod_stride, 0, {h, shift, scale, a})) {
     V4H_CUDA(launch_pdl(ln_mod_fwd_vec_kernel<T>, dim3((unsigned)ceil_div(M, 32)), dim3(256), 0, s, h, shift, scale, mod_stride, a, ld_a, stats, M, D, rows_per_sample));
     V4H_LAUNCH_CHECK();
