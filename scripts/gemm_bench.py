@@ -7,7 +7,7 @@ from vit4hep_b200 import _cabi
 
 lib = _cabi.load()
 dev = torch.device("cuda:0")
-M, D, H, T = 8640, 480, 1920, 135
+M, D, H, T = int(os.environ.get("GEMM_M", 8640)), 480, 1920, 135
 NAMES = ["p.wait_empty", "p.issue", "m.wait_acc", "m.wait_full", "m.issue", "e.wait_acc", "e.ld", "e.wait_in", "e.math",
          "e.bar", "e.copy", "e.tail"]
 
@@ -43,6 +43,7 @@ def run(name, kind, m, n, k, iters=20):
     c = cnt.cpu().tolist()
     tf = 2.0 * m * n * k / us / 1e6
     per = " ".join(f"{nm}={v / 148 / 1e3:.1f}k" for nm, v in zip(NAMES, c))
+    per += f" clk={c[12]/148/1e3:.1f}k" if len(c) > 12 and c[12] else ""
     print(f"{name:10s} {m}x{n}x{k}: {us:7.1f} us {tf:7.1f} TF | cycles/CTA: {per}", flush=True)
 
 

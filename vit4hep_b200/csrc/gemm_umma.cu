@@ -80,6 +80,7 @@ struct UmmaArgs {
   int tma_store;          // slab mode: results leave through TMA stores (bias / activation / act' epilogues)
   int nbuf;               // staging buffers (or in-flight ring slots) per epilogue group in that mode
   long long* dbg;         // optional device counters (cycles per role / phase), see v4h_debug_gemm
+  int dbg_skip;           // V4H_GEMM_DBG_SKIP (experiments only): 1 = no TMEM reads, 2 = no staging / stores, 4 = no activation
 };
 
 // cycle accounting for v4h_debug_gemm: T.lap(slot) books the cycles since the previous lap
@@ -359,10 +360,22 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    int stage = 0; uint32_t phase = 0;
-    int acc = 0; uint32_t acc_phase = 0;
-    if (rank == 0) {  // pairs: only the leader CTA issues MMAs (for both CTAs)
-      Lap T(lane == 0 ? g.dbg : nullptr);
+    // ONE thread runs the whole loop (pairs: of the leader CTA, for both CTAs).  Its instruction stream is a
+    // dependent chain that shares a scheduler with two epilogue warps, so every instruction per k-block
+    // counts: the shared-memory descriptors are linear in the address, base descriptors are built once and
+    // a k-block costs a few 32-bit adds on their low words (the address field, bits 0-13, in 16-byte units)
+    if (rank == 0 && lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      const uint32_t sa0 = smem_u32(smem);
+      const uint64_t adesc0 = g.a_mn ? make_smem_desc(sa0, BK * 128, 1024) : make_smem_desc(sa0, 0, 1024);
+      const uint64_t bdesc0 = g.b_mn ? make_smem_desc(sa0 + A_BYTES, BK * 128, 1024) : make_smem_desc(sa0 + A_BYTES, 0, 1024);
+      const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
+      const uint32_t a_lo0 = (uint32_t)adesc0, b_lo0 = (uint32_t)bdesc0;
+      const uint32_t a_kstep = (g.a_mn ? 16u * 128u : 32u) >> 4, b_kstep = (g.b_mn ? 16u * 128u : 32u) >> 4;
+      const uint32_t stage_step = (uint32_t)g.stage_bytes >> 4;
+      uint32_t stage_off = 0;  // stage * stage_step
+      Lap T(g.dbg);
       for (int work = unit; work < total_work; work += nunits) {
         const int split = work % g.splits;
         const int tile = work / g.splits;
@@ -373,39 +386,45 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         T.lap(0);
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * MAX_BN;
+        uint32_t accumulate = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           T.lap(1);
-          if (lane == 0) {
-            const uint32_t sa = smem_u32(smem + stage * g.stage_bytes);
-            const uint32_t sb = sa + A_BYTES;
-            // number of K=16 steps with any in-range data in this block (TMA zero-fills the rest)
-            const int ksteps = min(BK / 16, (g.K - kb * BK + 15) / 16);
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t adesc = g.a_mn ? make_smem_desc(sa + k * 16 * 128, BK * 128, 1024)
-                                            : make_smem_desc(sa + k * 32, 0, 1024);
-              const uint64_t bdesc = g.b_mn ? make_smem_desc(sb + k * 16 * 128, BK * 128, 1024)
-                                            : make_smem_desc(sb + k * 32, 0, 1024);
-              if (CTAS == 2) umma_bf16_pair(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-              else umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          const uint32_t a_lo = a_lo0 + stage_off, b_lo = b_lo0 + stage_off;
+          // K = 16 steps with any in-range data in this block (TMA zero-fills the rest): 4 except at the K edge
+          const int ksteps = min(BK / 16, (g.K - kb * BK + 15) / 16);
+          if (ksteps == BK / 16) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t ad = ((uint64_t)a_hi << 32) | (a_lo + k * a_kstep), bd = ((uint64_t)b_hi << 32) | (b_lo + k * b_kstep);
+              if (CTAS == 2) umma_bf16_pair(d_tmem, ad, bd, idesc, k == 0 ? accumulate : 1u);
+              else umma_bf16(d_tmem, ad, bd, idesc, k == 0 ? accumulate : 1u);
             }
-            if (CTAS == 2) {
-              umma_commit_pair(&empty[stage]);                    // frees the smem slot in both CTAs
-              if (kb == kb1 - 1) umma_commit_pair(&acc_full[acc]);  // accumulator complete, both epilogues
-            } else {
-              umma_commit(&empty[stage]);                    // frees the smem slot when the MMAs have read it
-              if (kb == kb1 - 1) umma_commit(&acc_full[acc]);  // accumulator complete
+          } else {
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t ad = ((uint64_t)a_hi << 32) | (a_lo + k * a_kstep), bd = ((uint64_t)b_hi << 32) | (b_lo + k * b_kstep);
+              if (CTAS == 2) umma_bf16_pair(d_tmem, ad, bd, idesc, k == 0 ? accumulate : 1u);
+              else umma_bf16(d_tmem, ad, bd, idesc, k == 0 ? accumulate : 1u);
             }
           }
-          __syncwarp();
+          accumulate = 1;
+          if (CTAS == 2) {
+            umma_commit_pair(&empty[stage]);                    // frees the smem slot in both CTAs
+            if (kb == kb1 - 1) umma_commit_pair(&acc_full[acc]);  // accumulator complete, both epilogues
+          } else {
+            umma_commit(&empty[stage]);                    // frees the smem slot when the MMAs have read it
+            if (kb == kb1 - 1) umma_commit(&acc_full[acc]);  // accumulator complete
+          }
           T.lap(2);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          stage_off += stage_step;
+          if (++stage == STAGES) { stage = 0; stage_off = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       T.flush(2, 3);
     }
+    __syncwarp();
   } else if (warp == 3) {
     // ===================================================================== epilogue-input producer
     if (HAS_IN && lane == 0) {
@@ -472,13 +491,16 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             load32(ep.gate + (size_t)(rr / ep.rows_per_sample) * ep.mod_stride + col0, nvalid, ep.vec_ok, gt);
           }
           float v[SLAB];
-          {
+          if (!(g.dbg_skip & 1)) {
             float lo[16], hi[16];
             tmem_ld16(t_row + j * SLAB, lo);
             tmem_ld16(t_row + j * SLAB + 16, hi);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i) { v[i] = lo[i]; v[16 + i] = hi[i]; }
+          } else {
+#pragma unroll
+            for (int i = 0; i < SLAB; ++i) v[i] = (float)(i + r);
           }
           T.lap(1);
           if (HAS_IN) mbar_wait(&in_full[slot], in_phase);
@@ -488,12 +510,13 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (EPI == EPI_BIAS_ACT) {
 #pragma unroll
             for (int i = 0; i < SLAB; ++i) v[i] += b32[i];
-            if (g.has_out2) box_write<TOut>(st_out2 + sbuf * OUT_BOX, r, v);
-            if (ACT != ACT_NONE) {
+            if (g.has_out2 && !(g.dbg_skip & 2)) box_write<TOut>(st_out2 + sbuf * OUT_BOX, r, v);
+            if (ACT != ACT_NONE && !(g.dbg_skip & 4)) {
 #pragma unroll
               for (int i = 0; i < SLAB; ++i) v[i] = act_f<ACT>(v[i]);
             }
-            box_write<TOut>(so, r, v);
+            if (!(g.dbg_skip & 2)) box_write<TOut>(so, r, v);
+            else if (v[0] == 123.456f) box_write<TOut>(so, r, v);  // keeps v alive
           } else if (EPI == EPI_GATE_RES) {
             uint8_t* box = ring + slot * IN_BOX;
 #pragma unroll
@@ -544,7 +567,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             group_bar_sync(grp);
             T.lap(4);
-            if (leader) {
+            if (leader && !(g.dbg_skip & 2)) {
               if (EPI == EPI_BIAS_ACT) {
                 tma_store_2d(&tmOut, so, col0, m0);
                 if (g.has_out2) tma_store_2d(&tmOut2, st_out2 + sbuf * OUT_BOX, col0, m0);
@@ -823,12 +846,15 @@ int gemm_umma(UmmaContext* ctx, const GemmDesc& d, cudaStream_t s) {
   static const int tma_store_enabled = [] { const char* e = getenv("V4H_GEMM_TMA_STORE"); return (e && e[0] == '0') ? 0 : 1; }();
   g.has_out2 = ep.out2 != nullptr;
   g.dbg = d.dbg;
+  static const int dbg_skip = [] { const char* e = getenv("V4H_GEMM_DBG_SKIP"); return e ? atoi(e) : 0; }();
+  g.dbg_skip = dbg_skip;
+  static const int pool_small = [] { const char* e = getenv("V4H_GEMM_POOL_SMALL"); return (e && e[0] == '1') ? 1 : 0; }();
   if (slab) {
     const int out_box = BM * SLAB * osz;
     switch (d.epi) {
       case EPI_BIAS_ACT:
         g.tma_store = tma_store_enabled;
-        g.nbuf = (g.has_out2 && ctas == 1) ? 2 : 3;  // out + out2 at 3 buffers would starve the mainloop ring
+        g.nbuf = ((g.has_out2 && ctas == 1) || pool_small) ? 2 : 3;  // out + out2 at 3 buffers would starve the mainloop ring
         pool_bytes = EG * (g.has_out2 ? 2 : 1) * (g.tma_store ? g.nbuf : 2) * out_box;
         if (g.tma_store) {
           V4H_TRY(get_map(ctx, ep.out, d.N, d.M, ep.ldo, SLAB, BM, osz, &m.out));
@@ -842,8 +868,8 @@ int gemm_umma(UmmaContext* ctx, const GemmDesc& d, cudaStream_t s) {
         break;
       case EPI_DACT:
         g.tma_store = tma_store_enabled;
-        g.nbuf = 3;
-        g.nslots = g.tma_store ? MAX_SLOTS : 6;  // with in-flight stores each group holds up to 3 slots
+        g.nbuf = pool_small ? 2 : 3;
+        g.nslots = g.tma_store ? (pool_small ? 5 : MAX_SLOTS) : 6;  // with in-flight stores each group holds up to nbuf slots
         pool_bytes = g.nslots * out_box;
         V4H_TRY(get_map(ctx, ep.aux, d.N, d.M, ep.ld_aux, SLAB, BM, osz, &m.in));
         if (g.tma_store) V4H_TRY(get_map(ctx, ep.out, d.N, d.M, ep.ldo, SLAB, BM, osz, &m.out));
