@@ -46,18 +46,27 @@ Profiler& profiler() { static Profiler p; return p; }
 }  // namespace
 
 bool profiling_enabled() { return profiler().on.load(std::memory_order_relaxed); }
+// inside a stream capture the scope's events become EXTERNAL event-record nodes: they are recorded again by
+// every replay of the graph and can be timed afterwards (scripts/graph_profile.py)
+static void record_scope_event(cudaEvent_t e, cudaStream_t s) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) == cudaSuccess && st == cudaStreamCaptureStatusActive)
+    cudaEventRecordWithFlags(e, s, cudaEventRecordExternal);
+  else
+    cudaEventRecord(e, s);
+}
 void profile_open(const char* tag, double flops, double bytes, cudaStream_t s, int* slot) {
   Profiler& p = profiler();
   std::lock_guard<std::mutex> lock(p.mu);
   ProfRecord r{tag, flops, bytes, p.get_event(), p.get_event()};
-  cudaEventRecord(r.e0, s);
+  record_scope_event(r.e0, s);
   p.records.push_back(r);
   *slot = (int)p.records.size() - 1;
 }
 void profile_close(int slot, cudaStream_t s) {
   Profiler& p = profiler();
   std::lock_guard<std::mutex> lock(p.mu);
-  if (slot >= 0 && slot < (int)p.records.size()) cudaEventRecord(p.records[slot].e1, s);
+  if (slot >= 0 && slot < (int)p.records.size()) record_scope_event(p.records[slot].e1, s);
 }
 
 struct Plan;

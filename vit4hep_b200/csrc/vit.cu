@@ -32,8 +32,23 @@ struct Plan {
   int njobs = 0;
   // weight-gradient GEMMs run on a side stream, off the dgrad -> LayerNorm -> attention chain: their CTAs fill
   // the SMs that the chain's kernels leave idle in their ragged tails (V4H_WGRAD_STREAM=0: same stream)
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t side = nullptr, side2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
+  // side streams in use (none while the per-kernel profiler wants launches that do not overlap)
+  bool forking() const { return side != nullptr && !profiling_enabled(); }
+  // q waits for everything issued on s so far
+  int fork(cudaStream_t s, cudaStream_t q) const {
+    V4H_CUDA(cudaEventRecord(ev_fork, s));
+    V4H_CUDA(cudaStreamWaitEvent(q, ev_fork, 0));
+    return V4H_OK;
+  }
+  // s waits for everything issued on the side stream q so far
+  int join(cudaStream_t q, cudaStream_t s) const {
+    cudaEvent_t ev = q == side ? ev_join : ev_join2;
+    V4H_CUDA(cudaEventRecord(ev, q));
+    V4H_CUDA(cudaStreamWaitEvent(s, ev, 0));
+    return V4H_OK;
+  }
 };
 
 namespace {
@@ -219,21 +234,28 @@ int forward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const floa
 
   // ---- positional embedding + patch embedding: h0 = x Wx^T + bx + PE   (nn/vit.py:192-195)
   const float* pe = w.pos_embed;
+  const bool fast = p.bf16 && p.use_umma;  // small Linears on the tensor cores with bf16 operand copies
+  // The embedding of x and the two conditioning MLPs are independent chains of small kernels (a few CTAs each,
+  // latency-bound): the x chain runs on one side stream, the first c_embedder Linear on a second one, the
+  // t_embedder on the caller's stream; they meet at c_embedder.2 (+ te) and before the first block
+  const bool forked = fast && p.forking();
+  cudaStream_t sx = forked ? p.side : s;   // x chain
+  cudaStream_t sc = forked ? p.side2 : s;  // c_embedder.0
+  if (forked) { V4H_TRY(p.fork(s, sx)); V4H_TRY(p.fork(s, sc)); }
   if (d.learn_pos_embed) {
-    V4H_TRY(pos_embedding_fwd(w.pos_embed_freqs, w.pos_z, w.pos_y, w.pos_x, ws.pe, Tn, D / 6, s));
+    V4H_TRY(pos_embedding_fwd(w.pos_embed_freqs, w.pos_z, w.pos_y, w.pos_x, ws.pe, Tn, D / 6, sx));
     pe = ws.pe;
   }
-  const bool fast = p.bf16 && p.use_umma;  // small Linears on the tensor cores with bf16 operand copies
   {
     GemmDesc g = linear_fwd(x, DT_F32, d.patch_dim, w.x_w, DT_F32, d.patch_dim, M, D, d.patch_dim);
     if (fast) {
-      V4H_TRY(cast_f32_to_bf16(x, ws.x_bf, (int64_t)M * d.patch_dim, s));
+      V4H_TRY(cast_f32_to_bf16(x, ws.x_bf, (int64_t)M * d.patch_dim, sx));
       g = linear_fwd(ws.x_bf, DT_BF16, d.patch_dim, wa + p.arena_x, DT_BF16, d.patch_dim, M, D, d.patch_dim);
     }
     g.ep.bias = w.x_b; g.ep.out = ws.h[0]; g.ep.ldo = D;
     g.ep.addend = pe; g.ep.addend_rows = Tn; g.ep.ld_addend = D;
     g.tag = "gemm.x_embed";
-    V4H_TRY(run_gemm(p, g, s));
+    V4H_TRY(run_gemm(p, g, sx));
   }
   // ---- conditioning: cond = t_embedder(t) + c_embedder(c); sc = SiLU(cond)   (nn/vit.py:197-199)
   V4H_TRY(timestep_embedding(t, shared_t ? 1 : 0, ws.temb_in, fast ? ws.temb_bf : nullptr, Bt, d.freq_dim, s));
@@ -249,7 +271,8 @@ int forward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const floa
     g = linear_fwd(c, DT_F32, d.cond_dim, w.c0_w, DT_F32, d.cond_dim, B, D, d.cond_dim); g.tag = "gemm.cond";
     g.act = ACT_SILU; g.out_dtype = DT_BF16;
     g.ep.bias = w.c0_b; g.ep.out = ws.c_h_bf; g.ep.out2 = ws.c_hpre_bf; g.ep.ldo = D;
-    V4H_TRY(run_gemm(p, g, s));
+    V4H_TRY(run_gemm(p, g, sc));
+    if (forked) V4H_TRY(p.join(sc, s));
     g = linear_fwd(ws.c_h_bf, DT_BF16, D, wa + p.arena_c2, DT_BF16, D, B, D, D); g.tag = "gemm.cond";
     g.act = ACT_SILU; g.ep.bias = w.c2_b; g.ep.out = ws.sc; g.ep.out2 = ws.cond; g.ep.ldo = D;
     g.ep.addend = ws.te; g.ep.addend_rows = shared_t ? 1 : 0; g.ep.ld_addend = D;
@@ -288,6 +311,7 @@ int forward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const floa
       V4H_TRY(run_gemm(p, g, s));
     }
   }
+  if (forked) V4H_TRY(p.join(sx, s));  // h0 is needed from here on
   // ---- transformer blocks   (nn/vit.py:327-333)
   for (int i = 0; i < d.depth; ++i) {
     const v4h_block_params& bw = w.blocks[i];
@@ -374,7 +398,7 @@ int backward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const v4h
   // wgrads read are written again (start of the next block) and before returning
   bool side_busy = false;
   auto on_side = [&](auto&& launch) -> int {
-    if (!p.side || profiling_enabled()) return launch(s);  // per-kernel timing wants launches that do not overlap
+    if (!p.forking()) return launch(s);
     V4H_CUDA(cudaEventRecord(p.ev_fork, s));
     V4H_CUDA(cudaStreamWaitEvent(p.side, p.ev_fork, 0));
     side_busy = true;
@@ -499,21 +523,28 @@ int backward_stage0(Plan& p, const v4h_vit_params& w, const char* arena, const v
   const int B = (int)B64, Tn = d.tokens, D = d.hidden_dim, M = B * Tn;
   const bool fast = p.bf16 && p.use_umma;
   const bf16* wa = reinterpret_cast<const bf16*>(arena);
+  // This stage is a long list of small kernels (a few CTAs each).  Only dgrad.adaln -> d SiLU -> the two
+  // MLP dgrads form a chain; the embedding gradients of x and every weight gradient hang off it, so with the
+  // side streams they run next to it: sx = x / positional embedding, sw = weight gradients of the adaLN and
+  // second MLP Linears
+  const bool forked = fast && p.forking();
+  cudaStream_t sx = forked ? p.side2 : s, sw = forked ? p.side : s;
+  if (forked) V4H_TRY(p.fork(s, sx));
   // x_embedder: dW = dh0^T x (the layer input x is not differentiated), db = colsum(dh0)
   if (fast) {
-    V4H_TRY(cast_f32_to_bf16(ws.dh, ws.dh_bf, (int64_t)M * D, s));
-    V4H_TRY(wgrad(p, ws.dh_bf, DT_BF16, D, ws.x_bf, DT_BF16, d.patch_dim, gr.x_w, D, d.patch_dim, M, s, "wgrad.x_embed"));
+    V4H_TRY(cast_f32_to_bf16(ws.dh, ws.dh_bf, (int64_t)M * D, sx));
+    V4H_TRY(wgrad(p, ws.dh_bf, DT_BF16, D, ws.x_bf, DT_BF16, d.patch_dim, gr.x_w, D, d.patch_dim, M, sx, "wgrad.x_embed"));
   } else {
-    V4H_TRY(wgrad(p, ws.dh, DT_F32, D, x, DT_F32, d.patch_dim, gr.x_w, D, d.patch_dim, M, s, "wgrad.x_embed"));
+    V4H_TRY(wgrad(p, ws.dh, DT_F32, D, x, DT_F32, d.patch_dim, gr.x_w, D, d.patch_dim, M, sx, "wgrad.x_embed"));
   }
-  V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<float>(ws.dh, D, gr.x_b, M, D, s); }));
+  V4H_TRY(prof("colsum", 0, 0, sx, [&] { return colsum_add<float>(ws.dh, D, gr.x_b, M, D, sx); }));
   if (d.learn_pos_embed) {
     // sum d h0 over the batch first (a column sum of the (B, T*D) view, into the now idle PE buffer), then
     // one pass over (T, D) applies d PE / d freq
-    V4H_CUDA(cudaMemsetAsync(ws.pe, 0, (size_t)Tn * D * sizeof(float), s));
-    V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<float>(ws.dh, Tn * D, ws.pe, B, Tn * D, s); }));
+    V4H_CUDA(cudaMemsetAsync(ws.pe, 0, (size_t)Tn * D * sizeof(float), sx));
+    V4H_TRY(prof("colsum", 0, 0, sx, [&] { return colsum_add<float>(ws.dh, Tn * D, ws.pe, B, Tn * D, sx); }));
     V4H_TRY(pos_embedding_bwd(ws.pe, w.pos_embed_freqs, w.pos_z, w.pos_y, w.pos_x, gr.pos_embed_freqs, 1, Tn,
-                              D / 6, s));
+                              D / 6, sx));
   }
   // adaLN Linears: d W = dmod^T sc, d b = colsum(dmod), d sc += dmod W
   V4H_CUDA(cudaMemsetAsync(ws.dsc, 0, (size_t)B * D * sizeof(float), s));
@@ -527,9 +558,10 @@ int backward_stage0(Plan& p, const v4h_vit_params& w, const char* arena, const v
   }
   if (ada_contig) {
     V4H_TRY(cast_f32_to_bf16(ws.dmod, ws.dmod_bf16, (int64_t)B * p.Nmod, s));
-    V4H_TRY(wgrad(p, ws.dmod_bf16, DT_BF16, p.Nmod, ws.sc_bf16, DT_BF16, D, gr.blocks[0].ada_w, p.Nmod, D, B, s,
+    if (forked) V4H_TRY(p.fork(s, sw));
+    V4H_TRY(wgrad(p, ws.dmod_bf16, DT_BF16, p.Nmod, ws.sc_bf16, DT_BF16, D, gr.blocks[0].ada_w, p.Nmod, D, B, sw,
                   "wgrad.adaln"));
-    V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<float>(ws.dmod, p.Nmod, gr.blocks[0].ada_b, B, p.Nmod, s); }));
+    V4H_TRY(prof("colsum", 0, 0, sw, [&] { return colsum_add<float>(ws.dmod, p.Nmod, gr.blocks[0].ada_b, B, p.Nmod, sw); }));
     GemmDesc g = dgrad(ws.dmod_bf16, DT_BF16, p.Nmod, wa + p.arena_ada, DT_BF16, D, B, D, p.Nmod, "dgrad.adaln");
     g.epi = EPI_ATOMIC; g.ep.out = ws.dsc; g.ep.ldo = D; g.splitk = 0;
     V4H_TRY(run_gemm(p, g, s));
@@ -563,9 +595,12 @@ int backward_stage0(Plan& p, const v4h_vit_params& w, const char* arena, const v
     Mlp mlps[2] = {
         {c, DT_F32, d.cond_dim, ws.c_hpre_bf, ws.c_h_bf, wa + p.arena_c2, gr.c0_w, gr.c0_b, gr.c2_w, gr.c2_b},
         {ws.temb_bf, DT_BF16, d.freq_dim, ws.t_hpre_bf, ws.t_h_bf, wa + p.arena_t2, gr.t0_w, gr.t0_b, gr.t2_w, gr.t2_b}};
+    if (forked) V4H_TRY(p.fork(s, sw));  // d cond is ready
     for (const Mlp& m : mlps) {
-      V4H_TRY(wgrad(p, ws.dcond_bf, DT_BF16, D, m.h, DT_BF16, D, m.dw2, D, D, B, s, "wgrad.cond"));
-      V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<float>(ws.dcond, D, m.db2, B, D, s); }));
+      V4H_TRY(wgrad(p, ws.dcond_bf, DT_BF16, D, m.h, DT_BF16, D, m.dw2, D, D, B, sw, "wgrad.cond"));
+      V4H_TRY(prof("colsum", 0, 0, sw, [&] { return colsum_add<float>(ws.dcond, D, m.db2, B, D, sw); }));
+    }
+    for (const Mlp& m : mlps) {
       GemmDesc g = dgrad(ws.dcond_bf, DT_BF16, D, m.w2, DT_BF16, D, B, D, D, "dgrad.cond");
       g.epi = EPI_DACT; g.act = ACT_SILU; g.out_dtype = DT_BF16;
       g.ep.out = ws.dvec_bf; g.ep.ldo = D; g.ep.aux = m.h_pre; g.ep.ld_aux = D;
@@ -573,6 +608,7 @@ int backward_stage0(Plan& p, const v4h_vit_params& w, const char* arena, const v
       V4H_TRY(wgrad(p, ws.dvec_bf, DT_BF16, D, m.in, m.in_dt, m.in_dim, m.dw0, D, m.in_dim, B, s, "wgrad.cond"));
       V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<bf16>(ws.dvec_bf, D, m.db0, B, D, s); }));
     }
+    if (forked) { V4H_TRY(p.join(sw, s)); V4H_TRY(p.join(sx, s)); }
   } else {
     struct Mlp { const float *in, *h_pre, *h; int in_dim; const float* w2; float *dw0, *db0, *dw2, *db2; };
     Mlp mlps[2] = {
@@ -620,10 +656,12 @@ int plan_create(const v4h_vit_dims* dims, Plan** out) {
     const char* e = getenv("V4H_WGRAD_STREAM");
     if (p->use_umma && !(e && e[0] == '0')) {
       if (cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaStreamCreateWithFlags(&p->side2, cudaStreamNonBlocking) != cudaSuccess ||
           cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-          cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+          cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&p->ev_join2, cudaEventDisableTiming) != cudaSuccess) {
         cudaGetLastError();
-        p->side = nullptr;  // no side stream: the weight gradients stay on the caller's stream
+        p->side = nullptr;  // no side streams: everything stays on the caller's stream
       }
     }
   }
@@ -669,7 +707,9 @@ void plan_destroy(Plan* p) {
   if (p->umma) umma_context_destroy(p->umma);
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
   if (p->ev_join) cudaEventDestroy(p->ev_join);
+  if (p->ev_join2) cudaEventDestroy(p->ev_join2);
   if (p->side) cudaStreamDestroy(p->side);
+  if (p->side2) cudaStreamDestroy(p->side2);
   delete p;
 }
 
