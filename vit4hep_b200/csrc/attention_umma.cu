@@ -5,22 +5,29 @@
 // Layouts are the ones the qkv Linear produces (reference nn/vit.py:427): qkv (B, T, 3, H, dh),
 // o / d_o (B, T, H, dh), lse and delta (B, H, T) fp32, lse = log sum_j exp(s_ij) of the scaled scores.
 //
-// Every operand tile lives in shared memory in ONE physical format ("G8"): element (row, col) of a
-// [ROWS x COLS] bf16 tile sits at  (col / 8) * gstride + row * 16 + (col % 8) * 2  bytes, i.e. 8x8 core
-// matrices of 128 contiguous bytes, the non-swizzled canonical UMMA layout.  The same bytes are read
-//   - as a K-major operand  (rows = M/N index, cols = K index):  LBO = gstride, SBO = 128
-//   - as an MN-major operand (rows = K index, cols = M/N index): LBO = 128,     SBO = gstride
-// so Q, K, V, dO are staged once and serve both Q K^T-like and P V-like products.  gstride carries one
-// 16-byte pad so that the 16-byte cp.async / st.shared writes of a warp spread over all banks.
+// Two shared-memory tile formats:
+//  - "W" tiles for everything TMA loads (Q, K, V, dO, O): ceil(dh / 64) boxes of [rows][64 columns], 128-byte
+//    swizzle (see w_boxes / desc_kmajor / desc_mnmajor below).  Forward and fused backward use them.
+//  - "G8" tiles for what threads write (P, dS) and for the dQ / dKdV kernels of long sequences: element
+//    (row, col) of a [ROWS x COLS] bf16 tile sits at  (col / 8) * gstride + row * 16 + (col % 8) * 2  bytes,
+//    i.e. 8x8 core matrices of 128 contiguous bytes, the non-swizzled canonical UMMA layout; gstride carries
+//    one 16-byte pad so that the 16-byte st.shared writes of a warp spread over all banks.
+// Either format is read
+//   - as a K-major operand  (rows = M/N index, cols = K index)
+//   - as an MN-major operand (rows = K index, cols = M/N index)
+// so Q, K, V, dO are staged once and serve both Q K^T-like and P V-like products, and one [q][key] tile of
+// P / dS feeds dV^T = dO^T P and dK^T = Q^T dS without a transposed copy.
 // Head dims that are not multiples of 64 (dh = 80 here) cost nothing: K steps are 16 wide.
 //
-// Three kernels, 128 threads each (thread = one TMEM lane = one row of the 128-row M tile):
-//   fwd  : CTA per (128 queries, sample-head); loops over key blocks with an online softmax
-//          S = Q K^T -> TMEM, p = exp2(..) -> bf16 P in smem, O += P V through TMEM
-//   dq   : CTA per (128 queries, sample-head); S and dP = dO V^T in TMEM, dS -> smem, dQ += dS K
-//          accumulated in TMEM over the key blocks; also emits delta = rowsum(dO * O)
-//   dkv  : CTA per (128 keys, sample-head); S^T = K Q^T and dP^T = V dO^T in TMEM, P^T / dS^T -> smem,
-//          dV += P^T dO, dK += dS^T Q accumulated in TMEM over the query blocks
+// Kernels (thread = one TMEM lane = one row of the 128-row M tile):
+//   fwd   : CTA per (128 queries, sample-head), 128 threads; loops over key blocks with an online softmax
+//           (one block, registers only, for T <= 160): S = Q K^T -> TMEM, p = exp2(..) -> bf16 P in smem,
+//           O += P V through TMEM
+//   fused : T <= 160: ONE CTA (256 threads) per (sample, head) computes dQ, dK, dV in one pass
+//   dq    : CTA per (128 queries, sample-head); S and dP = dO V^T in TMEM, dS -> smem, dQ += dS K
+//           accumulated in TMEM over the key blocks; also emits delta = rowsum(dO * O)
+//   dkv   : CTA per (128 keys, sample-head); S^T = K Q^T and dP^T = V dO^T in TMEM, P^T / dS^T -> smem,
+//           dV += P^T dO, dK += dS^T Q accumulated in TMEM over the query blocks
 // Rows / keys beyond T are zero-filled on load and masked in the softmax.
 #include <cuda.h>
 
