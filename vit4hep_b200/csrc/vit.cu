@@ -75,7 +75,7 @@ struct Workspace {
   bf16* sc_bf16;
   // bf16 mode: tensor-core operands of the embedding / conditioning / output Linears
   bf16 *x_bf, *temb_bf, *t_h_bf, *t_hpre_bf, *c_h_bf, *c_hpre_bf;
-  bf16 *dout_bf, *dh_bf, *dcond_bf, *dvec_bf;  // backward only
+  bf16 *dout_bf, *dh_bf, *dcond_bf, *dvec_bf, *dvec2_bf;  // backward only
   // residual stream (fp32): training keeps 2*depth+1 copies, inference 1
   std::vector<float*> h;
   std::vector<BlockBufs> blk;  // training: depth entries; inference: 1 shared entry
@@ -139,12 +139,12 @@ struct Workspace {
       attn_delta = (float*)take((size_t)B * d.num_heads * d.tokens * 4);
       if (p.bf16) {
         dout_bf = (bf16*)take(M * d.out_dim * 2); dh_bf = (bf16*)take(M * D * 2);
-        dcond_bf = (bf16*)take(B * D * 2); dvec_bf = (bf16*)take(B * D * 2);
+        dcond_bf = (bf16*)take(B * D * 2); dvec_bf = (bf16*)take(B * D * 2); dvec2_bf = (bf16*)take(B * D * 2);
       } else {
-        dout_bf = dh_bf = dcond_bf = dvec_bf = nullptr;
+        dout_bf = dh_bf = dcond_bf = dvec_bf = dvec2_bf = nullptr;
       }
     } else {
-      dout_bf = dh_bf = dcond_bf = dvec_bf = nullptr;
+      dout_bf = dh_bf = dcond_bf = dvec_bf = dvec2_bf = nullptr;
       dh = dmod = dsc = dcond = dvec = attn_delta = nullptr; dmod_bf16 = nullptr;
       dy_mlp[0] = dy_mlp[1] = dy_attn = du = dm = dqkv = nullptr;
     }
@@ -423,7 +423,7 @@ int backward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const v4h
       const void* dY = fast ? (const void*)ws.dout_bf : (const void*)dout;
       const int dy_dt = fast ? DT_BF16 : DT_F32;
       V4H_TRY(on_side([&](cudaStream_t q) { return wgrad(p, dY, dy_dt, d.out_dim, ws.a_f, TA, D, gr.final_w, d.out_dim, D, M, q, "wgrad.final"); }));
-      V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<float>(dout, d.out_dim, gr.final_b, M, d.out_dim, s); }));
+      V4H_TRY(on_side([&](cudaStream_t q) { return prof("colsum", 0, 0, q, [&] { return colsum_add<float>(dout, d.out_dim, gr.final_b, M, d.out_dim, q); }); }));
       {
         GemmDesc g = fast ? dgrad(dY, DT_BF16, d.out_dim, wa + p.arena_final, DT_BF16, D, M, D, d.out_dim, "dgrad.final")
                           : dgrad(dout, DT_F32, d.out_dim, w.final_w, DT_F32, D, M, D, d.out_dim, "dgrad.final");
@@ -600,13 +600,19 @@ int backward_stage0(Plan& p, const v4h_vit_params& w, const char* arena, const v
       V4H_TRY(wgrad(p, ws.dcond_bf, DT_BF16, D, m.h, DT_BF16, D, m.dw2, D, D, B, sw, "wgrad.cond"));
       V4H_TRY(prof("colsum", 0, 0, sw, [&] { return colsum_add<float>(ws.dcond, D, m.db2, B, D, sw); }));
     }
-    for (const Mlp& m : mlps) {
+    // the two MLPs are independent from here on: the t_embedder's chain (dgrad -> weight gradient) runs on the
+    // x side stream next to the c_embedder's on the caller's stream, each with its own d hidden buffer
+    if (forked) V4H_TRY(p.fork(s, sx));
+    for (int k = 0; k < 2; ++k) {
+      const Mlp& m = mlps[k];
+      cudaStream_t q = k == 1 ? sx : s;
+      bf16* dvec = k == 1 ? ws.dvec2_bf : ws.dvec_bf;
       GemmDesc g = dgrad(ws.dcond_bf, DT_BF16, D, m.w2, DT_BF16, D, B, D, D, "dgrad.cond");
       g.epi = EPI_DACT; g.act = ACT_SILU; g.out_dtype = DT_BF16;
-      g.ep.out = ws.dvec_bf; g.ep.ldo = D; g.ep.aux = m.h_pre; g.ep.ld_aux = D;
-      V4H_TRY(run_gemm(p, g, s));
-      V4H_TRY(wgrad(p, ws.dvec_bf, DT_BF16, D, m.in, m.in_dt, m.in_dim, m.dw0, D, m.in_dim, B, s, "wgrad.cond"));
-      V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<bf16>(ws.dvec_bf, D, m.db0, B, D, s); }));
+      g.ep.out = dvec; g.ep.ldo = D; g.ep.aux = m.h_pre; g.ep.ld_aux = D;
+      V4H_TRY(run_gemm(p, g, q));
+      V4H_TRY(wgrad(p, dvec, DT_BF16, D, m.in, m.in_dt, m.in_dim, m.dw0, D, m.in_dim, B, q, "wgrad.cond"));
+      V4H_TRY(prof("colsum", 0, 0, q, [&] { return colsum_add<bf16>(dvec, D, m.db0, B, D, q); }));
     }
     if (forked) { V4H_TRY(p.join(sw, s)); V4H_TRY(p.join(sx, s)); }
   } else {
