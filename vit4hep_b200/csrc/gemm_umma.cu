@@ -271,7 +271,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (HAS_IN) prefetch_tensormap(&tmIn);
     if (SLABMODE && g.tma_store) {
       prefetch_tensormap(&tmOut);
-      if (g.has_out2) prefetch_tensormap(&tmOut2);
+      if (g.has_out2 && EPI == EPI_BIAS_ACT) prefetch_tensormap(&tmOut2);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -453,7 +453,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // pool layout: [ring: nslots x IN_BOX] then per group [out: 2 x OUT_BOX] [out2: 2 x OUT_BOX]
     uint8_t* ring = pool;
     const int NB = g.tma_store ? g.nbuf : 2;  // staging buffers per output and group
-    const int group_staging = (EPI == EPI_BIAS_ACT ? (g.has_out2 ? 2 : 1) * NB : (EPI == EPI_GATE_RES ? 2 : 0)) * OUT_BOX;
+    const int group_staging =
+        (EPI == EPI_BIAS_ACT ? (g.has_out2 ? 2 : 1) * NB : (EPI == EPI_GATE_RES && !g.tma_store ? 2 : 0)) * OUT_BOX;
     uint8_t* st_out = pool + (HAS_IN ? g.nslots * IN_BOX : 0) + grp * group_staging;
     uint8_t* st_out2 = st_out + NB * OUT_BOX;
     const bool leader = (threadIdx.x & 127) == 0;  // first thread of the group: issues its TMA stores
@@ -521,7 +522,28 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint8_t* box = ring + slot * IN_BOX;
 #pragma unroll
             for (int i = 0; i < SLAB; ++i) v[i] += b32[i];                 // y
-            if (g.has_out2) box_write<TOut>(so, r, v);
+            if (g.has_out2) {
+              if (!g.tma_store) {
+                box_write<TOut>(so, r, v);
+              } else if (row < g.M) {
+                // TMA-store mode keeps no staging for y: the thread writes its row's 32 values directly (whole
+                // 32-byte sectors; y is only read again by the backward)
+                TOut* yrow = reinterpret_cast<TOut*>(ep.out2) + (size_t)row * ep.ldo + col0;
+                if (nvalid >= SLAB && ep.vec_ok) {
+                  if (sizeof(TOut) == 2) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) reinterpret_cast<uint4*>(yrow)[c] = pack8(&v[8 * c]);
+                  } else {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                      reinterpret_cast<float4*>(yrow)[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                  }
+                } else {
+                  for (int i = 0; i < SLAB; ++i)
+                    if (i < nvalid) yrow[i] = from_f<TOut>(v[i]);
+                }
+              }
+            }
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
               uint8_t* p = box + box_off(r, c, 4);
@@ -554,7 +576,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           T.lap(3);
-          if (EPI != EPI_GATE_RES && g.tma_store) {
+          if (g.tma_store) {
             // staged boxes complete -> TMA stores, asynchronous: the group goes on with the next slab while
             // they drain.  Before the barrier the leader makes sure the stores of NB - 1 slabs ago have
             // finished reading shared memory: their staging buffer is the one the NEXT slab writes, and
@@ -571,7 +593,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (EPI == EPI_BIAS_ACT) {
                 tma_store_2d(&tmOut, so, col0, m0);
                 if (g.has_out2) tma_store_2d(&tmOut2, st_out2 + sbuf * OUT_BOX, col0, m0);
-              } else {
+              } else {  // gate+residual / act': the transformed input box itself
                 tma_store_2d(&tmOut, ring + slot * IN_BOX, col0, m0);
               }
               tma_store_commit();
@@ -848,6 +870,7 @@ int gemm_umma(UmmaContext* ctx, const GemmDesc& d, cudaStream_t s) {
   g.dbg = d.dbg;
   static const int dbg_skip = [] { const char* e = getenv("V4H_GEMM_DBG_SKIP"); return e ? atoi(e) : 0; }();
   g.dbg_skip = dbg_skip;
+  static const int gate_res_tma_store = [] { const char* e = getenv("V4H_GEMM_GATE_TMA_STORE"); return (e && e[0] == '0') ? 0 : 1; }();
   static const int pool_small = [] { const char* e = getenv("V4H_GEMM_POOL_SMALL"); return (e && e[0] == '1') ? 1 : 0; }();
   if (slab) {
     const int out_box = BM * SLAB * osz;
@@ -862,8 +885,18 @@ int gemm_umma(UmmaContext* ctx, const GemmDesc& d, cudaStream_t s) {
         }
         break;
       case EPI_GATE_RES:
-        g.nslots = ctas == 2 ? 4 : 3;
-        pool_bytes = g.nslots * BM * SLAB * 4 + EG * 2 * out_box;
+        // TMA-store mode: the residual box is updated in place and stored from its ring slot, each group keeps
+        // up to nbuf slots in flight; y (out2) is written from registers, so the pool is the ring alone
+        g.tma_store = tma_store_enabled && gate_res_tma_store && ep.vec_ok;
+        if (g.tma_store) {
+          g.nbuf = 2;
+          g.nslots = 5;
+          pool_bytes = g.nslots * BM * SLAB * 4;
+          V4H_TRY(get_map(ctx, ep.res_out, d.N, d.M, ep.ldo, SLAB, BM, 4, &m.out));
+        } else {
+          g.nslots = ctas == 2 ? 4 : 3;
+          pool_bytes = g.nslots * BM * SLAB * 4 + EG * 2 * out_box;
+        }
         V4H_TRY(get_map(ctx, ep.res_in, d.N, d.M, ep.ldo, SLAB, BM, 4, &m.in));
         break;
       case EPI_DACT:
