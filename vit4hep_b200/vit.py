@@ -208,6 +208,7 @@ class ViT(nn.Module):
         self.initialize_weights()
         self._native = _Native()
         self._dp = None  # set by vit4hep_b200.dp.enable_data_parallel
+        self._aux_streams = {}
 
     # ------------------------------------------------------------------ reference-visible helpers
     def create_meshgrid(self):
@@ -281,6 +282,14 @@ class ViT(nn.Module):
         out += [(f"blocks.{i}.ada_b", a.bias) for i, a in enumerate(adas)]
         out.append(("final_ada_b", fl.adaLN_modulation[-1].bias))
         return out
+
+    def _aux_stream(self, device) -> "torch.cuda.Stream":
+        """side stream for host-issued work that is independent of the kernel chain (gradient buffer clear)"""
+        key = torch.device(device).index
+        st = self._aux_streams.get(key)
+        if st is None:
+            st = self._aux_streams[key] = torch.cuda.Stream(device=device)
+        return st
 
     FLAT_ALIGN = 4  # elements: every gradient starts on a 16-byte boundary of the flat buffer
 
@@ -436,7 +445,18 @@ class _ViTFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module: ViT, x, t, c, shared_t, *params):
         ordered = module.ordered_parameters()
+        # the flat gradient buffer (split-K weight gradients accumulate into it) is allocated and cleared on a
+        # side stream, next to the forward kernels, instead of at the head of the backward chain
+        _, total = module.flat_layout(ordered)
+        cur = torch.cuda.current_stream(x.device)
+        side = module._aux_stream(x.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            flat = torch.zeros(total, dtype=torch.float32, device=x.device)
+        ctx.flat, ctx.flat_ready = flat, side.record_event()
         out, ws, _ = module._run_forward(x, t, c, shared_t, True, ordered)
+        cur.wait_event(ctx.flat_ready)  # also rejoins the side stream when the step is being captured
+        flat.record_stream(cur)
         ctx.module = module
         ctx.ws = ws
         ctx.save_for_backward(x, c)
@@ -449,7 +469,7 @@ class _ViTFunction(torch.autograd.Function):
         x, c = ctx.saved_tensors
         ordered = module.ordered_parameters()
         offs, total = module.flat_layout(ordered)
-        flat = torch.zeros(total, dtype=torch.float32, device=x.device)
+        flat, ctx.flat = ctx.flat, None
         dout = dout.contiguous()
         depth = len(module.blocks)
         if module._dp is None:
