@@ -7,8 +7,8 @@
 //
 // Two shared-memory tile formats:
 //  - "W" tiles for everything TMA loads (Q, K, V, dO, O): ceil(dh / 64) boxes of [rows][64 columns], 128-byte
-//    swizzle (see w_boxes / desc_kmajor / desc_mnmajor below).  Forward and fused backward use them.
-//  - "G8" tiles for what threads write (P, dS) and for the dQ / dKdV kernels of long sequences: element
+//    swizzle (see w_boxes / desc_kmajor / desc_mnmajor below).
+//  - "G8" tiles for what threads write (P, dS, P^T, dS^T): element
 //    (row, col) of a [ROWS x COLS] bf16 tile sits at  (col / 8) * gstride + row * 16 + (col % 8) * 2  bytes,
 //    i.e. 8x8 core matrices of 128 contiguous bytes, the non-swizzled canonical UMMA layout; gstride carries
 //    one 16-byte pad so that the 16-byte st.shared writes of a warp spread over all banks.
@@ -89,39 +89,6 @@ __host__ __device__ constexpr uint32_t g8_stride(int rows) { return (uint32_t)(r
 __host__ __device__ constexpr uint32_t g8_bytes(int rows, int cols) { return (uint32_t)(cols / 8) * g8_stride(rows); }
 // allocation of a tile that TMA may write: 128-byte aligned extents
 __host__ __device__ constexpr uint32_t g8_alloc(int rows, int cols) { return (g8_bytes(rows, cols) + 127u) & ~127u; }
-
-// Stage `rows` x DHP (bf16) from global (row pitch `ld` elements) into a G8 tile; rows >= rows_valid
-// and column groups >= dh are zero-filled.
-// Only the first `load_rows` rows are touched (the rest of the tile keeps whatever it held: rows that no
-// stored result depends on).
-template <int DHP, int NTHREADS = ATT_THREADS>
-__device__ __forceinline__ void stage_tile(uint32_t dst, int rows, const bf16* __restrict__ src, size_t ld,
-                                           int rows_valid, int dh, int load_rows = -1) {
-  constexpr int NCG = DHP / 8;        // 16-byte column groups per row
-  constexpr int RPI = NTHREADS / NCG;  // rows per sweep: every thread keeps one column group
-  if ((int)threadIdx.x >= RPI * NCG) return;
-  const int r0 = (int)threadIdx.x / NCG, cg = (int)threadIdx.x - r0 * NCG;
-  const bool col_ok = cg * 8 < dh;
-  const bf16* p = src + (size_t)r0 * ld + cg * 8;
-  uint32_t d = dst + cg * g8_stride(rows) + r0 * 16;
-  const int nload = load_rows < 0 ? rows : load_rows;
-  for (int row = r0; row < nload; row += RPI, p += (size_t)RPI * ld, d += RPI * 16) {
-    const bool ok = col_ok && row < rows_valid;
-    cp_async16(d, ok ? (const void*)p : (const void*)src, ok);
-  }
-}
-
-// D[tmem 128 x n] (+)= A[128 x 16*ksteps] B, A always K-major G8 (128 rows); B either K-major G8
-// (rows = N index) or MN-major G8 (rows = K index).  One thread.
-__device__ __forceinline__ void issue_mma(uint32_t d_tmem, uint32_t a_base, uint32_t a_gs, uint32_t b_base,
-                                          uint32_t b_gs, bool b_mn, int n, int ksteps, bool accumulate_first) {
-  const uint32_t idesc = make_idesc_bf16(MT, n, false, b_mn);
-  for (int ks = 0; ks < ksteps; ++ks) {
-    const uint64_t ad = desc_ns(a_base + 2 * ks * a_gs, a_gs, 128);
-    const uint64_t bd = b_mn ? desc_ns(b_base + ks * 256, 128, b_gs) : desc_ns(b_base + 2 * ks * b_gs, b_gs, 128);
-    umma_bf16(d_tmem, ad, bd, idesc, (accumulate_first || ks > 0) ? 1u : 0u);
-  }
-}
 
 struct AttnSmem {
   uint64_t bar;      // MMA completion
@@ -546,18 +513,25 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_umma_kernel(const __grid
 
 // ------------------------------------------------------------------------------------------ dQ (+ delta)
 template <int DHP>
-__global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_umma_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_umma_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                       const __grid_constant__ CUtensorMap tmKV,
+                                                                       const __grid_constant__ CUtensorMap tmdO,
+                                                                       const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = align128(smem_raw);
+  uint8_t* smem = align1024(smem_raw);
   AttnSmem* ctl = reinterpret_cast<AttnSmem*>(smem);
+  uint8_t* tiles = smem + 1024;
   const int BN = a.BN, T = a.T, H = a.H, dh = a.dh;
-  const uint32_t sQ = smem_u32(smem + 128);
-  const uint32_t sdO = sQ + g8_bytes(MT, DHP);
-  const uint32_t sK = sdO + g8_bytes(MT, DHP);
-  const uint32_t sV = sK + g8_bytes(BN, DHP);
-  const uint32_t sdS = sV + g8_bytes(BN, DHP);
-  uint8_t* sdS_ptr = smem + 128 + 2 * g8_bytes(MT, DHP) + 2 * g8_bytes(BN, DHP);
-  const uint32_t gsQ = g8_stride(MT), gsKV = g8_stride(BN), gsS = g8_stride(MT);
+  uint8_t* pQ = tiles;
+  uint8_t* pdO = pQ + w_bytes(MT, DHP);
+  uint8_t* pK = pdO + w_bytes(MT, DHP);
+  uint8_t* pV = pK + w_bytes(BN, DHP);
+  uint8_t* sdS_ptr = pV + w_bytes(BN, DHP);
+  const uint32_t gsS = g8_stride(MT);
+  const Opnd oQ = opnd_w(smem_u32(pQ), MT), odO = opnd_w(smem_u32(pdO), MT), oK = opnd_w(smem_u32(pK), BN),
+             oV = opnd_w(smem_u32(pV), BN), odS = opnd_g8(smem_u32(sdS_ptr), gsS);
+  const bool tma = a.use_tma != 0;
+  uint32_t ld_phase = 0;
 
   const int bh = blockIdx.y, b = bh / H, hd = bh % H;
   const int q0 = blockIdx.x * MT;
@@ -574,8 +548,30 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_umma_kernel(const Att
   const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
   uint32_t phase = 0;
 
-  stage_tile<DHP>(sQ, MT, qbase + (size_t)q0 * ld, ld, T - q0, dh);
-  stage_tile<DHP>(sdO, MT, dobase + (size_t)q0 * ldo, ldo, T - q0, dh);
+  // Q and dO of this tile and the first K / V block are requested before the row statistics are read
+  auto load_kv = [&](int blk, bool with_q) {
+    const int n0 = blk * BN;
+    if (tma) {
+      if (tid == 0) {
+        mbar_expect_tx(&ctl->ld_bar, 2 * w_bytes(BN, DHP) + (with_q ? 2 * w_bytes(MT, DHP) : 0u));
+        if (with_q) {
+          tma_load_w<DHP>(pQ, MT, &tmQ, &ctl->ld_bar, hd * dh, q0, b);
+          tma_load_w<DHP>(pdO, MT, &tmdO, &ctl->ld_bar, hd * dh, q0, b);
+        }
+        tma_load_w<DHP>(pK, BN, &tmKV, &ctl->ld_bar, (H + hd) * dh, n0, b);
+        tma_load_w<DHP>(pV, BN, &tmKV, &ctl->ld_bar, (2 * H + hd) * dh, n0, b);
+      }
+    } else {
+      const int nvalid = min(BN, T - n0);
+      if (with_q) {
+        stage_tile_w<DHP, ATT_THREADS>(oQ.base, MT, qbase + (size_t)q0 * ld, ld, T - q0, dh, MT);
+        stage_tile_w<DHP, ATT_THREADS>(odO.base, MT, dobase + (size_t)q0 * ldo, ldo, T - q0, dh, MT);
+      }
+      stage_tile_w<DHP, ATT_THREADS>(oK.base, BN, kbase + (size_t)n0 * ld, ld, nvalid, dh, BN);
+      stage_tile_w<DHP, ATT_THREADS>(oV.base, BN, vbase + (size_t)n0 * ld, ld, nvalid, dh, BN);
+    }
+  };
+  load_kv(0, true);
 
   // this thread's row statistics: delta = sum_d dO * O, lse (in log2 units)
   const int q = q0 + tid;
@@ -608,13 +604,13 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_umma_kernel(const Att
   for (int blk = 0; blk < a.nblocks; ++blk) {
     const int n0 = blk * BN;
     const int nvalid = min(BN, T - n0);
-    stage_tile<DHP>(sK, BN, kbase + (size_t)n0 * ld, ld, nvalid, dh);
-    stage_tile<DHP>(sV, BN, vbase + (size_t)n0 * ld, ld, nvalid, dh);
-    cp_async_wait_all();
+    if (blk > 0) load_kv(blk, false);
+    if (tma) { mbar_wait(&ctl->ld_bar, ld_phase); ld_phase ^= 1; }
+    else cp_async_wait_all();
     publish_smem_and_sync();
     if (tid == 0) {
-      issue_mma(tS, sQ, gsQ, sK, gsKV, false, BN, DHP / 16, false);
-      issue_mma(tdP, sdO, gsQ, sV, gsKV, false, BN, DHP / 16, false);
+      issue_mma_x(tS, oQ, false, oK, false, BN, DHP / 16, false);
+      issue_mma_x(tdP, odO, false, oV, false, BN, DHP / 16, false);
       umma_commit(&ctl->bar);
     }
     mbar_wait(&ctl->bar, phase); phase ^= 1;
@@ -631,13 +627,13 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_umma_kernel(const Att
         const float p1 = c0 + i + 1 < nvalid ? exp2_fast(fmaf(s[i + 1], a.scale_log2, -lse2)) : 0.f;
         w[i / 2] = pack_bf16(p0 * (dp[i] - delta), p1 * (dp[i + 1] - delta));
       }
-      uint8_t* dst = sdS_ptr + (size_t)(c0 / 8) * gsS + tid * 16;
-      *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-      *reinterpret_cast<uint4*>(dst + gsS) = make_uint4(w[4], w[5], w[6], w[7]);
+      const uint32_t dst = odS.base + (uint32_t)(c0 / 8) * gsS + (uint32_t)tid * 16u;
+      sts128(dst, w[0], w[1], w[2], w[3]);
+      sts128(dst + gsS, w[4], w[5], w[6], w[7]);
     }
     publish_smem_and_sync();
     if (tid == 0) {
-      issue_mma(tdQ, sdS, gsS, sK, gsKV, true, DHP, BN / 16, blk > 0);
+      issue_mma_x(tdQ, odS, false, oK, true, DHP, BN / 16, blk > 0);
       umma_commit(&ctl->bar);
     }
     mbar_wait(&ctl->bar, phase); phase ^= 1;
@@ -672,23 +668,28 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_umma_kernel(const Att
 
 // ------------------------------------------------------------------------------------------ dK, dV
 template <int DHP>
-__global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_umma_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_umma_kernel(const __grid_constant__ CUtensorMap tmK,
+                                                                        const __grid_constant__ CUtensorMap tmQ,
+                                                                        const __grid_constant__ CUtensorMap tmdO,
+                                                                        const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = align128(smem_raw);
+  uint8_t* smem = align1024(smem_raw);
   AttnSmem* ctl = reinterpret_cast<AttnSmem*>(smem);
   const int BQ = a.BN, T = a.T, H = a.H, dh = a.dh;
   float* s_lse = reinterpret_cast<float*>(smem + 128);       // [BQ] lse * log2(e), +inf for padded queries
   float* s_delta = s_lse + 256;                              // [BQ]
-  uint8_t* tiles = smem + 128 + 2048;
-  const uint32_t sK = smem_u32(tiles);
-  const uint32_t sV = sK + g8_bytes(MT, DHP);
-  const uint32_t sQ = sV + g8_bytes(MT, DHP);
-  const uint32_t sdO = sQ + g8_bytes(BQ, DHP);
-  const uint32_t sPT = sdO + g8_bytes(BQ, DHP);
-  const uint32_t sdST = sPT + g8_bytes(MT, BQ);
-  uint8_t* sPT_ptr = tiles + 2 * g8_bytes(MT, DHP) + 2 * g8_bytes(BQ, DHP);
+  uint8_t* tiles = smem + 3072;
+  uint8_t* pK = tiles;
+  uint8_t* pV = pK + w_bytes(MT, DHP);
+  uint8_t* pQ = pV + w_bytes(MT, DHP);
+  uint8_t* pdO = pQ + w_bytes(BQ, DHP);
+  uint8_t* sPT_ptr = pdO + w_bytes(BQ, DHP);
   uint8_t* sdST_ptr = sPT_ptr + g8_bytes(MT, BQ);
-  const uint32_t gsKV = g8_stride(MT), gsQ = g8_stride(BQ), gsS = g8_stride(MT);
+  const uint32_t gsS = g8_stride(MT);
+  const Opnd oK = opnd_w(smem_u32(pK), MT), oV = opnd_w(smem_u32(pV), MT), oQ = opnd_w(smem_u32(pQ), BQ),
+             odO = opnd_w(smem_u32(pdO), BQ), oPT = opnd_g8(smem_u32(sPT_ptr), gsS), odST = opnd_g8(smem_u32(sdST_ptr), gsS);
+  const bool tma = a.use_tma != 0;
+  uint32_t ld_phase = 0;
 
   const int bh = blockIdx.y, b = bh / H, hd = bh % H;
   const int k0 = blockIdx.x * MT;
@@ -704,24 +705,38 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_umma_kernel(const At
   const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
   uint32_t phase = 0;
 
-  stage_tile<DHP>(sK, MT, kbase + (size_t)k0 * ld, ld, T - k0, dh);
-  stage_tile<DHP>(sV, MT, vbase + (size_t)k0 * ld, ld, T - k0, dh);
-
   for (int blk = 0; blk < a.nblocks; ++blk) {
     const int i0 = blk * BQ;
     const int nvalid = min(BQ, T - i0);
-    stage_tile<DHP>(sQ, BQ, qbase + (size_t)i0 * ld, ld, nvalid, dh);
-    stage_tile<DHP>(sdO, BQ, dobase + (size_t)i0 * ldo, ldo, nvalid, dh);
+    if (tma) {
+      if (tid == 0) {
+        mbar_expect_tx(&ctl->ld_bar, 2 * w_bytes(BQ, DHP) + (blk == 0 ? 2 * w_bytes(MT, DHP) : 0u));
+        if (blk == 0) {
+          tma_load_w<DHP>(pK, MT, &tmK, &ctl->ld_bar, (H + hd) * dh, k0, b);
+          tma_load_w<DHP>(pV, MT, &tmK, &ctl->ld_bar, (2 * H + hd) * dh, k0, b);
+        }
+        tma_load_w<DHP>(pQ, BQ, &tmQ, &ctl->ld_bar, hd * dh, i0, b);
+        tma_load_w<DHP>(pdO, BQ, &tmdO, &ctl->ld_bar, hd * dh, i0, b);
+      }
+    } else {
+      if (blk == 0) {
+        stage_tile_w<DHP, ATT_THREADS>(oK.base, MT, kbase + (size_t)k0 * ld, ld, T - k0, dh, MT);
+        stage_tile_w<DHP, ATT_THREADS>(oV.base, MT, vbase + (size_t)k0 * ld, ld, T - k0, dh, MT);
+      }
+      stage_tile_w<DHP, ATT_THREADS>(oQ.base, BQ, qbase + (size_t)i0 * ld, ld, nvalid, dh, BQ);
+      stage_tile_w<DHP, ATT_THREADS>(odO.base, BQ, dobase + (size_t)i0 * ldo, ldo, nvalid, dh, BQ);
+    }
     for (int i = tid; i < BQ; i += ATT_THREADS) {
       const bool ok = i < nvalid;
       s_lse[i] = ok ? a.lse[(size_t)bh * T + i0 + i] * 1.4426950408889634f : INFINITY;
       s_delta[i] = ok ? a.delta[(size_t)bh * T + i0 + i] : 0.f;
     }
-    cp_async_wait_all();
+    if (tma) { mbar_wait(&ctl->ld_bar, ld_phase); ld_phase ^= 1; }
+    else cp_async_wait_all();
     publish_smem_and_sync();
     if (tid == 0) {
-      issue_mma(tS, sK, gsKV, sQ, gsQ, false, BQ, DHP / 16, false);
-      issue_mma(tdP, sV, gsKV, sdO, gsQ, false, BQ, DHP / 16, false);
+      issue_mma_x(tS, oK, false, oQ, false, BQ, DHP / 16, false);
+      issue_mma_x(tdP, oV, false, odO, false, BQ, DHP / 16, false);
       umma_commit(&ctl->bar);
     }
     mbar_wait(&ctl->bar, phase); phase ^= 1;
@@ -739,16 +754,16 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_umma_kernel(const At
         wp[i / 2] = pack_bf16(p0, p1);
         wd[i / 2] = pack_bf16(p0 * (dp[i] - s_delta[c0 + i]), p1 * (dp[i + 1] - s_delta[c0 + i + 1]));
       }
-      const size_t off = (size_t)(c0 / 8) * gsS + tid * 16;
-      *reinterpret_cast<uint4*>(sPT_ptr + off) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
-      *reinterpret_cast<uint4*>(sPT_ptr + off + gsS) = make_uint4(wp[4], wp[5], wp[6], wp[7]);
-      *reinterpret_cast<uint4*>(sdST_ptr + off) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
-      *reinterpret_cast<uint4*>(sdST_ptr + off + gsS) = make_uint4(wd[4], wd[5], wd[6], wd[7]);
+      const uint32_t off = (uint32_t)(c0 / 8) * gsS + (uint32_t)tid * 16u;
+      sts128(oPT.base + off, wp[0], wp[1], wp[2], wp[3]);
+      sts128(oPT.base + off + gsS, wp[4], wp[5], wp[6], wp[7]);
+      sts128(odST.base + off, wd[0], wd[1], wd[2], wd[3]);
+      sts128(odST.base + off + gsS, wd[4], wd[5], wd[6], wd[7]);
     }
     publish_smem_and_sync();
     if (tid == 0) {
-      issue_mma(tdV, sPT, gsS, sdO, gsQ, true, DHP, BQ / 16, blk > 0);
-      issue_mma(tdK, sdST, gsS, sQ, gsQ, true, DHP, BQ / 16, blk > 0);
+      issue_mma_x(tdV, oPT, false, odO, true, DHP, BQ / 16, blk > 0);
+      issue_mma_x(tdK, odST, false, oQ, true, DHP, BQ / 16, blk > 0);
       umma_commit(&ctl->bar);
     }
     mbar_wait(&ctl->bar, phase); phase ^= 1;
@@ -1172,41 +1187,9 @@ int set_smem(K kernel, size_t bytes) {
   return V4H_OK;
 }
 
-// 5-d tensor map over a (B, T, nh, dh) bf16 tensor with row pitch `ld` elements between tokens: dims
-// (8, T, dh/8, nh, B), box (8, rows, dh/8, 1, 1): the box lands in shared memory as [dh/8][rows][8] = G8.
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-int make_g8_map(const void* base, int B, int T, int nh, int dh, size_t ld, int rows, CUtensorMap* out) {
-  static EncodeTiledFn encode = [] {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      fn = nullptr;
-    return reinterpret_cast<EncodeTiledFn>(fn);
-  }();
-  if (!encode) return fail(V4H_ERR_CUDA, "attention: cuTensorMapEncodeTiled is not available from the driver");
-  static std::mutex mu;
-  static std::map<std::tuple<const void*, int, int, int, int, size_t, int>, CUtensorMap> cache;
-  std::lock_guard<std::mutex> lock(mu);
-  const auto key = std::make_tuple(base, B, T, nh, dh, ld, rows);
-  auto it = cache.find(key);
-  if (it != cache.end()) { *out = it->second; return V4H_OK; }
-  cuuint64_t dims[5] = {8, (cuuint64_t)T, (cuuint64_t)(dh / 8), (cuuint64_t)nh, (cuuint64_t)B};
-  cuuint64_t strides[4] = {(cuuint64_t)ld * 2, 16, (cuuint64_t)dh * 2, (cuuint64_t)T * ld * 2};
-  cuuint32_t box[5] = {8, (cuuint32_t)rows, (cuuint32_t)(dh / 8), 1, 1};
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUtensorMap m;
-  const CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(V4H_ERR_CUDA, "attention: cuTensorMapEncodeTiled (5-d G8 view) failed (%d)", (int)r);
-  if (cache.size() > 1024) cache.clear();
-  cache[key] = m;
-  *out = m;
-  return V4H_OK;
-}
 bool attn_tma_enabled() {
   static const int on = [] { const char* e = getenv("V4H_ATTN_TMA"); return (e && e[0] == '0') ? 0 : 1; }();
   return on != 0;
@@ -1356,26 +1339,45 @@ int bwd_launch(AttnArgs a, int B, cudaStream_t s) {
     return V4H_OK;
   }
   dim3 grid((unsigned)ceil_div(a.T, MT), (unsigned)(B * a.H));
+  const int use_tma = (attn_tma_enabled() && a.dh == DHP) ? 1 : 0;
+  const size_t ldq = (size_t)3 * a.H * a.dh, ldo = (size_t)a.H * a.dh;
   {  // dQ + delta
     AttnArgs q = a;
     const int cap = std::min(160, (512 - DHP) / 2) / 16 * 16;
     pick_block(a.T, cap, &q.BN, &q.nblocks);
     q.tmem_cols = pow2_cols(2 * q.BN + DHP);
-    const size_t smem = 256 + 2 * g8_bytes(MT, DHP) + 2 * g8_bytes(q.BN, DHP) + g8_bytes(MT, q.BN);
+    q.use_tma = use_tma;
+    const size_t smem = 2048 + 2 * w_bytes(MT, DHP) + 2 * w_bytes(q.BN, DHP) + g8_bytes(MT, q.BN) + 16;
     static size_t configured = 0;
     if (smem > configured) { V4H_TRY(set_smem(attn_bwd_dq_umma_kernel<DHP>, smem)); configured = smem; }
-    V4H_CUDA(launch_pdl(attn_bwd_dq_umma_kernel<DHP>, dim3(grid), dim3(ATT_THREADS), smem, s, q));
+    CUtensorMap mq, mkv, mdo;
+    memset(&mq, 0, sizeof(mq)); memset(&mkv, 0, sizeof(mkv)); memset(&mdo, 0, sizeof(mdo));
+    if (use_tma) {
+      V4H_TRY(make_w_map(a.qkv, B, a.T, 3 * a.H * a.dh, ldq, MT, &mq));
+      V4H_TRY(make_w_map(a.qkv, B, a.T, 3 * a.H * a.dh, ldq, q.BN, &mkv));
+      V4H_TRY(make_w_map(a.d_o, B, a.T, a.H * a.dh, ldo, MT, &mdo));
+    }
+    V4H_CUDA(launch_pdl(attn_bwd_dq_umma_kernel<DHP>, dim3(grid), dim3(ATT_THREADS), smem, s, mq, mkv, mdo, q));
     V4H_LAUNCH_CHECK();
   }
-  {  // dK, dV
+  {  // dK, dV: K, V tiles of 128 keys; Q / dO stream through in blocks of at most 128 queries (the two [key][q]
+     // tiles of P^T and dS^T plus four operand tiles have to fit the 227 KB)
     AttnArgs k = a;
-    const int cap = std::min(160, (512 - 2 * DHP) / 2) / 16 * 16;
+    const int cap = std::min(128, (512 - 2 * DHP) / 2) / 16 * 16;
     pick_block(a.T, cap, &k.BN, &k.nblocks);
     k.tmem_cols = pow2_cols(2 * k.BN + 2 * DHP);
-    const size_t smem = 256 + 2048 + 2 * g8_bytes(MT, DHP) + 2 * g8_bytes(k.BN, DHP) + 2 * g8_bytes(MT, k.BN);
+    k.use_tma = use_tma;
+    const size_t smem = 4096 + 2 * w_bytes(MT, DHP) + 2 * w_bytes(k.BN, DHP) + 2 * g8_bytes(MT, k.BN) + 16;
     static size_t configured = 0;
     if (smem > configured) { V4H_TRY(set_smem(attn_bwd_dkv_umma_kernel<DHP>, smem)); configured = smem; }
-    V4H_CUDA(launch_pdl(attn_bwd_dkv_umma_kernel<DHP>, dim3(grid), dim3(ATT_THREADS), smem, s, k));
+    CUtensorMap mk, mq, mdo;
+    memset(&mk, 0, sizeof(mk)); memset(&mq, 0, sizeof(mq)); memset(&mdo, 0, sizeof(mdo));
+    if (use_tma) {
+      V4H_TRY(make_w_map(a.qkv, B, a.T, 3 * a.H * a.dh, ldq, MT, &mk));
+      V4H_TRY(make_w_map(a.qkv, B, a.T, 3 * a.H * a.dh, ldq, k.BN, &mq));
+      V4H_TRY(make_w_map(a.d_o, B, a.T, a.H * a.dh, ldo, k.BN, &mdo));
+    }
+    V4H_CUDA(launch_pdl(attn_bwd_dkv_umma_kernel<DHP>, dim3(grid), dim3(ATT_THREADS), smem, s, mk, mq, mdo, k));
     V4H_LAUNCH_CHECK();
   }
   return V4H_OK;
