@@ -169,6 +169,44 @@ def test_full_size_forward_and_grads_vs_oracle(dev, name, batch, precision):
             assert vo.rel_l2(named[k].grad, p.grad) < tol["grad"], k
 
 
+def test_side_streams_give_the_single_stream_result(dev, monkeypatch):
+    """The library forks weight gradients and the small embedding / conditioning chains onto its own streams
+    (fork after the producer, join before a buffer is rewritten).  A missing dependency would show up as a
+    gradient that differs from the single-stream run or changes between repeats.  Equality is not available:
+    the split-K atomics of dgrad.adaln reorder fp32 sums, a last-bit difference in d cond flips bf16 roundings
+    downstream, and the conditioning-MLP gradients then differ by a few 1e-4 between any two runs (measured
+    2.1e-4); a read of a half-written buffer would be orders of magnitude above the 2e-3 bound used here."""
+    name, batch = "ds2", 64
+    cfg = vo.CONFIGS[name]
+    geom, param = cfg["geom"], cfg["param"]
+    sd = vo.init_state_dict(param, seed=5)
+    gen = torch.Generator().manual_seed(17)
+    x = torch.randn(batch, geom.tokens, geom.patch_dim, generator=gen).to(dev)
+    t = torch.rand(batch, 1, generator=gen).to(dev)
+    c = torch.rand(batch, param["condition_dim"], generator=gen).to(dev)
+    dout = torch.randn(batch, geom.tokens, geom.patch_dim, generator=gen).to(dev)
+
+    def grads(side: bool, repeats: int):
+        monkeypatch.setenv("V4H_WGRAD_STREAM", "1" if side else "0")  # read when the plan is created
+        model = build_model(name, param, "bf16", dev)
+        model.net.load_state_dict(sd)
+        out = []
+        for _ in range(repeats):
+            model.net.zero_grad(set_to_none=True)
+            v = model.net(x, t, c)
+            v.backward(dout)
+            torch.cuda.synchronize()
+            out.append((v.detach().clone(), {k: p.grad.detach().clone() for k, p in model.net.named_parameters() if p.grad is not None}))
+        return out
+
+    ref_v, ref_g = grads(False, 1)[0]
+    for v, g in grads(True, 4):
+        assert torch.equal(v, ref_v)  # the forward has no atomics: bit-identical whatever the stream layout
+        assert g.keys() == ref_g.keys()
+        for k in g:
+            assert vo.rel_l2(g[k].cpu(), ref_g[k].cpu()) < 2e-3, k
+
+
 # ----------------------------------------------------------------------------------------------
 # elementwise kernels
 # ----------------------------------------------------------------------------------------------
