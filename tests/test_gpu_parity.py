@@ -328,6 +328,17 @@ def test_graphed_train_step_and_sampling_match_eager(dev):
         # the device RNG offsets differ inside / outside a graph, so the twins agree statistically only
         assert vo.rel_l2(p, q) < 0.1, name
     assert o_g._step_dev.item() == 2 + 4 and o_e._step_dev.item() == 2 + 4  # the device step counter advances per replay
+    # prefetched input path: batches staged from pinned host memory reach the static input buffers in order
+    hx = [x.cpu().pin_memory() for x in xs]; hc = [c.cpu().pin_memory() for c in cs]
+    graphed.stage(hx[1], hc[1])
+    for i in (1, 2, 3):
+        loss = graphed.step_staged()
+        if i < 3:
+            graphed.stage(hx[i + 1], hc[i + 1])  # issued while step i is still running
+        assert math.isfinite(loss.item())
+        if i == 3:
+            assert torch.equal(graphed.x, xs[3]) and torch.equal(graphed.c, cs[3])
+    assert o_g._step_dev.item() == 2 + 4 + 3
     # sampling: identical noise -> identical showers
     x_T = torch.randn(4, 1, 45, 16, 9, generator=g).to(dev)
     want = m_graph.integrate(x_T, cs[0])

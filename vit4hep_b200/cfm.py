@@ -422,6 +422,33 @@ class GraphedTrainStep:
         self.graph.replay()
         return self.loss
 
+    # ---- input prefetch: the host -> device copy of the NEXT batch runs on its own stream under the current
+    # step (what a DataLoader with pin_memory + non_blocking copies does for an eager loop)
+    def stage(self, x: torch.Tensor, c: torch.Tensor) -> None:
+        """start copying a (pinned) host batch into the staging buffers; returns immediately"""
+        if not hasattr(self, "_stage_stream"):
+            self._stage_stream = torch.cuda.Stream(device=self.x.device)
+            self._stage_x, self._stage_c = torch.empty_like(self.x), torch.empty_like(self.c)
+            self._staged = self._consumed = None
+        if self._consumed is not None:  # the previous staged batch must have been copied out
+            self._stage_stream.wait_event(self._consumed)
+        with torch.cuda.stream(self._stage_stream):
+            self._stage_x.copy_(x, non_blocking=True)
+            self._stage_c.copy_(c, non_blocking=True)
+            self._staged = self._stage_stream.record_event()
+
+    def step_staged(self) -> torch.Tensor:
+        """one training step on the batch passed to the last ``stage`` call"""
+        cur = torch.cuda.current_stream(self.x.device)
+        cur.wait_event(self._staged)
+        self.x.copy_(self._stage_x, non_blocking=True)
+        self.c.copy_(self._stage_c, non_blocking=True)
+        self._consumed = cur.record_event()
+        if hasattr(self.optimizer, "sync_lr"):
+            self.optimizer.sync_lr()
+        self.graph.replay()
+        return self.loss
+
 
 class CaloChallengeCFM(CFM):
     """Regular (L, A, R) grid: CaloChallenge ds2 / ds3 (reference calochallenge_cfm/model.py:8-94)."""
