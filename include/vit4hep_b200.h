@@ -235,6 +235,14 @@ int v4h_test_gemm(int32_t engine, int32_t layout, const void* A, const void* B, 
 int v4h_debug_gemm(int32_t kind, int32_t m, int32_t n, int32_t k, int32_t rows_per_sample, const void* A,
                    const void* B, const float* bias, void* out, void* out2, const float* res_in,
                    float* res_out, const float* gate, const void* aux, int64_t* counters, v4h_stream_t s);
+
+/* Measurement hook: feed rate of a TMA + mbarrier ring without a consumer.  `ctas` persistent CTAs each pull
+ * `iters` stages of `boxes` [box_rows x 64] bf16 boxes (box_rows 64 / 128 / 256: 8 / 16 / 32 KB, 128-byte
+ * swizzle) through a ring of `stages` stages out of the (rows x cols) bf16 matrix `buf` (rows % box_rows == 0,
+ * cols % 64 == 0; its size sets the working set); `producers` (1..4) warps share the issue of a stage's
+ * boxes; cycles[cta] receives the consumer's cycle count.  No reference counterpart. */
+int v4h_debug_tma_probe(const void* buf, int32_t rows, int32_t cols, int32_t stages, int32_t boxes, int32_t box_rows,
+                        int32_t producers, int32_t iters, int32_t ctas, int64_t* cycles, v4h_stream_t s);
 /* device array of 10 int64 cycle counters booked by thread 0 of every tcgen05 attention-forward CTA
  * (prologue, issue loads, wait loads, publish, S MMA, softmax, publish, PV MMA, output, teardown); NULL = off */
 int v4h_debug_attention_counters(int64_t* counters);

@@ -405,6 +405,13 @@ int v4h_debug_gemm(int32_t kind, int32_t m, int32_t n, int32_t k, int32_t rows_p
   return gemm_umma(ctx, g, (cudaStream_t)s);
 }
 
+int v4h_debug_tma_probe(const void* buf, int32_t rows, int32_t cols, int32_t stages, int32_t boxes, int32_t box_rows,
+                        int32_t producers, int32_t iters, int32_t ctas, int64_t* cycles, v4h_stream_t s) {
+  static UmmaContext* ctx = umma_context_create();
+  return tma_probe(ctx, buf, rows, cols, stages, boxes, box_rows, producers, iters, ctas,
+                   reinterpret_cast<long long*>(cycles), (cudaStream_t)s);
+}
+
 int v4h_debug_attention_counters(int64_t* counters) {
   attention_debug_counters(reinterpret_cast<long long*>(counters));
   return V4H_OK;

@@ -800,6 +800,73 @@ static bool slab_ok(const GemmDesc& d) {
   return false;
 }
 
+// ------------------------------------------------------------------------------------------
+// TMA feed probe (measurement only, v4h_debug_tma_probe): what a persistent CTA can pull through an
+// mbarrier ring of `stages` stages of `boxes` [128 x 64] bf16 boxes (16 KB each, 128-byte swizzle) when
+// nothing consumes the data -- the ceiling of the GEMM mainloop's operand feed for a given ring depth,
+// number of CTAs and working set (L2-resident or streamed from HBM).
+// ------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(160, 1) tma_probe_kernel(const __grid_constant__ CUtensorMap tm, int stages, int boxes,
+                                                           int box_rows, int producers, int iters, int tiles_cols,
+                                                           int tiles_total, long long* __restrict__ cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // full[16], empty[16]
+  uint64_t* full = bars;
+  uint64_t* empty = bars + 16;
+  uint8_t* ring = smem + 1024;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 16; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    fence_barrier_init();
+    prefetch_tensormap(&tm);
+  }
+  __syncthreads();
+  const uint32_t box_bytes = (uint32_t)box_rows * 128u, stage_bytes = (uint32_t)boxes * box_bytes;
+  if (warp < producers && lane == 0) {
+    // producer warp w issues the boxes b = w (mod producers) of every stage; warp 0 arms the stage's byte count
+    for (int it = 0; it < iters; ++it) {
+      const int st = it % stages;
+      if (it >= stages) mbar_wait(&empty[st], (uint32_t)((it / stages) - 1) & 1u);
+      if (warp == 0) mbar_expect_tx(&full[st], stage_bytes);
+      for (int b = warp; b < boxes; b += producers) {
+        const long long tile = ((long long)blockIdx.x * iters + it) * boxes + b;
+        const int t = (int)(tile % tiles_total);
+        tma_load_2d(ring + (size_t)st * stage_bytes + (size_t)b * box_bytes, &tm, &full[st], (t % tiles_cols) * 64,
+                    (t / tiles_cols) * box_rows);
+      }
+    }
+  } else if (warp == 4 && lane == 0) {  // consumer: hands every stage straight back
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const int st = it % stages;
+      mbar_wait(&full[st], (uint32_t)(it / stages) & 1u);
+      mbar_arrive(&empty[st]);
+    }
+    cycles[blockIdx.x] = clock64() - t0;
+  }
+}
+}  // namespace
+
+int tma_probe(UmmaContext* ctx, const void* buf, int rows, int cols, int stages, int boxes, int box_rows, int producers,
+              int iters, int ctas, long long* cycles, cudaStream_t s) {
+  V4H_REQUIRE(ctx && buf && cycles, "tma_probe: null argument");
+  V4H_REQUIRE((box_rows == 64 || box_rows == 128 || box_rows == 256) && rows % box_rows == 0 && cols % 64 == 0 &&
+                  stages >= 1 && stages <= 16 && boxes >= 1 && producers >= 1 && producers <= 4 && iters >= 1 &&
+                  ctas >= 1 && (size_t)stages * boxes * box_rows * 128 + 2048 <= (size_t)SMEM_LIMIT,
+              "tma_probe: bad configuration");
+  CUtensorMap tm;
+  V4H_TRY(get_map(ctx, buf, cols, rows, cols, 64, box_rows, 2, &tm));
+  const size_t smem = (size_t)stages * boxes * box_rows * 128 + 2048;
+  V4H_CUDA(cudaFuncSetAttribute(tma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+  // empty[] is armed with ONE arrival (the consumer's); every producer warp waits on it, none arrives
+  tma_probe_kernel<<<ctas, 160, smem, s>>>(tm, stages, boxes, box_rows, producers, iters, cols / 64,
+                                           (rows / box_rows) * (cols / 64), cycles);
+  V4H_LAUNCH_CHECK();
+  return V4H_OK;
+}
+
 int gemm_umma(UmmaContext* ctx, const GemmDesc& d, cudaStream_t s) {
   V4H_REQUIRE(ctx != nullptr, "gemm_umma: no context");
   V4H_REQUIRE(gemm_umma_supported(d), "gemm_umma: unsupported operands (M=%d N=%d K=%d lda=%d ldb=%d)", d.M, d.N, d.K,

@@ -41,6 +41,9 @@ UmmaContext* umma_context_create();
 void umma_context_destroy(UmmaContext*);
 bool gemm_umma_supported(const GemmDesc& g);
 int gemm_umma(UmmaContext* ctx, const GemmDesc& g, cudaStream_t s);
+// measurement only: see gemm_umma.cu
+int tma_probe(UmmaContext* ctx, const void* buf, int rows, int cols, int stages, int boxes, int box_rows, int producers,
+              int iters, int ctas, long long* cycles, cudaStream_t s);
 
 // attention_simt.cu: softmax(q k^T / sqrt(dh)) v per (batch, head); qkv (B,T,3,H,dh)
 template <typename T>
