@@ -31,7 +31,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout and would precede the JSON line
+# NCCL's INFO banner goes to stdout and would precede the JSON line: default to WARN, but keep whatever the
+# caller asked for (the driver reads NCCL's own log to count ranks)
+os.environ.setdefault("NCCL_DEBUG", "WARN")
 
 import torch  # noqa: E402
 
@@ -105,7 +107,9 @@ class ClockSampler:
 
 
 def ds2_setup(config: str):
-    from oracle import vit_oracle as vo  # geometry / hyper-parameter tables only
+    """(geometry, ViT param dict) of the CPU arm: the oracle's own tables (test infrastructure; only the
+    reference / cpu_baseline legs call this)"""
+    from oracle import vit_oracle as vo
     cfg = vo.CONFIGS[config]
     return cfg["geom"], dict(cfg["param"])
 
@@ -180,9 +184,63 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
+def cpu_showers_per_s(config: str, batch: int, nfe: int):
+    """CPU oracle port of the sampling path: `nfe` network evaluations of one batch (wrapper forward: patchify,
+    ViT, unpatchify), extrapolated to the 80 evaluations of a 20-step RK4 (3/8) solve."""
+    from oracle import vit_oracle as vo
+    geom, param = ds2_setup(config)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = vo.init_state_dict(param, seed=0)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(batch, *geom.sample_shape, generator=g)
+    c = torch.rand(batch, param["condition_dim"], generator=g)
+    t = torch.full((batch, 1), 0.5)
+    with torch.no_grad():
+        vo.cfm_forward(sd, x, t, c, geom, param["num_heads"])
+        t0 = time.perf_counter()
+        for _ in range(nfe):
+            vo.cfm_forward(sd, x, t, c, geom, param["num_heads"])
+        per = (time.perf_counter() - t0) / nfe
+    return batch / (80 * per), per * 1e3, threads
+
+
+def family_roofline(prof, psteps, peaks, traffic_key):
+    """roofline object of the tcgen05 GEMM kernel (every gemm.* / dgrad.* / wgrad.* class is ONE template,
+    csrc/gemm_umma.cu): achieved = algorithmic flops of its launches (2 M N K each) / their summed device time"""
+    total_ms = sum(e["ms"] for e in prof) or 1.0
+    kernels = []
+    for e in sorted(prof, key=lambda e: -e["ms"]):
+        per = e["ms"] / max(e["launches"], 1)
+        kernels.append({"name": e["name"], "launches_per_step": e["launches"] / psteps, "ms_per_step": e["ms"] / psteps,
+                        "share": e["ms"] / total_ms, "avg_ms": per,
+                        "tflops": e["flops"] / (e["ms"] * 1e-3) / 1e12 if e["ms"] > 0 else 0.0,
+                        "gbs": e["bytes"] / (e["ms"] * 1e-3) / 1e9 if e["ms"] > 0 else 0.0})
+    fam = [k for k in kernels if k["name"].startswith(("gemm", "wgrad", "dgrad"))]
+    fam_ms = sum(k["ms_per_step"] for k in fam)
+    if fam_ms <= 0:
+        return kernels, None
+    fam_flops = sum(k["tflops"] * 1e12 * k["ms_per_step"] * 1e-3 for k in fam)
+    fam_launches = sum(k["launches_per_step"] for k in fam)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh).get(traffic_key, {}).get("dram_bytes_per_launch")
+    ach = fam_flops / (fam_ms * 1e-3) / 1e12
+    roofline = {"kernel": "gemm_umma_kernel (tcgen05 GEMM: all gemm.* / dgrad.* / wgrad.* classes)",
+                "bound": "tensor", "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                "frac": ach / peaks["tflops_sustained"], "traffic": traffic,
+                "flops_per_launch": fam_flops / max(fam_launches, 1),
+                "avg_launch_ms": fam_ms / max(fam_launches, 1), "launches_per_step": fam_launches,
+                "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
+                "share_of_step": fam_ms / (total_ms / psteps)}
+    return kernels, roofline
+
+
 def run_b200(args):
     import torch.distributed as dist
-    from vit4hep_b200 import CaloChallengeCFM, FusedAdamW, GraphedTrainStep, ViT, _cabi, dp
+    from vit4hep_b200 import FusedAdamW, GraphedTrainStep, _cabi, configs, dp
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -197,15 +255,17 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    geom, param = ds2_setup(args.config)
-    param["precision"] = args.precision
-    torch.manual_seed(0)
-    net = ViT(param)
-    rerandomise(net)
-    seg = geom.segments[0]
-    model = CaloChallengeCFM(net, list(seg.patch), 1, "uniform", "linear",
-                             dict(method="rk4", options=dict(step_size=0.05)), shape=list(seg.shape)).to(dev)
-    model.device, model.dtype = dev, torch.float32
+    def make_model(precision):
+        torch.manual_seed(0)
+        m = configs.build(args.config, precision)
+        rerandomise(m.net)
+        m = m.to(dev)
+        m.device, m.dtype = dev, torch.float32
+        return m
+
+    model = make_model(args.precision)
+    geom = model.geometry
+    K = configs.MODELS[args.config]["net"]["param"]["condition_dim"]
     if world > 1:
         dp.enable_data_parallel(model.net)
     params = list(model.net.parameters())
@@ -215,7 +275,6 @@ def run_b200(args):
         opt = FusedAdamW(model.net, lr=1e-4, weight_decay=0.1, max_grad_norm=1000.0)
 
     B = args.batch
-    K = param["condition_dim"]
     g = torch.Generator().manual_seed(1234 + rank)
     npool = 8
     host_x = [torch.randn(B, *geom.sample_shape, generator=g).pin_memory() for _ in range(npool)]
@@ -224,14 +283,20 @@ def run_b200(args):
     dev_c = [c.to(dev) for c in host_c]
     lib = _cabi.load()
 
-    def train_step(batch, read_loss: bool):
-        loss = model._batch_loss(batch)
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        if args.torch_optimizer:
-            torch.nn.utils.clip_grad_norm_(params, 1000.0)
-        opt.step()
-        return loss.item() if read_loss else loss
+    def make_train_step(mdl, optimizer):
+        plist = list(mdl.net.parameters())
+
+        def train_step(batch, read_loss: bool):
+            loss = mdl._batch_loss(batch)
+            optimizer.zero_grad(set_to_none=True)
+            loss.backward()
+            if args.torch_optimizer:
+                torch.nn.utils.clip_grad_norm_(plist, 1000.0)
+            optimizer.step()
+            return loss.item() if read_loss else loss
+        return train_step
+
+    train_step = make_train_step(model, opt)
 
     def barrier():
         torch.cuda.synchronize()
@@ -260,16 +325,17 @@ def run_b200(args):
     for i in range(W):
         train_step((dev_x[i % npool], dev_c[i % npool]), False)
     # eager numbers first (every launch issued from Python), then the same step replayed as ONE CUDA graph
-    ms_eager, launches = timed(lambda i: train_step((dev_x[i % npool], dev_c[i % npool]), False), S)
+    S_eager = min(S, 50)
+    ms_eager, launches = timed(lambda i: train_step((dev_x[i % npool], dev_c[i % npool]), False), S_eager)
+    launches = launches * S // S_eager  # kernels of S steps (the graph replays the same launches)
     for i in range(2):
         train_step((host_x[i % npool], host_c[i % npool]), True)
-    ms_e2e_eager, _ = timed(lambda i: train_step((host_x[i % npool], host_c[i % npool]), True), S)
+    ms_e2e_eager, _ = timed(lambda i: train_step((host_x[i % npool], host_c[i % npool]), True), S_eager)
     use_graph = (not args.no_graph and not args.torch_optimizer
                  and (world == 1 or os.environ.get("V4H_GRAPH_DP", "1") == "1"))
     graphed = GraphedTrainStep(model, opt, dev_x[0], dev_c[0]) if use_graph else None
     if graphed is not None:
         step_dev = lambda i: graphed.step(dev_x[i % npool], dev_c[i % npool])
-        step_e2e = lambda i: graphed.step(host_x[i % npool], host_c[i % npool]).item()
         h2d = host_x[0].numel() * 4 + host_c[0].numel() * 4  # x and c; t is drawn on the device
     else:
         step_dev = lambda i: train_step((dev_x[i % npool], dev_c[i % npool]), False)
@@ -298,67 +364,74 @@ def run_b200(args):
     ms_e2e, _ = timed(step_e2e, S)
     e2e = world * B * S / (ms_e2e * 1e-3)
 
-    # per-kernel-class device time (separate pass: the bracketing events cost launch overhead)
+    # per-kernel-class device time INSIDE a replayed graph of the same step: the library's profiling scopes record
+    # their events as event nodes of the capture (v4h_profile_*), so every class is timed on the device, inside the
+    # step, without the host submission gaps of eager launches.  The profiled capture serialises the kernels on one
+    # stream (no side streams / sub-batch lanes), which is what a per-kernel duration needs.
     peaks = measured_peaks()
     kernels, roofline = [], None
-    if rank == 0 or world == 1:
-        pass
-    _cabi.profile_begin()
-    psteps = min(S, 3)
-    for i in range(psteps):
-        train_step((dev_x[i % npool], dev_c[i % npool]), False)
-    prof = _cabi.profile_end(128)
-    total_ms = sum(e["ms"] for e in prof) or 1.0
-    for e in sorted(prof, key=lambda e: -e["ms"]):
-        per = e["ms"] / max(e["launches"], 1)
-        kernels.append({"name": e["name"], "launches_per_step": e["launches"] / psteps, "ms_per_step": e["ms"] / psteps,
-                        "share": e["ms"] / total_ms, "avg_ms": per,
-                        "tflops": e["flops"] / (e["ms"] * 1e-3) / 1e12 if e["ms"] > 0 else 0.0,
-                        "gbs": e["bytes"] / (e["ms"] * 1e-3) / 1e9 if e["ms"] > 0 else 0.0})
-    # roofline of the dominant kernel: every gemm.* / dgrad.* / wgrad.* class is ONE kernel template
-    # (gemm_umma_kernel, csrc/gemm_umma.cu), which together takes the largest share of the step.
-    # achieved = algorithmic flops of those launches (2 M N K each) / their summed device time;
-    # traffic = DRAM bytes per launch of the same kernel from the committed ncu capture (profiles/traffic.json)
-    if kernels:
-        fam = [k for k in kernels if k["name"].startswith(("gemm", "wgrad", "dgrad"))]
-        fam_ms = sum(k["ms_per_step"] for k in fam)
-        fam_flops = sum(k["tflops"] * 1e12 * k["ms_per_step"] * 1e-3 for k in fam)
-        fam_launches = sum(k["launches_per_step"] for k in fam)
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.isfile(tpath):
-            with open(tpath) as fh:
-                traffic = json.load(fh).get("gemm_umma_kernel", {}).get("dram_bytes_per_launch")
-        if fam_ms > 0:
-            ach = fam_flops / (fam_ms * 1e-3) / 1e12
-            roofline = {"kernel": "gemm_umma_kernel (tcgen05 GEMM: all gemm.* / dgrad.* / wgrad.* classes)",
-                        "bound": "tensor", "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                        "frac": ach / peaks["tflops_sustained"], "traffic": traffic,
-                        "flops_per_launch": fam_flops / max(fam_launches, 1),
-                        "avg_launch_ms": fam_ms / max(fam_launches, 1), "launches_per_step": fam_launches,
-                        "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
-                        "share_of_step": fam_ms / (total_ms / psteps)}
+    if graphed is not None:
+        _cabi.profile_begin()
+        pg = GraphedTrainStep(model, opt, dev_x[0], dev_c[0], warmup=0)
+        for i in range(3):
+            pg.step(dev_x[i % npool], dev_c[i % npool])
+        torch.cuda.synchronize()
+        prof = _cabi.profile_end(128)
+        del pg
+        psteps = 1  # the events of the capture are re-recorded by every replay: the last replay is read
+    else:
+        _cabi.profile_begin()
+        psteps = min(S, 3)
+        for i in range(psteps):
+            train_step((dev_x[i % npool], dev_c[i % npool]), False)
+        prof = _cabi.profile_end(128)
+    kernels, roofline = family_roofline(prof, psteps, peaks, "gemm_umma_kernel")
+    if roofline is not None:
+        roofline["timing"] = ("CUDA events recorded as nodes of a replayed CUDA graph of the training step, kernels "
+                              "serialised on one stream" if graphed is not None else "CUDA events around eager launches")
 
-    # ODE sampling: 20 RK4 (3/8) steps = 80 network evaluations per shower, batches sharded over ranks
+    # ---- strong scaling (the reference's semantics: global batch 64, batchsize // world_size per rank,
+    # reference experiments/calochallenge/experiment.py:94-98)
+    strong = None
+    if world > 1 and B % world == 0 and not args.no_strong:
+        try:
+            Bs = B // world
+            sx = [x[:Bs].contiguous() for x in dev_x]
+            sc = [c[:Bs].contiguous() for c in dev_c]
+            gs = GraphedTrainStep(model, opt, sx[0], sc[0]) if graphed is not None else None
+            fn = (lambda i: gs.step(sx[i % npool], sc[i % npool])) if gs is not None else \
+                (lambda i: train_step((sx[i % npool], sc[i % npool]), False))
+            for i in range(W):
+                fn(i)
+            ms_s, _ = timed(fn, S)
+            strong = {"scaling": "strong", "global_batch": B, "per_gpu_batch": Bs, "value": B * S / (ms_s * 1e-3),
+                      "unit": UNIT, "ms_per_step": ms_s / S}
+            del gs
+        except Exception as exc:  # the headline line must survive a failure of this secondary measurement
+            strong = {"error": repr(exc)[:200]}
+
+    # ---- ODE sampling (BASELINE.json configs[3]): 20 RK4 (3/8) steps = 80 network evaluations per shower,
+    # conditions sharded over the ranks, one final all_gather, the result read back to the host
     sampling = None
     if not args.no_sampling:
-        SB = args.sample_batch
-        conds = torch.rand(SB, K, generator=g).to(dev)
-        model.sample_batch(conds[: min(SB, 32)])
-        nb = args.sample_batches
-        ms_s_eager, launches_s = timed(lambda i: model.sample_batch(conds), nb)
-        if not args.no_graph:
-            model.graph_sampling = True  # the whole 80-evaluation solve replayed as one CUDA graph
-            model.sample_batch(conds)
-        ms_s, _ = timed(lambda i: model.sample_batch(conds), nb)
-        showers = world * SB * nb / (ms_s * 1e-3)
-        sampling = {"metric": f"{args.config} ODE-sampled showers/s", "value": showers, "unit": "showers/s",
-                    "batch": SB, "batches": nb, "nfe_per_shower": 80, "ms_per_batch": ms_s / nb,
-                    "gpu_launches": launches_s, "cuda_graph": not args.no_graph,
-                    "eager_showers_per_s": world * SB * nb / (ms_s_eager * 1e-3),
-                    "model_tflops": showers * SAMPLE_GFLOP_PER_SHOWER[args.config] / 1e3 / world,
-                    "frac_of_peak": showers * SAMPLE_GFLOP_PER_SHOWER[args.config] / 1e3 / world
-                    / peaks["tflops_sustained"]}
+        sampling = measure_sampling(args, model, K, world, rank, dev, timed, peaks, lib)
+
+    # ---- the reference's own precision (fp32 SIMT GEMMs / attention): stated once beside bf16
+    fp32 = None
+    if world == 1 and args.precision == "bf16" and not args.no_fp32:
+        try:
+            m32 = make_model("fp32")
+            o32 = FusedAdamW(m32.net, lr=1e-4, weight_decay=0.1, max_grad_norm=1000.0)
+            ts32 = make_train_step(m32, o32)
+            for i in range(2):
+                ts32((dev_x[i], dev_c[i]), False)
+            n32 = 5
+            ms32, _ = timed(lambda i: ts32((dev_x[i % npool], dev_c[i % npool]), False), n32)
+            fp32 = {"value": B * n32 / (ms32 * 1e-3), "unit": UNIT, "ms_per_step": ms32 / n32, "steps": n32,
+                    "note": "precision='fp32' (parity mode, <= 1e-5 rel-L2): SIMT fp32 GEMMs and attention, eager launches"}
+            del m32, o32
+        except Exception as exc:
+            fp32 = {"error": repr(exc)[:200]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -390,12 +463,15 @@ def run_b200(args):
                                    "(GraphedTrainStep.stage / step_staged)") if graphed is not None
                                   else "inline, before each step"},
             "gpu_launches": launches,
-            "eager": {"value": world * B * S / (ms_eager * 1e-3), "e2e": world * B * S / (ms_e2e_eager * 1e-3)},
+            "eager": {"value": world * B * S_eager / (ms_eager * 1e-3), "e2e": world * B * S_eager / (ms_e2e_eager * 1e-3),
+                      "steps": S_eager},
             "model_tflops_per_gpu": value * gf / 1e3 / world,
             "frac_of_peak": value * gf / 1e3 / world / peaks["tflops_sustained"],
             "roofline": roofline,
-            "kernels": kernels[:32],
+            "kernels": kernels[:40],
+            "strong_scaling": strong,
             "sampling": sampling,
+            "fp32": fp32,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
@@ -409,17 +485,92 @@ def run_b200(args):
         os._exit(0)
 
 
+def measure_sampling(args, model, K, world, rank, dev, timed, peaks, lib):
+    """showers/s of the sharded ODE sampling job (dp.sample_sharded): device-resident conditions (`value`), and
+    end to end from pinned host conditions to host showers: H2D of the conditions, the solves, the final
+    all_gather over the ranks and the .cpu() of reference experiments/calochallenge/experiment.py:223 (`e2e`)."""
+    import torch.distributed as dist
+    from vit4hep_b200 import _cabi, dp
+    SB, total = args.sample_batch, args.sample_showers
+    g = torch.Generator().manual_seed(4321)  # identical conditions on every rank; each integrates its shard
+    conds_host = torch.rand(total, K, generator=g).pin_memory()
+    conds = conds_host.to(dev)
+    geom = model.geometry
+    voxels = geom.voxels
+    model.graph_sampling = False
+    model.sample_batch(conds[: min(SB, 32)])
+    nb_eager = 1
+    ms_eager, launches = timed(lambda i: model.sample_batch(conds[:SB]), nb_eager)
+    if not args.no_graph:
+        model.graph_sampling = True  # the whole 80-evaluation solve of a batch replayed as one CUDA graph
+        model.sample_batch(conds[:SB])
+        b, e = dp.shard_range(total, rank, world)
+        if (e - b) % SB:
+            model.sample_batch(conds[: (e - b) % SB])  # the shard's last, shorter batch has its own graph
+    ms, _ = timed(lambda i: dp.sample_sharded(model, conds, SB, gather=False), 1)
+    showers = total / (ms * 1e-3)
+    out_host = {}
+
+    def e2e_job(i):
+        c = conds_host.to(dev, non_blocking=True)
+        full = dp.sample_sharded(model, c, SB, gather=True)
+        if rank == 0:
+            out_host["showers"] = full.cpu()
+    ms_e2e, _ = timed(e2e_job, 1)
+    ok = True
+    if rank == 0:
+        sh = out_host["showers"]
+        ok = tuple(sh.shape) == (total, *geom.sample_shape) and bool(torch.isfinite(sh).all())
+    gf = SAMPLE_GFLOP_PER_SHOWER[args.config]
+    # the dominant kernel of a network evaluation, timed on the device around eager launches of 3 evaluations
+    x = torch.randn(SB, geom.tokens, geom.patch_dim, device=dev)
+    tt = torch.full((1,), 0.5, device=dev)
+    model.net(x, tt, conds[:SB], shared_t=True)
+    _cabi.profile_begin()
+    for _ in range(3):
+        model.net(x, tt, conds[:SB], shared_t=True)
+    prof = _cabi.profile_end(128)
+    kernels, roofline = family_roofline(prof, 3, peaks, "gemm_umma_kernel_sampling")
+    if roofline is not None:
+        roofline["timing"] = "CUDA events around eager launches of 3 network evaluations at the sampling batch"
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, per_ms, threads = cpu_showers_per_s(args.config, 64, 3)
+        cpu = {"value": v, "unit": "showers/s", "cores": threads, "kind": "port",
+               "sample": f"3 network evaluations of a 64-shower batch by the CPU oracle port ({per_ms:.0f} ms each), "
+                         f"extrapolated to the 80 evaluations of a shower"}
+    return {"metric": f"{args.config} ODE-sampled showers/s", "value": showers, "unit": "showers/s",
+            "n_gpus": world, "scaling": "strong (fixed job sharded over the ranks)",
+            "config": {"workload": f"CaloChallenge {args.config} ODE sampling of {total} showers (a stated subset of the "
+                                   f"100k of BASELINE.json configs[3]), RK4 3/8 rule, 20 steps = 80 network evaluations, "
+                                   f"sample batch {SB}, conditions sharded over {world} rank(s)",
+                       "showers": total, "batch": SB, "nfe_per_shower": 80,
+                       "execution": "one CUDA graph per batch solve" if not args.no_graph else "eager launches"},
+            "ms_total": ms, "ms_per_batch": ms / max(1, -(-(total // world) // SB)),
+            "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "showers/s", "ms_total": ms_e2e,
+                    "h2d_bytes_per_step": conds_host.numel() * 4, "d2h_bytes_per_step": total * voxels * 4,
+                    "includes": "H2D of the conditions, all solves, final all_gather over the ranks, .cpu() on rank 0",
+                    "output_ok": ok},
+            "eager_showers_per_s": world * SB * nb_eager / (ms_eager * 1e-3), "gpu_launches_per_batch": launches // nb_eager,
+            "model_tflops_per_gpu": showers * gf / 1e3 / world,
+            "frac_of_peak": showers * gf / 1e3 / world / peaks["tflops_sustained"],
+            "roofline": roofline, "kernels": kernels[:12], "cpu_baseline": cpu}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="ds2", choices=["ds2", "ds3"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=64, help="training batch per GPU")
     ap.add_argument("--sample-batch", type=int, default=256)
-    ap.add_argument("--sample-batches", type=int, default=2)
+    ap.add_argument("--sample-showers", type=int, default=25600,
+                    help="size of the sharded sampling job (BASELINE.json configs[3] is 100000)")
+    ap.add_argument("--no-fp32", action="store_true", help="skip the fp32 (reference precision) line")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling line at N > 1")
     ap.add_argument("--cpu-batch", type=int, default=64, help="batch of the bounded CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=12, help="timed steps of the cpu_baseline leg (2 warm-up)")
     ap.add_argument("--torch-optimizer", action="store_true", help="clip_grad_norm_ + torch.optim.AdamW(fused)")

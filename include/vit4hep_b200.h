@@ -91,6 +91,11 @@ typedef struct {
   int32_t freq_dim;     /* TimestepEmbedder.frequency_embedding_size (256) */
   int32_t learn_pos_embed; /* 1: pos_embed_freqs + pos_{z,y,x}; 0: fixed (T, D) table */
   int32_t precision;    /* V4H_FP32 | V4H_BF16 */
+  /* Finetuning structures (reference experiments/calochallenge/calochallenge_cfm/experiment_finetuning.py:79-118):
+   * x_embedder / c_embedder wrapped as Sequential(mapper Linear, SiLU, old embedder).  > 0: width of the
+   * network input x / c that the mapper Linear takes to patch_dim / cond_dim; 0: no mapper. */
+  int32_t x_map_dim;
+  int32_t c_map_dim;
 } v4h_vit_dims;
 
 typedef struct {
@@ -111,6 +116,8 @@ typedef struct {
   float *t0_w, *t0_b, *t2_w, *t2_b; /* t_embedder.mlp.0 (D, 256), .2 (D, D) */
   float *final_w, *final_b;         /* final_layer.linear (out_dim, D) */
   float *final_ada_w, *final_ada_b; /* final_layer.adaLN_modulation.1 (2D, D) */
+  float *xm_w, *xm_b;               /* x_embedder.0 of a mapped embedder (P, x_map_dim), (P); else null */
+  float *cm_w, *cm_b;               /* c_embedder.0 of a mapped embedder (K, c_map_dim), (K); else null */
   v4h_block_params blocks[V4H_MAX_DEPTH];
 } v4h_vit_params;
 
@@ -173,6 +180,7 @@ typedef struct {
   float* v;        /* exp_avg_sq */
   void* bf16_dst;  /* bf16 copy of the updated parameter inside the weight arena, or NULL */
   float* f32_dst;  /* fp32 copy inside the arena (the concatenated adaLN biases), or NULL */
+  float* ema;      /* exponential-moving-average shadow of the parameter (torch_ema), or NULL */
   int64_t n;
 } v4h_adamw_job;
 /* out[0] = sum of squares of n fp32 values (the squared global gradient norm when `flat` is the flat
@@ -182,9 +190,17 @@ int v4h_grad_norm_sq(const float* flat, int64_t n, float* out, v4h_stream_t s);
  * v4h_grad_norm_sq (NULL = no clipping); step = 1-based step count (bias correction).  step_dev / lr_dev
  * (optional device scalars) override step / lr so that a captured CUDA graph of the training step stays
  * correct across replays; v4h_counter_increment advances the device step counter in stream order. */
+/* ema_decay > 0: the same pass also updates jobs[i].ema like torch_ema.ExponentialMovingAverage.update()
+ * (reference experiments/base_experiment.py:127-134, :594): shadow -= (1 - d) (shadow - p) with
+ * d = min(ema_decay, (1 + n) / (10 + n)), n = ema_updates (1-based count including this update) or
+ * *ema_updates_dev when non-NULL. */
 int v4h_adamw_step(const v4h_adamw_job* jobs, int32_t njobs, int64_t max_n, const float* norm_sq, float max_norm,
                    float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
-                   const int32_t* step_dev, const float* lr_dev, v4h_stream_t s);
+                   const int32_t* step_dev, const float* lr_dev, float ema_decay, int32_t ema_updates,
+                   const int32_t* ema_updates_dev, v4h_stream_t s);
+/* ExponentialMovingAverage.update() alone (jobs[i].p, jobs[i].ema, jobs[i].n are read) */
+int v4h_ema_update(const v4h_adamw_job* jobs, int32_t njobs, int64_t max_n, float decay, int32_t num_updates,
+                   const int32_t* num_updates_dev, v4h_stream_t s);
 int v4h_counter_increment(int32_t* counter, v4h_stream_t s);
 /* byte offset inside the weight arena of the bf16 copy of a parameter, by its v4h_vit_params field
  * ("final_w", "x_w", "t0_w", "t2_w", "c2_w", "final_ada_w", "blocks.<i>.{qkv_w,proj_w,fc1_w,fc2_w,ada_w}"), or of the fp32 copy of an adaLN bias

@@ -27,7 +27,9 @@ def build_wrapper(ref, name, param, geom):
     if name in ("ds2", "ds3"):
         m = ref.CaloChallengeCFM(net, list(segs[0].patch), 1, "uniform", "linear", ode,
                                  shape=list(segs[0].shape))
-    elif name == "ds1_photons":
+    elif name == "lemurs":
+        m = ref.LEMURSCFM(net, list(segs[0].patch), 1, "uniform", "linear", ode, shape=list(segs[0].shape))
+    elif name in ("ds1_photons", "ds1_pions"):
         m = ref.CaloChallengeCFM_DS1(net, [list(s.shape) for s in segs], [s.voxels for s in segs],
                                      list(segs[0].patch), 1, "uniform", "linear", ode,
                                      shape=[geom.voxels])
@@ -105,6 +107,100 @@ def golden_net(ref, name, hidden, heads, depth, B, tag):
     print(tag, "loss", loss.item(), "sample rms", sample.pow(2).mean().sqrt().item())
 
 
+def golden_lemurs(ref, hidden=48, heads=2, depth=2, B=3):
+    """LEMURSCFM._batch_loss on a (B, R, A, L) batch (reference experiments/lemurs/model.py:62-65): loss and
+    every parameter gradient, plus sample_batch."""
+    cfg = tiny_config("lemurs", hidden_dim=hidden, depth=depth, num_heads=heads)
+    geom, param = cfg["geom"], cfg["param"]
+    torch.manual_seed(0)
+    model = build_wrapper(ref, "lemurs", param, geom)
+    ref_stubs.rerandomise_zero_init(model.net, seed=1)
+    g = torch.Generator().manual_seed(4321)
+    L, A, R = geom.segments[0].shape
+    x = torch.randn(B, R, A, L, generator=g)
+    c = torch.rand(B, param["condition_dim"], generator=g)
+    out = {"sd/" + k: v.detach().numpy() for k, v in model.net.state_dict().items()}
+    out.update(x=x.numpy(), c=c.numpy())
+    torch.manual_seed(55)
+    t = model.time_distribution.sample([B, 1, 1, 1, 1])
+    # randn_like of the PERMUTED view: the draw follows its (preserved) strides, not the logical order
+    x0 = torch.randn_like(x.permute(0, 3, 2, 1).unsqueeze(1)).contiguous()
+    torch.manual_seed(55)
+    loss = model._batch_loss([x.clone(), c])
+    loss.backward()
+    out.update(loss_t=t.numpy(), loss_x0=x0.numpy(), loss=np.asarray(loss.item(), dtype=np.float64))
+    for k, p in model.net.named_parameters():
+        out["grad/" + k] = p.grad.numpy()
+    out["meta"] = np.asarray([hidden, heads, depth, B], dtype=np.int32)
+    np.savez_compressed(os.path.join(OUT, "net_lemurs_tiny.npz"), **out)
+    print("lemurs_tiny loss", loss.item())
+
+
+def golden_finetune(ref, hidden=48, heads=2, depth=2, B=2):
+    """The module surgery of reference experiments/calochallenge/calochallenge_cfm/experiment_finetuning.py:75-165
+    on a ds2 backbone that is finetuned to the ds3 grid: x_embedder / c_embedder wrapped behind mapper Linears
+    (map_x_embedding / map_c_embedding), pos grid rebuilt for the new num_patches, final layer re-created for
+    the new patch_dim.  Records the network output and every parameter gradient of sum(out * wgt)."""
+    import torch.nn as nn
+    back = tiny_config("ds2", hidden_dim=hidden, depth=depth, num_heads=heads)["param"]
+    new = tiny_config("ds3", hidden_dim=hidden, depth=depth, num_heads=heads)
+    geom_new, p_new = new["geom"], new["param"]
+    torch.manual_seed(0)
+    net = ref.ViT(back)
+    # experiment_finetuning.py:79-91 (map_x_embedding) and :106-118 (map_c_embedding); the new task has 40 conditions
+    K_new = 40
+    net.x_embedder = nn.Sequential(nn.Linear(p_new["patch_dim"], back["patch_dim"]), nn.SiLU(), net.x_embedder)
+    net.c_embedder = nn.Sequential(nn.Linear(K_new, back["condition_dim"]), nn.SiLU(), net.c_embedder)
+    # :135-142 positional grid of the new geometry
+    net.num_patches = p_new["num_patches"]
+    pos_z, pos_y, pos_x = net.create_meshgrid()
+    net.pos_z, net.pos_y, net.pos_x = pos_z, pos_y, pos_x
+    # :160-165 new final layer
+    net.final_layer = ref.vit.FinalLayer(hidden, p_new["patch_dim"], back["out_channels"])
+    ref_stubs.rerandomise_zero_init(net, seed=2)
+    g = torch.Generator().manual_seed(99)
+    x = torch.randn(B, geom_new.tokens, p_new["patch_dim"], generator=g)
+    c = torch.rand(B, K_new, generator=g)
+    t = torch.rand(B, 1, generator=g)
+    wgt = torch.randn(B, geom_new.tokens, p_new["patch_dim"], generator=g)
+    out = {"sd/" + k: v.detach().numpy() for k, v in net.state_dict().items()}
+    y = net(x, t, c)
+    (y * wgt).sum().backward()
+    out.update(x=x.numpy(), c=c.numpy(), t=t.numpy(), wgt=wgt.numpy(), net_out=y.detach().numpy())
+    for k, p in net.named_parameters():
+        out["grad/" + k] = p.grad.numpy()
+    out["meta"] = np.asarray([hidden, heads, depth, B, K_new], dtype=np.int32)
+    np.savez_compressed(os.path.join(OUT, "net_finetune_tiny.npz"), **out)
+    print("finetune_tiny out rms", y.pow(2).mean().sqrt().item())
+
+
+def golden_fixed_pos_embed(ref, hidden=48, heads=2, depth=1, B=2):
+    """learn_pos_embed=False (reference nn/vit.py:92-103, :461-540): the fixed tables for both coordinate
+    systems and one forward with the cylindrical one."""
+    out = {}
+    for coords in ("cylindrical", "cartesian"):
+        cfg = tiny_config("ds3", hidden_dim=hidden, depth=depth, num_heads=heads)
+        # the fixed-table branch unpacks num_patches as ONE (L, A, R) triple (reference nn/vit.py:497)
+        param = dict(cfg["param"]); param.update(learn_pos_embed=False, pos_embedding_coords=coords,
+                                                 num_patches=list(cfg["param"]["num_patches"][0]))
+        torch.manual_seed(0)
+        net = ref.ViT(param)
+        out["table/" + coords] = net.pos_embed.numpy()
+        if coords == "cylindrical":
+            ref_stubs.rerandomise_zero_init(net, seed=3)
+            g = torch.Generator().manual_seed(5)
+            x = torch.randn(B, cfg["geom"].tokens, param["patch_dim"], generator=g)
+            c = torch.rand(B, param["condition_dim"], generator=g)
+            t = torch.rand(B, 1, generator=g)
+            with torch.no_grad():
+                y = net(x, t, c)
+            out.update({"sd/" + k: v.detach().numpy() for k, v in net.state_dict().items()})
+            out.update(x=x.numpy(), c=c.numpy(), t=t.numpy(), net_out=y.numpy())
+    out["meta"] = np.asarray([hidden, heads, depth, B], dtype=np.int32)
+    np.savez_compressed(os.path.join(OUT, "net_fixed_pos_tiny.npz"), **out)
+    print("fixed_pos_tiny written")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_stubs.load_reference()
@@ -112,6 +208,10 @@ def main():
     golden_patch_maps(ref)
     golden_net(ref, "ds2", hidden=48, heads=2, depth=2, B=3, tag="ds2_tiny")
     golden_net(ref, "calogan", hidden=48, heads=2, depth=2, B=2, tag="calogan_tiny")
+    golden_net(ref, "ds1_pions", hidden=48, heads=2, depth=1, B=2, tag="ds1_pions_tiny")
+    golden_lemurs(ref)
+    golden_finetune(ref)
+    golden_fixed_pos_embed(ref)
 
 
 if __name__ == "__main__":

@@ -130,8 +130,9 @@ def load_reference():
     cc = importlib.import_module("experiments.calochallenge.calochallenge_cfm.model")
     cg = importlib.import_module("experiments.calogan.model")
     ch = importlib.import_module("experiments.calohadronic.model")
+    lm = importlib.import_module("experiments.lemurs.model")
     return types.SimpleNamespace(
-        ViT=vit.ViT, vit=vit,
+        ViT=vit.ViT, vit=vit, LEMURSCFM=lm.LEMURSCFM,
         CaloChallengeCFM=cc.CaloChallengeCFM, CaloChallengeCFM_DS1=cc.CaloChallengeCFM_DS1,
         CaloGANCFM=cg.CaloGANCFM, CaloHadCFM=ch.CaloHadCFM,
     )

@@ -206,18 +206,59 @@ def attention(qkv: torch.Tensor, num_heads: int) -> torch.Tensor:
     return (p @ v).transpose(1, 2).reshape(B, T, D)
 
 
+def get_sincos_pos_embed(pos_embedding_coords: str, num_patches, hidden_dim: int, dim: int = 3,
+                         temperature: float = 10000.0) -> torch.Tensor:
+    """Fixed (T, D) positional table of ``learn_pos_embed=False`` (reference nn/vit.py:461-540, used by
+    nn/vit.py:92-103): frequencies temperature**(-i/(F-1)), F = D/6 per coordinate and sin/cos; coordinates
+    (radial, angular, layer) for "cylindrical", (r cos a, r sin a, layer) with a in [0, 2 pi) for "cartesian"."""
+    if len(num_patches) == 1 and isinstance(num_patches[0], (list, tuple)):
+        num_patches = num_patches[0]
+    L, A, R = num_patches
+    F_ = hidden_dim // 6
+    omega = torch.pow(torch.tensor(float(temperature)), -torch.arange(F_) / (F_ - 1))
+    z = (torch.arange(L) / L)[:, None, None].expand(L, A, R).reshape(-1)
+    if pos_embedding_coords == "cylindrical":
+        a = (torch.arange(A) / A)[None, :, None].expand(L, A, R).reshape(-1)
+        r = (torch.arange(R) / R)[None, None, :].expand(L, A, R).reshape(-1)
+        coords = (r, a, z)
+    elif pos_embedding_coords == "cartesian":
+        a = (torch.arange(A) * (2 * math.pi / A))[None, :, None].expand(L, A, R).reshape(-1)
+        r = (torch.arange(R) / R)[None, None, :].expand(L, A, R).reshape(-1)
+        coords = (r * a.cos(), r * a.sin(), z)
+    else:
+        raise ValueError(pos_embedding_coords)
+    parts = []
+    for cvals in coords:
+        arg = cvals[:, None] * omega[None, :]
+        parts += [arg.sin(), arg.cos()]
+    return torch.cat(parts, dim=1)
+
+
 def vit_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, t: torch.Tensor,
                 c: torch.Tensor, num_heads: int) -> torch.Tensor:
     """ViT.forward (reference nn/vit.py:185-206) as a pure function of a state dict with
-    the reference's key names.  x (B,T,P), t (B,1), c (B,K) -> (B,T,P*out_channels)."""
+    the reference's key names.  x (B,T,P), t (B,1), c (B,K) -> (B,T,P*out_channels).
+
+    Also accepts the finetuning structures of reference
+    experiments/calochallenge/calochallenge_cfm/experiment_finetuning.py:79-118: ``x_embedder`` =
+    Sequential(mapper, SiLU, old Linear) (keys x_embedder.0 / .2) and ``c_embedder`` =
+    Sequential(mapper, SiLU, old Sequential) (keys c_embedder.0, c_embedder.2.0, c_embedder.2.2)."""
     depth = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("blocks."))
-    h = F.linear(x, sd["x_embedder.weight"], sd["x_embedder.bias"])
+    if "x_embedder.weight" in sd:
+        h = F.linear(x, sd["x_embedder.weight"], sd["x_embedder.bias"])
+    else:
+        xm = F.silu(F.linear(x, sd["x_embedder.0.weight"], sd["x_embedder.0.bias"]))
+        h = F.linear(xm, sd["x_embedder.2.weight"], sd["x_embedder.2.bias"])
     if "pos_embed_freqs" in sd:
         h = h + learnable_pos_embedding(sd)
     else:
         h = h + sd["pos_embed"]
     temb = _mlp2(sd, "t_embedder.mlp.0", "t_embedder.mlp.2", timestep_embedding(t).to(x.dtype))
-    cemb = _mlp2(sd, "c_embedder.0", "c_embedder.2", c)
+    if "c_embedder.2.0.weight" in sd:
+        cm = F.silu(F.linear(c, sd["c_embedder.0.weight"], sd["c_embedder.0.bias"]))
+        cemb = _mlp2(sd, "c_embedder.2.0", "c_embedder.2.2", cm)
+    else:
+        cemb = _mlp2(sd, "c_embedder.0", "c_embedder.2", c)
     cond = F.silu(temb + cemb)
     for i in range(depth):
         p = f"blocks.{i}."
@@ -382,6 +423,22 @@ CONFIGS = {
                                       flat_input=True),
                         param=_vit_param(5, [[1, 8, 1], [1, 16, 2], [1, 19, 2], [1, 5, 1], [1, 5, 1]], 6)),
 }
+
+
+_DS1_PIONS_SHAPES = [(1, 8, 5), (1, 10, 10), (1, 10, 10), (1, 5, 5), (1, 15, 10), (1, 16, 10), (1, 10, 5)]
+# reference configs/model/cfm/cfm_ds1_pions.yaml
+CONFIGS["ds1_pions"] = dict(
+    geom=Geometry(tuple(Segment(s, (1, 1, 5)) for s in _DS1_PIONS_SHAPES), flat_input=True),
+    param=_vit_param(5, [[1, 8, 1], [1, 10, 2], [1, 10, 2], [1, 5, 1], [1, 15, 2], [1, 16, 2], [1, 10, 1]], 8))
+# reference configs/model/cfm_lemurs/cfm_lemurs.yaml: the ds2 grid with 53 conditions; batches arrive as
+# (B, R, A, L) and are permuted by LEMURSCFM._batch_loss (experiments/lemurs/model.py:62-65)
+CONFIGS["lemurs"] = dict(geom=Geometry((Segment((45, 16, 9), (3, 16, 1)),)),
+                         param=_vit_param(48, [[15, 1, 9]], 53))
+
+
+def lemurs_to_grid(x: torch.Tensor) -> torch.Tensor:
+    """(B, R, A, L) -> (B, 1, L, A, R) (reference experiments/lemurs/model.py:63-64)"""
+    return x.permute(0, 3, 2, 1).unsqueeze(1)
 
 
 def tiny_config(name: str = "ds2", hidden_dim: int = 96, depth: int = 2, num_heads: int = 2):

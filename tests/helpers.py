@@ -18,7 +18,9 @@ def build_model(name, param, precision, device="cuda"):
     segs = geom.segments
     if name in ("ds2", "ds3"):
         m = v4.CaloChallengeCFM(net, list(segs[0].patch), 1, "uniform", "linear", ODE, shape=list(segs[0].shape))
-    elif name == "ds1_photons":
+    elif name == "lemurs":
+        m = v4.LEMURSCFM(net, list(segs[0].patch), 1, "uniform", "linear", ODE, shape=list(segs[0].shape))
+    elif name in ("ds1_photons", "ds1_pions"):
         m = v4.CaloChallengeCFM_DS1(net, [list(s.shape) for s in segs], [s.voxels for s in segs],
                                     list(segs[0].patch), 1, "uniform", "linear", ODE, shape=[geom.voxels])
     elif name == "calogan":
@@ -37,7 +39,7 @@ def build_model(name, param, precision, device="cuda"):
 def load_golden(golden_dir, tag):
     z = np.load(os.path.join(golden_dir, f"net_{tag}.npz"))
     sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
-    hidden, heads, depth, B = (int(v) for v in z["meta"])
+    hidden, heads, depth, B = (int(v) for v in z["meta"][:4])
     return z, sd, dict(hidden_dim=hidden, num_heads=heads, depth=depth), B
 
 

@@ -43,6 +43,9 @@ def test_plan_buckets_groups_stages_in_backward_order():
     assert [(x.stage_begin, x.stage_end, x.start, x.stop) for x in b] == [(4, 2, 0, 210), (1, 0, 210, 400)]
     one = dp.plan_buckets(bounds, min_elems=10 ** 9)
     assert len(one) == 1 and (one[0].start, one[0].stop, one[0].stage_begin, one[0].stage_end) == (0, 400, 4, 0)
+    # a tail that is not stage 0 alone is merged into the bucket before it
+    merged = dp.plan_buckets([10, 110, 210, 230, 240], min_elems=100)
+    assert [(x.stage_begin, x.stage_end) for x in merged] == [(4, 3), (2, 0)]
     each = dp.plan_buckets(bounds, min_elems=1)
     assert [x.stop - x.start for x in each] == [10, 100, 100, 100, 90]
     # every element is covered exactly once, in order
@@ -83,7 +86,8 @@ def test_bucketed_allreduce_averages_while_the_backward_is_staged():
     want = torch.arange(100, dtype=torch.float32) * 1.5  # mean of x*1 and x*2
     for flat, calls, launched in out:
         assert torch.allclose(flat, want)
-        assert calls == [(3, 2), (1, 0)] and launched == 2  # the short tail bucket is merged
+        # block 0 closes its own bucket (32 >= 30), so the short stage-0 tail stays separate: only it is exposed
+        assert calls == [(3, 2), (1, 1), (0, 0)] and launched == 3
 
 
 class _FakeModel:

@@ -77,7 +77,7 @@ def test_patchify_round_trip_full_size(dev):
 # network / loss / gradients / sampling against the reference's golden vectors
 # ----------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-@pytest.mark.parametrize("tag,name", [("ds2_tiny", "ds2"), ("calogan_tiny", "calogan")])
+@pytest.mark.parametrize("tag,name", [("ds2_tiny", "ds2"), ("calogan_tiny", "calogan"), ("ds1_pions_tiny", "ds1_pions")])
 def test_golden_forward_loss_grads_sample(dev, golden_dir, tag, name, precision):
     z, sd, over, B = load_golden(golden_dir, tag)
     tol = TOL[precision]
@@ -135,7 +135,8 @@ def test_sample_batch_uses_the_reference_rng_stream(dev, golden_dir, precision):
 # full-size network against the oracle (oracle on CPU, seconds)
 # ----------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-@pytest.mark.parametrize("name,batch", [("ds2", 4), ("ds3", 2), ("calohad", 1), ("ds1_photons", 3)])
+@pytest.mark.parametrize("name,batch", [("ds2", 4), ("ds3", 2), ("calohad", 1), ("ds1_photons", 3), ("ds1_pions", 3),
+                                        ("calogan", 5), ("lemurs", 2), ("ds2", 64)])
 def test_full_size_forward_and_grads_vs_oracle(dev, name, batch, precision):
     cfg = vo.CONFIGS[name]
     geom, param = cfg["geom"], cfg["param"]
@@ -167,6 +168,166 @@ def test_full_size_forward_and_grads_vs_oracle(dev, name, batch, precision):
     for k, p in params.items():
         if p.requires_grad:
             assert vo.rel_l2(named[k].grad, p.grad) < tol["grad"], k
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_ds2_forward_at_the_sampling_batch_vs_oracle(dev, precision):
+    """ds2 forward at the sampling batch 256 (shared t, like every network evaluation of the ODE solve):
+    other GEMM tile counts, persistent multi-tile schedules and sub-batch split than the small-batch cases."""
+    cfg = vo.CONFIGS["ds2"]
+    geom, param = cfg["geom"], cfg["param"]
+    sd = vo.init_state_dict(param, seed=3)
+    model = build_model("ds2", param, precision, dev)
+    model.net.load_state_dict(sd)
+    gen = torch.Generator().manual_seed(21)
+    B = 256
+    x = torch.randn(B, geom.tokens, geom.patch_dim, generator=gen)
+    c = torch.rand(B, param["condition_dim"], generator=gen)
+    t = torch.tensor([0.37])
+    with torch.no_grad():
+        want = vo.vit_forward(sd, x, t.repeat(B, 1), c, param["num_heads"])
+        got = model.net(x.to(dev), t.to(dev), c.to(dev), shared_t=True)
+        per_sample = model.net(x.to(dev), t.repeat(B, 1).to(dev), c.to(dev))
+    assert vo.rel_l2(got, want) < TOL[precision]["out"]
+    assert torch.equal(got, per_sample)  # shared_t is the same arithmetic as one t per sample
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_full_size_rk4_solve_vs_oracle(dev, precision):
+    """Full-size ds2 network, the whole 20-step RK4 (3/8 rule) solve = 80 chained network evaluations from a
+    fixed x_T against the oracle's fp32 solve (bf16 drift over the trajectory), and the
+    size-independent link to the sampling batch: every row of the computation is independent of the batch it
+    sits in, so the first showers of a 256-shower solve equal the 4-shower solve."""
+    cfg = vo.CONFIGS["ds2"]
+    geom, param = cfg["geom"], cfg["param"]
+    sd = vo.init_state_dict(param, seed=3)
+    model = build_model("ds2", param, precision, dev)
+    model.net.load_state_dict(sd)
+    gen = torch.Generator().manual_seed(31)
+    B = 4
+    x_T = torch.randn(B, *geom.sample_shape, generator=gen)
+    c = torch.rand(B, param["condition_dim"], generator=gen)
+    with torch.no_grad():
+        want = vo.sample_batch(sd, c, x_T, geom, param["num_heads"], step_size=0.05)
+    got = model.integrate(x_T.to(dev), c.to(dev))
+    assert torch.isfinite(got).all()
+    assert vo.rel_l2(got, want) < TOL[precision]["sample"]
+    if precision == "bf16":
+        big_x = torch.cat([x_T, torch.randn(252, *geom.sample_shape, generator=gen)]).to(dev)
+        big_c = torch.cat([c, torch.rand(252, param["condition_dim"], generator=gen)]).to(dev)
+        big = model.integrate(big_x, big_c)
+        assert vo.rel_l2(big[:B], got) < 1e-6
+        model.graph_sampling = True
+        assert torch.equal(model.integrate(big_x, big_c), big)
+
+
+def test_lemurs_batch_loss_golden(dev, golden_dir):
+    """LEMURSCFM._batch_loss: (B, R, A, L) batches, K = 53 (reference experiments/lemurs/model.py:62-65)"""
+    z, sd, over, B = load_golden(golden_dir, "lemurs_tiny")
+    param = dict(vo.CONFIGS["lemurs"]["param"]); param.update(over)
+    for precision in ("fp32", "bf16"):
+        tol = TOL[precision]
+        model = build_model("lemurs", param, precision, dev)
+        model.net.load_state_dict(sd)
+        want_x0 = torch.from_numpy(z["loss_x0"]).to(dev)
+        orig = torch.randn_like
+        torch.randn_like = lambda *_a, **_k: want_x0
+        try:
+            torch.manual_seed(55)
+            loss = model._batch_loss([torch.from_numpy(z["x"]), torch.from_numpy(z["c"])])
+        finally:
+            torch.randn_like = orig
+        loss.backward()
+        assert abs(loss.item() - float(z["loss"])) / float(z["loss"]) < tol["out"]
+        named = dict(model.net.named_parameters())
+        for k in z.files:
+            if k.startswith("grad/"):
+                assert vo.rel_l2(named[k[5:]].grad, torch.from_numpy(z[k])) < tol["grad"], (precision, k)
+        # graphed training passes device_rng through the override (ADVICE r1)
+        assert torch.isfinite(model._batch_loss([torch.from_numpy(z["x"]), torch.from_numpy(z["c"])], device_rng=True))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_finetuning_structures_golden(dev, golden_dir, precision):
+    """The reference's finetuning surgery (experiment_finetuning.py:75-165) applied to a vit4hep_b200.ViT:
+    mapper Linears in front of x_embedder / c_embedder, pos grid of the new geometry, a new final layer --
+    output and every parameter gradient against the reference's."""
+    import torch.nn as nn
+    import vit4hep_b200 as v4
+    from vit4hep_b200.vit import FinalLayer
+    z, sd, over, B = load_golden(golden_dir, "finetune_tiny")
+    tol = TOL[precision]
+    back = dict(vo.CONFIGS["ds2"]["param"]); back.update(over); back["precision"] = precision
+    new = vo.CONFIGS["ds3"]["param"]
+    K_new = int(z["meta"][4])
+    net = v4.ViT(back)
+    net.x_embedder = nn.Sequential(nn.Linear(new["patch_dim"], back["patch_dim"]), nn.SiLU(), net.x_embedder)
+    net.c_embedder = nn.Sequential(nn.Linear(K_new, back["condition_dim"]), nn.SiLU(), net.c_embedder)
+    net.num_patches = new["num_patches"]
+    net.pos_z, net.pos_y, net.pos_x = net.create_meshgrid()
+    net.final_layer = FinalLayer(back["hidden_dim"], new["patch_dim"], back["out_channels"])
+    net = net.to(dev)
+    net.load_state_dict(sd)
+    x, t, c, wgt = (torch.from_numpy(z[k]).to(dev) for k in ("x", "t", "c", "wgt"))
+    y = net(x, t, c)
+    assert vo.rel_l2(y, torch.from_numpy(z["net_out"])) < tol["out"]
+    (y * wgt).sum().backward()
+    named = dict(net.named_parameters())
+    for k in z.files:
+        if k.startswith("grad/"):
+            assert named[k[5:]].grad is not None, k
+            assert vo.rel_l2(named[k[5:]].grad, torch.from_numpy(z[k])) < tol["grad"], k
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_fixed_positional_embedding_golden(dev, golden_dir, precision):
+    """learn_pos_embed=False (reference nn/vit.py:92-103): the table is a constant buffer the x_embedder epilogue adds"""
+    import vit4hep_b200 as v4
+    z, sd, over, B = load_golden(golden_dir, "fixed_pos_tiny")
+    param = dict(vo.CONFIGS["ds3"]["param"]); param.update(over)
+    param.update(learn_pos_embed=False, pos_embedding_coords="cylindrical", precision=precision,
+                 num_patches=list(param["num_patches"][0]))
+    net = v4.ViT(param)
+    assert vo.rel_l2(net.pos_embed, torch.from_numpy(z["table/cylindrical"])) < 1e-6
+    net = net.to(dev)
+    net.load_state_dict(sd)
+    with torch.no_grad():
+        y = net(*(torch.from_numpy(z[k]).to(dev) for k in ("x", "t", "c")))
+    assert vo.rel_l2(y, torch.from_numpy(z["net_out"])) < TOL[precision]["out"]
+
+
+def test_sub_batch_lanes_give_the_single_chain_result(dev, monkeypatch):
+    """The library runs a batch as two sub-batches on two streams (csrc/vit.cu Lane).  Every output row depends
+    on its own sample only and a GEMM element sees the same k order whatever M is, so the forward is
+    bit-identical to the unsplit run; gradients are sums over samples whose fp32 atomics reorder (same bound
+    as for the side streams)."""
+    name, batch = "ds2", 64
+    cfg = vo.CONFIGS[name]
+    geom, param = cfg["geom"], cfg["param"]
+    sd = vo.init_state_dict(param, seed=5)
+    gen = torch.Generator().manual_seed(19)
+    x = torch.randn(batch, geom.tokens, geom.patch_dim, generator=gen).to(dev)
+    t = torch.rand(batch, 1, generator=gen).to(dev)
+    c = torch.rand(batch, param["condition_dim"], generator=gen).to(dev)
+    dout = torch.randn(batch, geom.tokens, geom.patch_dim, generator=gen).to(dev)
+    res = {}
+    for mode in ("1", "2"):
+        monkeypatch.setenv("V4H_MICROBATCH", mode)  # read when the plan is created
+        model = build_model(name, param, "bf16", dev)
+        model.net.load_state_dict(sd)
+        v = model.net(x, t, c)
+        v.backward(dout)
+        torch.cuda.synchronize()
+        res[mode] = (v.detach().clone(), {k: p.grad.detach().clone() for k, p in model.net.named_parameters()})
+    assert torch.equal(res["1"][0], res["2"][0])
+    for k, g in res["2"][1].items():
+        assert vo.rel_l2(g, res["1"][1][k]) < 2e-3, k
+    # odd batch: sub-batches of 3 and 2
+    monkeypatch.setenv("V4H_MICROBATCH", "2")
+    model = build_model(name, param, "bf16", dev)
+    model.net.load_state_dict(sd)
+    with torch.no_grad():
+        assert torch.equal(model.net(x[:5], t[:5], c[:5]), res["1"][0][:5])
 
 
 def test_side_streams_give_the_single_stream_result(dev, monkeypatch):
@@ -287,6 +448,117 @@ def test_fused_adamw_matches_torch_adamw_with_clipping(dev):
         net._native.arena_key = None  # force the recast path
         want = net(x, t, c)
     assert torch.equal(got, want)
+
+
+def test_fused_adamw_resumes_from_a_checkpoint_and_tracks_ema(dev):
+    """load_state_dict must reach the kernel (job table with the loaded moments, step counters for the
+    bias correction), also under graph-style device counters; the EMA fused into the optimizer pass follows
+    torch_ema's update rule (reference experiments/base_experiment.py:127-134, :594)."""
+    import copy
+    import vit4hep_b200 as v4
+    cfg = vo.tiny_config("ds2", hidden_dim=96, depth=2, num_heads=2)
+    param = dict(cfg["param"]); param["precision"] = "bf16"
+    torch.manual_seed(0)
+    net = v4.ViT(param).to(dev)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.copy_(torch.randn_like(p) * 0.05)
+    ref = copy.deepcopy(net)
+    g = torch.Generator().manual_seed(5)
+    B, T, P = 4, net.pos_z.numel(), param["patch_dim"]
+    decay = 0.9
+    ema = v4.ExponentialMovingAverage(net.parameters(), decay=decay)
+    ema.to(dev)
+    shadow = [p.detach().clone() for p in ref.parameters()]  # torch_ema arithmetic, restated
+    fused = v4.FusedAdamW(net, lr=1e-2, weight_decay=0.1, max_grad_norm=0.5, ema=ema)
+    opt = torch.optim.AdamW(ref.parameters(), lr=1e-2, weight_decay=0.1)
+    n_updates = 0
+
+    def one_step(fused_opt, the_ema):
+        nonlocal n_updates
+        x = torch.randn(B, T, P, generator=g).to(dev)
+        t = torch.rand(B, 1, generator=g).to(dev)
+        c = torch.rand(B, param["condition_dim"], generator=g).to(dev)
+        net(x, t, c).square().mean().backward()
+        for p, q in zip(net.parameters(), ref.parameters()):
+            q.grad = p.grad.clone()
+        torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.5)
+        opt.step()
+        fused_opt.step()
+        the_ema.update()  # the reference's loop calls it after optimizer.step(): recognised as already done
+        n_updates += 1
+        d = min(decay, (1 + n_updates) / (10 + n_updates))
+        with torch.no_grad():
+            for s_, q in zip(shadow, ref.parameters()):
+                s_.sub_((1 - d) * (s_ - q))
+        fused_opt.zero_grad(set_to_none=True)
+
+    for _ in range(3):
+        one_step(fused, ema)
+    # checkpoint, then resume in fresh objects
+    ckpt = {"optimizer": copy.deepcopy(fused.state_dict()), "ema": copy.deepcopy(ema.state_dict())}
+    assert ckpt["ema"]["num_updates"] == 3
+    assert {int(s_["step"]) for s_ in ckpt["optimizer"]["state"].values()} == {3}
+    ema2 = v4.ExponentialMovingAverage(net.parameters(), decay=decay)
+    ema2.load_state_dict(ckpt["ema"]); ema2.to(dev)
+    fused2 = v4.FusedAdamW(net, lr=1e-2, weight_decay=0.1, max_grad_norm=0.5, ema=ema2)
+    fused2.load_state_dict(ckpt["optimizer"])
+    for _ in range(2):
+        one_step(fused2, ema2)
+    for (name, p), q in zip(net.named_parameters(), ref.parameters()):
+        assert vo.rel_l2(p, q) < 1e-6, name
+    for (name, _), s_, w in zip(net.named_parameters(), ema2.shadow_params, shadow):
+        assert vo.rel_l2(s_, w) < 1e-6, name
+    # loading in the SAME optimizer object must not reuse the job table of the old moments
+    fused2.load_state_dict(ckpt["optimizer"])
+    assert fused2._key is None and not fused2._tables and fused2._step == 3 and fused2._step_dev.item() == 3
+    # stand-alone update() (EMA not attached to the optimizer) and average_parameters()
+    ema3 = v4.ExponentialMovingAverage(net.parameters(), decay=decay); ema3.to(dev)
+    before = [p.detach().clone() for p in net.parameters()]
+    with torch.no_grad():
+        for p in net.parameters():
+            p.add_(0.01)
+    ema3.update()
+    d = min(decay, 2 / 11)
+    for s_, b, p in zip(ema3.shadow_params, before, net.parameters()):
+        assert vo.rel_l2(s_, b - (1 - d) * (b - p)) < 1e-6
+    with ema3.average_parameters():
+        assert all(torch.equal(p, s_) for p, s_ in zip(net.parameters(), ema3.shadow_params))
+    assert all(torch.equal(p, b + 0.01) for p, b in zip(net.parameters(), before))
+
+
+def test_second_backward_and_interleaved_forward(dev):
+    """a forward with another token count between forward and backward must not disturb the pending
+    graph (plans are kept per shape and travel with the autograd context); a second backward raises clearly."""
+    import vit4hep_b200 as v4
+    cfg = vo.tiny_config("ds2", hidden_dim=96, depth=2, num_heads=2)
+    param = dict(cfg["param"]); param["precision"] = "bf16"
+    torch.manual_seed(0)
+    net = v4.ViT(param).to(dev)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.copy_(torch.randn_like(p) * 0.05)
+    g = torch.Generator().manual_seed(5)
+    T, P, K = net.pos_z.numel(), param["patch_dim"], param["condition_dim"]
+    x = torch.randn(3, T, P, generator=g).to(dev); t = torch.rand(3, 1, generator=g).to(dev)
+    c = torch.rand(3, K, generator=g).to(dev)
+    net(x, t, c).square().mean().backward()
+    want = {k: p.grad.clone() for k, p in net.named_parameters()}
+    net.zero_grad(set_to_none=True)
+    loss = net(x, t, c).square().mean()
+    # another geometry in between (finetuning / validation on a different grid re-assigns the pos buffers)
+    keep = (net.pos_z, net.pos_y, net.pos_x)
+    net.pos_z, net.pos_y, net.pos_x = (b[:60].clone() for b in keep)
+    with torch.no_grad():
+        net(x[:, :60].contiguous(), t, c)
+    net.pos_z, net.pos_y, net.pos_x = keep
+    loss.backward()
+    for k, p in net.named_parameters():
+        assert vo.rel_l2(p.grad, want[k]) < 2e-3, k
+    loss2 = net(x, t, c).square().mean()
+    loss2.backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="already consumed"):
+        loss2.backward()
 
 
 def test_graphed_train_step_and_sampling_match_eager(dev):

@@ -131,3 +131,105 @@ def test_fixed_pos_embed_tables():
     assert pe.shape == (135, 48)
     # token 0 sits at the origin: sin = 0, cos = 1
     assert torch.allclose(pe[0, 0:8], torch.zeros(8)) and torch.allclose(pe[0, 8:16], torch.ones(8))
+
+
+# ----------------------------------------------------------------------------------------------
+# Hydra-free instantiation from the reference's own YAML
+# ----------------------------------------------------------------------------------------------
+REF_CFG = "/root/reference/configs/model"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CFG), reason="reference configs not present (GPU box)")
+@pytest.mark.parametrize("rel,name", [("cfm/cfm_ds2_electrons.yaml", "ds2"), ("cfm/cfm_ds3_electrons.yaml", "ds3"),
+                                      ("cfm/cfm_ds1_photons.yaml", "ds1_photons"), ("cfm/cfm_ds1_pions.yaml", "ds1_pions"),
+                                      ("cfm_calogan/cfm_eplus.yaml", "calogan"), ("cfm_calohad/cfm_calohad.yaml", "calohad"),
+                                      ("cfm_lemurs/cfm_lemurs.yaml", "lemurs")])
+def test_instantiate_from_the_reference_yaml(rel, name):
+    """The reference's model YAML, unchanged except for its two ``_target_`` strings (here remapped on the fly),
+    builds the B200 drop-ins; the tables in vit4hep_b200.configs restate exactly these files."""
+    import yaml
+    import vit4hep_b200 as v4
+    from vit4hep_b200 import configs
+    with open(os.path.join(REF_CFG, rel)) as fh:
+        cfg = yaml.safe_load(fh)
+    model = configs.instantiate(cfg, remap=True)
+    assert type(model).__module__.startswith("vit4hep_b200") and isinstance(model.net, v4.ViT)
+    og = vo.CONFIGS[name]["geom"]
+    assert (model.geometry.tokens, model.geometry.patch_dim, model.geometry.voxels) == (og.tokens, og.patch_dim, og.voxels)
+    assert model.net.pos_z.numel() == og.tokens
+    # the restated table builds the same thing
+    mine = configs.MODELS[name]
+    want = dict(cfg); want["_target_"] = configs.TARGETS[cfg["_target_"]]
+    want["net"] = dict(cfg["net"]); want["net"]["_target_"] = configs.TARGETS[cfg["net"]["_target_"]]
+    want["net"]["param"] = {k: v for k, v in cfg["net"]["param"].items() if k != "use_rotary_emb"}
+    assert {k: v for k, v in mine.items() if k != "net"} == {k: v for k, v in want.items() if k != "net"}
+    assert mine["net"]["param"] == want["net"]["param"]
+    # edited-by-hand variant of INTEGRATION.md: explicit drop-in targets, no remapping
+    same = configs.instantiate(want)
+    assert {k: tuple(v.shape) for k, v in same.net.state_dict().items()} == \
+        {k: tuple(v.shape) for k, v in model.net.state_dict().items()}
+
+
+def test_finetuning_structures_are_accepted_on_the_host():
+    """x / c embedders behind mapper Linears and a swapped final layer (reference experiment_finetuning.py:75-165)
+    change the parameter list and the plan key; anything else still raises NotImplementedError."""
+    import torch.nn as nn
+    import vit4hep_b200 as v4
+    p = dict(vo.tiny_config("ds2", hidden_dim=48, depth=1, num_heads=2)["param"])
+    net = v4.ViT(p)
+    n0 = len(net.ordered_parameters())
+    net.x_embedder = nn.Sequential(nn.Linear(90, p["patch_dim"]), nn.SiLU(), net.x_embedder)
+    net.c_embedder = nn.Sequential(nn.Linear(40, p["condition_dim"]), nn.SiLU(), net.c_embedder)
+    fields = [f for f, _ in net.ordered_parameters()]
+    assert len(fields) == n0 + 4 and {"xm_w", "xm_b", "cm_w", "cm_b"} <= set(fields)
+    assert {id(q) for _, q in net.ordered_parameters()} == {id(q) for q in net.parameters()}
+    offs, total = net.flat_layout(net.ordered_parameters())
+    assert net.stage_boundaries()[-1] == total
+    net.c_embedder = nn.Sequential(nn.Linear(40, 48), nn.ReLU(), nn.Linear(48, 48))
+    with pytest.raises(NotImplementedError):
+        net.ordered_parameters()
+
+
+def test_stage_boundaries_follow_backward_completion():
+    """final layer (with its adaLN Linear), blocks depth-1..0 (each with its adaLN Linear), stage 0"""
+    import vit4hep_b200 as v4
+    p = dict(vo.tiny_config("ds2", hidden_dim=48, depth=3, num_heads=2)["param"])
+    net = v4.ViT(p)
+    ordered = net.ordered_parameters()
+    offs, total = net.flat_layout(ordered)
+    bounds = net.stage_boundaries()
+    assert len(bounds) == 3 + 2 and bounds[-1] == total and bounds == sorted(bounds)
+    names = [f for f, _ in ordered]
+    ends = dict(zip(names, offs[1:] + [total]))
+    assert bounds[0] == ends["final_ada_b"]
+    assert bounds[1] == ends["blocks.2.ada_b"] and bounds[3] == ends["blocks.0.ada_b"]
+    stage0 = names[names.index("blocks.0.ada_b") + 1:]
+    assert stage0[0] == "pos_embed_freqs" and not any(n.startswith("blocks.") or "ada" in n for n in stage0)
+    from vit4hep_b200 import dp
+    full = v4.ViT(dict(vo.CONFIGS["ds2"]["param"]))
+    b = dp.plan_buckets(full.stage_boundaries(), 4_000_000)
+    assert (b[-1].stage_begin, b[-1].stage_end) == (0, 0) and b[-1].stop - b[-1].start < 1_000_000
+    assert len(b) == 7 and all(x.stop - x.start >= 4_000_000 for x in b[:-1])
+
+
+def test_ema_host_logic_matches_torch_ema_semantics():
+    """ExponentialMovingAverage mirrors torch_ema's container behaviour (state_dict keys, store / restore /
+    average_parameters, to()); the update itself is a CUDA kernel and raises on CPU tensors (no fallback)."""
+    import vit4hep_b200 as v4
+    params = [torch.nn.Parameter(torch.randn(4, 3)), torch.nn.Parameter(torch.randn(5))]
+    ema = v4.ExponentialMovingAverage(params, decay=0.99)
+    sd = ema.state_dict()
+    assert set(sd) == {"decay", "num_updates", "shadow_params", "collected_params"} and sd["num_updates"] == 0
+    assert all(torch.equal(s, p) for s, p in zip(sd["shadow_params"], params))
+    with torch.no_grad():
+        params[0].add_(1.0)
+    with ema.average_parameters():
+        assert torch.equal(params[0], ema.shadow_params[0])
+    assert not torch.equal(params[0], ema.shadow_params[0])
+    other = v4.ExponentialMovingAverage(params, decay=0.5)
+    other.load_state_dict(sd)
+    assert other.decay == 0.99 and torch.equal(other.shadow_params[1], ema.shadow_params[1])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ema.update()
+    with pytest.raises(ValueError):
+        v4.ExponentialMovingAverage(params, decay=1.5)

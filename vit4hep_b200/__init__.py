@@ -7,6 +7,6 @@ from .vit import ViT  # noqa: F401
 from .cfm import (CFM, CaloChallengeCFM, CaloChallengeCFM_DS1, CaloGANCFM, CaloHadCFM, LEMURSCFM,  # noqa: F401
                   GraphedTrainStep, PatchGeometry)
 
-from .optim import FusedAdamW  # noqa: F401
+from .optim import ExponentialMovingAverage, FusedAdamW  # noqa: F401
 
 __version__ = "0.1.0"

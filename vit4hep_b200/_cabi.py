@@ -21,7 +21,7 @@ _f32p = C.c_void_p  # device pointers travel as integers
 class VitDims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "hidden_dim", "depth", "num_heads", "mlp_hidden", "patch_dim", "out_dim", "cond_dim",
-        "tokens", "freq_dim", "learn_pos_embed", "precision")]
+        "tokens", "freq_dim", "learn_pos_embed", "precision", "x_map_dim", "c_map_dim")]
 
 
 class BlockParams(C.Structure):
@@ -33,12 +33,12 @@ class VitParams(C.Structure):
     _fields_ = [(n, _f32p) for n in (
         "pos_embed_freqs", "pos_z", "pos_y", "pos_x", "pos_embed", "x_w", "x_b",
         "c0_w", "c0_b", "c2_w", "c2_b", "t0_w", "t0_b", "t2_w", "t2_b",
-        "final_w", "final_b", "final_ada_w", "final_ada_b")] + [("blocks", BlockParams * V4H_MAX_DEPTH)]
+        "final_w", "final_b", "final_ada_w", "final_ada_b", "xm_w", "xm_b", "cm_w", "cm_b")] + [("blocks", BlockParams * V4H_MAX_DEPTH)]
 
 
 class AdamWJob(C.Structure):
     _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("bf16_dst", C.c_void_p),
-                ("f32_dst", C.c_void_p), ("n", C.c_int64)]
+                ("f32_dst", C.c_void_p), ("ema", C.c_void_p), ("n", C.c_int64)]
 
 
 class ProfileEntry(C.Structure):
@@ -73,7 +73,8 @@ SIGNATURES = {
     "v4h_cfm_loss": (C.c_int, [_vp, _vp, _i64, _fl, _vp, _vp, _vp]),
     "v4h_axpy4": (C.c_int, [_vp, _vp, _vp, _fl, _vp, _fl, _vp, _fl, _vp, _fl, _i64, _vp]),
     "v4h_grad_norm_sq": (C.c_int, [_vp, _i64, _vp, _vp]),
-    "v4h_adamw_step": (C.c_int, [_vp, _i32, _i64, _vp, _fl, _fl, _fl, _fl, _fl, _fl, _i32, _vp, _vp, _vp]),
+    "v4h_adamw_step": (C.c_int, [_vp, _i32, _i64, _vp, _fl, _fl, _fl, _fl, _fl, _fl, _i32, _vp, _vp, _fl, _i32, _vp, _vp]),
+    "v4h_ema_update": (C.c_int, [_vp, _i32, _i64, _fl, _i32, _vp, _vp]),
     "v4h_counter_increment": (C.c_int, [_vp, _vp]),
     "v4h_vit_arena_offset": (C.c_int64, [_vp, C.c_char_p]),
     "v4h_launch_count": (C.c_int64, []),

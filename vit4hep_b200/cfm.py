@@ -412,6 +412,9 @@ class GraphedTrainStep:
         loss = self.model._batch_loss((self.x, self.c), device_rng=True)
         loss.backward()
         self.optimizer.step()
+        ema = getattr(self.optimizer, "ema", None)
+        if ema is not None:  # the fused pass has updated it; nobody calls ema.update() inside the graph
+            ema._fused_pending = False
         return loss.detach()
 
     def step(self, x: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
@@ -527,7 +530,7 @@ class CaloHadCFM(CaloGANCFM):
 class LEMURSCFM(CaloChallengeCFM):
     """LEMURS: ds2-like grid whose batches arrive as (B, R, A, L) (reference experiments/lemurs/model.py:8-99)."""
 
-    def _batch_loss(self, x):
+    def _batch_loss(self, x, device_rng: bool = False):
         x = list(x)
         x[0] = x[0].permute(0, 3, 2, 1).unsqueeze(1)  # layers first, then add the channel axis
-        return super()._batch_loss(x)
+        return super()._batch_loss(x, device_rng=device_rng)

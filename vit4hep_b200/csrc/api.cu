@@ -292,10 +292,17 @@ int v4h_grad_norm_sq(const float* flat, int64_t n, float* out, v4h_stream_t s) {
 }
 int v4h_adamw_step(const v4h_adamw_job* jobs, int32_t njobs, int64_t max_n, const float* norm_sq, float max_norm,
                    float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
-                   const int32_t* step_dev, const float* lr_dev, v4h_stream_t s) {
+                   const int32_t* step_dev, const float* lr_dev, float ema_decay, int32_t ema_updates,
+                   const int32_t* ema_updates_dev, v4h_stream_t s) {
   V4H_REQUIRE(jobs && njobs > 0 && njobs <= 65535 && max_n > 0 && (step >= 1 || step_dev), "adamw_step: bad arguments");
+  V4H_REQUIRE(ema_decay < 1.f, "adamw_step: ema_decay must be < 1");
   return adamw_step(jobs, njobs, max_n, norm_sq, max_norm, lr, beta1, beta2, eps, weight_decay, step, step_dev, lr_dev,
-                    (cudaStream_t)s);
+                    ema_decay, ema_updates, ema_updates_dev, (cudaStream_t)s);
+}
+int v4h_ema_update(const v4h_adamw_job* jobs, int32_t njobs, int64_t max_n, float decay, int32_t num_updates,
+                   const int32_t* num_updates_dev, v4h_stream_t s) {
+  V4H_REQUIRE(jobs && njobs > 0 && njobs <= 65535 && max_n > 0 && decay > 0.f && decay < 1.f, "ema_update: bad arguments");
+  return ema_update(jobs, njobs, max_n, decay, num_updates, num_updates_dev, (cudaStream_t)s);
 }
 int v4h_counter_increment(int32_t* counter, v4h_stream_t s) {
   V4H_REQUIRE(counter, "counter_increment: null");

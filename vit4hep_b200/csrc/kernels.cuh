@@ -93,6 +93,7 @@ int pos_embedding_bwd(const float* dh, const float* freqs, const float* pz, cons
 int dsilu_mul(const float* x, const float* pre, float* out, bf16* out_bf, int64_t n, cudaStream_t s);
 int silu_to_bf16(const float* x, bf16* out, int64_t n, cudaStream_t s);
 int cast_f32_to_bf16(const float* x, bf16* out, int64_t n, cudaStream_t s);
+int cast_f32_to_bf16_2d(const float* x, int ld_x, bf16* out, int ld_out, int rows, int cols, cudaStream_t s);
 struct CastJob { const float* src; bf16* dst; int64_t n; };
 int cast_many_f32_to_bf16(const CastJob* jobs_dev, int njobs, int64_t max_n, cudaStream_t s);
 int cfm_prepare(const float* x1, const float* x0, const float* t, const int32_t* table, float* xt_tok,
@@ -106,7 +107,9 @@ int axpy4(float* out, const float* y, const float* k0, float a0, const float* k1
 int grad_norm_sq(const float* flat, int64_t n, float* out, cudaStream_t s);
 int adamw_step(const v4h_adamw_job* jobs_dev, int njobs, int64_t max_n, const float* norm_sq, float max_norm, float lr,
                float beta1, float beta2, float eps, float weight_decay, int step, const int* step_dev,
-               const float* lr_dev, cudaStream_t s);
+               const float* lr_dev, float ema_decay, int ema_updates, const int* ema_updates_dev, cudaStream_t s);
+int ema_update(const v4h_adamw_job* jobs_dev, int njobs, int64_t max_n, float decay, int num_updates,
+               const int* num_updates_dev, cudaStream_t s);
 int counter_increment(int* counter, cudaStream_t s);
 
 // patchify.cu:  dst[b, j] = src[b, table[j]] staged through shared memory per chunk

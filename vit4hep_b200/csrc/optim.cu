@@ -46,7 +46,18 @@ struct AdamArgs {
   float bc1, bc2_sqrt;   // 1 - beta1^t, sqrt(1 - beta2^t) from the host step count ...
   const int* step_dev;   // ... or, when non-null, computed from this device step counter (CUDA-graph replay)
   const float* lr_dev;   // optional device learning rate overriding `lr` (schedulers under graph replay)
+  // exponential moving average of the parameters (torch_ema arithmetic, reference experiments/base_experiment.py:
+  // 127-134, :594): shadow -= (1 - d) (shadow - p), d = min(decay, (1 + n) / (10 + n)), n = updates so far
+  float ema_decay;           // <= 0: no EMA
+  int ema_updates;           // n from the host ...
+  const int* ema_updates_dev;  // ... or from this device counter (CUDA-graph replay)
 };
+
+__device__ __forceinline__ float ema_one_minus_decay(const AdamArgs& a) {
+  const float n = (float)(a.ema_updates_dev ? *a.ema_updates_dev : a.ema_updates);
+  const float d = fminf(a.ema_decay, (1.f + n) / (10.f + n));
+  return 1.f - d;
+}
 
 __global__ void counter_increment_kernel(int* c) {
   pdl_wait(); *c += 1; }
@@ -82,7 +93,9 @@ __global__ void __launch_bounds__(OPT_THREADS) adamw_kernel(const v4h_adamw_job*
   const bool vec = ((reinterpret_cast<uintptr_t>(j.p) | reinterpret_cast<uintptr_t>(j.g) | reinterpret_cast<uintptr_t>(j.m) |
                      reinterpret_cast<uintptr_t>(j.v) | reinterpret_cast<uintptr_t>(j.f32_dst)) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(dst) & 7) == 0;
-  const int64_t n4 = vec ? j.n / 4 : 0;
+  const bool ema = a.ema_decay > 0.f && j.ema != nullptr;
+  const float omd = ema ? ema_one_minus_decay(a) : 0.f;
+  const int64_t n4 = (vec && (reinterpret_cast<uintptr_t>(j.ema) & 15) == 0) ? j.n / 4 : 0;
   for (int64_t i = tid; i < n4; i += stride) {
     float4 p = reinterpret_cast<float4*>(j.p)[i];
     const float4 g = reinterpret_cast<const float4*>(j.g)[i];
@@ -96,6 +109,11 @@ __global__ void __launch_bounds__(OPT_THREADS) adamw_kernel(const v4h_adamw_job*
     reinterpret_cast<float4*>(j.m)[i] = m;
     reinterpret_cast<float4*>(j.v)[i] = v;
     if (j.f32_dst) reinterpret_cast<float4*>(j.f32_dst)[i] = p;
+    if (ema) {
+      float4 e = reinterpret_cast<float4*>(j.ema)[i];
+      e.x -= omd * (e.x - p.x); e.y -= omd * (e.y - p.y); e.z -= omd * (e.z - p.z); e.w -= omd * (e.w - p.w);
+      reinterpret_cast<float4*>(j.ema)[i] = e;
+    }
     if (dst) {
       const __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y), hi = __floats2bfloat162_rn(p.z, p.w);
       reinterpret_cast<uint2*>(dst)[i] =
@@ -108,7 +126,27 @@ __global__ void __launch_bounds__(OPT_THREADS) adamw_kernel(const v4h_adamw_job*
     j.p[i] = p; j.m[i] = m; j.v[i] = v;
     if (dst) dst[i] = __float2bfloat16_rn(p);
     if (j.f32_dst) j.f32_dst[i] = p;
+    if (ema) { const float e = j.ema[i]; j.ema[i] = e - omd * (e - p); }
   }
+}
+
+// stand-alone EMA update (ExponentialMovingAverage.update() when it is not fused into the optimizer pass)
+__global__ void __launch_bounds__(OPT_THREADS) ema_kernel(const v4h_adamw_job* __restrict__ jobs, AdamArgs a) {
+  pdl_wait();
+  const v4h_adamw_job j = jobs[blockIdx.y];
+  if (j.ema == nullptr) return;
+  const float omd = ema_one_minus_decay(a);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const bool vec = ((reinterpret_cast<uintptr_t>(j.p) | reinterpret_cast<uintptr_t>(j.ema)) & 15) == 0;
+  const int64_t n4 = vec ? j.n / 4 : 0;
+  for (int64_t i = tid; i < n4; i += stride) {
+    const float4 p = reinterpret_cast<const float4*>(j.p)[i];
+    float4 e = reinterpret_cast<float4*>(j.ema)[i];
+    e.x -= omd * (e.x - p.x); e.y -= omd * (e.y - p.y); e.z -= omd * (e.z - p.z); e.w -= omd * (e.w - p.w);
+    reinterpret_cast<float4*>(j.ema)[i] = e;
+  }
+  for (int64_t i = n4 * 4 + tid; i < j.n; i += stride) { const float e = j.ema[i]; j.ema[i] = e - omd * (e - j.p[i]); }
 }
 
 }  // namespace
@@ -129,10 +167,24 @@ int counter_increment(int* counter, cudaStream_t s) {
   return V4H_OK;
 }
 
+int ema_update(const v4h_adamw_job* jobs_dev, int njobs, int64_t max_n, float decay, int num_updates,
+               const int* num_updates_dev, cudaStream_t s) {
+  AdamArgs a;
+  memset(&a, 0, sizeof(a));
+  a.ema_decay = decay; a.ema_updates = num_updates; a.ema_updates_dev = num_updates_dev;
+  int64_t gx = ceil_div(max_n, (int64_t)OPT_THREADS * 4 * 4);
+  if (gx < 1) gx = 1;
+  if (gx > 128) gx = 128;
+  V4H_CUDA(launch_pdl(ema_kernel, dim3(dim3((unsigned)gx, (unsigned)njobs)), dim3(OPT_THREADS), 0, s, jobs_dev, a));
+  V4H_LAUNCH_CHECK();
+  return V4H_OK;
+}
+
 int adamw_step(const v4h_adamw_job* jobs_dev, int njobs, int64_t max_n, const float* norm_sq, float max_norm, float lr,
                float beta1, float beta2, float eps, float weight_decay, int step, const int* step_dev,
-               const float* lr_dev, cudaStream_t s) {
+               const float* lr_dev, float ema_decay, int ema_updates, const int* ema_updates_dev, cudaStream_t s) {
   AdamArgs a;
+  a.ema_decay = ema_decay; a.ema_updates = ema_updates; a.ema_updates_dev = ema_updates_dev;
   a.step_dev = step_dev; a.lr_dev = lr_dev;
   a.norm_sq = norm_sq; a.max_norm = max_norm;
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;

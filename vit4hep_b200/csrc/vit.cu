@@ -10,6 +10,19 @@
 
 namespace v4h {
 
+// Streams of one sub-batch ("lane").  The batch is split into up to two sub-batches whose kernel chains are
+// issued on two streams: every kernel of the chain keeps all SMs busy only in the middle of its run (launch
+// gap, prologue, ragged last round, exposed last epilogue: about 4 + 2..7 us of a 15..30 us GEMM at batch 64),
+// and a second, independent chain fills exactly those holes -- its CTAs are already queued when an SM frees.
+// Results do not depend on the split (a GEMM output element sees the same k order whatever M is).
+struct Lane {
+  cudaStream_t main = nullptr;  // lane 0 runs on the caller's stream (nullptr here)
+  // weight-gradient GEMMs and the small embedding / conditioning chains run on side streams, off the
+  // dgrad -> LayerNorm -> attention chain (V4H_WGRAD_STREAM=0: same stream)
+  cudaStream_t side = nullptr, side2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_done = nullptr;
+};
+
 struct Plan {
   v4h_vit_dims d;
   int Nmod = 0;           // depth * 6D + 2D columns of the concatenated adaLN output
@@ -30,26 +43,32 @@ struct Plan {
   CastJob* jobs_dev = nullptr;
   CastJob* jobs_host = nullptr;
   int njobs = 0;
-  // weight-gradient GEMMs run on a side stream, off the dgrad -> LayerNorm -> attention chain: their CTAs fill
-  // the SMs that the chain's kernels leave idle in their ragged tails (V4H_WGRAD_STREAM=0: same stream)
-  cudaStream_t side = nullptr, side2 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
+  Lane lanes[2];
+  cudaEvent_t ev_split = nullptr;
+  int microbatch = -1;  // V4H_MICROBATCH: -1 auto, 1 never split, 2 always split
   // side streams in use (none while the per-kernel profiler wants launches that do not overlap)
-  bool forking() const { return side != nullptr && !profiling_enabled(); }
-  // q waits for everything issued on s so far
-  int fork(cudaStream_t s, cudaStream_t q) const {
-    V4H_CUDA(cudaEventRecord(ev_fork, s));
-    V4H_CUDA(cudaStreamWaitEvent(q, ev_fork, 0));
-    return V4H_OK;
-  }
-  // s waits for everything issued on the side stream q so far
-  int join(cudaStream_t q, cudaStream_t s) const {
-    cudaEvent_t ev = q == side ? ev_join : ev_join2;
-    V4H_CUDA(cudaEventRecord(ev, q));
-    V4H_CUDA(cudaStreamWaitEvent(s, ev, 0));
-    return V4H_OK;
+  bool forking() const { return lanes[0].side != nullptr && !profiling_enabled(); }
+  // number of sub-batches a batch of B samples runs as (fixed per (plan, B): the workspace layout follows it)
+  int sub_batches(int64_t B) const {
+    if (!use_umma || lanes[0].side == nullptr || B < 2 || microbatch == 1) return 1;
+    if (microbatch == 2) return 2;
+    return B * d.tokens <= 16384 && B * d.tokens >= 1024 ? 2 : 1;
   }
 };
+
+// q waits for everything issued on s so far
+static int fork_to(const Lane& L, cudaStream_t s, cudaStream_t q) {
+  V4H_CUDA(cudaEventRecord(L.ev_fork, s));
+  V4H_CUDA(cudaStreamWaitEvent(q, L.ev_fork, 0));
+  return V4H_OK;
+}
+// s waits for everything issued on the side stream q so far
+static int join_from(const Lane& L, cudaStream_t q, cudaStream_t s) {
+  cudaEvent_t ev = q == L.side ? L.ev_join : L.ev_join2;
+  V4H_CUDA(cudaEventRecord(ev, q));
+  V4H_CUDA(cudaStreamWaitEvent(s, ev, 0));
+  return V4H_OK;
+}
 
 namespace {
 
@@ -76,6 +95,9 @@ struct Workspace {
   // bf16 mode: tensor-core operands of the embedding / conditioning / output Linears
   bf16 *x_bf, *temb_bf, *t_h_bf, *t_hpre_bf, *c_h_bf, *c_hpre_bf;
   bf16 *dout_bf, *dh_bf, *dcond_bf, *dvec_bf, *dvec2_bf;  // backward only
+  // finetuning mappers (fp32): SiLU(x Wm^T + bm) / SiLU(c Wm^T + bm), their pre-activations, and the gradients
+  // flowing back into them
+  float *xm, *xm_pre, *cm, *cm_pre, *dxm, *dcm;
   // residual stream (fp32): training keeps 2*depth+1 copies, inference 1
   std::vector<float*> h;
   std::vector<BlockBufs> blk;  // training: depth entries; inference: 1 shared entry
@@ -111,6 +133,17 @@ struct Workspace {
       c_h_bf = (bf16*)take(B * D * 2); c_hpre_bf = (bf16*)take(B * D * 2);
     } else {
       x_bf = temb_bf = t_h_bf = t_hpre_bf = c_h_bf = c_hpre_bf = nullptr;
+    }
+    xm = xm_pre = cm = cm_pre = dxm = dcm = nullptr;
+    if (d.x_map_dim > 0) {
+      xm = (float*)take(M * d.patch_dim * 4);
+      if (train) { xm_pre = (float*)take(M * d.patch_dim * 4); dxm = (float*)take(M * d.patch_dim * 4); }
+    }
+    if (d.c_map_dim > 0) {
+      cm = (float*)take((size_t)B * d.cond_dim * 4);
+      if (train) {
+        cm_pre = (float*)take((size_t)B * d.cond_dim * 4); dcm = (float*)take((size_t)B * d.cond_dim * 4);
+      }
     }
     const int nh = train ? 2 * d.depth + 1 : 1;
     h.resize(nh);
@@ -222,34 +255,52 @@ int wgrad(const Plan& p, const void* A, int a_dt, int lda, const void* B, int b_
   return run_gemm(p, g, s);
 }
 
+// one sub-batch of a forward / backward call: its slice of the inputs, its own workspace and streams
+struct Sub {
+  const float *x = nullptr, *t = nullptr, *c = nullptr, *dout = nullptr;
+  float* out = nullptr;
+  int B = 0;
+  Workspace ws;
+  cudaStream_t s = nullptr;
+  const Lane* lane = nullptr;
+  bool side_busy = false;  // backward: a weight gradient is running on lane->side
+};
+
+// ---- positional embedding + patch embedding, conditioning, every adaLN modulation   (nn/vit.py:192-199, :328-330)
 template <typename T>
-int forward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const float* x, const float* t,
-                 const float* c, float* out, int64_t B64, bool shared_t, bool train, Workspace& ws,
-                 cudaStream_t s) {
+int forward_prologue(Plan& p, const v4h_vit_params& w, const char* arena, Sub& u, bool shared_t, bool train) {
   const v4h_vit_dims& d = p.d;
-  const int B = (int)B64, Tn = d.tokens, D = d.hidden_dim, Hm = d.mlp_hidden, M = B * Tn;
-  const int TA = p.bf16 ? DT_BF16 : DT_F32;
+  Workspace& ws = u.ws;
+  cudaStream_t s = u.s;
+  const Lane& L = *u.lane;
+  const int B = u.B, Tn = d.tokens, D = d.hidden_dim, M = B * Tn;
   const int Bt = shared_t ? 1 : B;
   const bf16* wa = reinterpret_cast<const bf16*>(arena);
-
-  // ---- positional embedding + patch embedding: h0 = x Wx^T + bx + PE   (nn/vit.py:192-195)
   const float* pe = w.pos_embed;
   const bool fast = p.bf16 && p.use_umma;  // small Linears on the tensor cores with bf16 operand copies
   // The embedding of x and the two conditioning MLPs are independent chains of small kernels (a few CTAs each,
   // latency-bound): the x chain runs on one side stream, the first c_embedder Linear on a second one, the
   // t_embedder on the caller's stream; they meet at c_embedder.2 (+ te) and before the first block
   const bool forked = fast && p.forking();
-  cudaStream_t sx = forked ? p.side : s;   // x chain
-  cudaStream_t sc = forked ? p.side2 : s;  // c_embedder.0
-  if (forked) { V4H_TRY(p.fork(s, sx)); V4H_TRY(p.fork(s, sc)); }
+  cudaStream_t sx = forked ? L.side : s;   // x chain
+  cudaStream_t sc = forked ? L.side2 : s;  // c_embedder.0
+  if (forked) { V4H_TRY(fork_to(L, s, sx)); V4H_TRY(fork_to(L, s, sc)); }
   if (d.learn_pos_embed) {
     V4H_TRY(pos_embedding_fwd(w.pos_embed_freqs, w.pos_z, w.pos_y, w.pos_x, ws.pe, Tn, D / 6, sx));
     pe = ws.pe;
   }
+  const float* xin = u.x;
+  if (d.x_map_dim > 0) {  // finetuning: x_embedder = Sequential(mapper, SiLU, old Linear)
+    GemmDesc g = linear_fwd(u.x, DT_F32, d.x_map_dim, w.xm_w, DT_F32, d.x_map_dim, M, d.patch_dim, d.x_map_dim);
+    g.tag = "gemm.x_map"; g.act = ACT_SILU; g.ep.bias = w.xm_b; g.ep.out = ws.xm; g.ep.out2 = train ? ws.xm_pre : nullptr;
+    g.ep.ldo = d.patch_dim;
+    V4H_TRY(run_gemm(p, g, sx));
+    xin = ws.xm;
+  }
   {
-    GemmDesc g = linear_fwd(x, DT_F32, d.patch_dim, w.x_w, DT_F32, d.patch_dim, M, D, d.patch_dim);
+    GemmDesc g = linear_fwd(xin, DT_F32, d.patch_dim, w.x_w, DT_F32, d.patch_dim, M, D, d.patch_dim);
     if (fast) {
-      V4H_TRY(cast_f32_to_bf16(x, ws.x_bf, (int64_t)M * d.patch_dim, sx));
+      V4H_TRY(cast_f32_to_bf16(xin, ws.x_bf, (int64_t)M * d.patch_dim, sx));
       g = linear_fwd(ws.x_bf, DT_BF16, d.patch_dim, wa + p.arena_x, DT_BF16, d.patch_dim, M, D, d.patch_dim);
     }
     g.ep.bias = w.x_b; g.ep.out = ws.h[0]; g.ep.ldo = D;
@@ -258,7 +309,15 @@ int forward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const floa
     V4H_TRY(run_gemm(p, g, sx));
   }
   // ---- conditioning: cond = t_embedder(t) + c_embedder(c); sc = SiLU(cond)   (nn/vit.py:197-199)
-  V4H_TRY(timestep_embedding(t, shared_t ? 1 : 0, ws.temb_in, fast ? ws.temb_bf : nullptr, Bt, d.freq_dim, s));
+  const float* cin = u.c;
+  if (d.c_map_dim > 0) {  // finetuning: c_embedder = Sequential(mapper, SiLU, old Sequential)
+    GemmDesc g = linear_fwd(u.c, DT_F32, d.c_map_dim, w.cm_w, DT_F32, d.c_map_dim, B, d.cond_dim, d.c_map_dim);
+    g.tag = "gemm.c_map"; g.act = ACT_SILU; g.ep.bias = w.cm_b; g.ep.out = ws.cm; g.ep.out2 = train ? ws.cm_pre : nullptr;
+    g.ep.ldo = d.cond_dim;
+    V4H_TRY(run_gemm(p, g, sc));
+    cin = ws.cm;
+  }
+  V4H_TRY(timestep_embedding(u.t, shared_t ? 1 : 0, ws.temb_in, fast ? ws.temb_bf : nullptr, Bt, d.freq_dim, s));
   if (fast) {
     // t_embedder.mlp and c_embedder.2 on the tensor cores; hidden activations kept in bf16
     GemmDesc g = linear_fwd(ws.temb_bf, DT_BF16, d.freq_dim, wa + p.arena_t0, DT_BF16, d.freq_dim, Bt, D, d.freq_dim);
@@ -268,11 +327,11 @@ int forward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const floa
     g = linear_fwd(ws.t_h_bf, DT_BF16, D, wa + p.arena_t2, DT_BF16, D, Bt, D, D); g.tag = "gemm.cond";
     g.ep.bias = w.t2_b; g.ep.out = ws.te; g.ep.ldo = D;
     V4H_TRY(run_gemm(p, g, s));
-    g = linear_fwd(c, DT_F32, d.cond_dim, w.c0_w, DT_F32, d.cond_dim, B, D, d.cond_dim); g.tag = "gemm.cond";
+    g = linear_fwd(cin, DT_F32, d.cond_dim, w.c0_w, DT_F32, d.cond_dim, B, D, d.cond_dim); g.tag = "gemm.cond";
     g.act = ACT_SILU; g.out_dtype = DT_BF16;
     g.ep.bias = w.c0_b; g.ep.out = ws.c_h_bf; g.ep.out2 = ws.c_hpre_bf; g.ep.ldo = D;
     V4H_TRY(run_gemm(p, g, sc));
-    if (forked) V4H_TRY(p.join(sc, s));
+    if (forked) V4H_TRY(join_from(L, sc, s));
     g = linear_fwd(ws.c_h_bf, DT_BF16, D, wa + p.arena_c2, DT_BF16, D, B, D, D); g.tag = "gemm.cond";
     g.act = ACT_SILU; g.ep.bias = w.c2_b; g.ep.out = ws.sc; g.ep.out2 = ws.cond; g.ep.ldo = D;
     g.ep.addend = ws.te; g.ep.addend_rows = shared_t ? 1 : 0; g.ep.ld_addend = D;
@@ -284,7 +343,7 @@ int forward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const floa
     g = linear_fwd(ws.t_h, DT_F32, D, w.t2_w, DT_F32, D, Bt, D, D); g.tag = "gemm.cond";
     g.ep.bias = w.t2_b; g.ep.out = ws.te; g.ep.ldo = D;
     V4H_TRY(run_gemm(p, g, s));
-    g = linear_fwd(c, DT_F32, d.cond_dim, w.c0_w, DT_F32, d.cond_dim, B, D, d.cond_dim); g.tag = "gemm.cond";
+    g = linear_fwd(cin, DT_F32, d.cond_dim, w.c0_w, DT_F32, d.cond_dim, B, D, d.cond_dim); g.tag = "gemm.cond";
     g.act = ACT_SILU; g.ep.bias = w.c0_b; g.ep.out = ws.c_h; g.ep.out2 = ws.c_h_pre; g.ep.ldo = D;
     V4H_TRY(run_gemm(p, g, s));
     g = linear_fwd(ws.c_h, DT_F32, D, w.c2_w, DT_F32, D, B, D, D); g.tag = "gemm.cond";
@@ -293,7 +352,7 @@ int forward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const floa
     V4H_TRY(run_gemm(p, g, s));
   }
   // ---- every adaLN modulation of the network in one pass: mod = sc Wada^T + bada   (nn/vit.py:328-330, :348)
-  if (p.bf16 && p.use_umma) {
+  if (fast) {
     V4H_TRY(cast_f32_to_bf16(ws.sc, ws.sc_bf16, (int64_t)B * D, s));
     GemmDesc g = linear_fwd(ws.sc_bf16, DT_BF16, D, wa + p.arena_ada, DT_BF16, D, B, p.Nmod, D);
     g.tag = "gemm.adaln";
@@ -311,66 +370,85 @@ int forward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const floa
       V4H_TRY(run_gemm(p, g, s));
     }
   }
-  if (forked) V4H_TRY(p.join(sx, s));  // h0 is needed from here on
-  // ---- transformer blocks   (nn/vit.py:327-333)
-  for (int i = 0; i < d.depth; ++i) {
-    const v4h_block_params& bw = w.blocks[i];
-    BlockBufs& bb = ws.blk[train ? i : 0];
-    float* hin = ws.h[hidx(train, 2 * i)];
-    float* hmid = ws.h[hidx(train, 2 * i + 1)];
-    float* hout = ws.h[hidx(train, 2 * i + 2)];
-    const float* mod = ws.mod + (size_t)i * 6 * D;
-    const void* Wqkv = p.bf16 ? (const void*)(wa + p.arena_blocks[i].qkv) : (const void*)bw.qkv_w;
-    const void* Wproj = p.bf16 ? (const void*)(wa + p.arena_blocks[i].proj) : (const void*)bw.proj_w;
-    const void* Wfc1 = p.bf16 ? (const void*)(wa + p.arena_blocks[i].fc1) : (const void*)bw.fc1_w;
-    const void* Wfc2 = p.bf16 ? (const void*)(wa + p.arena_blocks[i].fc2) : (const void*)bw.fc2_w;
+  if (forked) V4H_TRY(join_from(L, sx, s));  // h0 is needed from here on
+  return V4H_OK;
+}
 
-    V4H_TRY(prof("ln.fwd", 0, (double)M * D * (4 + sizeof(T)), s, [&] { return ln_modulate_fwd<T>(hin, mod + 0 * D, mod + 1 * D, p.Nmod, (T*)bb.a, p.ldx, bb.stats1, M, D, Tn, s); }));
-    {
-      GemmDesc g = linear_fwd(bb.a, TA, p.ldx, Wqkv, TA, D, M, 3 * D, D);
-      g.tag = "gemm.qkv";
-      g.ep.bias = bw.qkv_b; g.ep.out = bb.qkv; g.ep.ldo = 3 * D; g.out_dtype = TA;
-      V4H_TRY(run_gemm(p, g, s));
-    }
-    V4H_TRY(prof("attn.fwd", 4.0 * B * d.num_heads * Tn * Tn * (D / d.num_heads), (double)M * 4 * D * sizeof(T), s, [&] { return attn_fwd<T>(p, bb.qkv, bb.o, bb.lse, B, Tn, d.num_heads, D / d.num_heads, s); }));
-    {
-      GemmDesc g = linear_fwd(bb.o, TA, D, Wproj, TA, D, M, D, D);
-      g.tag = "gemm.proj";
-      g.epi = EPI_GATE_RES; g.out_dtype = TA;
-      g.ep.bias = bw.proj_b; g.ep.out2 = bb.y1; g.ep.ldo = D;
-      g.ep.gate = mod + 2 * D; g.ep.mod_stride = p.Nmod; g.ep.rows_per_sample = Tn;
-      g.ep.res_in = hin; g.ep.res_out = hmid;
-      V4H_TRY(run_gemm(p, g, s));
-    }
-    V4H_TRY(prof("ln.fwd", 0, (double)M * D * (4 + sizeof(T)), s, [&] { return ln_modulate_fwd<T>(hmid, mod + 3 * D, mod + 4 * D, p.Nmod, (T*)bb.m, p.ldx, bb.stats2, M, D, Tn, s); }));
-    {
-      GemmDesc g = linear_fwd(bb.m, TA, p.ldx, Wfc1, TA, D, M, Hm, D);
-      g.tag = "gemm.fc1";
-      g.act = ACT_GELU_TANH; g.out_dtype = TA;
-      g.ep.bias = bw.fc1_b; g.ep.out = bb.g; g.ep.out2 = bb.u; g.ep.ldo = Hm;
-      V4H_TRY(run_gemm(p, g, s));
-    }
-    {
-      GemmDesc g = linear_fwd(bb.g, TA, Hm, Wfc2, TA, Hm, M, D, Hm);
-      g.tag = "gemm.fc2";
-      g.epi = EPI_GATE_RES; g.out_dtype = TA;
-      g.ep.bias = bw.fc2_b; g.ep.out2 = bb.y2; g.ep.ldo = D;
-      g.ep.gate = mod + 5 * D; g.ep.mod_stride = p.Nmod; g.ep.rows_per_sample = Tn;
-      g.ep.res_in = hmid; g.ep.res_out = hout;
-      V4H_TRY(run_gemm(p, g, s));
-    }
-  }
-  // ---- final layer   (nn/vit.py:347-351)
+// ---- transformer block i   (nn/vit.py:327-333)
+template <typename T>
+int forward_block(Plan& p, const v4h_vit_params& w, const char* arena, Sub& u, int i, bool train) {
+  const v4h_vit_dims& d = p.d;
+  Workspace& ws = u.ws;
+  cudaStream_t s = u.s;
+  const int B = u.B, Tn = d.tokens, D = d.hidden_dim, Hm = d.mlp_hidden, M = B * Tn;
+  const int TA = p.bf16 ? DT_BF16 : DT_F32;
+  const bf16* wa = reinterpret_cast<const bf16*>(arena);
+  const v4h_block_params& bw = w.blocks[i];
+  BlockBufs& bb = ws.blk[train ? i : 0];
+  float* hin = ws.h[hidx(train, 2 * i)];
+  float* hmid = ws.h[hidx(train, 2 * i + 1)];
+  float* hout = ws.h[hidx(train, 2 * i + 2)];
+  const float* mod = ws.mod + (size_t)i * 6 * D;
+  const void* Wqkv = p.bf16 ? (const void*)(wa + p.arena_blocks[i].qkv) : (const void*)bw.qkv_w;
+  const void* Wproj = p.bf16 ? (const void*)(wa + p.arena_blocks[i].proj) : (const void*)bw.proj_w;
+  const void* Wfc1 = p.bf16 ? (const void*)(wa + p.arena_blocks[i].fc1) : (const void*)bw.fc1_w;
+  const void* Wfc2 = p.bf16 ? (const void*)(wa + p.arena_blocks[i].fc2) : (const void*)bw.fc2_w;
+
+  V4H_TRY(prof("ln.fwd", 0, (double)M * D * (4 + sizeof(T)), s, [&] { return ln_modulate_fwd<T>(hin, mod + 0 * D, mod + 1 * D, p.Nmod, (T*)bb.a, p.ldx, bb.stats1, M, D, Tn, s); }));
   {
-    const float* mod = ws.mod + (size_t)d.depth * 6 * D;
-    float* hl = ws.h[hidx(train, 2 * d.depth)];
-    V4H_TRY(prof("ln.fwd", 0, (double)M * D * (4 + sizeof(T)), s, [&] { return ln_modulate_fwd<T>(hl, mod, mod + D, p.Nmod, (T*)ws.a_f, D, ws.stats_f, M, D, Tn, s); }));
-    GemmDesc g = fast ? linear_fwd(ws.a_f, TA, D, wa + p.arena_final, DT_BF16, D, M, d.out_dim, D)
-                      : linear_fwd(ws.a_f, TA, D, w.final_w, DT_F32, D, M, d.out_dim, D);
-    g.tag = "gemm.final";
-    g.ep.bias = w.final_b; g.ep.out = out; g.ep.ldo = d.out_dim; g.out_dtype = DT_F32;
+    GemmDesc g = linear_fwd(bb.a, TA, p.ldx, Wqkv, TA, D, M, 3 * D, D);
+    g.tag = "gemm.qkv";
+    g.ep.bias = bw.qkv_b; g.ep.out = bb.qkv; g.ep.ldo = 3 * D; g.out_dtype = TA;
     V4H_TRY(run_gemm(p, g, s));
   }
+  V4H_TRY(prof("attn.fwd", 4.0 * B * d.num_heads * Tn * Tn * (D / d.num_heads), (double)M * 4 * D * sizeof(T), s, [&] { return attn_fwd<T>(p, bb.qkv, bb.o, bb.lse, B, Tn, d.num_heads, D / d.num_heads, s); }));
+  {
+    GemmDesc g = linear_fwd(bb.o, TA, D, Wproj, TA, D, M, D, D);
+    g.tag = "gemm.proj";
+    g.epi = EPI_GATE_RES; g.out_dtype = TA;
+    g.ep.bias = bw.proj_b; g.ep.out2 = bb.y1; g.ep.ldo = D;
+    g.ep.gate = mod + 2 * D; g.ep.mod_stride = p.Nmod; g.ep.rows_per_sample = Tn;
+    g.ep.res_in = hin; g.ep.res_out = hmid;
+    V4H_TRY(run_gemm(p, g, s));
+  }
+  V4H_TRY(prof("ln.fwd", 0, (double)M * D * (4 + sizeof(T)), s, [&] { return ln_modulate_fwd<T>(hmid, mod + 3 * D, mod + 4 * D, p.Nmod, (T*)bb.m, p.ldx, bb.stats2, M, D, Tn, s); }));
+  {
+    GemmDesc g = linear_fwd(bb.m, TA, p.ldx, Wfc1, TA, D, M, Hm, D);
+    g.tag = "gemm.fc1";
+    g.act = ACT_GELU_TANH; g.out_dtype = TA;
+    g.ep.bias = bw.fc1_b; g.ep.out = bb.g; g.ep.out2 = bb.u; g.ep.ldo = Hm;
+    V4H_TRY(run_gemm(p, g, s));
+  }
+  {
+    GemmDesc g = linear_fwd(bb.g, TA, Hm, Wfc2, TA, Hm, M, D, Hm);
+    g.tag = "gemm.fc2";
+    g.epi = EPI_GATE_RES; g.out_dtype = TA;
+    g.ep.bias = bw.fc2_b; g.ep.out2 = bb.y2; g.ep.ldo = D;
+    g.ep.gate = mod + 5 * D; g.ep.mod_stride = p.Nmod; g.ep.rows_per_sample = Tn;
+    g.ep.res_in = hmid; g.ep.res_out = hout;
+    V4H_TRY(run_gemm(p, g, s));
+  }
+  return V4H_OK;
+}
+
+// ---- final layer   (nn/vit.py:347-351)
+template <typename T>
+int forward_final(Plan& p, const v4h_vit_params& w, const char* arena, Sub& u, bool train) {
+  const v4h_vit_dims& d = p.d;
+  Workspace& ws = u.ws;
+  cudaStream_t s = u.s;
+  const int B = u.B, Tn = d.tokens, D = d.hidden_dim, M = B * Tn;
+  const int TA = p.bf16 ? DT_BF16 : DT_F32;
+  const bf16* wa = reinterpret_cast<const bf16*>(arena);
+  const bool fast = p.bf16 && p.use_umma;
+  const float* mod = ws.mod + (size_t)d.depth * 6 * D;
+  float* hl = ws.h[hidx(train, 2 * d.depth)];
+  V4H_TRY(prof("ln.fwd", 0, (double)M * D * (4 + sizeof(T)), s, [&] { return ln_modulate_fwd<T>(hl, mod, mod + D, p.Nmod, (T*)ws.a_f, D, ws.stats_f, M, D, Tn, s); }));
+  GemmDesc g = fast ? linear_fwd(ws.a_f, TA, D, wa + p.arena_final, DT_BF16, D, M, d.out_dim, D)
+                    : linear_fwd(ws.a_f, TA, D, w.final_w, DT_F32, D, M, d.out_dim, D);
+  g.tag = "gemm.final";
+  g.ep.bias = w.final_b; g.ep.out = u.out; g.ep.ldo = d.out_dim; g.out_dtype = DT_F32;
+  V4H_TRY(run_gemm(p, g, s));
   return V4H_OK;
 }
 
@@ -384,160 +462,195 @@ GemmDesc dgrad(const void* dY, int dy_dt, int ld_dy, const void* W, int w_dt, in
   return g;
 }
 
-template <typename T>
-int backward_impl(Plan& p, const v4h_vit_params& w, const char* arena, const v4h_vit_params& gr,
-                  const float* dout, int64_t B64, int stage_begin, int stage_end, Workspace& ws,
-                  cudaStream_t s) {
-  const v4h_vit_dims& d = p.d;
-  const int B = (int)B64, Tn = d.tokens, D = d.hidden_dim, Hm = d.mlp_hidden, M = B * Tn;
-  const int TA = p.bf16 ? DT_BF16 : DT_F32;
-  const bf16* wa = reinterpret_cast<const bf16*>(arena);
-  const int H = d.num_heads, dh = D / H;
-
-  // side-stream weight gradients: fork after the kernel that produced dY, join before the buffers a block's
-  // wgrads read are written again (start of the next block) and before returning
-  bool side_busy = false;
-  auto on_side = [&](auto&& launch) -> int {
-    if (!p.forking()) return launch(s);
-    V4H_CUDA(cudaEventRecord(p.ev_fork, s));
-    V4H_CUDA(cudaStreamWaitEvent(p.side, p.ev_fork, 0));
-    side_busy = true;
-    return launch(p.side);
-  };
-  auto join_side = [&]() -> int {
-    if (!side_busy) return V4H_OK;
-    V4H_CUDA(cudaEventRecord(p.ev_join, p.side));
-    V4H_CUDA(cudaStreamWaitEvent(s, p.ev_join, 0));
-    side_busy = false;
-    return V4H_OK;
-  };
-
-  for (int stage = stage_begin; stage >= stage_end; --stage) {
-    V4H_TRY(join_side());
-    if (stage == d.depth + 1) {
-      // ---------------- final layer
-      V4H_CUDA(cudaMemsetAsync(ws.dmod, 0, (size_t)B * p.Nmod * sizeof(float), s));
-      const size_t offF = (size_t)d.depth * 6 * D;
-      const bool fast = p.bf16 && p.use_umma;
-      if (fast) V4H_TRY(cast_f32_to_bf16(dout, ws.dout_bf, (int64_t)M * d.out_dim, s));
-      const void* dY = fast ? (const void*)ws.dout_bf : (const void*)dout;
-      const int dy_dt = fast ? DT_BF16 : DT_F32;
-      V4H_TRY(on_side([&](cudaStream_t q) { return wgrad(p, dY, dy_dt, d.out_dim, ws.a_f, TA, D, gr.final_w, d.out_dim, D, M, q, "wgrad.final"); }));
-      V4H_TRY(on_side([&](cudaStream_t q) { return prof("colsum", 0, 0, q, [&] { return colsum_add<float>(dout, d.out_dim, gr.final_b, M, d.out_dim, q); }); }));
-      {
-        GemmDesc g = fast ? dgrad(dY, DT_BF16, d.out_dim, wa + p.arena_final, DT_BF16, D, M, D, d.out_dim, "dgrad.final")
-                          : dgrad(dout, DT_F32, d.out_dim, w.final_w, DT_F32, D, M, D, d.out_dim, "dgrad.final");
-        g.ep.out = ws.dm; g.ep.ldo = D; g.out_dtype = TA;
-        V4H_TRY(run_gemm(p, g, s));
-      }
-      const int last = d.depth - 1;
-      const float* modL = ws.mod + (size_t)last * 6 * D;
-      float* dmodL = ws.dmod + (size_t)last * 6 * D;
-      V4H_TRY(prof("ln.bwd", 0, (double)M * D * (12 + 3 * sizeof(T)), s, [&] { return ln_modulate_bwd<T>((const T*)ws.dm, ws.h[2 * d.depth], ws.stats_f, ws.mod + offF + D, p.Nmod,
-                                 ws.dh, false, ws.dmod + offF, ws.dmod + offF + D, p.Nmod,
-                                 (const T*)ws.blk[last].y2, modL + 5 * D, (T*)ws.dy_mlp[last & 1], dmodL + 5 * D,
-                                 gr.blocks[last].fc2_b, M, D, Tn, s); }));
-    } else if (stage >= 1) {
-      // ---------------- transformer block i
-      const int i = stage - 1;
-      const v4h_block_params& bw = w.blocks[i];
-      const v4h_block_params& bg = gr.blocks[i];
-      BlockBufs& bb = ws.blk[i];
-      const float* mod = ws.mod + (size_t)i * 6 * D;
-      float* dmod = ws.dmod + (size_t)i * 6 * D;
-      const void* Wqkv = p.bf16 ? (const void*)(wa + p.arena_blocks[i].qkv) : (const void*)bw.qkv_w;
-      const void* Wproj = p.bf16 ? (const void*)(wa + p.arena_blocks[i].proj) : (const void*)bw.proj_w;
-      const void* Wfc1 = p.bf16 ? (const void*)(wa + p.arena_blocks[i].fc1) : (const void*)bw.fc1_w;
-      const void* Wfc2 = p.bf16 ? (const void*)(wa + p.arena_blocks[i].fc2) : (const void*)bw.fc2_w;
-
-      // MLP branch: dy = gate_mlp * dh is ready in dy_mlp[i & 1]; the attention branch uses dy_attn, and the
-      // LayerNorm backward that closes this block writes dy_mlp[(i - 1) & 1]: no buffer a side-stream wgrad of
-      // this block reads is rewritten before the join at the start of the next block
-      void* dy1 = ws.dy_mlp[i & 1];
-      void* dy2 = ws.dy_attn;
-      V4H_TRY(on_side([&](cudaStream_t q) { return wgrad(p, dy1, TA, D, bb.g, TA, Hm, bg.fc2_w, D, Hm, M, q, "wgrad.fc2"); }));
-      {
-        GemmDesc g = dgrad(dy1, TA, D, Wfc2, TA, Hm, M, Hm, D, "dgrad.fc2");
-        g.epi = EPI_DACT; g.act = ACT_GELU_TANH; g.out_dtype = TA;
-        g.ep.out = ws.du; g.ep.ldo = Hm; g.ep.aux = bb.u; g.ep.ld_aux = Hm;
-        V4H_TRY(run_gemm(p, g, s));
-      }
-      if (p.ldx > D) {  // the ones column of m: fc1 bias gradient out of the same GEMM
-        V4H_TRY(on_side([&](cudaStream_t q) { return wgrad(p, ws.du, TA, Hm, bb.m, TA, p.ldx, bg.fc1_w, Hm, D, M, q, "wgrad.fc1", bg.fc1_b); }));
-      } else {
-        V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<T>((const T*)ws.du, Hm, bg.fc1_b, M, Hm, s); }));
-        V4H_TRY(on_side([&](cudaStream_t q) { return wgrad(p, ws.du, TA, Hm, bb.m, TA, D, bg.fc1_w, Hm, D, M, q, "wgrad.fc1"); }));
-      }
-      {
-        GemmDesc g = dgrad(ws.du, TA, Hm, Wfc1, TA, D, M, D, Hm, "dgrad.fc1");
-        g.ep.out = ws.dm; g.ep.ldo = D; g.out_dtype = TA;
-        V4H_TRY(run_gemm(p, g, s));
-      }
-      V4H_TRY(prof("ln.bwd", 0, (double)M * D * (12 + 3 * sizeof(T)), s, [&] { return ln_modulate_bwd<T>((const T*)ws.dm, ws.h[2 * i + 1], bb.stats2, mod + 4 * D, p.Nmod, ws.dh, true,
-                                 dmod + 3 * D, dmod + 4 * D, p.Nmod, (const T*)bb.y1, mod + 2 * D, (T*)dy2,
-                                 dmod + 2 * D, bg.proj_b, M, D, Tn, s); }));
-      // attention branch: dy = gate_msa * dh
-      V4H_TRY(on_side([&](cudaStream_t q) { return wgrad(p, dy2, TA, D, bb.o, TA, D, bg.proj_w, D, D, M, q, "wgrad.proj"); }));
-      {
-        GemmDesc g = dgrad(dy2, TA, D, Wproj, TA, D, M, D, D, "dgrad.proj");
-        g.ep.out = ws.dm; g.ep.ldo = D; g.out_dtype = TA;
-        V4H_TRY(run_gemm(p, g, s));
-      }
-      V4H_TRY(prof("attn.bwd", 10.0 * B * H * Tn * Tn * dh, (double)M * 9 * D * sizeof(T), s, [&] { return attn_bwd<T>(p, bb.qkv, bb.o, bb.lse, ws.dm, ws.attn_delta, ws.dqkv, B, Tn, H, dh, s); }));
-      if (p.ldx > D) {
-        V4H_TRY(on_side([&](cudaStream_t q) { return wgrad(p, ws.dqkv, TA, 3 * D, bb.a, TA, p.ldx, bg.qkv_w, 3 * D, D, M, q, "wgrad.qkv", bg.qkv_b); }));
-      } else {
-        V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<T>((const T*)ws.dqkv, 3 * D, bg.qkv_b, M, 3 * D, s); }));
-        V4H_TRY(on_side([&](cudaStream_t q) { return wgrad(p, ws.dqkv, TA, 3 * D, bb.a, TA, D, bg.qkv_w, 3 * D, D, M, q, "wgrad.qkv"); }));
-      }
-      {
-        GemmDesc g = dgrad(ws.dqkv, TA, 3 * D, Wqkv, TA, D, M, D, 3 * D, "dgrad.qkv");
-        g.ep.out = ws.dm; g.ep.ldo = D; g.out_dtype = TA;
-        V4H_TRY(run_gemm(p, g, s));
-      }
-      if (i > 0) {
-        const float* modP = ws.mod + (size_t)(i - 1) * 6 * D;
-        float* dmodP = ws.dmod + (size_t)(i - 1) * 6 * D;
-        V4H_TRY(prof("ln.bwd", 0, (double)M * D * (12 + 3 * sizeof(T)), s, [&] { return ln_modulate_bwd<T>((const T*)ws.dm, ws.h[2 * i], bb.stats1, mod + 1 * D, p.Nmod, ws.dh, true,
-                                   dmod + 0 * D, dmod + 1 * D, p.Nmod, (const T*)ws.blk[i - 1].y2, modP + 5 * D,
-                                   (T*)ws.dy_mlp[(i - 1) & 1], dmodP + 5 * D, gr.blocks[i - 1].fc2_b, M, D, Tn, s); }));
-      } else {
-        V4H_TRY(prof("ln.bwd", 0, (double)M * D * (12 + 3 * sizeof(T)), s, [&] { return ln_modulate_bwd<T>((const T*)ws.dm, ws.h[0], bb.stats1, mod + 1 * D, p.Nmod, ws.dh, true,
-                                   dmod + 0 * D, dmod + 1 * D, p.Nmod, (const T*)nullptr, nullptr, (T*)nullptr,
-                                   nullptr, nullptr, M, D, Tn, s); }));
-      }
-    } else {
-      // ---------------- stage 0: embeddings and conditioning.  ws.dh = d loss / d h0
-      // x_embedder and the positional frequencies; the layer input x is not differentiated
-      // (training feeds leaf tensors without grad)
-      return fail(V4H_ERR_INVALID, "internal: stage 0 must be run through backward_stage0");
-    }
-  }
-  V4H_TRY(join_side());
+// side-stream weight gradients of one sub-batch: fork after the kernel that produced dY, join before the
+// buffers a block's wgrads read are written again (start of the next stage) and before returning
+template <typename F>
+int on_side(const Plan& p, Sub& u, F&& launch) {
+  if (!p.forking()) return launch(u.s);
+  V4H_CUDA(cudaEventRecord(u.lane->ev_fork, u.s));
+  V4H_CUDA(cudaStreamWaitEvent(u.lane->side, u.lane->ev_fork, 0));
+  u.side_busy = true;
+  return launch(u.lane->side);
+}
+int join_side(Sub& u) {
+  if (!u.side_busy) return V4H_OK;
+  V4H_CUDA(cudaEventRecord(u.lane->ev_join, u.lane->side));
+  V4H_CUDA(cudaStreamWaitEvent(u.s, u.lane->ev_join, 0));
+  u.side_busy = false;
   return V4H_OK;
 }
 
-int backward_stage0(Plan& p, const v4h_vit_params& w, const char* arena, const v4h_vit_params& gr, const float* x,
-                    const float* c, int64_t B64, Workspace& ws, cudaStream_t s) {
+// adaLN modulation Linear `i` (depth = the final layer's): d W = dmod_i^T sc, d b = colsum(dmod_i).  The
+// modulation gradients of a block are complete when its backward stage ends, so its weight gradient is issued
+// there (side stream) and lands in that block's slice of the flat gradient buffer: nothing but the small
+// embedding / conditioning Linears is left for stage 0, whose data-parallel bucket is the one nothing hides.
+int ada_wgrad(Plan& p, const v4h_vit_params& gr, Sub& u, int i) {
   const v4h_vit_dims& d = p.d;
-  const int B = (int)B64, Tn = d.tokens, D = d.hidden_dim, M = B * Tn;
+  Workspace& ws = u.ws;
+  const int B = u.B, D = d.hidden_dim;
+  const bool fin = i == d.depth;
+  const int n = fin ? 2 * D : 6 * D;
+  const size_t off = (size_t)i * 6 * D;
+  float* dW = fin ? gr.final_ada_w : gr.blocks[i].ada_w;
+  float* db = fin ? gr.final_ada_b : gr.blocks[i].ada_b;
+  const bool fast = p.bf16 && p.use_umma;
+  if (fast) {  // bf16 copy of the slice, in place of the (B, Nmod) layout the stage-0 dgrad reads as a whole
+    V4H_TRY(on_side(p, u, [&](cudaStream_t q) { return cast_f32_to_bf16_2d(ws.dmod + off, p.Nmod, ws.dmod_bf16 + off, p.Nmod, B, n, q); }));
+    V4H_TRY(on_side(p, u, [&](cudaStream_t q) { return wgrad(p, ws.dmod_bf16 + off, DT_BF16, p.Nmod, ws.sc_bf16, DT_BF16, D, dW, n, D, B, q, "wgrad.adaln"); }));
+  } else {
+    V4H_TRY(on_side(p, u, [&](cudaStream_t q) { return wgrad(p, ws.dmod + off, DT_F32, p.Nmod, ws.sc, DT_F32, D, dW, n, D, B, q, "wgrad.adaln"); }));
+  }
+  V4H_TRY(on_side(p, u, [&](cudaStream_t q) { return prof("colsum", 0, 0, q, [&] { return colsum_add<float>(ws.dmod + off, p.Nmod, db, B, n, q); }); }));
+  return V4H_OK;
+}
+
+// one backward stage of one sub-batch: depth + 1 = final layer, depth .. 1 = blocks depth-1 .. 0
+template <typename T>
+int backward_stage(Plan& p, const v4h_vit_params& w, const char* arena, const v4h_vit_params& gr, Sub& u, int stage) {
+  const v4h_vit_dims& d = p.d;
+  Workspace& ws = u.ws;
+  cudaStream_t s = u.s;
+  const int B = u.B, Tn = d.tokens, D = d.hidden_dim, Hm = d.mlp_hidden, M = B * Tn;
+  const int TA = p.bf16 ? DT_BF16 : DT_F32;
+  const bf16* wa = reinterpret_cast<const bf16*>(arena);
+  const int H = d.num_heads, dh = D / H;
+  const float* dout = u.dout;
+
+  V4H_TRY(join_side(u));
+  if (stage == d.depth + 1) {
+    // ---------------- final layer
+    V4H_CUDA(cudaMemsetAsync(ws.dmod, 0, (size_t)B * p.Nmod * sizeof(float), s));
+    const size_t offF = (size_t)d.depth * 6 * D;
+    const bool fast = p.bf16 && p.use_umma;
+    if (fast) V4H_TRY(cast_f32_to_bf16(dout, ws.dout_bf, (int64_t)M * d.out_dim, s));
+    const void* dY = fast ? (const void*)ws.dout_bf : (const void*)dout;
+    const int dy_dt = fast ? DT_BF16 : DT_F32;
+    V4H_TRY(on_side(p, u, [&](cudaStream_t q) { return wgrad(p, dY, dy_dt, d.out_dim, ws.a_f, TA, D, gr.final_w, d.out_dim, D, M, q, "wgrad.final"); }));
+    V4H_TRY(on_side(p, u, [&](cudaStream_t q) { return prof("colsum", 0, 0, q, [&] { return colsum_add<float>(dout, d.out_dim, gr.final_b, M, d.out_dim, q); }); }));
+    {
+      GemmDesc g = fast ? dgrad(dY, DT_BF16, d.out_dim, wa + p.arena_final, DT_BF16, D, M, D, d.out_dim, "dgrad.final")
+                        : dgrad(dout, DT_F32, d.out_dim, w.final_w, DT_F32, D, M, D, d.out_dim, "dgrad.final");
+      g.ep.out = ws.dm; g.ep.ldo = D; g.out_dtype = TA;
+      V4H_TRY(run_gemm(p, g, s));
+    }
+    const int last = d.depth - 1;
+    const float* modL = ws.mod + (size_t)last * 6 * D;
+    float* dmodL = ws.dmod + (size_t)last * 6 * D;
+    V4H_TRY(prof("ln.bwd", 0, (double)M * D * (12 + 3 * sizeof(T)), s, [&] { return ln_modulate_bwd<T>((const T*)ws.dm, ws.h[2 * d.depth], ws.stats_f, ws.mod + offF + D, p.Nmod,
+                               ws.dh, false, ws.dmod + offF, ws.dmod + offF + D, p.Nmod,
+                               (const T*)ws.blk[last].y2, modL + 5 * D, (T*)ws.dy_mlp[last & 1], dmodL + 5 * D,
+                               gr.blocks[last].fc2_b, M, D, Tn, s); }));
+    V4H_TRY(ada_wgrad(p, gr, u, d.depth));  // d shift / d scale of the final layer are complete
+    return V4H_OK;
+  }
+  if (stage < 1) return fail(V4H_ERR_INVALID, "internal: stage 0 must be run through backward_stage0");
+  // ---------------- transformer block i
+  const int i = stage - 1;
+  const v4h_block_params& bw = w.blocks[i];
+  const v4h_block_params& bg = gr.blocks[i];
+  BlockBufs& bb = ws.blk[i];
+  const float* mod = ws.mod + (size_t)i * 6 * D;
+  float* dmod = ws.dmod + (size_t)i * 6 * D;
+  const void* Wqkv = p.bf16 ? (const void*)(wa + p.arena_blocks[i].qkv) : (const void*)bw.qkv_w;
+  const void* Wproj = p.bf16 ? (const void*)(wa + p.arena_blocks[i].proj) : (const void*)bw.proj_w;
+  const void* Wfc1 = p.bf16 ? (const void*)(wa + p.arena_blocks[i].fc1) : (const void*)bw.fc1_w;
+  const void* Wfc2 = p.bf16 ? (const void*)(wa + p.arena_blocks[i].fc2) : (const void*)bw.fc2_w;
+
+  // MLP branch: dy = gate_mlp * dh is ready in dy_mlp[i & 1]; the attention branch uses dy_attn, and the
+  // LayerNorm backward that closes this block writes dy_mlp[(i - 1) & 1]: no buffer a side-stream wgrad of
+  // this block reads is rewritten before the join at the start of the next block
+  void* dy1 = ws.dy_mlp[i & 1];
+  void* dy2 = ws.dy_attn;
+  V4H_TRY(on_side(p, u, [&](cudaStream_t q) { return wgrad(p, dy1, TA, D, bb.g, TA, Hm, bg.fc2_w, D, Hm, M, q, "wgrad.fc2"); }));
+  {
+    GemmDesc g = dgrad(dy1, TA, D, Wfc2, TA, Hm, M, Hm, D, "dgrad.fc2");
+    g.epi = EPI_DACT; g.act = ACT_GELU_TANH; g.out_dtype = TA;
+    g.ep.out = ws.du; g.ep.ldo = Hm; g.ep.aux = bb.u; g.ep.ld_aux = Hm;
+    V4H_TRY(run_gemm(p, g, s));
+  }
+  if (p.ldx > D) {  // the ones column of m: fc1 bias gradient out of the same GEMM
+    V4H_TRY(on_side(p, u, [&](cudaStream_t q) { return wgrad(p, ws.du, TA, Hm, bb.m, TA, p.ldx, bg.fc1_w, Hm, D, M, q, "wgrad.fc1", bg.fc1_b); }));
+  } else {
+    V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<T>((const T*)ws.du, Hm, bg.fc1_b, M, Hm, s); }));
+    V4H_TRY(on_side(p, u, [&](cudaStream_t q) { return wgrad(p, ws.du, TA, Hm, bb.m, TA, D, bg.fc1_w, Hm, D, M, q, "wgrad.fc1"); }));
+  }
+  {
+    GemmDesc g = dgrad(ws.du, TA, Hm, Wfc1, TA, D, M, D, Hm, "dgrad.fc1");
+    g.ep.out = ws.dm; g.ep.ldo = D; g.out_dtype = TA;
+    V4H_TRY(run_gemm(p, g, s));
+  }
+  V4H_TRY(prof("ln.bwd", 0, (double)M * D * (12 + 3 * sizeof(T)), s, [&] { return ln_modulate_bwd<T>((const T*)ws.dm, ws.h[2 * i + 1], bb.stats2, mod + 4 * D, p.Nmod, ws.dh, true,
+                             dmod + 3 * D, dmod + 4 * D, p.Nmod, (const T*)bb.y1, mod + 2 * D, (T*)dy2,
+                             dmod + 2 * D, bg.proj_b, M, D, Tn, s); }));
+  // attention branch: dy = gate_msa * dh
+  V4H_TRY(on_side(p, u, [&](cudaStream_t q) { return wgrad(p, dy2, TA, D, bb.o, TA, D, bg.proj_w, D, D, M, q, "wgrad.proj"); }));
+  {
+    GemmDesc g = dgrad(dy2, TA, D, Wproj, TA, D, M, D, D, "dgrad.proj");
+    g.ep.out = ws.dm; g.ep.ldo = D; g.out_dtype = TA;
+    V4H_TRY(run_gemm(p, g, s));
+  }
+  V4H_TRY(prof("attn.bwd", 10.0 * B * H * Tn * Tn * dh, (double)M * 9 * D * sizeof(T), s, [&] { return attn_bwd<T>(p, bb.qkv, bb.o, bb.lse, ws.dm, ws.attn_delta, ws.dqkv, B, Tn, H, dh, s); }));
+  if (p.ldx > D) {
+    V4H_TRY(on_side(p, u, [&](cudaStream_t q) { return wgrad(p, ws.dqkv, TA, 3 * D, bb.a, TA, p.ldx, bg.qkv_w, 3 * D, D, M, q, "wgrad.qkv", bg.qkv_b); }));
+  } else {
+    V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<T>((const T*)ws.dqkv, 3 * D, bg.qkv_b, M, 3 * D, s); }));
+    V4H_TRY(on_side(p, u, [&](cudaStream_t q) { return wgrad(p, ws.dqkv, TA, 3 * D, bb.a, TA, D, bg.qkv_w, 3 * D, D, M, q, "wgrad.qkv"); }));
+  }
+  {
+    GemmDesc g = dgrad(ws.dqkv, TA, 3 * D, Wqkv, TA, D, M, D, 3 * D, "dgrad.qkv");
+    g.ep.out = ws.dm; g.ep.ldo = D; g.out_dtype = TA;
+    V4H_TRY(run_gemm(p, g, s));
+  }
+  if (i > 0) {
+    const float* modP = ws.mod + (size_t)(i - 1) * 6 * D;
+    float* dmodP = ws.dmod + (size_t)(i - 1) * 6 * D;
+    V4H_TRY(prof("ln.bwd", 0, (double)M * D * (12 + 3 * sizeof(T)), s, [&] { return ln_modulate_bwd<T>((const T*)ws.dm, ws.h[2 * i], bb.stats1, mod + 1 * D, p.Nmod, ws.dh, true,
+                               dmod + 0 * D, dmod + 1 * D, p.Nmod, (const T*)ws.blk[i - 1].y2, modP + 5 * D,
+                               (T*)ws.dy_mlp[(i - 1) & 1], dmodP + 5 * D, gr.blocks[i - 1].fc2_b, M, D, Tn, s); }));
+  } else {
+    V4H_TRY(prof("ln.bwd", 0, (double)M * D * (12 + 3 * sizeof(T)), s, [&] { return ln_modulate_bwd<T>((const T*)ws.dm, ws.h[0], bb.stats1, mod + 1 * D, p.Nmod, ws.dh, true,
+                               dmod + 0 * D, dmod + 1 * D, p.Nmod, (const T*)nullptr, nullptr, (T*)nullptr,
+                               nullptr, nullptr, M, D, Tn, s); }));
+  }
+  // every modulation gradient of block i is final: d gate_mlp came from the LayerNorm backward that closed the
+  // stage above, the other five from this stage
+  V4H_TRY(ada_wgrad(p, gr, u, i));
+  return V4H_OK;
+}
+
+// stage 0: embeddings and conditioning.  ws.dh = d loss / d h0
+int backward_stage0(Plan& p, const v4h_vit_params& w, const char* arena, const v4h_vit_params& gr, Sub& u) {
+  const v4h_vit_dims& d = p.d;
+  Workspace& ws = u.ws;
+  cudaStream_t s = u.s;
+  const Lane& L = *u.lane;
+  const int B = u.B, Tn = d.tokens, D = d.hidden_dim, M = B * Tn;
   const bool fast = p.bf16 && p.use_umma;
   const bf16* wa = reinterpret_cast<const bf16*>(arena);
+  V4H_TRY(join_side(u));
   // This stage is a long list of small kernels (a few CTAs each).  Only dgrad.adaln -> d SiLU -> the two
   // MLP dgrads form a chain; the embedding gradients of x and every weight gradient hang off it, so with the
-  // side streams they run next to it: sx = x / positional embedding, sw = weight gradients of the adaLN and
-  // second MLP Linears
+  // side streams they run next to it: sx = x / positional embedding, sw = weight gradients of the second MLP Linears
   const bool forked = fast && p.forking();
-  cudaStream_t sx = forked ? p.side2 : s, sw = forked ? p.side : s;
-  if (forked) V4H_TRY(p.fork(s, sx));
-  // x_embedder: dW = dh0^T x (the layer input x is not differentiated), db = colsum(dh0)
+  cudaStream_t sx = forked ? L.side2 : s, sw = forked ? L.side : s;
+  if (forked) V4H_TRY(fork_to(L, s, sx));
+  // x_embedder: dW = dh0^T x, db = colsum(dh0); the network input is only differentiated for a finetuning mapper
+  const float* xin = d.x_map_dim > 0 ? ws.xm : u.x;
   if (fast) {
     V4H_TRY(cast_f32_to_bf16(ws.dh, ws.dh_bf, (int64_t)M * D, sx));
     V4H_TRY(wgrad(p, ws.dh_bf, DT_BF16, D, ws.x_bf, DT_BF16, d.patch_dim, gr.x_w, D, d.patch_dim, M, sx, "wgrad.x_embed"));
   } else {
-    V4H_TRY(wgrad(p, ws.dh, DT_F32, D, x, DT_F32, d.patch_dim, gr.x_w, D, d.patch_dim, M, sx, "wgrad.x_embed"));
+    V4H_TRY(wgrad(p, ws.dh, DT_F32, D, xin, DT_F32, d.patch_dim, gr.x_w, D, d.patch_dim, M, sx, "wgrad.x_embed"));
   }
   V4H_TRY(prof("colsum", 0, 0, sx, [&] { return colsum_add<float>(ws.dh, D, gr.x_b, M, D, sx); }));
+  if (d.x_map_dim > 0) {
+    // d xm_pre = (dh0 Wx) * SiLU'(xm_pre);  d Wm = d xm_pre^T x;  d bm = colsum(d xm_pre)
+    GemmDesc g = dgrad(ws.dh, DT_F32, D, w.x_w, DT_F32, d.patch_dim, M, d.patch_dim, D, "dgrad.x_embed");
+    g.epi = EPI_DACT; g.act = ACT_SILU; g.ep.out = ws.dxm; g.ep.ldo = d.patch_dim; g.ep.aux = ws.xm_pre; g.ep.ld_aux = d.patch_dim;
+    V4H_TRY(run_gemm(p, g, sx));
+    V4H_TRY(wgrad(p, ws.dxm, DT_F32, d.patch_dim, u.x, DT_F32, d.x_map_dim, gr.xm_w, d.patch_dim, d.x_map_dim, M, sx, "wgrad.x_map"));
+    V4H_TRY(prof("colsum", 0, 0, sx, [&] { return colsum_add<float>(ws.dxm, d.patch_dim, gr.xm_b, M, d.patch_dim, sx); }));
+  }
   if (d.learn_pos_embed) {
     // sum d h0 over the batch first (a column sum of the (B, T*D) view, into the now idle PE buffer), then
     // one pass over (T, D) applies d PE / d freq
@@ -546,22 +659,9 @@ int backward_stage0(Plan& p, const v4h_vit_params& w, const char* arena, const v
     V4H_TRY(pos_embedding_bwd(ws.pe, w.pos_embed_freqs, w.pos_z, w.pos_y, w.pos_x, gr.pos_embed_freqs, 1, Tn,
                               D / 6, sx));
   }
-  // adaLN Linears: d W = dmod^T sc, d b = colsum(dmod), d sc += dmod W
+  // adaLN Linears: d sc = dmod Wada (their weight gradients were issued stage by stage, ada_wgrad)
   V4H_CUDA(cudaMemsetAsync(ws.dsc, 0, (size_t)B * D * sizeof(float), s));
-  // The host lays the adaLN gradients out as ONE (Nmod, D) matrix + ONE (Nmod) vector in block order
-  // (ViT.ordered_parameters): then the whole conditioning backward is two tensor-core GEMMs.
-  bool ada_contig = fast;
-  for (int i = 0; i < d.depth && ada_contig; ++i) {
-    const float* next_w = i + 1 < d.depth ? gr.blocks[i + 1].ada_w : gr.final_ada_w;
-    const float* next_b = i + 1 < d.depth ? gr.blocks[i + 1].ada_b : gr.final_ada_b;
-    ada_contig = next_w == gr.blocks[i].ada_w + (size_t)6 * D * D && next_b == gr.blocks[i].ada_b + (size_t)6 * D;
-  }
-  if (ada_contig) {
-    V4H_TRY(cast_f32_to_bf16(ws.dmod, ws.dmod_bf16, (int64_t)B * p.Nmod, s));
-    if (forked) V4H_TRY(p.fork(s, sw));
-    V4H_TRY(wgrad(p, ws.dmod_bf16, DT_BF16, p.Nmod, ws.sc_bf16, DT_BF16, D, gr.blocks[0].ada_w, p.Nmod, D, B, sw,
-                  "wgrad.adaln"));
-    V4H_TRY(prof("colsum", 0, 0, sw, [&] { return colsum_add<float>(ws.dmod, p.Nmod, gr.blocks[0].ada_b, B, p.Nmod, sw); }));
+  if (fast) {
     GemmDesc g = dgrad(ws.dmod_bf16, DT_BF16, p.Nmod, wa + p.arena_ada, DT_BF16, D, B, D, p.Nmod, "dgrad.adaln");
     g.epi = EPI_ATOMIC; g.ep.out = ws.dsc; g.ep.ldo = D; g.splitk = 0;
     V4H_TRY(run_gemm(p, g, s));
@@ -569,40 +669,30 @@ int backward_stage0(Plan& p, const v4h_vit_params& w, const char* arena, const v
     for (int i = 0; i <= d.depth; ++i) {
       const bool fin = i == d.depth;
       const int n = fin ? 2 * D : 6 * D;
-      const float* dmod = ws.dmod + (size_t)i * 6 * D;
-      float* dW = fin ? gr.final_ada_w : gr.blocks[i].ada_w;
-      float* db = fin ? gr.final_ada_b : gr.blocks[i].ada_b;
-      const float* W = fin ? w.final_ada_w : w.blocks[i].ada_w;
-      {
-        GemmDesc g;
-        g.tag = "wgrad.adaln";
-        g.layout = GEMM_TN; g.A = dmod; g.a_dtype = DT_F32; g.lda = p.Nmod; g.B = ws.sc; g.b_dtype = DT_F32;
-        g.ldb = D; g.M = n; g.N = D; g.K = B; g.epi = EPI_ATOMIC; g.ep.out = dW; g.ep.ldo = D; g.splitk = 1;
-        V4H_TRY(run_gemm(p, g, s));
-      }
-      V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<float>(dmod, p.Nmod, db, B, n, s); }));
-      {
-        GemmDesc g = dgrad(dmod, DT_F32, p.Nmod, W, DT_F32, D, B, D, n, "dgrad.adaln");
-        g.epi = EPI_ATOMIC; g.ep.out = ws.dsc; g.ep.ldo = D; g.splitk = std::max(1, n / 240);
-        V4H_TRY(run_gemm(p, g, s));
-      }
+      GemmDesc g = dgrad(ws.dmod + (size_t)i * 6 * D, DT_F32, p.Nmod, fin ? w.final_ada_w : w.blocks[i].ada_w, DT_F32, D, B,
+                         D, n, "dgrad.adaln");
+      g.epi = EPI_ATOMIC; g.ep.out = ws.dsc; g.ep.ldo = D; g.splitk = std::max(1, n / 240);
+      V4H_TRY(run_gemm(p, g, s));
     }
   }
   V4H_TRY(dsilu_mul(ws.dsc, ws.cond, ws.dcond, fast ? ws.dcond_bf : nullptr, (int64_t)B * D, s));
   // c_embedder (nn/vit.py:77-81) and t_embedder.mlp (nn/vit.py:361-365): Linear -> SiLU -> Linear
+  const float* cin = d.c_map_dim > 0 ? ws.cm : u.c;
+  const void* dvec_c = nullptr;  // d c_embedder.0 output (B, D), for the mapper below
+  int dvec_c_dt = DT_F32;
   if (fast) {
     struct Mlp { const void* in; int in_dt, in_dim; const bf16 *h_pre, *h; const bf16* w2; float *dw0, *db0, *dw2, *db2; };
     Mlp mlps[2] = {
-        {c, DT_F32, d.cond_dim, ws.c_hpre_bf, ws.c_h_bf, wa + p.arena_c2, gr.c0_w, gr.c0_b, gr.c2_w, gr.c2_b},
+        {cin, DT_F32, d.cond_dim, ws.c_hpre_bf, ws.c_h_bf, wa + p.arena_c2, gr.c0_w, gr.c0_b, gr.c2_w, gr.c2_b},
         {ws.temb_bf, DT_BF16, d.freq_dim, ws.t_hpre_bf, ws.t_h_bf, wa + p.arena_t2, gr.t0_w, gr.t0_b, gr.t2_w, gr.t2_b}};
-    if (forked) V4H_TRY(p.fork(s, sw));  // d cond is ready
+    if (forked) V4H_TRY(fork_to(L, s, sw));  // d cond is ready
     for (const Mlp& m : mlps) {
       V4H_TRY(wgrad(p, ws.dcond_bf, DT_BF16, D, m.h, DT_BF16, D, m.dw2, D, D, B, sw, "wgrad.cond"));
       V4H_TRY(prof("colsum", 0, 0, sw, [&] { return colsum_add<float>(ws.dcond, D, m.db2, B, D, sw); }));
     }
     // the two MLPs are independent from here on: the t_embedder's chain (dgrad -> weight gradient) runs on the
     // x side stream next to the c_embedder's on the caller's stream, each with its own d hidden buffer
-    if (forked) V4H_TRY(p.fork(s, sx));
+    if (forked) V4H_TRY(fork_to(L, s, sx));
     for (int k = 0; k < 2; ++k) {
       const Mlp& m = mlps[k];
       cudaStream_t q = k == 1 ? sx : s;
@@ -614,13 +704,13 @@ int backward_stage0(Plan& p, const v4h_vit_params& w, const char* arena, const v
       V4H_TRY(wgrad(p, dvec, DT_BF16, D, m.in, m.in_dt, m.in_dim, m.dw0, D, m.in_dim, B, q, "wgrad.cond"));
       V4H_TRY(prof("colsum", 0, 0, q, [&] { return colsum_add<bf16>(dvec, D, m.db0, B, D, q); }));
     }
-    if (forked) { V4H_TRY(p.join(sw, s)); V4H_TRY(p.join(sx, s)); }
+    dvec_c = ws.dvec_bf; dvec_c_dt = DT_BF16;
   } else {
     struct Mlp { const float *in, *h_pre, *h; int in_dim; const float* w2; float *dw0, *db0, *dw2, *db2; };
     Mlp mlps[2] = {
-        {c, ws.c_h_pre, ws.c_h, d.cond_dim, w.c2_w, gr.c0_w, gr.c0_b, gr.c2_w, gr.c2_b},
-        {ws.temb_in, ws.t_h_pre, ws.t_h, d.freq_dim, w.t2_w, gr.t0_w, gr.t0_b, gr.t2_w, gr.t2_b}};
-    for (const Mlp& m : mlps) {
+        {ws.temb_in, ws.t_h_pre, ws.t_h, d.freq_dim, w.t2_w, gr.t0_w, gr.t0_b, gr.t2_w, gr.t2_b},
+        {cin, ws.c_h_pre, ws.c_h, d.cond_dim, w.c2_w, gr.c0_w, gr.c0_b, gr.c2_w, gr.c2_b}};
+    for (const Mlp& m : mlps) {  // c_embedder last: its d hidden stays in ws.dvec for the mapper
       V4H_TRY(wgrad(p, ws.dcond, DT_F32, D, m.h, DT_F32, D, m.dw2, D, D, B, s, "wgrad.cond"));
       V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<float>(ws.dcond, D, m.db2, B, D, s); }));
       GemmDesc g = dgrad(ws.dcond, DT_F32, D, m.w2, DT_F32, D, B, D, D, "dgrad.cond");
@@ -629,8 +719,88 @@ int backward_stage0(Plan& p, const v4h_vit_params& w, const char* arena, const v
       V4H_TRY(wgrad(p, ws.dvec, DT_F32, D, m.in, DT_F32, m.in_dim, m.dw0, D, m.in_dim, B, s, "wgrad.cond"));
       V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<float>(ws.dvec, D, m.db0, B, D, s); }));
     }
+    dvec_c = ws.dvec;
   }
+  if (d.c_map_dim > 0) {
+    // d cm_pre = (d c_h_pre Wc0) * SiLU'(cm_pre);  d Wm = d cm_pre^T c;  d bm = colsum(d cm_pre)   (caller's stream:
+    // the c_embedder chain above ran there)
+    GemmDesc g = dgrad(dvec_c, dvec_c_dt, D, w.c0_w, DT_F32, d.cond_dim, B, d.cond_dim, D, "dgrad.cond");
+    g.epi = EPI_DACT; g.act = ACT_SILU; g.ep.out = ws.dcm; g.ep.ldo = d.cond_dim; g.ep.aux = ws.cm_pre; g.ep.ld_aux = d.cond_dim;
+    V4H_TRY(run_gemm(p, g, s));
+    V4H_TRY(wgrad(p, ws.dcm, DT_F32, d.cond_dim, u.c, DT_F32, d.c_map_dim, gr.cm_w, d.cond_dim, d.c_map_dim, B, s, "wgrad.c_map"));
+    V4H_TRY(prof("colsum", 0, 0, s, [&] { return colsum_add<float>(ws.dcm, d.cond_dim, gr.cm_b, B, d.cond_dim, s); }));
+  }
+  if (forked) { V4H_TRY(join_from(L, sw, s)); V4H_TRY(join_from(L, sx, s)); }
   return V4H_OK;
+}
+
+// Split a call over B samples into the plan's sub-batches: slices of the inputs, one workspace each (laid out
+// back to back in the caller's buffer), lane 0 on the caller's stream and lane 1 on its own stream.
+int make_subs(Plan& p, char* workspace, size_t workspace_bytes, int64_t B, bool train, bool shared_t, const float* x,
+              const float* t, const float* c, float* out, const float* dout, cudaStream_t s, Sub (&subs)[2], int* nsub) {
+  const v4h_vit_dims& d = p.d;
+  const int n = p.sub_batches(B);
+  const int in_dim = d.x_map_dim > 0 ? d.x_map_dim : d.patch_dim;
+  const int c_dim = d.c_map_dim > 0 ? d.c_map_dim : d.cond_dim;
+  size_t off = 0;
+  int64_t b0 = 0;
+  for (int k = 0; k < n; ++k) {
+    Sub& u = subs[k];
+    const int64_t bk = n == 1 ? B : (k == 0 ? (B + 1) / 2 : B - (B + 1) / 2);
+    u.B = (int)bk;
+    u.x = x ? x + (size_t)b0 * d.tokens * in_dim : nullptr;
+    u.t = t ? t + (shared_t ? 0 : b0) : nullptr;
+    u.c = c ? c + (size_t)b0 * c_dim : nullptr;
+    u.out = out ? out + (size_t)b0 * d.tokens * d.out_dim : nullptr;
+    u.dout = dout ? dout + (size_t)b0 * d.tokens * d.out_dim : nullptr;
+    u.ws.layout(p, workspace + off, bk, train);
+    off += align_up(u.ws.bytes, 1024);
+    u.lane = &p.lanes[k];
+    u.s = (k == 0 || !p.forking()) ? s : p.lanes[k].main;
+    b0 += bk;
+  }
+  V4H_REQUIRE(off <= workspace_bytes, "vit: workspace too small (%zu < %zu)", workspace_bytes, off);
+  *nsub = n;
+  return V4H_OK;
+}
+// lane 1 starts after everything issued on the caller's stream so far / the caller's stream waits for lane 1
+int split_lanes(Plan& p, Sub (&subs)[2], int nsub, cudaStream_t s) {
+  if (nsub < 2 || subs[1].s == s) return V4H_OK;
+  V4H_CUDA(cudaEventRecord(p.ev_split, s));
+  V4H_CUDA(cudaStreamWaitEvent(subs[1].s, p.ev_split, 0));
+  return V4H_OK;
+}
+int merge_lanes(Plan& p, Sub (&subs)[2], int nsub, cudaStream_t s) {
+  if (nsub < 2 || subs[1].s == s) return V4H_OK;
+  V4H_CUDA(cudaEventRecord(p.lanes[1].ev_done, subs[1].s));
+  V4H_CUDA(cudaStreamWaitEvent(s, p.lanes[1].ev_done, 0));
+  return V4H_OK;
+}
+
+template <typename T>
+int forward_all(Plan& p, const v4h_vit_params& w, const char* arena, Sub (&subs)[2], int nsub, bool shared_t, bool train,
+                cudaStream_t s) {
+  V4H_TRY(split_lanes(p, subs, nsub, s));
+  // issue order alternates between the sub-batches stage by stage, so that both streams have work queued early
+  // whether the launches come from the host (eager) or from a replayed graph
+  for (int k = 0; k < nsub; ++k) V4H_TRY(forward_prologue<T>(p, w, arena, subs[k], shared_t, train));
+  for (int i = 0; i < p.d.depth; ++i)
+    for (int k = 0; k < nsub; ++k) V4H_TRY(forward_block<T>(p, w, arena, subs[k], i, train));
+  for (int k = 0; k < nsub; ++k) V4H_TRY(forward_final<T>(p, w, arena, subs[k], train));
+  return merge_lanes(p, subs, nsub, s);
+}
+
+template <typename T>
+int backward_all(Plan& p, const v4h_vit_params& w, const char* arena, const v4h_vit_params& gr, Sub (&subs)[2], int nsub,
+                 int stage_begin, int stage_end, cudaStream_t s) {
+  V4H_TRY(split_lanes(p, subs, nsub, s));
+  const int lo = stage_end < 1 ? 1 : stage_end;
+  for (int stage = stage_begin; stage >= lo; --stage)
+    for (int k = 0; k < nsub; ++k) V4H_TRY(backward_stage<T>(p, w, arena, gr, subs[k], stage));
+  if (stage_end == 0)
+    for (int k = 0; k < nsub; ++k) V4H_TRY(backward_stage0(p, w, arena, gr, subs[k]));
+  for (int k = 0; k < nsub; ++k) V4H_TRY(join_side(subs[k]));
+  return merge_lanes(p, subs, nsub, s);
 }
 
 }  // namespace
@@ -647,6 +817,7 @@ int plan_create(const v4h_vit_dims* dims, Plan** out) {
               "plan_create: invalid dimensions");
   V4H_REQUIRE(!d.learn_pos_embed || d.hidden_dim % 6 == 0, "plan_create: hidden_dim must be a multiple of 6");
   V4H_REQUIRE(d.precision == V4H_FP32 || d.precision == V4H_BF16, "plan_create: unknown precision");
+  V4H_REQUIRE(d.x_map_dim >= 0 && d.c_map_dim >= 0, "plan_create: negative mapper width");
   if (d.hidden_dim > 512)
     return fail(V4H_ERR_UNSUPPORTED, "hidden_dim %d > 512 is not supported by the LayerNorm kernels", d.hidden_dim);
   if (d.hidden_dim / d.num_heads > 128)
@@ -661,15 +832,25 @@ int plan_create(const v4h_vit_dims* dims, Plan** out) {
   {
     const char* e = getenv("V4H_WGRAD_STREAM");
     if (p->use_umma && !(e && e[0] == '0')) {
-      if (cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess ||
-          cudaStreamCreateWithFlags(&p->side2, cudaStreamNonBlocking) != cudaSuccess ||
-          cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-          cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming) != cudaSuccess ||
-          cudaEventCreateWithFlags(&p->ev_join2, cudaEventDisableTiming) != cudaSuccess) {
+      bool ok = cudaEventCreateWithFlags(&p->ev_split, cudaEventDisableTiming) == cudaSuccess;
+      for (int k = 0; k < 2 && ok; ++k) {
+        Lane& L = p->lanes[k];
+        ok = (k == 0 || cudaStreamCreateWithFlags(&L.main, cudaStreamNonBlocking) == cudaSuccess) &&
+             cudaStreamCreateWithFlags(&L.side, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaStreamCreateWithFlags(&L.side2, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&L.ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&L.ev_join, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&L.ev_join2, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming) == cudaSuccess;
+      }
+      if (!ok) {
         cudaGetLastError();
-        p->side = nullptr;  // no side streams: everything stays on the caller's stream
+        p->lanes[0].side = nullptr;  // no side streams: everything stays on the caller's stream
       }
     }
+    const char* mb = getenv("V4H_MICROBATCH");
+    if (mb && (mb[0] == '0' || mb[0] == '1')) p->microbatch = 1;
+    else if (mb && mb[0] == '2') p->microbatch = 2;
   }
   p->ldx = (p->use_umma && d.hidden_dim % 8 == 0) ? d.hidden_dim + 8 : d.hidden_dim;
   const char* no_umma_attn = getenv("V4H_DISABLE_UMMA_ATTN");
@@ -711,18 +892,26 @@ void plan_destroy(Plan* p) {
   if (p->jobs_dev) cudaFree(p->jobs_dev);
   if (p->jobs_host) cudaFreeHost(p->jobs_host);
   if (p->umma) umma_context_destroy(p->umma);
-  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
-  if (p->ev_join) cudaEventDestroy(p->ev_join);
-  if (p->ev_join2) cudaEventDestroy(p->ev_join2);
-  if (p->side) cudaStreamDestroy(p->side);
-  if (p->side2) cudaStreamDestroy(p->side2);
+  if (p->ev_split) cudaEventDestroy(p->ev_split);
+  for (Lane& L : p->lanes) {
+    for (cudaEvent_t e : {L.ev_fork, L.ev_join, L.ev_join2, L.ev_done})
+      if (e) cudaEventDestroy(e);
+    for (cudaStream_t q : {L.main, L.side, L.side2})
+      if (q) cudaStreamDestroy(q);
+  }
   delete p;
 }
 
 size_t plan_workspace_bytes(const Plan* p, int64_t B, bool train) {
-  Workspace ws;
-  ws.layout(*p, nullptr, B, train);
-  return ws.bytes;
+  const int n = p->sub_batches(B);
+  size_t total = 0;
+  for (int k = 0; k < n; ++k) {
+    const int64_t bk = n == 1 ? B : (k == 0 ? (B + 1) / 2 : B - (B + 1) / 2);
+    Workspace ws;
+    ws.layout(*p, nullptr, bk, train);
+    total += align_up(ws.bytes, 1024);
+  }
+  return total;
 }
 
 size_t plan_arena_bytes(const Plan* p) { return p->arena_bytes; }
@@ -788,7 +977,12 @@ int plan_prepare_weights(Plan* p, const v4h_vit_params* w, void* arena, cudaStre
   add(w->t2_w, wa + p->arena_t2, D * D);
   add(w->c2_w, wa + p->arena_c2, D * D);
   if (memcmp(jobs.data(), p->jobs_host, sizeof(CastJob) * jobs.size()) != 0) {
-    // parameter storage moved: wait for earlier uses of the staging table, then refresh it
+    // parameter storage moved: wait for earlier uses of the staging table, then refresh it -- impossible inside
+    // a stream capture (the synchronisation would invalidate it): fail with a message instead
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone)
+      return fail(V4H_ERR_INVALID, "prepare_weights: parameter storage moved during CUDA-graph capture; run one "
+                                   "eager forward after (re)allocating parameters and before capturing");
     V4H_CUDA(cudaStreamSynchronize(s));
     memcpy(p->jobs_host, jobs.data(), sizeof(CastJob) * jobs.size());
     V4H_CUDA(cudaMemcpyAsync(p->jobs_dev, p->jobs_host, sizeof(CastJob) * jobs.size(), cudaMemcpyHostToDevice, s));
@@ -807,12 +1001,14 @@ int plan_forward(Plan* p, const v4h_vit_params* w, const void* arena, const floa
   V4H_REQUIRE(p && w && x && t && c && out && workspace, "vit_forward: null argument");
   V4H_REQUIRE(B > 0 && B * p->d.tokens < (1ll << 31) / 4096, "vit_forward: batch out of range");
   V4H_REQUIRE(!p->bf16 || arena, "vit_forward: bf16 precision needs the weight arena");
-  Workspace ws;
-  ws.layout(*p, reinterpret_cast<char*>(workspace), B, train);
-  V4H_REQUIRE(ws.bytes <= workspace_bytes, "vit_forward: workspace too small (%zu < %zu)", workspace_bytes, ws.bytes);
-  if (p->bf16)
-    return forward_impl<bf16>(*p, *w, (const char*)arena, x, t, c, out, B, shared_t, train, ws, s);
-  return forward_impl<float>(*p, *w, (const char*)arena, x, t, c, out, B, shared_t, train, ws, s);
+  V4H_REQUIRE(p->d.x_map_dim == 0 || (w->xm_w && w->xm_b), "vit_forward: x mapper weights are null");
+  V4H_REQUIRE(p->d.c_map_dim == 0 || (w->cm_w && w->cm_b), "vit_forward: c mapper weights are null");
+  Sub subs[2];
+  int nsub = 0;
+  V4H_TRY(make_subs(*p, reinterpret_cast<char*>(workspace), workspace_bytes, B, train, shared_t, x, t, c, out, nullptr, s,
+                    subs, &nsub));
+  if (p->bf16) return forward_all<bf16>(*p, *w, (const char*)arena, subs, nsub, shared_t, train, s);
+  return forward_all<float>(*p, *w, (const char*)arena, subs, nsub, shared_t, train, s);
 }
 
 int plan_backward(Plan* p, const v4h_vit_params* w, const void* arena, const v4h_vit_params* grads,
@@ -822,21 +1018,13 @@ int plan_backward(Plan* p, const v4h_vit_params* w, const void* arena, const v4h
   V4H_REQUIRE(stage_begin <= p->d.depth + 1 && stage_end >= 0 && stage_begin >= stage_end,
               "vit_backward: bad stage range [%d, %d]", stage_begin, stage_end);
   V4H_REQUIRE(stage_begin != p->d.depth + 1 || dout, "vit_backward: dout is null");
-  Workspace ws;
-  ws.layout(*p, reinterpret_cast<char*>(workspace), B, true);
-  V4H_REQUIRE(ws.bytes <= workspace_bytes, "vit_backward: workspace too small (%zu < %zu)", workspace_bytes, ws.bytes);
-  const int lo = stage_end < 1 ? 1 : stage_end;
-  if (stage_begin >= lo) {
-    if (p->bf16)
-      V4H_TRY(backward_impl<bf16>(*p, *w, (const char*)arena, *grads, dout, B, stage_begin, lo, ws, s));
-    else
-      V4H_TRY(backward_impl<float>(*p, *w, (const char*)arena, *grads, dout, B, stage_begin, lo, ws, s));
-  }
-  if (stage_end == 0) {
-    V4H_REQUIRE(x && c, "vit_backward: stage 0 needs the forward inputs x and c");
-    V4H_TRY(backward_stage0(*p, *w, (const char*)arena, *grads, x, c, B, ws, s));
-  }
-  return V4H_OK;
+  V4H_REQUIRE(stage_end != 0 || (x && c), "vit_backward: stage 0 needs the forward inputs x and c");
+  Sub subs[2];
+  int nsub = 0;
+  V4H_TRY(make_subs(*p, reinterpret_cast<char*>(workspace), workspace_bytes, B, true, false, x, nullptr, c, nullptr, dout,
+                    s, subs, &nsub));
+  if (p->bf16) return backward_all<bf16>(*p, *w, (const char*)arena, *grads, subs, nsub, stage_begin, stage_end, s);
+  return backward_all<float>(*p, *w, (const char*)arena, *grads, subs, nsub, stage_begin, stage_end, s);
 }
 
 }  // namespace v4h

@@ -38,8 +38,9 @@ def plan_buckets(stage_bounds: Sequence[int], min_elems: int) -> List[Bucket]:
     """Group consecutive backward stages into buckets of at least ``min_elems`` gradient elements.
 
     ``stage_bounds[k]`` is the flat-buffer offset at which stage ``depth + 1 - k`` ends
-    (ViT.stage_boundaries()).  The last bucket absorbs what is left so nothing is below the minimum
-    except when the whole model is.
+    (ViT.stage_boundaries()).  A short tail is merged into the bucket before it -- except a tail that is
+    stage 0 alone (embeddings / conditioning, 2.5 MB at ds2): the all-reduce of the LAST bucket is the one
+    nothing overlaps, so block 0's bucket is issued before stage 0 runs and only the small one is exposed.
     """
     nstages = len(stage_bounds)
     top = nstages - 1  # stage index of the final layer = depth + 1
@@ -50,7 +51,7 @@ def plan_buckets(stage_bounds: Sequence[int], min_elems: int) -> List[Bucket]:
         if stop - start >= min_elems or stage == 0:
             buckets.append(Bucket(first, stage, start, stop))
             start, first = stop, stage - 1
-    if len(buckets) >= 2 and buckets[-1].stop - buckets[-1].start < min_elems:
+    if len(buckets) >= 2 and buckets[-1].stop - buckets[-1].start < min_elems and buckets[-1].stage_begin != 0:
         a, b = buckets[-2], buckets[-1]
         buckets[-2:] = [Bucket(a.stage_begin, b.stage_end, a.start, b.stop)]
     return buckets
@@ -86,9 +87,9 @@ class GradReducer:
             w.wait()
 
     # called by vit._ViTFunction.backward
-    def backward(self, module, x, c, dout, ws, ordered, flat) -> None:
+    def backward(self, module, plan, x, c, dout, ws, ordered, flat) -> None:
         buckets = plan_buckets(module.stage_boundaries(), self.min_bucket_elems)
-        self.run(buckets, flat, lambda hi, lo: module._run_backward(x, c, dout, ws, ordered, flat, hi, lo))
+        self.run(buckets, flat, lambda hi, lo: module._run_backward(plan, x, c, dout, ws, ordered, flat, hi, lo))
 
 
 class _Scaled:

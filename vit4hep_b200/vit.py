@@ -144,18 +144,23 @@ def _dev_ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 class _Native:
-    """Per-module native state: plan handle, bf16 weight arena, cached pointer tables."""
+    """Per-module native state: plan handles (one per shape key), bf16 weight arena, cached pointer tables."""
 
     def __init__(self):
-        self.plan = None
+        self.plans = {}       # key -> handle, kept until the module dies: a pending autograd graph may hold one
+        self.plan = None      # the plan of the most recent call
         self.plan_key = None
         self.arena = None
         self.arena_key = None
+        self.arena_layout = None  # the part of the plan key the arena layout depends on
 
     def close(self):
-        if self.plan is not None:
-            _cabi.load().v4h_plan_destroy(self.plan)
-            self.plan = None
+        lib = _cabi.load() if self.plans else None
+        for handle in self.plans.values():
+            lib.v4h_plan_destroy(handle)
+        self.plans = {}
+        self.plan = None
+        self.plan_key = None
 
     def __del__(self):
         try:
@@ -188,6 +193,10 @@ class ViT(nn.Module):
             raise NotImplementedError("causal_attn is not implemented (no shipped config enables it)")
         if self.hidden_dim % self.num_heads != 0:
             raise AssertionError("dim should be divisible by num_heads")
+        if self.checkpoint_grads:
+            import warnings
+            warnings.warn("vit4hep_b200.ViT: checkpoint_grads=True has no effect (the fused backward always uses the "
+                          "saved activation workspace; results are identical)")
 
         self.x_embedder = nn.Linear(self.patch_dim, self.hidden_dim)
         self.c_embedder = nn.Sequential(nn.Linear(self.condition_dim, self.hidden_dim), nn.SiLU(),
@@ -244,43 +253,68 @@ class ViT(nn.Module):
 
     # ------------------------------------------------------------------ parameter plumbing
     @staticmethod
-    def _mlp2(seq, what: str) -> Tuple[nn.Linear, nn.Linear]:
-        ok = (isinstance(seq, nn.Sequential) and len(seq) == 3 and isinstance(seq[0], nn.Linear)
-              and isinstance(seq[1], nn.SiLU) and isinstance(seq[2], nn.Linear))
-        if not ok:
-            raise NotImplementedError(
-                f"{what} must be Sequential(Linear, SiLU, Linear) for the fused path (got {seq}); "
-                "re-structured embedders (finetuning) are not implemented yet")
+    def _is_mlp2(seq) -> bool:
+        return (isinstance(seq, nn.Sequential) and len(seq) == 3 and isinstance(seq[0], nn.Linear)
+                and isinstance(seq[1], nn.SiLU) and isinstance(seq[2], nn.Linear))
+
+    @classmethod
+    def _mlp2(cls, seq, what: str) -> Tuple[nn.Linear, nn.Linear]:
+        if not cls._is_mlp2(seq):
+            raise NotImplementedError(f"{what} must be Sequential(Linear, SiLU, Linear) for the fused path (got {seq})")
         return seq[0], seq[2]
+
+    def _x_parts(self) -> Tuple[Optional[nn.Linear], nn.Linear]:
+        """(mapper or None, embedding Linear) of ``x_embedder``: a Linear, or the finetuning structure
+        Sequential(mapper Linear, SiLU, old Linear) (reference experiment_finetuning.py:79-91)."""
+        xe = self.x_embedder
+        if isinstance(xe, nn.Linear):
+            return None, xe
+        if self._is_mlp2(xe):
+            return xe[0], xe[2]
+        raise NotImplementedError(f"x_embedder must be a Linear or Sequential(Linear, SiLU, Linear) for the fused "
+                                  f"path (got {xe})")
+
+    def _c_parts(self) -> Tuple[Optional[nn.Linear], nn.Linear, nn.Linear]:
+        """(mapper or None, first, second Linear) of ``c_embedder``: Sequential(Linear, SiLU, Linear), or the
+        finetuning structure Sequential(mapper Linear, SiLU, old Sequential) (reference experiment_finetuning.py:106-118)."""
+        ce = self.c_embedder
+        if self._is_mlp2(ce):
+            return None, ce[0], ce[2]
+        if (isinstance(ce, nn.Sequential) and len(ce) == 3 and isinstance(ce[0], nn.Linear)
+                and isinstance(ce[1], nn.SiLU) and self._is_mlp2(ce[2])):
+            return ce[0], ce[2][0], ce[2][2]
+        raise NotImplementedError(f"c_embedder must be Sequential(Linear, SiLU, Linear), optionally behind a mapper "
+                                  f"Linear + SiLU, for the fused path (got {ce})")
 
     def ordered_parameters(self) -> List[Tuple[str, nn.Parameter]]:
         """Parameters as (struct field, tensor), in the order the backward chain completes their
-        gradients: final layer, blocks depth-1..0, then embeddings / conditioning / adaLN (stage 0).
+        gradients: final layer (with its adaLN Linear), blocks depth-1..0 (each with its adaLN Linear: a block's
+        modulation gradients are final when its backward stage ends), then embeddings / conditioning (stage 0).
         The flat gradient buffer and the data-parallel buckets use this order."""
         out: List[Tuple[str, nn.Parameter]] = []
         fl = self.final_layer
-        out += [("final_w", fl.linear.weight), ("final_b", fl.linear.bias)]
+        out += [("final_w", fl.linear.weight), ("final_b", fl.linear.bias),
+                ("final_ada_w", fl.adaLN_modulation[-1].weight), ("final_ada_b", fl.adaLN_modulation[-1].bias)]
         for i in reversed(range(len(self.blocks))):
             b = self.blocks[i]
+            ada = b.adaLN_modulation[-1]
             out += [(f"blocks.{i}.qkv_w", b.attn.qkv.weight), (f"blocks.{i}.qkv_b", b.attn.qkv.bias),
                     (f"blocks.{i}.proj_w", b.attn.proj.weight), (f"blocks.{i}.proj_b", b.attn.proj.bias),
                     (f"blocks.{i}.fc1_w", b.mlp.fc1.weight), (f"blocks.{i}.fc1_b", b.mlp.fc1.bias),
-                    (f"blocks.{i}.fc2_w", b.mlp.fc2.weight), (f"blocks.{i}.fc2_b", b.mlp.fc2.bias)]
+                    (f"blocks.{i}.fc2_w", b.mlp.fc2.weight), (f"blocks.{i}.fc2_b", b.mlp.fc2.bias),
+                    (f"blocks.{i}.ada_w", ada.weight), (f"blocks.{i}.ada_b", ada.bias)]
         if self.learn_pos_embed:
             out.append(("pos_embed_freqs", self.pos_embed_freqs))
-        c0, c2 = self._mlp2(self.c_embedder, "c_embedder")
+        xm, xe = self._x_parts()
+        cm, c0, c2 = self._c_parts()
         t0, t2 = self._mlp2(self.t_embedder.mlp, "t_embedder.mlp")
-        out += [("x_w", self.x_embedder.weight), ("x_b", self.x_embedder.bias),
-                ("c0_w", c0.weight), ("c0_b", c0.bias), ("c2_w", c2.weight), ("c2_b", c2.bias),
-                ("t0_w", t0.weight), ("t0_b", t0.bias), ("t2_w", t2.weight), ("t2_b", t2.bias)]
-        # every adaLN weight, then every adaLN bias, in block order: their gradients form ONE
-        # (depth*6D + 2D, D) matrix and ONE vector in the flat buffer, which lets the native backward
-        # compute them with a single tensor-core GEMM / column sum (csrc/vit.cu backward_stage0)
-        adas = [b.adaLN_modulation[-1] for b in self.blocks]
-        out += [(f"blocks.{i}.ada_w", a.weight) for i, a in enumerate(adas)]
-        out.append(("final_ada_w", fl.adaLN_modulation[-1].weight))
-        out += [(f"blocks.{i}.ada_b", a.bias) for i, a in enumerate(adas)]
-        out.append(("final_ada_b", fl.adaLN_modulation[-1].bias))
+        out += [("x_w", xe.weight), ("x_b", xe.bias)]
+        if xm is not None:
+            out += [("xm_w", xm.weight), ("xm_b", xm.bias)]
+        out += [("c0_w", c0.weight), ("c0_b", c0.bias), ("c2_w", c2.weight), ("c2_b", c2.bias)]
+        if cm is not None:
+            out += [("cm_w", cm.weight), ("cm_b", cm.bias)]
+        out += [("t0_w", t0.weight), ("t0_b", t0.bias), ("t2_w", t2.weight), ("t2_b", t2.bias)]
         return out
 
     def _aux_stream(self, device) -> "torch.cuda.Stream":
@@ -311,10 +345,10 @@ class ViT(nn.Module):
         names = self.ordered_parameters()
         offs, total = self.flat_layout(names)
         ends = offs[1:] + [total]
-        bounds = [ends[1]]                       # final_w, final_b
-        idx = 2
+        bounds = [ends[3]]                       # final_w, final_b, final_ada_w, final_ada_b
+        idx = 4
         for _ in range(len(self.blocks)):
-            idx += 8
+            idx += 10
             bounds.append(ends[idx - 1])
         bounds.append(total)
         return bounds
@@ -338,21 +372,36 @@ class ViT(nn.Module):
         return w
 
     def _plan(self, tokens: int):
-        cond_in = self._mlp2(self.c_embedder, "c_embedder")[0].in_features
+        xm, xe = self._x_parts()
+        cm, c0, _ = self._c_parts()
         out_dim = self.final_layer.linear.out_features
         key = (self.hidden_dim, len(self.blocks), self.num_heads, self.blocks[0].mlp.fc1.out_features,
-               self.x_embedder.in_features, out_dim, cond_in, tokens,
-               self.t_embedder.frequency_embedding_size, bool(self.learn_pos_embed), self.precision)
+               xe.in_features, out_dim, c0.in_features, tokens,
+               self.t_embedder.frequency_embedding_size, bool(self.learn_pos_embed), self.precision,
+               xm.in_features if xm is not None else 0, cm.in_features if cm is not None else 0)
         nat = self._native
         if nat.plan_key != key:
-            nat.close()
-            dims = _cabi.VitDims(*[int(v) for v in key[:9]], int(key[9]),
-                                 _cabi.V4H_BF16 if self.precision == "bf16" else _cabi.V4H_FP32)
-            handle = ctypes.c_void_p()
-            _cabi.check(_cabi.load().v4h_plan_create(ctypes.byref(dims), ctypes.byref(handle)))
+            handle = nat.plans.get(key)
+            if handle is None:
+                dims = _cabi.VitDims(*[int(v) for v in key[:9]], int(key[9]),
+                                     _cabi.V4H_BF16 if self.precision == "bf16" else _cabi.V4H_FP32,
+                                     int(key[11]), int(key[12]))
+                handle = ctypes.c_void_p()
+                _cabi.check(_cabi.load().v4h_plan_create(ctypes.byref(dims), ctypes.byref(handle)))
+                nat.plans[key] = handle
             nat.plan, nat.plan_key = handle, key
-            nat.arena, nat.arena_key = None, None
+            layout = key[:7] + key[8:]  # the weight arena does not depend on the token count
+            if nat.arena_layout != layout:
+                nat.arena, nat.arena_key, nat.arena_layout = None, None, layout
+            else:
+                nat.arena_key = None  # same layout, another plan's cast-job table: refresh through this plan once
         return nat.plan
+
+    def invalidate_weights(self) -> None:
+        """Force the bf16 operand copies to be rebuilt by the next forward.  Writers that change parameter
+        storage WITHOUT bumping ``Tensor._version`` (native kernels, collectives into raw pointers) must call
+        this; in-place torch ops, optimizers and ``load_state_dict`` are detected through ``_version``."""
+        self._native.arena_key = None
 
     def _prepare_arena(self, plan, ordered, w, stream: int):
         """bf16 operand copies of the GEMM weights, rebuilt whenever a parameter was written
@@ -379,8 +428,10 @@ class ViT(nn.Module):
         for name, v in (("x", x), ("t", t), ("c", c)):
             if v.dtype != torch.float32:
                 raise TypeError(f"{name} must be float32 (the reference supports fp32/fp64; fp64 is not implemented)")
-        if x.dim() != 3 or x.shape[2] != self.x_embedder.in_features:
-            raise ValueError(f"x must be (B, T, {self.x_embedder.in_features}), got {tuple(x.shape)}")
+        xm, xe = self._x_parts()
+        in_features = (xm if xm is not None else xe).in_features
+        if x.dim() != 3 or x.shape[2] != in_features:
+            raise ValueError(f"x must be (B, T, {in_features}), got {tuple(x.shape)}")
         B = x.shape[0]
         tokens = self.pos_z.numel() if self.learn_pos_embed else self.pos_embed.shape[0]
         if x.shape[1] != tokens:
@@ -390,8 +441,10 @@ class ViT(nn.Module):
                 raise ValueError("shared_t expects a single time value")
         elif t.numel() != B:
             raise ValueError(f"t must hold one time per sample ({B}), got {tuple(t.shape)}")
-        if c.dim() != 2 or c.shape[0] != B:
-            raise ValueError(f"c must be (B, K), got {tuple(c.shape)}")
+        cm, c0, _ = self._c_parts()
+        k_in = (cm if cm is not None else c0).in_features
+        if c.dim() != 2 or c.shape[0] != B or c.shape[1] != k_in:
+            raise ValueError(f"c must be (B, {k_in}), got {tuple(c.shape)}")
         if x.requires_grad or t.requires_grad or c.requires_grad:
             raise NotImplementedError("gradients w.r.t. x, t, c are not implemented (training feeds leaf inputs)")
 
@@ -420,11 +473,10 @@ class ViT(nn.Module):
         out = torch.empty((B, T, self.final_layer.linear.out_features), dtype=torch.float32, device=x.device)
         _cabi.check(lib.v4h_vit_forward(plan, ctypes.byref(w), arena, x.data_ptr(), t.data_ptr(), c.data_ptr(),
                                         out.data_ptr(), B, int(shared_t), int(save), ws.data_ptr(), nbytes, stream))
-        return out, ws, w
+        return out, ws, plan
 
-    def _run_backward(self, x, c, dout, ws, ordered, flat_grad, stage_begin: int, stage_end: int):
+    def _run_backward(self, plan, x, c, dout, ws, ordered, flat_grad, stage_begin: int, stage_end: int):
         lib = _cabi.load()
-        plan = self._native.plan
         stream = torch.cuda.current_stream(x.device).cuda_stream
         w = self._weights_struct(ordered)
         g = _cabi.VitParams()
@@ -454,7 +506,8 @@ class _ViTFunction(torch.autograd.Function):
         with torch.cuda.stream(side):
             flat = torch.zeros(total, dtype=torch.float32, device=x.device)
         ctx.flat, ctx.flat_ready = flat, side.record_event()
-        out, ws, _ = module._run_forward(x, t, c, shared_t, True, ordered)
+        out, ws, plan = module._run_forward(x, t, c, shared_t, True, ordered)
+        ctx.plan = plan  # the backward must lay the workspace out like this forward did, whatever ran in between
         cur.wait_event(ctx.flat_ready)  # also rejoins the side stream when the step is being captured
         flat.record_stream(cur)
         ctx.module = module
@@ -469,13 +522,16 @@ class _ViTFunction(torch.autograd.Function):
         x, c = ctx.saved_tensors
         ordered = module.ordered_parameters()
         offs, total = module.flat_layout(ordered)
+        if ctx.flat is None:
+            raise RuntimeError("vit4hep_b200.ViT: the saved activations of this forward were already consumed by a "
+                               "backward pass (retain_graph / a second backward are not supported: run the forward again)")
         flat, ctx.flat = ctx.flat, None
         dout = dout.contiguous()
         depth = len(module.blocks)
         if module._dp is None:
-            module._run_backward(x, c, dout, ctx.ws, ordered, flat, depth + 1, 0)
+            module._run_backward(ctx.plan, x, c, dout, ctx.ws, ordered, flat, depth + 1, 0)
         else:
-            module._dp.backward(module, x, c, dout, ctx.ws, ordered, flat)
+            module._dp.backward(module, ctx.plan, x, c, dout, ctx.ws, ordered, flat)
         ctx.ws = None
         grads = []
         for (_, p), off in zip(ordered, offs):
