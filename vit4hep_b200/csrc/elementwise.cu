@@ -188,32 +188,6 @@ __global__ void cast_kernel(const float* __restrict__ x, bf16* __restrict__ out,
   cast_span(x, out, n, blockIdx.x * (int64_t)blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
 }
 
-// strided 2-d cast: dst[r * ld_dst + c] = src[r * ld_src + c] (a column slice of a wider matrix); cols % 4 == 0 and
-// 16 / 8-byte aligned rows take the vector path
-__global__ void cast2d_kernel(const float* __restrict__ src, int ld_src, bf16* __restrict__ dst, int ld_dst, int rows,
-                              int cols) {
-  pdl_wait();
-  const bool vec = cols % 4 == 0 && ld_src % 4 == 0 && ld_dst % 4 == 0 && (((uintptr_t)src & 15) == 0) &&
-                   (((uintptr_t)dst & 7) == 0);
-  if (vec) {
-    const int c4 = cols / 4;
-    const int64_t n = (int64_t)rows * c4;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-      const int r = (int)(i / c4), c = (int)(i % c4) * 4;
-      const float4 a = *reinterpret_cast<const float4*>(src + (size_t)r * ld_src + c);
-      const __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
-      *reinterpret_cast<uint2*>(dst + (size_t)r * ld_dst + c) =
-          make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
-    }
-  } else {
-    const int64_t n = (int64_t)rows * cols;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-      const int r = (int)(i / cols), c = (int)(i % cols);
-      dst[(size_t)r * ld_dst + c] = __float2bfloat16_rn(src[(size_t)r * ld_src + c]);
-    }
-  }
-}
-
 // one launch for every weight tensor: blockIdx.y = job
 __global__ void cast_many_kernel(const CastJob* __restrict__ jobs) {
   pdl_wait();
@@ -344,13 +318,6 @@ int dsilu_mul(const float* x, const float* pre, float* out, bf16* out_bf, int64_
 
 int cast_f32_to_bf16(const float* x, bf16* out, int64_t n, cudaStream_t s) {
   V4H_CUDA(launch_pdl(cast_kernel, dim3(ew_grid(n, 8)), dim3(EW_THREADS), 0, s, x, out, n));
-  V4H_LAUNCH_CHECK();
-  return V4H_OK;
-}
-
-int cast_f32_to_bf16_2d(const float* x, int ld_x, bf16* out, int ld_out, int rows, int cols, cudaStream_t s) {
-  V4H_CUDA(launch_pdl(cast2d_kernel, dim3(ew_grid((int64_t)rows * cols, 4)), dim3(EW_THREADS), 0, s, x, ld_x, out, ld_out,
-                      rows, cols));
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }

@@ -62,6 +62,10 @@ constexpr int SLAB = 32;                       // epilogue slab width in columns
 constexpr int MAX_SLOTS = 8;                   // epilogue-input ring
 constexpr int BAR_BYTES = 512;
 constexpr int SMEM_LIMIT = 227 * 1024;
+// per-tile epilogue vectors staged in shared memory by each epilogue group (slab mode): the tile's bias
+// [MAX_BN] and the gate rows of the (at most two) samples its 128 rows belong to [2][MAX_BN], fp32
+constexpr int VEC_FLOATS = 3 * MAX_BN;
+constexpr int VEC_BYTES = EG * VEC_FLOATS * 4;
 
 struct UmmaArgs {
   int M, N, K;
@@ -252,6 +256,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* pool = smem + g.stages * g.stage_bytes;  // epilogue boxes (1024-byte aligned: stage_bytes is)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (SMEM_LIMIT - BAR_BYTES));  // fixed place at the end
+  float* vecs = reinterpret_cast<float*>(smem_raw + (SMEM_LIMIT - BAR_BYTES - VEC_BYTES));  // just below them
   uint64_t* full = bars;                        // [MAX_STAGES]  TMA -> MMA
   uint64_t* empty = full + MAX_STAGES;          // [MAX_STAGES]  MMA -> TMA
   uint64_t* acc_full = empty + MAX_STAGES;      // [2]  MMA -> epilogue
@@ -467,10 +472,34 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int tn = tile / g.tiles_m;
       const int width = tile_width(tn);
       const int m0 = (tile % g.tiles_m) * (BM * CTAS) + (int)rank * BM, n0 = tn * g.bn;
+      const int row = m0 + r;
+      // Per-tile vectors -> shared memory, BEFORE the accumulator is waited for: the global-load latency of the
+      // bias / gate values (the first thing every slab consumed: 8 % of the kernel's stall samples sat on it) is
+      // paid once per tile, under the mainloop, and the slabs read them back as broadcast LDS.128
+      float* bias_s = vecs + grp * VEC_FLOATS;
+      float* gate_s = bias_s + MAX_BN;
+      bool gate_staged = false;
+      int b_lo = 0;
+      if (SLABMODE && EPI != EPI_DACT) {
+        const int t128 = (int)threadIdx.x & 127;
+        for (int i = t128; i < width; i += 128) bias_s[i] = (ep.bias != nullptr && n0 + i < g.N) ? __ldg(ep.bias + n0 + i) : 0.f;
+        if (EPI == EPI_GATE_RES) {
+          b_lo = min(m0, g.M - 1) / ep.rows_per_sample;
+          const int b_hi = min(m0 + BM - 1, g.M - 1) / ep.rows_per_sample;
+          gate_staged = b_hi - b_lo <= 1;
+          if (gate_staged) {
+            for (int i = t128; i < 2 * width; i += 128) {
+              const int srow = i >= width ? 1 : 0, c = i - srow * width;
+              gate_s[srow * MAX_BN + c] =
+                  n0 + c < g.N ? __ldg(ep.gate + (size_t)min(b_lo + srow, b_hi) * ep.mod_stride + n0 + c) : 0.f;
+            }
+          }
+        }
+        group_bar_sync(grp);
+      }
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       T.lap(0);
-      const int row = m0 + r;
       const uint32_t t_row = tmem_base + (uint32_t)acc * MAX_BN + ((uint32_t)(q * 32) << 16);
       if (SLABMODE) {
         const int nslab = width / SLAB;
@@ -481,15 +510,24 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t in_phase = HAS_IN ? (uint32_t)(((slab_base + j) / g.nslots) & 1) : 0u;
           float b32[SLAB], gt[SLAB];
           if (EPI != EPI_DACT) {
-            if (ep.bias) load32(ep.bias + col0, nvalid, ep.vec_ok, b32);
-            else {
 #pragma unroll
-              for (int i = 0; i < SLAB; ++i) b32[i] = 0.f;
+            for (int c = 0; c < 8; ++c) {
+              const float4 t4 = *reinterpret_cast<const float4*>(bias_s + j * SLAB + 4 * c);
+              b32[4 * c] = t4.x; b32[4 * c + 1] = t4.y; b32[4 * c + 2] = t4.z; b32[4 * c + 3] = t4.w;
             }
           }
           if (EPI == EPI_GATE_RES) {
             const int rr = min(row, g.M - 1);
-            load32(ep.gate + (size_t)(rr / ep.rows_per_sample) * ep.mod_stride + col0, nvalid, ep.vec_ok, gt);
+            if (gate_staged) {
+              const float* gp = gate_s + (rr / ep.rows_per_sample - b_lo) * MAX_BN + j * SLAB;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const float4 t4 = *reinterpret_cast<const float4*>(gp + 4 * c);
+                gt[4 * c] = t4.x; gt[4 * c + 1] = t4.y; gt[4 * c + 2] = t4.z; gt[4 * c + 3] = t4.w;
+              }
+            } else {  // more than two samples under one 128-row tile (rows_per_sample < 127)
+              load32(ep.gate + (size_t)(rr / ep.rows_per_sample) * ep.mod_stride + col0, nvalid, ep.vec_ok, gt);
+            }
           }
           float v[SLAB];
           if (!(g.dbg_skip & 1)) {
@@ -976,7 +1014,7 @@ int gemm_umma(UmmaContext* ctx, const GemmDesc& d, cudaStream_t s) {
         break;
     }
   }
-  g.stages = (SMEM_LIMIT - 1024 - BAR_BYTES - pool_bytes) / g.stage_bytes;
+  g.stages = (SMEM_LIMIT - 1024 - BAR_BYTES - VEC_BYTES - pool_bytes) / g.stage_bytes;
   static const int max_stages = [] { const char* e = getenv("V4H_GEMM_MAX_STAGES"); const int v = e ? atoi(e) : MAX_STAGES; return v >= 2 && v <= MAX_STAGES ? v : MAX_STAGES; }();
   if (g.stages > max_stages) g.stages = max_stages;
   V4H_REQUIRE(g.stages >= 2, "gemm_umma: internal shared-memory budget error");

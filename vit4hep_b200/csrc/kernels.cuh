@@ -93,7 +93,6 @@ int pos_embedding_bwd(const float* dh, const float* freqs, const float* pz, cons
 int dsilu_mul(const float* x, const float* pre, float* out, bf16* out_bf, int64_t n, cudaStream_t s);
 int silu_to_bf16(const float* x, bf16* out, int64_t n, cudaStream_t s);
 int cast_f32_to_bf16(const float* x, bf16* out, int64_t n, cudaStream_t s);
-int cast_f32_to_bf16_2d(const float* x, int ld_x, bf16* out, int ld_out, int rows, int cols, cudaStream_t s);
 struct CastJob { const float* src; bf16* dst; int64_t n; };
 int cast_many_f32_to_bf16(const CastJob* jobs_dev, int njobs, int64_t max_n, cudaStream_t s);
 int cfm_prepare(const float* x1, const float* x0, const float* t, const int32_t* table, float* xt_tok,

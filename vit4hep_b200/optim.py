@@ -121,8 +121,8 @@ class ExponentialMovingAverage:
         decay = float(self.decay)
         with torch.cuda.device(dev):
             if self.num_updates is not None:
+                cnt = self._device_counter(dev)  # created from the host count BEFORE this update is booked
                 self.num_updates += 1
-                cnt = self._device_counter(dev)
                 _cabi.check(lib.v4h_counter_increment(cnt.data_ptr(), stream))
                 cnt_ptr = cnt.data_ptr()
             else:  # fixed decay: a huge update count makes (1 + n) / (10 + n) irrelevant
@@ -374,8 +374,8 @@ class FusedAdamW(torch.optim.Optimizer):
                 ema = self.ema
                 ema_decay = float(ema.decay)
                 if ema.num_updates is not None:
+                    cnt = ema._device_counter(dev)  # created from the host count BEFORE this update is booked
                     ema.num_updates += 1
-                    cnt = ema._device_counter(dev)
                     _cabi.check(lib.v4h_counter_increment(cnt.data_ptr(), stream))
                     ema_n, ema_ptr = int(ema.num_updates), cnt.data_ptr()
                 else:
