@@ -216,6 +216,22 @@ int v4h_axpy4(float* out, const float* y, const float* k0, float a0, const float
               const float* k2, float a2, const float* k3, float a3, int64_t n, v4h_stream_t s);
 
 /* ------------------------------------------------------------------------------------
+ * Post-processing of sampled showers (reference experiments/calochallenge/experiment.py:286-289: the transforms of
+ * configs/calochallenge/cfm/calochallenge_ds2.yaml:15-28 applied in reverse; classes in
+ * experiments/calochallenge/transforms.py): Reshape, AddFeaturesToCond, ScaleEnergy(e_min, e_max), LogEnergy(alpha),
+ * GlobalStandardizeFromFile(mean, std), ExclusiveLogitTransform(delta, rescale=True), CutValues(cut),
+ * ScaleTotalEnergy(factor), NormalizeByElayer(eps, norm_cut) in ONE kernel.
+ * x (n, voxels): sampled showers; cond (n, n_layers + 1): the u features then the scaled log incident energy (the
+ * conditions the shape network was sampled with); layer_bounds (n_layers + 1) DEVICE int32 voxel offsets of the
+ * calorimeter layers (XMLHandler.GetBinEdges in the reference).  out (n, voxels): energy per voxel; e_out (n):
+ * incident energies.
+ * ------------------------------------------------------------------------------------ */
+int v4h_postprocess_showers(const float* x, const float* cond, int64_t n, int32_t voxels, int32_t n_layers,
+                            const int32_t* layer_bounds, float mean, float std, float delta, float cut, float factor,
+                            float e_min, float e_max, float alpha, float eps, float norm_cut, float* out,
+                            float* e_out, v4h_stream_t s);
+
+/* ------------------------------------------------------------------------------------
  * Measurement hooks (bench.py): how many kernels the library launched, and per-kernel-class device
  * time from CUDA events recorded on the launching stream around each launch.
  * ------------------------------------------------------------------------------------ */

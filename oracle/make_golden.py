@@ -201,6 +201,38 @@ def golden_fixed_pos_embed(ref, hidden=48, heads=2, depth=1, B=2):
     print("fixed_pos_tiny written")
 
 
+def golden_postprocess():
+    """The reference's transform objects of configs/calochallenge/cfm/calochallenge_ds2.yaml:15-28 run back to front
+    on synthetic sampled showers, as experiments/calochallenge/experiment.py:286-289 does.  NormalizeByElayer and
+    GlobalStandardizeFromFile read files in their constructors (binning XML, means.npy): the objects are created
+    without __init__ and given the attributes those files would provide; their __call__ is the reference's."""
+    import importlib
+    tr = importlib.import_module("experiments.calochallenge.transforms")
+    L, per = 45, 12                       # 45 layers of 12 voxels: the ds2 structure at a size that keeps the file small
+    V = L * per
+    bounds = np.arange(0, V + 1, per)
+    mean, std = -7.5, 2.25
+    norm = object.__new__(tr.NormalizeByElayer)
+    norm.eps, norm.cut, norm.layer_boundaries, norm.n_layers = 1.0e-10, 0.0, bounds, L
+    gs = object.__new__(tr.GlobalStandardizeFromFile)
+    gs.mean, gs.std = torch.tensor(mean), torch.tensor(std)
+    chain = [norm, tr.ScaleTotalEnergy(factor=0.35, n_layers=L), tr.CutValues(cut=1.0e-7, n_layers=L),
+             tr.ExclusiveLogitTransform(delta=1.0e-6, rescale=True), gs, tr.LogEnergy(),
+             tr.ScaleEnergy(e_min=6.907755, e_max=13.815510), tr.AddFeaturesToCond(split_index=V),
+             tr.Reshape(shape=[1, L, 4, 3])]
+    g = torch.Generator().manual_seed(2024)
+    N = 64
+    samples = torch.randn(N, 1, L, 4, 3, generator=g) * 1.5
+    cond = torch.cat([torch.randn(N, L, generator=g) * 1.2 + 3.0, torch.rand(N, 1, generator=g)], dim=1)
+    x, c = samples.clone().squeeze(1), cond.clone()
+    for fn in chain[::-1]:
+        x, c = fn(x, c, rev=True)
+    np.savez_compressed(os.path.join(OUT, "postprocess_ds2.npz"), samples=samples.numpy(), cond=cond.numpy(),
+                        bounds=bounds.astype(np.int32), mean=np.float32(mean), std=np.float32(std),
+                        showers=x.numpy(), energies=c.numpy())
+    print("postprocess golden: showers", tuple(x.shape), "nonzero frac", float((x > 0).float().mean()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_stubs.load_reference()
@@ -212,6 +244,7 @@ def main():
     golden_lemurs(ref)
     golden_finetune(ref)
     golden_fixed_pos_embed(ref)
+    golden_postprocess()
 
 
 if __name__ == "__main__":

@@ -285,6 +285,17 @@ int v4h_axpy4(float* out, const float* y, const float* k0, float a0, const float
   return axpy4(out, y, k0, a0, k1, a1, k2, a2, k3, a3, n, (cudaStream_t)s);
 }
 
+// ------------------------------------------------------------------------------------ post-processing
+int v4h_postprocess_showers(const float* x, const float* cond, int64_t n, int32_t voxels, int32_t n_layers,
+                            const int32_t* layer_bounds, float mean, float std, float delta, float cut, float factor,
+                            float e_min, float e_max, float alpha, float eps, float norm_cut, float* out,
+                            float* e_out, v4h_stream_t s) {
+  V4H_REQUIRE(x && cond && layer_bounds && out && e_out && n > 0 && voxels > 0, "postprocess_showers: bad arguments");
+  V4H_REQUIRE(std != 0.f && factor != 0.f && delta >= 0.f && delta < 0.5f, "postprocess_showers: bad transform parameters");
+  return postprocess_showers(x, cond, n, voxels, n_layers, layer_bounds, mean, std, delta, cut, factor, e_min, e_max,
+                             alpha, eps, norm_cut, out, e_out, (cudaStream_t)s);
+}
+
 // ------------------------------------------------------------------------------------ optimizer
 int v4h_grad_norm_sq(const float* flat, int64_t n, float* out, v4h_stream_t s) {
   V4H_REQUIRE(flat && out && n > 0, "grad_norm_sq: bad arguments");

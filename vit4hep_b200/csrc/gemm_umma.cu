@@ -84,6 +84,7 @@ struct UmmaArgs {
   int tma_store;          // slab mode: results leave through TMA stores (bias / activation / act' epilogues)
   int nbuf;               // staging buffers (or in-flight ring slots) per epilogue group in that mode
   long long* dbg;         // optional device counters (cycles per role / phase), see v4h_debug_gemm
+  int stage_vecs;         // slab mode: bias / gate vectors of a tile staged in shared memory (V4H_GEMM_STAGE_VECS=0: per-slab global loads)
   int dbg_skip;           // V4H_GEMM_DBG_SKIP (experiments only): 1 = no TMEM reads, 2 = no staging / stores, 4 = no activation
 };
 
@@ -480,7 +481,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       float* gate_s = bias_s + MAX_BN;
       bool gate_staged = false;
       int b_lo = 0;
-      if (SLABMODE && EPI != EPI_DACT) {
+      if (SLABMODE && EPI != EPI_DACT && g.stage_vecs) {
         const int t128 = (int)threadIdx.x & 127;
         for (int i = t128; i < width; i += 128) bias_s[i] = (ep.bias != nullptr && n0 + i < g.N) ? __ldg(ep.bias + n0 + i) : 0.f;
         if (EPI == EPI_GATE_RES) {
@@ -510,10 +511,17 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t in_phase = HAS_IN ? (uint32_t)(((slab_base + j) / g.nslots) & 1) : 0u;
           float b32[SLAB], gt[SLAB];
           if (EPI != EPI_DACT) {
+            if (g.stage_vecs) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const float4 t4 = *reinterpret_cast<const float4*>(bias_s + j * SLAB + 4 * c);
-              b32[4 * c] = t4.x; b32[4 * c + 1] = t4.y; b32[4 * c + 2] = t4.z; b32[4 * c + 3] = t4.w;
+              for (int c = 0; c < 8; ++c) {
+                const float4 t4 = *reinterpret_cast<const float4*>(bias_s + j * SLAB + 4 * c);
+                b32[4 * c] = t4.x; b32[4 * c + 1] = t4.y; b32[4 * c + 2] = t4.z; b32[4 * c + 3] = t4.w;
+              }
+            } else if (ep.bias) {
+              load32(ep.bias + col0, nvalid, ep.vec_ok, b32);
+            } else {
+#pragma unroll
+              for (int i = 0; i < SLAB; ++i) b32[i] = 0.f;
             }
           }
           if (EPI == EPI_GATE_RES) {
@@ -973,6 +981,8 @@ int gemm_umma(UmmaContext* ctx, const GemmDesc& d, cudaStream_t s) {
   static const int tma_store_enabled = [] { const char* e = getenv("V4H_GEMM_TMA_STORE"); return (e && e[0] == '0') ? 0 : 1; }();
   g.has_out2 = ep.out2 != nullptr;
   g.dbg = d.dbg;
+  static const int stage_vecs = [] { const char* e = getenv("V4H_GEMM_STAGE_VECS"); return (e && e[0] == '0') ? 0 : 1; }();
+  g.stage_vecs = stage_vecs;
   static const int dbg_skip = [] { const char* e = getenv("V4H_GEMM_DBG_SKIP"); return e ? atoi(e) : 0; }();
   g.dbg_skip = dbg_skip;
   static const int gate_res_tma_store = [] { const char* e = getenv("V4H_GEMM_GATE_TMA_STORE"); return (e && e[0] == '0') ? 0 : 1; }();

@@ -111,6 +111,11 @@ int ema_update(const v4h_adamw_job* jobs_dev, int njobs, int64_t max_n, float de
                const int* num_updates_dev, cudaStream_t s);
 int counter_increment(int* counter, cudaStream_t s);
 
+// postprocess.cu: reverse transform chain of the CaloChallenge ds2 / ds3 shape model, one fused pass
+int postprocess_showers(const float* x, const float* cond, int64_t n, int voxels, int n_layers, const int32_t* bounds_dev,
+                        float mean, float std, float delta, float cut, float factor, float e_min, float e_max, float alpha,
+                        float eps, float norm_cut, float* out, float* e_out, cudaStream_t s);
+
 // patchify.cu:  dst[b, j] = src[b, table[j]] staged through shared memory per chunk
 int patch_permute(const float* src, float* dst, const int32_t* table, const int32_t* chunk_bounds,
                   int num_chunks, int max_chunk, int64_t B, int per_sample, cudaStream_t s);

@@ -1,0 +1,120 @@
+// Post-processing of sampled showers on the GPU: the REVERSE pass of the
+// CaloChallenge ds2 / ds3 shape-model transform chain (reference configs/calochallenge/cfm/calochallenge_ds2.yaml:15-28,
+// applied back to front by experiments/calochallenge/experiment.py:286-289):
+//   Reshape, AddFeaturesToCond, ScaleEnergy, LogEnergy, GlobalStandardizeFromFile, ExclusiveLogitTransform(rescale),
+//   CutValues, ScaleTotalEnergy, NormalizeByElayer        (reference experiments/calochallenge/transforms.py)
+// The reference runs these as ~10 elementwise passes plus two 45-iteration Python loops on the CPU after
+// `.cpu()`; here one CTA per shower does all of it in two sweeps over the voxels (first sweep: per-layer sums of
+// the un-standardised, un-logited, cut voxels; second: the same values normalised per layer and scaled by the
+// layer energies that the u-recursion of NormalizeByElayer gives).  HBM-bound: 4 B read twice (the second read
+// hits L2) + 4 B written per voxel.
+#include "kernels.cuh"
+
+namespace v4h {
+
+namespace {
+
+constexpr int PP_THREADS = 256;
+constexpr int PP_MAX_LAYERS = 128;
+
+struct PostArgs {
+  const float* x;     // (n, voxels) sampled showers in the network's normalised space
+  const float* cond;  // (n, n_layers + 1): the n_layers u features, then the scaled log incident energy
+  int n, voxels, n_layers;
+  const int* bounds;  // (n_layers + 1) voxel offsets of the layers (device)
+  float mean, std;    // GlobalStandardizeFromFile
+  float delta, one_minus_2delta;  // ExclusiveLogitTransform(rescale=True)
+  float cut;          // CutValues (voxels only)
+  float factor;       // ScaleTotalEnergy (u_0 only)
+  float e_scale, e_min, alpha;  // ScaleEnergy (e_max - e_min, e_min), LogEnergy
+  float eps, norm_cut;          // NormalizeByElayer
+  float* out;         // (n, voxels) energies per voxel
+  float* e_out;       // (n) incident energies
+};
+
+// GlobalStandardize rev -> ExclusiveLogit rev: sigmoid(v * std + mean), rescaled from [delta, 1 - delta] to [0, 1].
+// Separate multiply / add and a true division, like the reference's tensor ops (no fused multiply-add).
+__device__ __forceinline__ float unlogit(float v, const PostArgs& a) {
+  const float t = __fadd_rn(__fmul_rn(v, a.std), a.mean);
+  const float z = 1.f / (1.f + expf(-t));
+  return __fdiv_rn(__fsub_rn(z, a.delta), a.one_minus_2delta);
+}
+__device__ __forceinline__ float voxel_value(float v, const PostArgs& a) {
+  const float z = unlogit(v, a);
+  return (a.cut != 0.f && z <= a.cut) ? 0.f : z;  // CutValues rev (skipped entirely when cut == 0)
+}
+
+__global__ void __launch_bounds__(PP_THREADS) postprocess_kernel(PostArgs a) {
+  pdl_wait();
+  __shared__ float lsum[PP_MAX_LAYERS];
+  __shared__ float layer_e[PP_MAX_LAYERS];
+  __shared__ float us[PP_MAX_LAYERS];
+  __shared__ int lb[PP_MAX_LAYERS + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = PP_THREADS / 32;
+  for (int i = threadIdx.x; i <= a.n_layers; i += PP_THREADS) lb[i] = a.bounds[i];
+  __syncthreads();
+  for (int s = blockIdx.x; s < a.n; s += gridDim.x) {
+    const float* x = a.x + (size_t)s * a.voxels;
+    const float* c = a.cond + (size_t)s * (a.n_layers + 1);
+    // u features: same standardisation / logit chain (they carry `u_transform`), then ScaleTotalEnergy rev on
+    // u_0 and the clip of NormalizeByElayer rev on u_{i>0}
+    for (int i = threadIdx.x; i < a.n_layers; i += PP_THREADS) {
+      float u = unlogit(c[i], a);
+      if (i == 0) u = __fdiv_rn(u, a.factor);
+      else u = fminf(fmaxf(u, 0.f), 1.f);
+      us[i] = u;
+    }
+    // sweep 1: layer sums, one warp per layer
+    for (int l = warp; l < a.n_layers; l += nwarps) {
+      float acc = 0.f;
+      for (int v = lb[l] + lane; v < lb[l + 1]; v += 32) acc += voxel_value(x[v], a);
+      acc = warp_sum(acc);
+      if (lane == 0) lsum[l] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      // ScaleEnergy rev, LogEnergy rev; then the layer energies from the u's (reference transforms.py:363-371)
+      const float e_inc = __fsub_rn(expf(__fadd_rn(__fmul_rn(c[a.n_layers], a.e_scale), a.e_min)), a.alpha);
+      a.e_out[s] = e_inc;
+      const float total = __fmul_rn(e_inc, us[0]);
+      float cum = 0.f;
+      for (int i = 0; i + 1 < a.n_layers; ++i) {
+        const float le = __fmul_rn(__fsub_rn(total, cum), us[i + 1]);
+        layer_e[i] = le;
+        cum = __fadd_rn(cum, le);
+      }
+      layer_e[a.n_layers - 1] = __fsub_rn(total, cum);
+    }
+    __syncthreads();
+    // sweep 2: normalise each layer to unit sum, apply the normalised cut, scale to the layer energy
+    float* out = a.out + (size_t)s * a.voxels;
+    for (int l = warp; l < a.n_layers; l += nwarps) {
+      const float denom = __fadd_rn(lsum[l], a.eps), le = layer_e[l];
+      for (int v = lb[l] + lane; v < lb[l + 1]; v += 32) {
+        float z = __fdiv_rn(voxel_value(x[v], a), denom);
+        if (z <= a.norm_cut) z = 0.f;
+        out[v] = __fmul_rn(z, le);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+int postprocess_showers(const float* x, const float* cond, int64_t n, int voxels, int n_layers, const int32_t* bounds_dev,
+                        float mean, float std, float delta, float cut, float factor, float e_min, float e_max, float alpha,
+                        float eps, float norm_cut, float* out, float* e_out, cudaStream_t s) {
+  V4H_REQUIRE(n_layers >= 1 && n_layers <= PP_MAX_LAYERS, "postprocess: 1 <= n_layers <= %d", PP_MAX_LAYERS);
+  PostArgs a;
+  a.x = x; a.cond = cond; a.n = (int)n; a.voxels = voxels; a.n_layers = n_layers; a.bounds = bounds_dev;
+  a.mean = mean; a.std = std; a.delta = delta; a.one_minus_2delta = (float)(1.0 - 2.0 * (double)delta);
+  a.cut = cut; a.factor = factor; a.e_scale = (float)((double)e_max - (double)e_min); a.e_min = e_min; a.alpha = alpha;
+  a.eps = eps; a.norm_cut = norm_cut; a.out = out; a.e_out = e_out;
+  const int64_t grid = n < 148 * 8 ? n : 148 * 8;
+  V4H_CUDA(launch_pdl(postprocess_kernel, dim3((unsigned)grid), dim3(PP_THREADS), 0, s, a));
+  V4H_LAUNCH_CHECK();
+  return V4H_OK;
+}
+
+}  // namespace v4h
