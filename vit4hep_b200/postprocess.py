@@ -82,9 +82,12 @@ class FusedReverseTransforms:
         if samples.dtype != torch.float32 or conditions.dtype != torch.float32:
             raise TypeError("samples and conditions must be float32")
         N = samples.shape[0]
-        x = samples.reshape(N, -1).contiguous()
         c = conditions.contiguous()
-        if x.shape[1] != self.voxels or tuple(c.shape) != (N, self.n_layers + 1):
+        per_sample = 1
+        for d in samples.shape[1:]:
+            per_sample *= int(d)
+        x = samples.reshape(N, per_sample).contiguous()
+        if per_sample != self.voxels or tuple(c.shape) != (N, self.n_layers + 1):
             raise ValueError(f"expected samples with {self.voxels} voxels and conditions (N, {self.n_layers + 1}), got "
                              f"{tuple(samples.shape)} and {tuple(conditions.shape)}")
         dev = x.device
