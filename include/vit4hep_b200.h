@@ -216,6 +216,63 @@ int v4h_axpy4(float* out, const float* y, const float* k0, float a0, const float
               const float* k2, float a2, const float* k3, float a3, int64_t n, v4h_stream_t s);
 
 /* ------------------------------------------------------------------------------------
+ * Energy-ratio velocity network, forward only (reference nn/cfm/transformer_cfm.py:12-119 ParallelTransformer with
+ * embeds = True around torch.nn.Transformer; sampled before every shape-sampling job, reference
+ * experiments/calochallenge/experiment.py:225-247).  Parameters stay in the caller's nn.Module with the
+ * reference's state_dict names; the structs carry their device addresses (all fp32).
+ * ------------------------------------------------------------------------------------ */
+#define V4H_ENERGY_MAX_LAYERS 16
+typedef struct {
+  int32_t dims_in;        /* tokens of x (45 energy ratios) */
+  int32_t dims_c;         /* tokens of the condition (1; 3 for LEMURS), <= 16 */
+  int32_t dim_embedding;  /* x embedding width; d_model = encode_t_dim + dim_embedding */
+  int32_t encode_t_dim;   /* time embedding width (64) */
+  int32_t nhead;
+  int32_t n_enc, n_dec;   /* num_encoder_layers, num_decoder_layers */
+  int32_t dim_feedforward;
+  int32_t precision;      /* V4H_FP32 | V4H_BF16 */
+} v4h_energy_dims;
+typedef struct {  /* transformer.encoder.layers.i */
+  float *in_w, *in_b, *out_w, *out_b;      /* self_attn.in_proj_{weight,bias} (3E, E), self_attn.out_proj (E, E) */
+  float *l1_w, *l1_b, *l2_w, *l2_b;        /* linear1 (F, E), linear2 (E, F) */
+  float *n1_w, *n1_b, *n2_w, *n2_b;        /* norm1, norm2 (E) */
+} v4h_energy_enc_layer;
+typedef struct {  /* transformer.decoder.layers.i */
+  float *sa_in_w, *sa_in_b, *sa_out_w, *sa_out_b;  /* self_attn */
+  float *ca_in_w, *ca_in_b, *ca_out_w, *ca_out_b;  /* multihead_attn (cross attention over the encoded condition) */
+  float *l1_w, *l1_b, *l2_w, *l2_b;
+  float *n1_w, *n1_b, *n2_w, *n2_b, *n3_w, *n3_b;
+} v4h_energy_dec_layer;
+typedef struct {
+  float *gfp_w;                       /* time_embed.0.W (encode_t_dim / 2) */
+  float *time_w, *time_b;             /* time_embed.1 (Dt, Dt) */
+  float *x_embed_w, *x_embed_b;       /* x_embed (De, 1) */
+  float *c_embed_w, *c_embed_b;       /* c_embed (E, 1) */
+  float *pos_x, *pos_c;               /* pos_embed_x.weight (dims_in, De), pos_embed_c.weight (dims_c, E) */
+  float *enc_norm_w, *enc_norm_b;     /* transformer.encoder.norm */
+  float *dec_norm_w, *dec_norm_b;     /* transformer.decoder.norm */
+  float *head0_w, *head0_b;           /* layers.0 (= layer) (F, Dt + E) */
+  float *head2_w, *head2_b;           /* layers.2 (1, F) */
+  v4h_energy_enc_layer enc[V4H_ENERGY_MAX_LAYERS];
+  v4h_energy_dec_layer dec[V4H_ENERGY_MAX_LAYERS];
+} v4h_energy_params;
+typedef struct v4h_energy_plan v4h_energy_plan;
+
+int v4h_energy_plan_create(const v4h_energy_dims* dims, v4h_energy_plan** out);
+void v4h_energy_plan_destroy(v4h_energy_plan* p);
+size_t v4h_energy_workspace_bytes(const v4h_energy_plan* p, int64_t batch);
+size_t v4h_energy_weight_arena_bytes(const v4h_energy_plan* p); /* bf16 operand copies; 0 in fp32 precision */
+int v4h_energy_prepare_weights(v4h_energy_plan* p, const v4h_energy_params* w, void* arena, v4h_stream_t s);
+/* condition side, once per batch: c (B, dims_c) -> encoder memory and the cross-attention K / V of every decoder
+ * layer, kept in `workspace` for the v4h_energy_forward calls that follow (same workspace, same batch) */
+int v4h_energy_encode(v4h_energy_plan* p, const v4h_energy_params* w, const void* arena, const float* c, int64_t batch,
+                      void* workspace, size_t workspace_bytes, v4h_stream_t s);
+/* one velocity evaluation: x (B, dims_in), t (B) [one value when shared_t] -> out (B, dims_in) */
+int v4h_energy_forward(v4h_energy_plan* p, const v4h_energy_params* w, const void* arena, const float* x, const float* t,
+                       int32_t shared_t, float* out, int64_t batch, void* workspace, size_t workspace_bytes,
+                       v4h_stream_t s);
+
+/* ------------------------------------------------------------------------------------
  * Post-processing of sampled showers (reference experiments/calochallenge/experiment.py:286-289: the transforms of
  * configs/calochallenge/cfm/calochallenge_ds2.yaml:15-28 applied in reverse; classes in
  * experiments/calochallenge/transforms.py): Reshape, AddFeaturesToCond, ScaleEnergy(e_min, e_max), LogEnergy(alpha),

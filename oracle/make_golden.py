@@ -233,6 +233,42 @@ def golden_postprocess():
     print("postprocess golden: showers", tuple(x.shape), "nonzero frac", float((x > 0).float().mean()))
 
 
+def golden_energy():
+    """The reference's ParallelTransformer (nn/cfm/transformer_cfm.py) at a small size, dims_c = 1 and 3: velocity
+    for per-sample times, and a CFM.sample_batch solve of the base class (models/base_model.py:220-244)."""
+    import importlib
+    tc = importlib.import_module("nn.cfm.transformer_cfm")
+    bm = importlib.import_module("models.base_model")
+    for dims_c in (1, 3):
+        param = dict(dims_in=7, dims_c=dims_c, dim_embedding=16, encode_t_dim=16, nhead=2, num_encoder_layers=2,
+                     num_decoder_layers=2, dim_feedforward=64, dropout=0.0, activation="relu", embeds=True,
+                     encode_t_scale=30)
+        torch.manual_seed(3)
+        net = tc.ParallelTransformer(param)
+        with torch.no_grad():  # LayerNorm affine / biases away from their 1 / 0 initial values
+            for name, p in net.named_parameters():
+                if p.requires_grad and ("norm" in name or name.endswith("bias")):
+                    p.add_(0.1 * torch.randn_like(p))
+        model = bm.CFM(net, "uniform", "linear", dict(method="rk4", options=dict(step_size=0.05)), shape=[7])
+        model.device, model.dtype = torch.device("cpu"), torch.float32
+        g = torch.Generator().manual_seed(17)
+        B = 5
+        x = torch.randn(B, 7, generator=g); t = torch.rand(B, 1, generator=g); c = torch.rand(B, dims_c, generator=g)
+        out = {"sd/" + k: v.detach().numpy() for k, v in net.state_dict().items()}
+        with torch.no_grad():
+            out["velocity"] = net(x, t, c).numpy()
+        torch.manual_seed(99)
+        x_T = torch.randn((B, 7))
+        torch.manual_seed(99)
+        sample = model.sample_batch(c)
+        out.update(x=x.numpy(), t=t.numpy(), c=c.numpy(), x_T=x_T.numpy(), sample=sample.numpy())
+        out["meta"] = np.asarray([param[k] for k in ("dims_in", "dims_c", "dim_embedding", "encode_t_dim", "nhead",
+                                                      "num_encoder_layers", "num_decoder_layers", "dim_feedforward")],
+                                 dtype=np.int32)
+        np.savez_compressed(os.path.join(OUT, f"energy_tiny_c{dims_c}.npz"), **out)
+        print("energy_tiny", dims_c, "velocity rms", float(np.sqrt((out["velocity"] ** 2).mean())))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_stubs.load_reference()
@@ -245,6 +281,7 @@ def main():
     golden_finetune(ref)
     golden_fixed_pos_embed(ref)
     golden_postprocess()
+    golden_energy()
 
 
 if __name__ == "__main__":

@@ -8,5 +8,7 @@ from .cfm import (CFM, CaloChallengeCFM, CaloChallengeCFM_DS1, CaloGANCFM, CaloH
                   GraphedTrainStep, PatchGeometry)
 
 from .optim import ExponentialMovingAverage, FusedAdamW  # noqa: F401
+from .energy import ParallelTransformer  # noqa: F401
+from .postprocess import FusedReverseTransforms  # noqa: F401
 
 __version__ = "0.1.0"

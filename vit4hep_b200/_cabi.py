@@ -36,6 +36,32 @@ class VitParams(C.Structure):
         "final_w", "final_b", "final_ada_w", "final_ada_b", "xm_w", "xm_b", "cm_w", "cm_b")] + [("blocks", BlockParams * V4H_MAX_DEPTH)]
 
 
+V4H_ENERGY_MAX_LAYERS = 16
+
+
+class EnergyDims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "dims_in", "dims_c", "dim_embedding", "encode_t_dim", "nhead", "n_enc", "n_dec", "dim_feedforward", "precision")]
+
+
+class EnergyEncLayer(C.Structure):
+    _fields_ = [(n, _f32p) for n in (
+        "in_w", "in_b", "out_w", "out_b", "l1_w", "l1_b", "l2_w", "l2_b", "n1_w", "n1_b", "n2_w", "n2_b")]
+
+
+class EnergyDecLayer(C.Structure):
+    _fields_ = [(n, _f32p) for n in (
+        "sa_in_w", "sa_in_b", "sa_out_w", "sa_out_b", "ca_in_w", "ca_in_b", "ca_out_w", "ca_out_b",
+        "l1_w", "l1_b", "l2_w", "l2_b", "n1_w", "n1_b", "n2_w", "n2_b", "n3_w", "n3_b")]
+
+
+class EnergyParams(C.Structure):
+    _fields_ = [(n, _f32p) for n in (
+        "gfp_w", "time_w", "time_b", "x_embed_w", "x_embed_b", "c_embed_w", "c_embed_b", "pos_x", "pos_c",
+        "enc_norm_w", "enc_norm_b", "dec_norm_w", "dec_norm_b", "head0_w", "head0_b", "head2_w", "head2_b")] + [
+        ("enc", EnergyEncLayer * V4H_ENERGY_MAX_LAYERS), ("dec", EnergyDecLayer * V4H_ENERGY_MAX_LAYERS)]
+
+
 class AdamWJob(C.Structure):
     _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("bf16_dst", C.c_void_p),
                 ("f32_dst", C.c_void_p), ("ema", C.c_void_p), ("n", C.c_int64)]
@@ -72,6 +98,13 @@ SIGNATURES = {
     "v4h_cfm_prepare": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "v4h_cfm_loss": (C.c_int, [_vp, _vp, _i64, _fl, _vp, _vp, _vp]),
     "v4h_axpy4": (C.c_int, [_vp, _vp, _vp, _fl, _vp, _fl, _vp, _fl, _vp, _fl, _i64, _vp]),
+    "v4h_energy_plan_create": (C.c_int, [C.POINTER(EnergyDims), C.POINTER(_vp)]),
+    "v4h_energy_plan_destroy": (None, [_vp]),
+    "v4h_energy_workspace_bytes": (_sz, [_vp, _i64]),
+    "v4h_energy_weight_arena_bytes": (_sz, [_vp]),
+    "v4h_energy_prepare_weights": (C.c_int, [_vp, C.POINTER(EnergyParams), _vp, _vp]),
+    "v4h_energy_encode": (C.c_int, [_vp, C.POINTER(EnergyParams), _vp, _vp, _i64, _vp, _sz, _vp]),
+    "v4h_energy_forward": (C.c_int, [_vp, C.POINTER(EnergyParams), _vp, _vp, _vp, _i32, _vp, _i64, _vp, _sz, _vp]),
     "v4h_postprocess_showers": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _fl, _fl, _fl, _fl, _fl, _fl, _fl, _fl, _fl,
                                           _fl, _vp, _vp, _vp]),
     "v4h_grad_norm_sq": (C.c_int, [_vp, _i64, _vp, _vp]),

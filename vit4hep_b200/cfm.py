@@ -234,21 +234,22 @@ class CFM(nn.Module):
         raise NotImplementedError
 
     # -- geometry ----------------------------------------------------------------------
-    def _make_geometry(self) -> PatchGeometry:
-        """Base CFM: the sample already is (T, P) tokens (reference CFM.forward calls net directly)."""
-        raise NotImplementedError
+    def _make_geometry(self) -> Optional[PatchGeometry]:
+        """Base CFM: no patch geometry, the network takes the sample as it is (reference CFM.forward calls the net
+        directly, models/base_model.py:199-201; used with the energy-ratio network, shape [45])."""
+        return None
 
     @property
-    def geometry(self) -> PatchGeometry:
+    def geometry(self) -> Optional[PatchGeometry]:
         if self._geometry is None:
             self._geometry = self._make_geometry()
         return self._geometry
 
     def to_patches(self, x):
-        return _Permute.apply(self.geometry, x, True)
+        return x if self.geometry is None else _Permute.apply(self.geometry, x, True)
 
     def from_patches(self, x):
-        return _Permute.apply(self.geometry, x, False)
+        return x if self.geometry is None else _Permute.apply(self.geometry, x, False)
 
     def _net(self):
         """the ViT itself when `net` was wrapped (e.g. by DistributedDataParallel)"""
@@ -278,6 +279,9 @@ class CFM(nn.Module):
             t = self.time_distribution.sample([x.shape[0]] + [1] * (x.dim() - 1))
             t = t.to(device, dtype, non_blocking=True)
         x_0 = torch.randn_like(x)
+        if self.geometry is None:
+            raise NotImplementedError("CFM._batch_loss without a patch geometry (the energy-ratio network) is not "
+                                      "implemented: vit4hep_b200.ParallelTransformer is forward-only")
         x_t, target = self.geometry.cfm_prepare(x, x_0, t.view(-1))
         velocity = self.net(x_t, t.view(-1, 1), c)
         return _MSELoss.apply(velocity, target)
@@ -351,7 +355,13 @@ class CFM(nn.Module):
         geom = self.geometry
         lib = _cabi.load()
         net = self._net()
-        y = geom.to_patches(x_T)
+        _require_cuda_f32("x_T", x_T)
+        # a network that caches work depending only on the condition (the energy network's encoder) starts afresh
+        # with every solve, so that a captured solve contains that work and never reuses another batch's
+        new_condition = getattr(net, "new_condition", None)
+        if new_condition is not None:
+            new_condition()
+        y = x_T.contiguous().clone() if geom is None else geom.to_patches(x_T)
         n = y.numel()
         stage_y = torch.empty_like(y)
         s = _stream(y.device)
@@ -379,7 +389,7 @@ class CFM(nn.Module):
                     ks.append(net(src, t_dev[i:i + 1], cond, shared_t=True))
                     i += 1
                 axpy(y, y, ks, [dt * b for b in scheme["final"]])
-        return geom.from_patches(y)
+        return y if geom is None else geom.from_patches(y)
 
 
 class GraphedTrainStep:

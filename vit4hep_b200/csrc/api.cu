@@ -69,6 +69,17 @@ void profile_close(int slot, cudaStream_t s) {
   if (slot >= 0 && slot < (int)p.records.size()) record_scope_event(p.records[slot].e1, s);
 }
 
+struct EnergyPlan;
+int energy_plan_create(const v4h_energy_dims* dims, EnergyPlan** out);
+void energy_plan_destroy(EnergyPlan* p);
+size_t energy_workspace_bytes(const EnergyPlan* p, int64_t B);
+size_t energy_arena_bytes(const EnergyPlan* p);
+int energy_prepare_weights(EnergyPlan* p, const v4h_energy_params* w, void* arena, cudaStream_t s);
+int energy_encode(EnergyPlan* p, const v4h_energy_params* w, const void* arena, const float* c, int64_t B, void* workspace,
+                  size_t workspace_bytes, cudaStream_t s);
+int energy_forward(EnergyPlan* p, const v4h_energy_params* w, const void* arena, const float* x, const float* t, bool shared_t,
+                   float* out, int64_t B, void* workspace, size_t workspace_bytes, cudaStream_t s);
+
 struct Plan;
 int plan_create(const v4h_vit_dims* dims, Plan** out);
 void plan_destroy(Plan* p);
@@ -283,6 +294,28 @@ int v4h_axpy4(float* out, const float* y, const float* k0, float a0, const float
               float a2, const float* k3, float a3, int64_t n, v4h_stream_t s) {
   V4H_REQUIRE(out && y && n > 0, "axpy4: bad arguments");
   return axpy4(out, y, k0, a0, k1, a1, k2, a2, k3, a3, n, (cudaStream_t)s);
+}
+
+// ------------------------------------------------------------------------------------ energy network
+int v4h_energy_plan_create(const v4h_energy_dims* dims, v4h_energy_plan** out) {
+  return energy_plan_create(dims, reinterpret_cast<EnergyPlan**>(out));
+}
+void v4h_energy_plan_destroy(v4h_energy_plan* p) { energy_plan_destroy(reinterpret_cast<EnergyPlan*>(p)); }
+size_t v4h_energy_workspace_bytes(const v4h_energy_plan* p, int64_t batch) {
+  return energy_workspace_bytes(reinterpret_cast<const EnergyPlan*>(p), batch);
+}
+size_t v4h_energy_weight_arena_bytes(const v4h_energy_plan* p) { return energy_arena_bytes(reinterpret_cast<const EnergyPlan*>(p)); }
+int v4h_energy_prepare_weights(v4h_energy_plan* p, const v4h_energy_params* w, void* arena, v4h_stream_t s) {
+  return energy_prepare_weights(reinterpret_cast<EnergyPlan*>(p), w, arena, (cudaStream_t)s);
+}
+int v4h_energy_encode(v4h_energy_plan* p, const v4h_energy_params* w, const void* arena, const float* c, int64_t batch,
+                      void* workspace, size_t workspace_bytes, v4h_stream_t s) {
+  return energy_encode(reinterpret_cast<EnergyPlan*>(p), w, arena, c, batch, workspace, workspace_bytes, (cudaStream_t)s);
+}
+int v4h_energy_forward(v4h_energy_plan* p, const v4h_energy_params* w, const void* arena, const float* x, const float* t,
+                       int32_t shared_t, float* out, int64_t batch, void* workspace, size_t workspace_bytes, v4h_stream_t s) {
+  return energy_forward(reinterpret_cast<EnergyPlan*>(p), w, arena, x, t, shared_t != 0, out, batch, workspace,
+                        workspace_bytes, (cudaStream_t)s);
 }
 
 // ------------------------------------------------------------------------------------ post-processing

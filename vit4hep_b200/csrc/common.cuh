@@ -113,7 +113,7 @@ template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __flo
 // ---------------------------------------------------------------- activations
 // ACT_GELU_TANH_FAST: same function with the hardware tanh.approx (abs. error ~5e-4, below bf16
 // resolution); used by the bf16 tensor-core epilogues only
-enum Act { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU_TANH = 2, ACT_GELU_TANH_FAST = 3 };
+enum Act { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU_TANH = 2, ACT_GELU_TANH_FAST = 3, ACT_RELU = 4 };
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -159,12 +159,14 @@ template <int ACT> __device__ __forceinline__ float act_f(float x) {
   if (ACT == ACT_GELU_TANH_FAST) return gelu_tanh_fast_f(x);
   if (ACT == ACT_SILU) return silu_f(x);
   if (ACT == ACT_GELU_TANH) return gelu_tanh_f(x);
+  if (ACT == ACT_RELU) return fmaxf(x, 0.f);
   return x;
 }
 template <int ACT> __device__ __forceinline__ float dact_f(float x) {
   if (ACT == ACT_GELU_TANH_FAST) return dgelu_tanh_fast_f(x);
   if (ACT == ACT_SILU) return dsilu_f(x);
   if (ACT == ACT_GELU_TANH) return dgelu_tanh_f(x);
+  if (ACT == ACT_RELU) return x > 0.f ? 1.f : 0.f;
   return 1.f;
 }
 

@@ -122,6 +122,7 @@ int dispatch_epi(const GemmDesc& d, cudaStream_t s) {
     case EPI_BIAS_ACT:
       if (d.act == ACT_NONE) return launch<TA, TB, EPI_BIAS_ACT, ACT_NONE, TOut>(d, s);
       if (d.act == ACT_SILU) return launch<TA, TB, EPI_BIAS_ACT, ACT_SILU, TOut>(d, s);
+      if (d.act == ACT_RELU) return launch<TA, TB, EPI_BIAS_ACT, ACT_RELU, TOut>(d, s);
       return launch<TA, TB, EPI_BIAS_ACT, ACT_GELU_TANH, TOut>(d, s);
     case EPI_GATE_RES:
       return launch<TA, TB, EPI_GATE_RES, ACT_NONE, TOut>(d, s);

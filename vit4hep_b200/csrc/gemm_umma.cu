@@ -1044,6 +1044,7 @@ int gemm_umma(UmmaContext* ctx, const GemmDesc& d, cudaStream_t s) {
       if (d.act == ACT_SILU)
         return obf ? launch2<EPI_BIAS_ACT, ACT_SILU, bf16>(slab, m, g, ep, ctas, grid, s)
                    : launch2<EPI_BIAS_ACT, ACT_SILU, float>(slab, m, g, ep, ctas, grid, s);
+      if (d.act == ACT_RELU && obf) return launch2<EPI_BIAS_ACT, ACT_RELU, bf16>(slab, m, g, ep, ctas, grid, s);
       break;
     case EPI_GATE_RES:
       if (obf) return launch2<EPI_GATE_RES, ACT_NONE, bf16>(slab, m, g, ep, ctas, grid, s);
