@@ -533,6 +533,31 @@ def measure_sampling(args, model, K, world, rank, dev, timed, peaks, lib):
     kernels, roofline = family_roofline(prof, 3, peaks, "gemm_umma_kernel_sampling")
     if roofline is not None:
         roofline["timing"] = "CUDA events around eager launches of 3 network evaluations at the sampling batch"
+    # the energy-ratio CFM that the reference samples for the same conditions right before the shape model
+    # (experiments/calochallenge/experiment.py:225-247): same sharding, its own line
+    energy = None
+    try:
+        from vit4hep_b200 import configs
+        torch.manual_seed(1)
+        em = configs.build(args.config + "_energy", args.precision).to(dev)
+        with torch.no_grad():
+            for p in em.net.parameters():
+                if p.requires_grad and p.dim() == 1:
+                    p.add_(0.05 * torch.randn_like(p))
+        em.graph_sampling = not args.no_graph
+        econd = conds[:, -1:].contiguous()
+        em.sample_batch(econd[:SB])
+        b, e = dp.shard_range(total, rank, world)
+        if (e - b) % SB:
+            em.sample_batch(econd[: (e - b) % SB])
+        ms_en, _ = timed(lambda i: dp.sample_sharded(em, econd, SB, gather=False), 1)
+        energy = {"metric": f"{args.config} energy-ratio CFM ODE-sampled vectors/s", "value": total / (ms_en * 1e-3),
+                  "unit": "showers/s", "ms_total": ms_en, "batch": SB, "nfe_per_shower": 80,
+                  "share_of_pipeline": ms_en / (ms_en + ms)}
+        del em
+    except Exception as exc:  # secondary measurement: never take the main line down
+        energy = {"error": repr(exc)[:200]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, per_ms, threads = cpu_showers_per_s(args.config, 64, 3)
@@ -554,7 +579,7 @@ def measure_sampling(args, model, K, world, rank, dev, timed, peaks, lib):
             "eager_showers_per_s": world * SB * nb_eager / (ms_eager * 1e-3), "gpu_launches_per_batch": launches // nb_eager,
             "model_tflops_per_gpu": showers * gf / 1e3 / world,
             "frac_of_peak": showers * gf / 1e3 / world / peaks["tflops_sustained"],
-            "roofline": roofline, "kernels": kernels[:12], "cpu_baseline": cpu}
+            "roofline": roofline, "kernels": kernels[:12], "energy_model": energy, "cpu_baseline": cpu}
 
 
 def main():

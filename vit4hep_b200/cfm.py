@@ -17,6 +17,7 @@ seeds give identical ``t``, ``x_0`` and ``x_T``.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import math
 from typing import List, Optional, Sequence
@@ -356,11 +357,6 @@ class CFM(nn.Module):
         lib = _cabi.load()
         net = self._net()
         _require_cuda_f32("x_T", x_T)
-        # a network that caches work depending only on the condition (the energy network's encoder) starts afresh
-        # with every solve, so that a captured solve contains that work and never reuses another batch's
-        new_condition = getattr(net, "new_condition", None)
-        if new_condition is not None:
-            new_condition()
         y = x_T.contiguous().clone() if geom is None else geom.to_patches(x_T)
         n = y.numel()
         stage_y = torch.empty_like(y)
@@ -374,7 +370,10 @@ class CFM(nn.Module):
                                       ptrs[3], cf[3], n, s))
 
         i = 0
-        with torch.cuda.device(y.device):
+        # a network whose condition side is independent of (x, t) (the energy network's encoder) computes it once
+        # per solve inside this scope -- also inside a captured solve, whose replays then re-encode new conditions
+        scope = getattr(net, "condition_scope", None)
+        with torch.cuda.device(y.device), (scope() if scope is not None else contextlib.nullcontext()):
             for step, (ta, tb) in enumerate(zip(grid[:-1], grid[1:])):
                 if max_steps is not None and step >= max_steps:
                     break

@@ -114,6 +114,15 @@ MODELS: Dict[str, dict] = {
 }
 
 
+_ENERGY = dict(dims_in=45, dims_c=1, dim_embedding=64, nhead=4, num_encoder_layers=4, num_decoder_layers=4,
+               dim_feedforward=512, dropout=0.0, activation="relu", embeds=True, encode_t_scale=30)
+# reference configs/model/cfm/cfm_ds2_energy.yaml (cfm_ds3_energy.yaml is identical): the energy-ratio CFM that is
+# sampled before the shape model
+MODELS["ds2_energy"] = dict(_target_="vit4hep_b200.CFM", shape=[45], time_distribution="uniform", trajectory="linear",
+                            odeint_kwargs=_ODE, net=dict(_target_="vit4hep_b200.ParallelTransformer", param=dict(_ENERGY)))
+MODELS["ds3_energy"] = MODELS["ds2_energy"]
+
+
 def build(name: str, precision: str = "bf16", **param_overrides):
     """The named model (wrapper + net) with the shipped hyper-parameters; ``param_overrides`` update the ViT's
     ``param`` mapping (e.g. hidden_dim=96, depth=2 for a small instance)."""

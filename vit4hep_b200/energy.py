@@ -11,8 +11,8 @@ dicts are interchangeable) and raises.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
-import math
 import os
 
 import torch
@@ -76,6 +76,7 @@ class ParallelTransformer(nn.Module):
         self._arena_key = None
         self._ws = {}        # batch size -> persistent workspace (holds the encoded condition between evaluations)
         self._encoded = {}   # batch size -> (condition data_ptr, version) the workspace was encoded for
+        self._in_scope = False
 
     def __del__(self):
         try:
@@ -133,9 +134,19 @@ class ParallelTransformer(nn.Module):
         self._arena_key = None
         self._encoded.clear()
 
-    def new_condition(self) -> None:
-        """forget the cached condition encoding (called by CFM at the start of every ODE solve)"""
+    @contextlib.contextmanager
+    def condition_scope(self):
+        """Inside this scope (CFM wraps every ODE solve in it) the condition side -- c_embed, the encoder and the
+        cross-attention K / V of every decoder layer -- is computed once per condition tensor and reused by the
+        evaluations that follow; outside it every forward encodes its condition (a tensor's address and version are
+        not a safe cache key across allocations)."""
         self._encoded.clear()
+        self._in_scope = True
+        try:
+            yield self
+        finally:
+            self._in_scope = False
+            self._encoded.clear()
 
     def _prepare(self, dev, w, stream):
         lib = _cabi.load()
@@ -189,7 +200,7 @@ class ParallelTransformer(nn.Module):
             # the condition side only depends on the condition: encode once per condition batch (the 80 evaluations of
             # an ODE solve pass the same tensor), again when it changes
             ckey = (condition.data_ptr(), condition._version)
-            if self._encoded.get((B, dev)) != ckey:
+            if not self._in_scope or self._encoded.get((B, dev)) != ckey:
                 _cabi.check(lib.v4h_energy_encode(plan, ctypes.byref(w), arena, condition.data_ptr(), B, ws.data_ptr(),
                                                   ws.numel(), stream))
                 self._encoded[(B, dev)] = ckey
