@@ -238,6 +238,68 @@ def family_roofline(prof, psteps, peaks, traffic_key):
     return kernels, roofline
 
 
+def gemm_class_roofline(lib, dev, M, param, tokens, peaks, fam_eager):
+    """Per-call-site timing of the tcgen05 GEMM (v4h_debug_gemm launches the library's kernel with the epilogue of
+    the named call site): TFLOP/s per class and, weighted by launches per step, for the family."""
+    from vit4hep_b200 import _cabi
+    D, Hm, depth = param["hidden_dim"], int(param["hidden_dim"] * param["mlp_ratio"]), param["depth"]
+    bf = torch.bfloat16
+    s = torch.cuda.current_stream(dev).cuda_stream
+    # (class, kind of v4h_debug_gemm, m, n, k): forward, dgrad and wgrad GEMMs of one block
+    classes = [("gemm.qkv", 1, M, 3 * D, D), ("gemm.proj", 2, M, D, D), ("gemm.fc1", 0, M, Hm, D), ("gemm.fc2", 2, M, D, Hm),
+               ("dgrad.fc2", 3, M, Hm, D), ("dgrad.fc1", 4, M, D, Hm), ("dgrad.proj", 4, M, D, D), ("dgrad.qkv", 4, M, D, 3 * D),
+               ("wgrad.fc2", 5, D, Hm, M), ("wgrad.fc1", 5, Hm, D, M), ("wgrad.proj", 5, D, D, M), ("wgrad.qkv", 5, 3 * D, D, M)]
+    g = torch.Generator().manual_seed(0)
+    rows, tot_flops, tot_ms = [], 0.0, 0.0
+    for name, kind, m, n, k in classes:
+        A = (torch.randn((k, m) if kind == 5 else (m, k), generator=g) * 0.1).to(dev, bf)
+        Bm = (torch.randn((n, k) if kind <= 2 else (k, n), generator=g) * 0.1).to(dev, bf)
+        bias = torch.randn(n, generator=g).to(dev)
+        out = torch.zeros((m, n), device=dev, dtype=torch.float32 if kind == 5 else bf)
+        out2 = torch.zeros((m, n), device=dev, dtype=bf)
+        res_in = torch.randn(m, n, generator=g).to(dev) if kind == 2 else None
+        res_out = torch.empty(m, n, device=dev) if kind == 2 else None
+        gate = torch.randn((m + tokens - 1) // tokens, n, generator=g).to(dev) if kind == 2 else None
+        aux = torch.randn(m, n, generator=g).to(dev, bf) if kind == 3 else None
+        ptr = lambda t: None if t is None else t.data_ptr()
+
+        def call():
+            _cabi.check(lib.v4h_debug_gemm(kind, m, n, k, tokens, A.data_ptr(), Bm.data_ptr(), bias.data_ptr(), out.data_ptr(),
+                                           out2.data_ptr(), ptr(res_in), ptr(res_out), ptr(gate), ptr(aux), None, s))
+        for _ in range(3):
+            call()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters = 20
+        e0.record()
+        for _ in range(iters):
+            call()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        flops = 2.0 * m * n * k
+        rows.append({"class": name, "M": m, "N": n, "K": k, "us": ms * 1e3, "tflops": flops / (ms * 1e-3) / 1e12,
+                     "frac": flops / (ms * 1e-3) / 1e12 / peaks["tflops_sustained"], "launches_per_step": depth})
+        tot_flops += flops * depth
+        tot_ms += ms * depth
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh).get("gemm_umma_kernel", {}).get("dram_bytes_per_launch")
+    ach = tot_flops / (tot_ms * 1e-3) / 1e12
+    n_launch = depth * len(classes)
+    return {"kernel": "gemm_umma_kernel (tcgen05 GEMM: the 12 GEMM call sites of a transformer block, forward + dgrad + wgrad)",
+            "bound": "tensor", "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+            "frac": ach / peaks["tflops_sustained"], "traffic": traffic, "flops_per_launch": tot_flops / n_launch,
+            "avg_launch_ms": tot_ms / n_launch, "launches_per_step": n_launch,
+            "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
+            "timing": "20 back-to-back launches per call site between two CUDA events on the launching stream, operands "
+                      "L2-hot as in the step; weighted by launches per step",
+            "share_of_step_eager_brackets": None if fam_eager is None else fam_eager["share_of_step"],
+            "frac_eager_brackets": None if fam_eager is None else fam_eager["frac"],
+            "classes": rows}
+
+
 def run_b200(args):
     import torch.distributed as dist
     from vit4hep_b200 import FusedAdamW, GraphedTrainStep, _cabi, configs, dp
@@ -364,31 +426,23 @@ def run_b200(args):
     ms_e2e, _ = timed(step_e2e, S)
     e2e = world * B * S / (ms_e2e * 1e-3)
 
-    # per-kernel-class device time INSIDE a replayed graph of the same step: the library's profiling scopes record
-    # their events as event nodes of the capture (v4h_profile_*), so every class is timed on the device, inside the
-    # step, without the host submission gaps of eager launches.  The profiled capture serialises the kernels on one
-    # stream (no side streams / sub-batch lanes), which is what a per-kernel duration needs.
+    # per-kernel-class device time of one eager step (the library brackets every launch with two CUDA events on the
+    # launching stream; each bracket adds ~3 us, so these are upper bounds that show the SHARES of the step) ...
     peaks = measured_peaks()
-    kernels, roofline = [], None
-    if graphed is not None:
-        _cabi.profile_begin()
-        pg = GraphedTrainStep(model, opt, dev_x[0], dev_c[0], warmup=0)
-        for i in range(3):
-            pg.step(dev_x[i % npool], dev_c[i % npool])
-        torch.cuda.synchronize()
-        prof = _cabi.profile_end(128)
-        del pg
-        psteps = 1  # the events of the capture are re-recorded by every replay: the last replay is read
-    else:
-        _cabi.profile_begin()
-        psteps = min(S, 3)
-        for i in range(psteps):
-            train_step((dev_x[i % npool], dev_c[i % npool]), False)
-        prof = _cabi.profile_end(128)
-    kernels, roofline = family_roofline(prof, psteps, peaks, "gemm_umma_kernel")
-    if roofline is not None:
-        roofline["timing"] = ("CUDA events recorded as nodes of a replayed CUDA graph of the training step, kernels "
-                              "serialised on one stream" if graphed is not None else "CUDA events around eager launches")
+    _cabi.profile_begin()
+    psteps = min(S, 3)
+    for i in range(psteps):
+        train_step((dev_x[i % npool], dev_c[i % npool]), False)
+    prof = _cabi.profile_end(128)
+    kernels, fam_eager = family_roofline(prof, psteps, peaks, "gemm_umma_kernel")
+    # ... and the roofline of the dominant kernel, the tcgen05 GEMM: every GEMM call site of a transformer block is
+    # replayed with its exact shape and epilogue, 20 launches back to back between two CUDA events on the launching
+    # stream (no per-launch bracket, operands L2-hot as inside the step where the producing kernel has just written
+    # them), weighted by its launches per step
+    roofline = None
+    if args.precision == "bf16":
+        roofline = gemm_class_roofline(lib, dev, B * geom.tokens, configs.MODELS[args.config]["net"]["param"], geom.tokens,
+                                       peaks, fam_eager)
 
     # ---- strong scaling (the reference's semantics: global batch 64, batchsize // world_size per rank,
     # reference experiments/calochallenge/experiment.py:94-98)

@@ -199,7 +199,8 @@ class ParallelTransformer(nn.Module):
                 self._encoded.pop((B, dev), None)
             # the condition side only depends on the condition: encode once per condition batch (the 80 evaluations of
             # an ODE solve pass the same tensor), again when it changes
-            ckey = (condition.data_ptr(), condition._version)
+            # (inference tensors do not track a version; within a scope the condition of a solve is not rewritten)
+            ckey = (condition.data_ptr(), 0 if condition.is_inference() else condition._version)
             if not self._in_scope or self._encoded.get((B, dev)) != ckey:
                 _cabi.check(lib.v4h_energy_encode(plan, ctypes.byref(w), arena, condition.data_ptr(), B, ws.data_ptr(),
                                                   ws.numel(), stream))
