@@ -92,3 +92,42 @@ def test_attention_fwd_bwd(precision, engine, B, T, H, dh):
     assert vo.rel_l2(o, want) < tol
     assert vo.rel_l2(lse, torch.logsumexp(sc, -1)) < (1e-5 if not precision else 2e-3)
     assert vo.rel_l2(dqkv, ref.grad) < tol
+
+
+@pytest.mark.parametrize("m,n,k,T", [(8640, 480, 480, 135), (8640, 480, 1920, 135), (19000, 480, 480, 135),
+                                     (1000, 96, 96, 88), (300, 64, 200, 125), (540, 480, 480, 135), (4000, 224, 480, 450)])
+def test_gate_residual_gemm_with_layernorm_epilogue(m, n, k, T):
+    """csrc/gemm_umma.cu gemm_gate_res_ln against torch: a 2-CTA cluster splits the columns when the row tiles do not
+    fill the GPU (first shapes), one CTA owns whole rows otherwise (m = 19000); ragged m / k, several samples per tile."""
+    from vit4hep_b200 import _cabi
+    lib = _cabi.load()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(m + n + k)
+    bf = torch.bfloat16
+    nb = (m + T - 1) // T
+    A = (torch.randn(m, k, generator=g) * 0.5).to(dev, bf)
+    W = (torch.randn(n, k, generator=g) / k ** 0.5).to(dev, bf)
+    bias = torch.randn(n, generator=g).to(dev)
+    res = (torch.randn(m, n, generator=g) * 2 + 0.5).to(dev)
+    gate, shift, scale = (torch.randn(nb, n, generator=g).to(dev) * s for s in (1.0, 0.5, 0.3))
+    ld = n + 8
+    y = torch.zeros(m, n, device=dev, dtype=bf)
+    res_out = torch.zeros(m, n, device=dev)
+    ln = torch.full((m, ld), 7.0, device=dev, dtype=bf)
+    stats = torch.zeros(m, 2, device=dev)
+    _cabi.check(lib.v4h_debug_gemm_ln(m, n, k, T, A.data_ptr(), W.data_ptr(), bias.data_ptr(), y.data_ptr(), res.data_ptr(),
+                                      res_out.data_ptr(), gate.data_ptr(), shift.data_ptr(), scale.data_ptr(),
+                                      ln.data_ptr(), ld, stats.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    sample = torch.arange(m, device=dev) // T
+    want_y = A.double() @ W.double().T + bias.double()
+    want_h = res.double() + gate.double()[sample] * want_y
+    mu = want_h.mean(1, keepdim=True)
+    var = ((want_h - mu) ** 2).mean(1, keepdim=True)
+    want_ln = (want_h - mu) / torch.sqrt(var + 1e-6) * (1 + scale.double()[sample]) + shift.double()[sample]
+    assert vo.rel_l2(y, want_y) < 4e-3            # bf16 output rounding
+    assert vo.rel_l2(res_out, want_h) < 1e-5      # fp32 residual stream: tensor-core accumulation only
+    assert vo.rel_l2(ln[:, :n], want_ln) < 4e-3
+    assert vo.rel_l2(stats[:, 0], mu.flatten()) < 1e-4 and vo.rel_l2(stats[:, 1], 1 / torch.sqrt(var.flatten() + 1e-6)) < 1e-4
+    ones = torch.zeros(m, 8, device=dev, dtype=bf); ones[:, 0] = 1
+    assert torch.equal(ln[:, n:], ones)           # the "ones" column of the wider pitch

@@ -456,6 +456,22 @@ int v4h_debug_gemm(int32_t kind, int32_t m, int32_t n, int32_t k, int32_t rows_p
   return gemm_umma(ctx, g, (cudaStream_t)s);
 }
 
+int v4h_debug_gemm_ln(int32_t m, int32_t n, int32_t k, int32_t rows_per_sample, const void* A, const void* W,
+                      const float* bias, void* y, const float* res_in, float* res_out, const float* gate,
+                      const float* shift, const float* scale, void* ln_out, int32_t ld_ln, float* stats, v4h_stream_t s) {
+  V4H_REQUIRE(A && W && res_in && res_out && gate && shift && scale && ln_out, "debug_gemm_ln: null argument");
+  static UmmaContext* ctx = umma_context_create();
+  GemmDesc g;
+  g.tag = "gemm.ln"; g.layout = GEMM_NT; g.A = A; g.B = W; g.M = m; g.N = n; g.K = k; g.lda = k; g.ldb = k;
+  g.a_dtype = g.b_dtype = DT_BF16; g.out_dtype = DT_BF16; g.epi = EPI_GATE_RES;
+  g.ep.bias = bias; g.ep.out2 = y; g.ep.ldo = n; g.ep.gate = gate; g.ep.mod_stride = n; g.ep.rows_per_sample = rows_per_sample;
+  g.ep.res_in = res_in; g.ep.res_out = res_out;
+  g.ep.ln_shift = shift; g.ep.ln_scale = scale; g.ep.ln_out = ln_out; g.ep.ld_ln = ld_ln;
+  g.ep.ln_stats = reinterpret_cast<float2*>(stats); g.ep.ln_eps = 1e-6f;
+  V4H_REQUIRE(gemm_gate_res_ln_supported(g), "debug_gemm_ln: shape not supported by the fused kernel");
+  return gemm_gate_res_ln(ctx, g, (cudaStream_t)s);
+}
+
 int v4h_debug_tma_probe(const void* buf, int32_t rows, int32_t cols, int32_t stages, int32_t boxes, int32_t box_rows,
                         int32_t producers, int32_t iters, int32_t ctas, int64_t* cycles, v4h_stream_t s) {
   static UmmaContext* ctx = umma_context_create();

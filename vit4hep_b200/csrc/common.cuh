@@ -212,6 +212,16 @@ struct EpiParams {
   float* extra_out = nullptr;
   int extra_col = -1;
   bool vec_ok = false;  // set by the launcher (epilogue_vec_ok)
+  // EPI_GATE_RES only, tcgen05 engine (gemm_gate_res_ln): the LayerNorm + adaLN modulation that consumes res_out,
+  // fused into this epilogue: ln_out[row, :] = LN(res_out[row, :]) * (1 + ln_scale[b, :]) + ln_shift[b, :] in bf16
+  // (row pitch ld_ln >= N; the column N of a wider pitch receives the "ones" column of layernorm.cu), statistics
+  // (mean, rstd) per row into ln_stats when non-null.  Shift / scale rows use mod_stride like the gate.
+  const float* ln_shift = nullptr;
+  const float* ln_scale = nullptr;
+  void* ln_out = nullptr;
+  int ld_ln = 0;
+  float2* ln_stats = nullptr;
+  float ln_eps = 1e-6f;
 };
 
 // ---- vector access helpers: NV consecutive values of one row, 16-byte transactions when `vec`

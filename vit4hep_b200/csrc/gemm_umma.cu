@@ -33,6 +33,7 @@
 // Split-K work items (EPI_ATOMIC) cover disjoint K ranges of one output tile.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <map>
 #include <mutex>
@@ -704,6 +705,364 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Gated-residual GEMM with the following LayerNorm + adaLN modulation in its epilogue
+// (reference nn/vit.py:331-332: x = x + gate * branch(modulate(norm(x), shift, scale)); the norm + modulate of the
+// NEXT branch is applied here, where the new residual row is produced).
+//
+// One CTA per 128-row tile owns whole output rows -- CN = 1: all N columns in two accumulators (N = 480: 2 x 240
+// TMEM columns); CN = 2: a 2-CTA cluster splits the columns (256 + 224) and exchanges the per-row partial sums
+// through distributed shared memory -- so the row statistics never leave the SM.  Not persistent: after the
+// mainloop the operand stages are free and hold the epilogue's boxes.
+//   pass 1 (per 32-column chunk): y = acc + bias; x = res_in + gate * y (in place on the TMA-loaded residual box,
+//           stored to res_out by TMA); x also goes BACK INTO TMEM over the accumulator (tcgen05.st) and into the
+//           thread's running sum / sum of squares (a thread owns one row);
+//   row statistics: two epilogue groups (+ the peer CTA) combine their partial sums;
+//   pass 2: x from TMEM -> (x - mean) * rstd * (1 + scale) + shift -> bf16 box -> TMA store to ln_out.
+// Warp roles as in gemm_umma_kernel: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator + residual-box producer,
+// 4-11 two epilogue groups that alternate chunks.
+// ------------------------------------------------------------------------------------------
+constexpr int LN_MAX_SAMPLES = 3;   // samples a 128-row tile may span (rows_per_sample >= 64)
+constexpr int LN_MAX_SLOTS = 16;
+constexpr int LN_NBUF = 3;          // bf16 staging boxes per epilogue group (pass 2)
+
+struct LnArgs {
+  int M, N, K, kblocks;
+  int col0[2], wc[2];   // per cluster rank: first column, width (multiple of 32)
+  int a0w[2], a1w[2];   // accumulator widths (a1w = 0: one accumulator); a0w + a1w = wc
+  int stage_bytes, stages;
+  int nslots_pre, nslots_post;  // residual ring: dedicated slots / slots inside the freed operand stages
+  int vec_w;            // floats per staged vector (max wc)
+  int tmem_cols;
+  int has_y, ld_ln;
+};
+
+__device__ __forceinline__ void st_cluster_f2(uint32_t cluster_addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void epi_bar_sync_all() {  // the 256 threads of both epilogue groups
+  asm volatile("bar.sync 3, 256;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_n(uint32_t* slot, int cols) {
+  if (cols <= COLS) tmem_alloc<COLS>(slot);
+}
+
+template <int CN>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_gate_res_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
+                        const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmIn,
+                        const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmLn,
+                        const LnArgs g, const EpiParams ep) {
+  constexpr int IN_BOX = BM * SLAB * 4;   // fp32 residual box
+  constexpr int LN_BOX = BM * SLAB * 2;   // bf16 output box
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_area = g.stages * g.stage_bytes;
+  uint8_t* ring_pre = smem + stage_area;                       // dedicated residual slots
+  uint8_t* ring_post = smem;                                   // residual slots inside the freed stages
+  uint8_t* ln_stage = smem + stage_area - EG * LN_NBUF * LN_BOX;  // pass-2 staging, at the top of the stage area
+  float* vecs = reinterpret_cast<float*>(ring_pre + g.nslots_pre * IN_BOX);
+  float* bias_s = vecs;                                         // [vec_w]
+  float* gate_s = bias_s + g.vec_w;                             // [LN_MAX_SAMPLES][vec_w]
+  float* shift_s = gate_s + LN_MAX_SAMPLES * g.vec_w;           // [LN_MAX_SAMPLES][vec_w]
+  float* scale_s = shift_s + LN_MAX_SAMPLES * g.vec_w;          // [LN_MAX_SAMPLES][vec_w]  holds 1 + scale
+  float* part = scale_s + LN_MAX_SAMPLES * g.vec_w;             // [EG][BM][2] partial (sum, sum of squares)
+  float* peer_part = part + EG * BM * 2;                        // [BM][2] written by the peer CTA (CN = 2)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (SMEM_LIMIT - BAR_BYTES));
+  uint64_t* full = bars;                        // [MAX_STAGES]
+  uint64_t* empty = full + MAX_STAGES;          // [MAX_STAGES]
+  uint64_t* acc_full = empty + MAX_STAGES;      // [1]
+  uint64_t* peer_bar = acc_full + 1;            // [1]
+  uint64_t* in_full = peer_bar + 1;             // [LN_MAX_SLOTS]
+  uint64_t* in_empty = in_full + LN_MAX_SLOTS;  // [LN_MAX_SLOTS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_empty + LN_MAX_SLOTS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CN == 2 ? cluster_ctarank() : 0u;
+  const int tile = (int)blockIdx.x / CN;
+  const int m0 = tile * BM;
+  const int col0 = g.col0[rank], wc = g.wc[rank], a0w = g.a0w[rank], a1w = g.a1w[rank];
+  const int nch = wc / SLAB;
+  const int nslots = g.nslots_pre + g.nslots_post;
+  auto slot_of = [&](int j) { return j < g.nslots_pre ? j : g.nslots_pre + (j - g.nslots_pre) % g.nslots_post; };
+  auto use_of = [&](int j) { return j < g.nslots_pre ? 0 : (j - g.nslots_pre) / g.nslots_post; };  // n-th use of its slot
+  auto slot_ptr = [&](int sl) { return sl < g.nslots_pre ? ring_pre + sl * IN_BOX : ring_post + (sl - g.nslots_pre) * IN_BOX; };
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA); prefetch_tensormap(&tmB0); prefetch_tensormap(&tmIn);
+    prefetch_tensormap(&tmOut); prefetch_tensormap(&tmLn);
+    if (CN == 2) prefetch_tensormap(&tmB1);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(peer_bar, BM);
+    for (int i = 0; i < LN_MAX_SLOTS; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    if (g.tmem_cols > 256) tmem_alloc<512>(tmem_slot);
+    else if (g.tmem_cols > 128) tmem_alloc<256>(tmem_slot);
+    else if (g.tmem_cols > 64) tmem_alloc<128>(tmem_slot);
+    else if (g.tmem_cols > 32) tmem_alloc<64>(tmem_slot);
+    else tmem_alloc<32>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CN == 2) cluster_sync_all();  // the peer's barriers exist before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer (A and this CTA's rows of W)
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const CUtensorMap* tmB = (CN == 2 && rank == 1) ? &tmB1 : &tmB0;
+      for (int kb = 0; kb < g.kblocks; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * g.stage_bytes;
+        uint8_t* sb = sa + A_BYTES;
+        mbar_expect_tx(&full[stage], A_BYTES + (uint32_t)wc * BK * 2);
+        tma_load_2d(sa, &tmA, &full[stage], kb * BK, m0);
+        tma_load_2d(sb, tmB, &full[stage], kb * BK, col0);
+        if (a1w) tma_load_2d(sb + a0w * BK * 2, tmB, &full[stage], kb * BK, col0 + a0w);
+        if (++stage == g.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t sa0 = smem_u32(smem);
+      const uint64_t adesc0 = make_smem_desc(sa0, 0, 1024), bdesc0 = make_smem_desc(sa0 + A_BYTES, 0, 1024);
+      const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
+      const uint32_t a_lo0 = (uint32_t)adesc0, b_lo0 = (uint32_t)bdesc0;
+      const uint32_t b1_off = (uint32_t)(a0w * BK * 2) >> 4;
+      const uint32_t idesc0 = make_idesc_bf16(BM, a0w, false, false);
+      const uint32_t idesc1 = make_idesc_bf16(BM, a1w ? a1w : 16, false, false);
+      const uint32_t stage_step = (uint32_t)g.stage_bytes >> 4;
+      uint32_t stage_off = 0, accumulate = 0;
+      for (int kb = 0; kb < g.kblocks; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const int ksteps = min(BK / 16, (g.K - kb * BK + 15) / 16);
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t ad = ((uint64_t)a_hi << 32) | (a_lo0 + stage_off + k * 2u);
+          const uint64_t bd = ((uint64_t)b_hi << 32) | (b_lo0 + stage_off + k * 2u);
+          umma_bf16(tmem_base, ad, bd, idesc0, k == 0 ? accumulate : 1u);
+          if (a1w) umma_bf16(tmem_base + 256u, ad, bd + b1_off, idesc1, k == 0 ? accumulate : 1u);
+        }
+        accumulate = 1;
+        umma_commit(&empty[stage]);
+        if (kb == g.kblocks - 1) umma_commit(acc_full);
+        stage_off += stage_step;
+        if (++stage == g.stages) { stage = 0; stage_off = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 2) {
+    // ===================================================================== residual-box producer
+    if (lane == 0) {
+      bool waited_acc = false;
+      for (int j = 0; j < nch; ++j) {
+        const int sl = slot_of(j), use = use_of(j);
+        if (j >= g.nslots_pre && !waited_acc) {  // the slot lives in the operand stages: the mainloop must be over
+          mbar_wait(acc_full, 0);
+          waited_acc = true;
+        }
+        if (use > 0) mbar_wait(&in_empty[sl], (uint32_t)(use - 1) & 1u);
+        mbar_expect_tx(&in_full[sl], IN_BOX);
+        tma_load_2d(slot_ptr(sl), &tmIn, &in_full[sl], col0 + j * SLAB, m0);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================================== epilogue
+    const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;
+    const int r = q * 32 + lane;
+    const int row = m0 + r;
+    const int et = (int)threadIdx.x - 128;         // 0..255 over both groups
+    const bool leader = (threadIdx.x & 127) == 0;
+    // per-tile vectors -> shared memory while the mainloop runs
+    const int rps = ep.rows_per_sample;
+    const int b_lo = min(m0, g.M - 1) / rps, b_hi = min(m0 + BM - 1, g.M - 1) / rps;
+    for (int i = et; i < wc; i += 256) bias_s[i] = ep.bias ? __ldg(ep.bias + col0 + i) : 0.f;
+    for (int i = et; i < LN_MAX_SAMPLES * wc; i += 256) {
+      const int sidx = i / wc, c = i - sidx * wc;
+      const size_t off = (size_t)min(b_lo + sidx, b_hi) * ep.mod_stride + col0 + c;
+      gate_s[sidx * g.vec_w + c] = __ldg(ep.gate + off);
+      shift_s[sidx * g.vec_w + c] = __ldg(ep.ln_shift + off);
+      scale_s[sidx * g.vec_w + c] = 1.f + __ldg(ep.ln_scale + off);
+    }
+    epi_bar_sync_all();
+    const int sidx = min(row, g.M - 1) / rps - b_lo;   // which staged sample this thread's row belongs to
+    const float* gate_r = gate_s + sidx * g.vec_w;
+    const float* shift_r = shift_s + sidx * g.vec_w;
+    const float* scale_r = scale_s + sidx * g.vec_w;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    // TMEM column of output column c of this CTA (second accumulator starts at column 256)
+    auto tcol = [&](int c) { return (uint32_t)(c < a0w ? c : 256 + (c - a0w)); };
+
+    // ---------------- pass 1
+    float s1 = 0.f, s2 = 0.f;
+    int hist[2] = {-1, -1};
+    for (int j = grp; j < nch; j += EG) {
+      const int sl = slot_of(j);
+      const int c0 = j * SLAB;
+      float v[SLAB];
+      {
+        float lo[16], hi[16];
+        tmem_ld16(t_row + tcol(c0), lo);
+        tmem_ld16(t_row + tcol(c0 + 16), hi);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { v[i] = lo[i]; v[16 + i] = hi[i]; }
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * c);
+        v[4 * c] += b4.x; v[4 * c + 1] += b4.y; v[4 * c + 2] += b4.z; v[4 * c + 3] += b4.w;
+      }
+      if (g.has_y && row < g.M) {  // y = branch output, kept for the backward (d gate = sum dh * y)
+        bf16* yrow = reinterpret_cast<bf16*>(ep.out2) + (size_t)row * ep.ldo + col0 + c0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) reinterpret_cast<uint4*>(yrow)[c] = pack8(&v[8 * c]);
+      }
+      mbar_wait(&in_full[sl], (uint32_t)use_of(j) & 1u);
+      uint8_t* box = slot_ptr(sl);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint8_t* pbox = box + box_off(r, c, 4);
+        float4 x = lds4(pbox);
+        const float4 g4 = *reinterpret_cast<const float4*>(gate_r + c0 + 4 * c);
+        x.x += g4.x * v[4 * c]; x.y += g4.y * v[4 * c + 1]; x.z += g4.z * v[4 * c + 2]; x.w += g4.w * v[4 * c + 3];
+        sts4(pbox, x);
+        v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
+        s1 += (x.x + x.y) + (x.z + x.w);
+        s2 += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+      }
+      {  // the new residual row goes back into TMEM: pass 2 reads it from there
+        float lo[16], hi[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { lo[i] = v[i]; hi[i] = v[16 + i]; }
+        tmem_st16(t_row + tcol(c0), lo);
+        tmem_st16(t_row + tcol(c0 + 16), hi);
+      }
+      fence_proxy_async();
+      if (leader) {
+        tma_store_wait_read1();                 // stores of two chunks ago have read their slot
+        if (hist[1] >= 0) mbar_arrive(&in_empty[hist[1]]);
+      }
+      group_bar_sync(grp);
+      if (leader) {
+        tma_store_2d(&tmOut, box, col0 + c0, m0);
+        tma_store_commit();
+      }
+      hist[1] = hist[0]; hist[0] = sl;
+    }
+    tmem_st_wait();
+    if (leader) {
+      tma_store_wait_read0();
+      if (hist[1] >= 0) mbar_arrive(&in_empty[hist[1]]);
+      if (hist[0] >= 0) mbar_arrive(&in_empty[hist[0]]);
+    }
+    // ---------------- row statistics
+    part[(grp * BM + r) * 2] = s1;
+    part[(grp * BM + r) * 2 + 1] = s2;
+    epi_bar_sync_all();
+    float t1 = part[r * 2] + part[(BM + r) * 2], t2 = part[r * 2 + 1] + part[(BM + r) * 2 + 1];
+    if (CN == 2) {
+      if (grp == 0) {
+        st_cluster_f2(map_to_cta(smem_u32(peer_part + r * 2), rank ^ 1u), t1, t2);
+        mbar_arrive_cluster(map_to_cta(smem_u32(peer_bar), rank ^ 1u));  // release.cluster: orders the store above
+      }
+      {  // bounded like mbar_wait: a protocol bug traps instead of hanging the GPU
+        uint32_t spins = 0;
+        uint64_t t0 = 0;
+        while (!mbar_try_wait_cluster(peer_bar, 0)) {
+          if ((++spins & 4095u) == 0) {
+            const uint64_t now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) __trap();
+          }
+        }
+      }
+      t1 += peer_part[r * 2];
+      t2 += peer_part[r * 2 + 1];
+    }
+    const float inv_n = 1.f / (float)g.N;
+    const float mean = t1 * inv_n;
+    const float rstd = rsqrtf(fmaxf(t2 * inv_n - mean * mean, 0.f) + ep.ln_eps);
+    if (ep.ln_stats != nullptr && grp == 0 && rank == 0 && row < g.M) ep.ln_stats[row] = make_float2(mean, rstd);
+    // ---------------- pass 2
+    uint8_t* stg = ln_stage + grp * LN_NBUF * LN_BOX;
+    uint32_t it = 0;
+    for (int j = grp; j < nch; j += EG, ++it) {
+      const int c0 = j * SLAB;
+      float v[SLAB];
+      {
+        float lo[16], hi[16];
+        tmem_ld16(t_row + tcol(c0), lo);
+        tmem_ld16(t_row + tcol(c0 + 16), hi);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { v[i] = lo[i]; v[16 + i] = hi[i]; }
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 sc4 = *reinterpret_cast<const float4*>(scale_r + c0 + 4 * c);
+        const float4 sh4 = *reinterpret_cast<const float4*>(shift_r + c0 + 4 * c);
+        v[4 * c] = fmaf((v[4 * c] - mean) * rstd, sc4.x, sh4.x);
+        v[4 * c + 1] = fmaf((v[4 * c + 1] - mean) * rstd, sc4.y, sh4.y);
+        v[4 * c + 2] = fmaf((v[4 * c + 2] - mean) * rstd, sc4.z, sh4.z);
+        v[4 * c + 3] = fmaf((v[4 * c + 3] - mean) * rstd, sc4.w, sh4.w);
+      }
+      uint8_t* so = stg + (it % LN_NBUF) * LN_BOX;
+      box_write<bf16>(so, r, v);
+      fence_proxy_async();
+      if (leader) tma_store_wait_read1();
+      group_bar_sync(grp);
+      if (leader) {
+        tma_store_2d(&tmLn, so, col0 + c0, m0);
+        tma_store_commit();
+      }
+    }
+    // the "ones" column of a wider pitch (layernorm.cu): turns the weight-gradient GEMM into [dW | bias gradient]
+    if (g.ld_ln > g.N && rank == CN - 1 && grp == 0 && row < g.M) {
+      bf16* orow = reinterpret_cast<bf16*>(ep.ln_out) + (size_t)row * g.ld_ln + g.N;
+      for (int i = 0; i < g.ld_ln - g.N; ++i) orow[i] = __float2bfloat16_rn(i == 0 ? 1.f : 0.f);
+    }
+    if (leader) tma_store_wait_read0();
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (CN == 2) cluster_sync_all();  // the peer may still write this CTA's partial sums / signal its barrier
+  if (warp == 2) {
+    tc_fence_after();
+    if (g.tmem_cols > 256) tmem_dealloc<512>(tmem_base);
+    else if (g.tmem_cols > 128) tmem_dealloc<256>(tmem_base);
+    else if (g.tmem_cols > 64) tmem_dealloc<128>(tmem_base);
+    else if (g.tmem_cols > 32) tmem_dealloc<64>(tmem_base);
+    else tmem_dealloc<32>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -1058,6 +1417,145 @@ int gemm_umma(UmmaContext* ctx, const GemmDesc& d, cudaStream_t s) {
   }
   return fail(V4H_ERR_UNSUPPORTED, "gemm_umma: epilogue %d / activation %d / output dtype %d is not instantiated", d.epi,
               d.act, d.out_dtype);
+}
+
+// ------------------------------------------------------------------------------------------
+// gemm_gate_res_ln: host side
+// ------------------------------------------------------------------------------------------
+// tile / cluster / shared-memory plan of one problem; false: not representable (the caller runs the unfused path)
+static bool ln_plan(const GemmDesc& d, int num_sms, LnArgs* out, int* cn_out) {
+  LnArgs g;
+  memset(&g, 0, sizeof(g));
+  g.M = d.M; g.N = d.N; g.K = d.K;
+  g.kblocks = (int)ceil_div(d.K, BK);
+  const int tiles_m = (int)ceil_div(d.M, BM);
+  // one CTA per row tile when that fills the GPU; otherwise a 2-CTA cluster splits the columns so that twice as many
+  // SMs work on the problem (V4H_GEMM_LN_CLUSTER = 1 / 2 forces the choice)
+  static const int forced = [] { const char* e = getenv("V4H_GEMM_LN_CLUSTER"); return e ? atoi(e) : 0; }();
+  int cn = tiles_m >= num_sms ? 1 : 2;
+  if (forced == 1 || forced == 2) cn = forced;
+  if (d.N < 64) cn = 1;
+  auto split_acc = [&](int wc, int* a0, int* a1) {
+    if (wc <= 256) { *a0 = wc; *a1 = 0; }
+    else { *a0 = (int)ceil_div(wc / 2, 16) * 16; *a1 = wc - *a0; }
+  };
+  if (cn == 1) {
+    g.col0[0] = 0; g.wc[0] = d.N;
+  } else {
+    g.wc[0] = (int)ceil_div(d.N / 2, 32) * 32; g.wc[1] = d.N - g.wc[0];
+    g.col0[0] = 0; g.col0[1] = g.wc[0];
+  }
+  int max_wc = 0, tmem_cols = 0;
+  for (int r = 0; r < cn; ++r) {
+    split_acc(g.wc[r], &g.a0w[r], &g.a1w[r]);
+    if (g.a1w[r] != 0 && g.a1w[r] != g.a0w[r]) return false;  // both halves come through one tensor map (same box)
+    max_wc = std::max(max_wc, g.wc[r]);
+    tmem_cols = std::max(tmem_cols, g.a1w[r] ? 256 + g.a1w[r] : g.a0w[r]);
+  }
+  g.vec_w = (int)align_up(max_wc, 4);
+  g.tmem_cols = tmem_cols;
+  g.stage_bytes = (int)align_up((size_t)A_BYTES + (size_t)max_wc * BK * 2, 1024);
+  g.has_y = d.ep.out2 != nullptr;
+  g.ld_ln = d.ep.ld_ln;
+  // shared memory: [stages][dedicated residual slots][vectors + partial sums] ... [barriers]
+  const int vec_bytes = (int)align_up((size_t)(1 + 3 * LN_MAX_SAMPLES) * g.vec_w * 4 + (EG + 1) * BM * 2 * 4, 1024);
+  const int in_box = BM * SLAB * 4, ln_box = BM * SLAB * 2;
+  const int nch_max = max_wc / SLAB;
+  const int avail = SMEM_LIMIT - 1024 - BAR_BYTES - vec_bytes;
+  for (int st = std::min(MAX_STAGES, std::max(2, g.kblocks)); st >= 2; --st) {
+    const int left = avail - st * g.stage_bytes;
+    if (left < 2 * in_box) continue;
+    const int pre = std::min(std::min(left / in_box, nch_max), LN_MAX_SLOTS - 1);
+    int post = 0;
+    if (pre < nch_max) {
+      // the freed operand stages hold the pass-2 staging boxes and the remaining residual slots.  A slot is handed
+      // back two chunks of its group (four chunks) after its own, so a ring that wraps needs at least 5 slots
+      const int room = (st * g.stage_bytes - EG * LN_NBUF * ln_box) / in_box;
+      post = std::min(std::min(room, LN_MAX_SLOTS - pre), nch_max - pre);
+      if (post < nch_max - pre && post < 5) continue;
+      if (post < 1) continue;
+    } else if (st * g.stage_bytes < EG * LN_NBUF * ln_box) {
+      continue;
+    }
+    g.stages = st; g.nslots_pre = pre; g.nslots_post = std::max(post, 1);
+    *out = g; *cn_out = cn;
+    return true;
+  }
+  return false;
+}
+
+bool gemm_gate_res_ln_supported(const GemmDesc& d) {
+  static const int enabled = [] { const char* e = getenv("V4H_GEMM_LN_FUSE"); return (e && e[0] == '0') ? 0 : 1; }();
+  if (!enabled) return false;
+  const EpiParams& p = d.ep;
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (d.epi != EPI_GATE_RES || d.layout != GEMM_NT || d.out_dtype != DT_BF16 || !gemm_umma_supported(d)) return false;
+  if (!p.ln_out || !p.ln_shift || !p.ln_scale || !p.gate || !p.res_in || !p.res_out) return false;
+  if (d.N % 32 != 0 || d.N > 512 || d.N < 32 || p.ldo != d.N || p.ld_ln < d.N || p.ld_ln - d.N > 64 || p.ld_ln % 8) return false;
+  if (p.rows_per_sample < 64) return false;  // a 128-row tile must not span more than LN_MAX_SAMPLES samples
+  if (!al(p.res_in) || !al(p.res_out) || !al(p.ln_out) || !al(p.out2)) return false;
+  LnArgs g; int cn;
+  return ln_plan(d, 148, &g, &cn);
+}
+
+int gemm_gate_res_ln(UmmaContext* ctx, const GemmDesc& d, cudaStream_t s) {
+  V4H_REQUIRE(ctx != nullptr && gemm_gate_res_ln_supported(d), "gemm_gate_res_ln: unsupported problem");
+  LnArgs g;
+  int cn = 1;
+  V4H_REQUIRE(ln_plan(d, ctx->num_sms, &g, &cn), "gemm_gate_res_ln: shared-memory budget (N = %d)", d.N);
+  const int tiles_m = (int)ceil_div(d.M, BM);
+
+  Maps m;
+  memset(&m, 0, sizeof(m));
+  CUtensorMap mB1, mLn;
+  memset(&mB1, 0, sizeof(mB1)); memset(&mLn, 0, sizeof(mLn));
+  V4H_TRY(get_map(ctx, d.A, d.K, d.M, d.lda, BK, BM, 2, &m.a));
+  V4H_TRY(get_map(ctx, d.B, d.K, d.N, d.ldb, BK, g.a0w[0], 2, &m.b));       // W rows of rank 0 (box = accumulator width)
+  if (cn == 2) V4H_TRY(get_map(ctx, d.B, d.K, d.N, d.ldb, BK, g.a0w[1], 2, &mB1));
+  V4H_TRY(get_map(ctx, d.ep.res_in, d.N, d.M, d.ep.ldo, SLAB, BM, 4, &m.in));
+  V4H_TRY(get_map(ctx, d.ep.res_out, d.N, d.M, d.ep.ldo, SLAB, BM, 4, &m.out));
+  V4H_TRY(get_map(ctx, d.ep.ln_out, d.N, d.M, d.ep.ld_ln, SLAB, BM, 2, &mLn));
+  if (launch_sync_enabled())
+    fprintf(stderr, "[v4h] gemm_ln %s M=%d N=%d K=%d cn=%d wc=%d/%d acc=%d+%d stages=%d pre=%d post=%d tmem=%d y=%d\n", d.tag, d.M,
+            d.N, d.K, cn, g.wc[0], g.wc[1], g.a0w[0], g.a1w[0], g.stages, g.nslots_pre, g.nslots_post, g.tmem_cols, g.has_y);
+  EpiParams ep = d.ep;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(tiles_m * cn));
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SMEM_LIMIT;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cn == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  if (cn == 2) {
+    static bool configured = false;
+    if (!configured) {
+      V4H_CUDA(cudaFuncSetAttribute(gemm_gate_res_ln_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+      configured = true;
+    }
+    V4H_CUDA(cudaLaunchKernelEx(&cfg, gemm_gate_res_ln_kernel<2>, m.a, m.b, mB1, m.in, m.out, mLn, g, ep));
+  } else {
+    static bool configured = false;
+    if (!configured) {
+      V4H_CUDA(cudaFuncSetAttribute(gemm_gate_res_ln_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+      configured = true;
+    }
+    V4H_CUDA(cudaLaunchKernelEx(&cfg, gemm_gate_res_ln_kernel<1>, m.a, m.b, m.b, m.in, m.out, mLn, g, ep));
+  }
+  V4H_LAUNCH_CHECK();
+  return V4H_OK;
 }
 
 }  // namespace v4h

@@ -41,6 +41,10 @@ UmmaContext* umma_context_create();
 void umma_context_destroy(UmmaContext*);
 bool gemm_umma_supported(const GemmDesc& g);
 int gemm_umma(UmmaContext* ctx, const GemmDesc& g, cudaStream_t s);
+// EPI_GATE_RES GEMM whose epilogue also applies the LayerNorm + modulation that follows it (EpiParams::ln_*): one
+// CTA (or a 2-CTA cluster splitting the columns) owns whole output rows, so the row statistics never leave the SM
+bool gemm_gate_res_ln_supported(const GemmDesc& g);
+int gemm_gate_res_ln(UmmaContext* ctx, const GemmDesc& g, cudaStream_t s);
 // measurement only: see gemm_umma.cu
 int tma_probe(UmmaContext* ctx, const void* buf, int rows, int cols, int stages, int boxes, int box_rows, int producers,
               int iters, int ctas, long long* cycles, cudaStream_t s);

@@ -229,9 +229,27 @@ int run_gemm(const Plan& p, const GemmDesc& g, cudaStream_t s) {
   const double esz_o = g.epi == EPI_ATOMIC ? 4 : (g.out_dtype == DT_BF16 ? 2 : 4);
   ProfScope ps(g.tag, 2.0 * g.M * g.N * g.K,
                esz_a * g.M * g.K + esz_b * g.N * g.K + esz_o * (double)g.M * g.N, s);
-  if (p.use_umma && g.a_dtype == DT_BF16 && g.b_dtype == DT_BF16 && gemm_umma_supported(g))
+  if (p.use_umma && g.a_dtype == DT_BF16 && g.b_dtype == DT_BF16 && gemm_umma_supported(g)) {
+    if (g.ep.ln_out != nullptr) return gemm_gate_res_ln(p.umma, g, s);
     return gemm_umma(p.umma, g, s);
+  }
+  if (g.ep.ln_out != nullptr) return fail(V4H_ERR_INVALID, "internal: fused LayerNorm epilogue on the SIMT engine");
   return gemm_simt(g, s);
+}
+
+// Gated-residual GEMM followed by the LayerNorm + modulation of the NEXT branch (reference nn/vit.py:331-332: the
+// norm + modulate that consumes the new residual stream).  bf16 tensor-core path: ONE kernel, the LayerNorm lives in
+// the GEMM epilogue (gemm_gate_res_ln); otherwise the GEMM and the stand-alone LayerNorm kernel.
+template <typename T>
+int gate_res_then_ln(const Plan& p, GemmDesc g, const float* shift, const float* scale, void* ln_out, int ld_ln,
+                     float2* stats, int M, int D, int Tn, cudaStream_t s) {
+  GemmDesc f = g;
+  f.ep.ln_shift = shift; f.ep.ln_scale = scale; f.ep.ln_out = ln_out; f.ep.ld_ln = ld_ln; f.ep.ln_stats = stats;
+  f.ep.ln_eps = 1e-6f;
+  if (p.use_umma && g.a_dtype == DT_BF16 && g.b_dtype == DT_BF16 && gemm_gate_res_ln_supported(f)) return run_gemm(p, f, s);
+  V4H_TRY(run_gemm(p, g, s));
+  return prof("ln.fwd", 0, (double)M * D * (4 + sizeof(T)), s, [&] {
+    return ln_modulate_fwd<T>(g.ep.res_out, shift, scale, g.ep.mod_stride, (T*)ln_out, ld_ln, stats, M, D, Tn, s); });
 }
 
 GemmDesc linear_fwd(const void* A, int a_dt, int lda, const void* W, int w_dt, int ldw, int M, int N, int K) {
@@ -397,7 +415,10 @@ int forward_block(Plan& p, const v4h_vit_params& w, const char* arena, Sub& u, i
   const void* Wfc1 = p.bf16 ? (const void*)(wa + p.arena_blocks[i].fc1) : (const void*)bw.fc1_w;
   const void* Wfc2 = p.bf16 ? (const void*)(wa + p.arena_blocks[i].fc2) : (const void*)bw.fc2_w;
 
-  V4H_TRY(prof("ln.fwd", 0, (double)M * D * (4 + sizeof(T)), s, [&] { return ln_modulate_fwd<T>(hin, mod + 0 * D, mod + 1 * D, p.Nmod, (T*)bb.a, p.ldx, bb.stats1, M, D, Tn, s); }));
+  // LN1 + modulate of block 0 follows the x_embedder; for the later blocks it was applied where their input was
+  // produced (the fc2 step of the block before, below)
+  if (i == 0)
+    V4H_TRY(prof("ln.fwd", 0, (double)M * D * (4 + sizeof(T)), s, [&] { return ln_modulate_fwd<T>(hin, mod + 0 * D, mod + 1 * D, p.Nmod, (T*)bb.a, p.ldx, bb.stats1, M, D, Tn, s); }));
   {
     GemmDesc g = linear_fwd(bb.a, TA, p.ldx, Wqkv, TA, D, M, 3 * D, D);
     g.tag = "gemm.qkv";
@@ -412,9 +433,8 @@ int forward_block(Plan& p, const v4h_vit_params& w, const char* arena, Sub& u, i
     g.ep.bias = bw.proj_b; g.ep.out2 = bb.y1; g.ep.ldo = D;
     g.ep.gate = mod + 2 * D; g.ep.mod_stride = p.Nmod; g.ep.rows_per_sample = Tn;
     g.ep.res_in = hin; g.ep.res_out = hmid;
-    V4H_TRY(run_gemm(p, g, s));
+    V4H_TRY(gate_res_then_ln<T>(p, g, mod + 3 * D, mod + 4 * D, bb.m, p.ldx, bb.stats2, M, D, Tn, s));  // + LN2, modulate
   }
-  V4H_TRY(prof("ln.fwd", 0, (double)M * D * (4 + sizeof(T)), s, [&] { return ln_modulate_fwd<T>(hmid, mod + 3 * D, mod + 4 * D, p.Nmod, (T*)bb.m, p.ldx, bb.stats2, M, D, Tn, s); }));
   {
     GemmDesc g = linear_fwd(bb.m, TA, p.ldx, Wfc1, TA, D, M, Hm, D);
     g.tag = "gemm.fc1";
@@ -429,7 +449,15 @@ int forward_block(Plan& p, const v4h_vit_params& w, const char* arena, Sub& u, i
     g.ep.bias = bw.fc2_b; g.ep.out2 = bb.y2; g.ep.ldo = D;
     g.ep.gate = mod + 5 * D; g.ep.mod_stride = p.Nmod; g.ep.rows_per_sample = Tn;
     g.ep.res_in = hmid; g.ep.res_out = hout;
-    V4H_TRY(run_gemm(p, g, s));
+    // + the LayerNorm / modulation that consumes this block's output: LN1 of the next block, or the final layer's
+    if (i + 1 < d.depth) {
+      const float* modn = ws.mod + (size_t)(i + 1) * 6 * D;
+      BlockBufs& bn = ws.blk[train ? i + 1 : 0];
+      V4H_TRY(gate_res_then_ln<T>(p, g, modn + 0 * D, modn + 1 * D, bn.a, p.ldx, bn.stats1, M, D, Tn, s));
+    } else {
+      const float* modf = ws.mod + (size_t)d.depth * 6 * D;
+      V4H_TRY(gate_res_then_ln<T>(p, g, modf, modf + D, ws.a_f, D, ws.stats_f, M, D, Tn, s));
+    }
   }
   return V4H_OK;
 }
@@ -444,9 +472,7 @@ int forward_final(Plan& p, const v4h_vit_params& w, const char* arena, Sub& u, b
   const int TA = p.bf16 ? DT_BF16 : DT_F32;
   const bf16* wa = reinterpret_cast<const bf16*>(arena);
   const bool fast = p.bf16 && p.use_umma;
-  const float* mod = ws.mod + (size_t)d.depth * 6 * D;
-  float* hl = ws.h[hidx(train, 2 * d.depth)];
-  V4H_TRY(prof("ln.fwd", 0, (double)M * D * (4 + sizeof(T)), s, [&] { return ln_modulate_fwd<T>(hl, mod, mod + D, p.Nmod, (T*)ws.a_f, D, ws.stats_f, M, D, Tn, s); }));
+  // (the final LayerNorm + modulation was applied by the last block's fc2 step into ws.a_f)
   GemmDesc g = fast ? linear_fwd(ws.a_f, TA, D, wa + p.arena_final, DT_BF16, D, M, d.out_dim, D)
                     : linear_fwd(ws.a_f, TA, D, w.final_w, DT_F32, D, M, d.out_dim, D);
   g.tag = "gemm.final";
