@@ -147,5 +147,6 @@ def test_full_size_sampling_graphed_and_sharded():
             model.graph_sampling = True
             assert torch.equal(model.integrate(bx, bc), big)
             bc2 = torch.rand(256, 1, generator=g).to(dev)  # the replay must re-encode the new conditions
-            want2 = model._integrate(bx, bc2)
+            with torch.inference_mode():
+                want2 = model._integrate(bx, bc2)
             assert torch.equal(model.integrate(bx, bc2), want2)
