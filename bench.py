@@ -246,24 +246,37 @@ def gemm_class_roofline(lib, dev, M, param, tokens, peaks, fam_eager):
     bf = torch.bfloat16
     s = torch.cuda.current_stream(dev).cuda_stream
     # (class, kind of v4h_debug_gemm, m, n, k): forward, dgrad and wgrad GEMMs of one block
-    classes = [("gemm.qkv", 1, M, 3 * D, D), ("gemm.proj", 2, M, D, D), ("gemm.fc1", 0, M, Hm, D), ("gemm.fc2", 2, M, D, Hm),
+    # kind 7: gated residual + the following LayerNorm / modulation in the epilogue (v4h_debug_gemm_ln), as the step runs it
+    classes = [("gemm.qkv", 1, M, 3 * D, D), ("gemm.proj+ln", 7, M, D, D), ("gemm.fc1", 0, M, Hm, D), ("gemm.fc2+ln", 7, M, D, Hm),
                ("dgrad.fc2", 3, M, Hm, D), ("dgrad.fc1", 4, M, D, Hm), ("dgrad.proj", 4, M, D, D), ("dgrad.qkv", 4, M, D, 3 * D),
                ("wgrad.fc2", 5, D, Hm, M), ("wgrad.fc1", 5, Hm, D, M), ("wgrad.proj", 5, D, D, M), ("wgrad.qkv", 5, 3 * D, D, M)]
     g = torch.Generator().manual_seed(0)
     rows, tot_flops, tot_ms = [], 0.0, 0.0
     for name, kind, m, n, k in classes:
         A = (torch.randn((k, m) if kind == 5 else (m, k), generator=g) * 0.1).to(dev, bf)
-        Bm = (torch.randn((n, k) if kind <= 2 else (k, n), generator=g) * 0.1).to(dev, bf)
+        Bm = (torch.randn((n, k) if kind in (0, 1, 2, 7) else (k, n), generator=g) * 0.1).to(dev, bf)
         bias = torch.randn(n, generator=g).to(dev)
         out = torch.zeros((m, n), device=dev, dtype=torch.float32 if kind == 5 else bf)
         out2 = torch.zeros((m, n), device=dev, dtype=bf)
-        res_in = torch.randn(m, n, generator=g).to(dev) if kind == 2 else None
-        res_out = torch.empty(m, n, device=dev) if kind == 2 else None
-        gate = torch.randn((m + tokens - 1) // tokens, n, generator=g).to(dev) if kind == 2 else None
+        gated = kind in (2, 7)
+        nb = (m + tokens - 1) // tokens
+        res_in = torch.randn(m, n, generator=g).to(dev) if gated else None
+        res_out = torch.empty(m, n, device=dev) if gated else None
+        gate = torch.randn(nb, n, generator=g).to(dev) if gated else None
         aux = torch.randn(m, n, generator=g).to(dev, bf) if kind == 3 else None
         ptr = lambda t: None if t is None else t.data_ptr()
+        if kind == 7:
+            shift, scale = torch.randn(nb, n, generator=g).to(dev), torch.randn(nb, n, generator=g).to(dev)
+            ln = torch.zeros(m, n + 8, device=dev, dtype=bf)
+            stats = torch.zeros(m, 2, device=dev)
 
         def call():
+            if kind == 7:
+                _cabi.check(lib.v4h_debug_gemm_ln(m, n, k, tokens, A.data_ptr(), Bm.data_ptr(), bias.data_ptr(),
+                                                  out2.data_ptr(), res_in.data_ptr(), res_out.data_ptr(), gate.data_ptr(),
+                                                  shift.data_ptr(), scale.data_ptr(), ln.data_ptr(), n + 8,
+                                                  stats.data_ptr(), s))
+                return
             _cabi.check(lib.v4h_debug_gemm(kind, m, n, k, tokens, A.data_ptr(), Bm.data_ptr(), bias.data_ptr(), out.data_ptr(),
                                            out2.data_ptr(), ptr(res_in), ptr(res_out), ptr(gate), ptr(aux), None, s))
         for _ in range(3):
@@ -288,7 +301,8 @@ def gemm_class_roofline(lib, dev, M, param, tokens, peaks, fam_eager):
             traffic = json.load(fh).get("gemm_umma_kernel", {}).get("dram_bytes_per_launch")
     ach = tot_flops / (tot_ms * 1e-3) / 1e12
     n_launch = depth * len(classes)
-    return {"kernel": "gemm_umma_kernel (tcgen05 GEMM: the 12 GEMM call sites of a transformer block, forward + dgrad + wgrad)",
+    return {"kernel": "gemm_umma_kernel / gemm_gate_res_ln_kernel (tcgen05 GEMMs: the 12 GEMM call sites of a transformer block, "
+                      "forward + dgrad + wgrad; proj / fc2 with the LayerNorm epilogue)",
             "bound": "tensor", "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
             "frac": ach / peaks["tflops_sustained"], "traffic": traffic, "flops_per_launch": tot_flops / n_launch,
             "avg_launch_ms": tot_ms / n_launch, "launches_per_step": n_launch,

@@ -94,8 +94,9 @@ __global__ void energy_cond_embed_kernel(const float* __restrict__ c, const floa
 // out = LayerNorm(x + y) * gamma + beta (eps 1e-5, biased variance): the post-norm residual step of
 // nn.TransformerEncoderLayer / DecoderLayer; y == nullptr: plain LayerNorm (the stacks' final norms).
 // One warp per row, E <= 32 * 8.  Writes the fp32 stream (may alias x) and the GEMM-operand copy with its own pitch.
+// y_div > 1: y has one row per y_div rows of x (a per-sample vector broadcast over the sample's tokens).
 template <typename T>
-__global__ void __launch_bounds__(256) add_ln_kernel(const float* x, const float* __restrict__ y,
+__global__ void __launch_bounds__(256) add_ln_kernel(const float* x, const float* __restrict__ y, int y_div,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      float* out, T* __restrict__ out_t, int ld_t, int64_t rows, int E) {
   pdl_wait();
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(256) add_ln_kernel(const float* x, const float
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int e = lane + 32 * i;
-    v[i] = e < E ? x[row * E + e] + (y ? y[row * E + e] : 0.f) : 0.f;
+    v[i] = e < E ? x[row * E + e] + (y ? y[(row / y_div) * E + e] : 0.f) : 0.f;
     s += v[i];
   }
   const float mean = warp_sum(s) / (float)E;
@@ -186,6 +187,7 @@ struct EnergyWs {
   float* mem_f;  // (B*S, E)
   T* mem_t;
   T* kv[V4H_ENERGY_MAX_LAYERS];  // (B*S, 2E) per decoder layer
+  float* yca[V4H_ENERGY_MAX_LAYERS];  // dims_c == 1: the whole cross-attention branch output per sample (B, E)
   // scratch
   float *x_f, *y_f, *lse;
   T *x_t, *qkv, *att, *q, *ff, *head_in, *head_h;
@@ -197,6 +199,7 @@ struct EnergyWs {
     auto take = [&](size_t n) -> char* { char* q = base ? base + off : nullptr; off += align_up(n, 256); return q; };
     mem_f = (float*)take(Ms * E * 4); mem_t = (T*)take(Ms * E * sizeof(T));
     for (int l = 0; l < d.n_dec; ++l) kv[l] = (T*)take(Ms * 2 * E * sizeof(T));
+    for (int l = 0; l < d.n_dec; ++l) yca[l] = d.dims_c == 1 ? (float*)take((size_t)B * E * 4) : nullptr;
     x_f = (float*)take(M * E * 4); y_f = (float*)take(M * E * 4); lse = (float*)take(M * d.nhead * 4);
     x_t = (T*)take(M * E * sizeof(T)); qkv = (T*)take(M * 3 * E * sizeof(T)); att = (T*)take(M * E * sizeof(T));
     q = (T*)take(M * E * sizeof(T)); ff = (T*)take(M * F * sizeof(T));
@@ -242,10 +245,10 @@ int self_attention<bf16>(const EnergyPlan& p, const bf16* qkv, bf16* o, float* l
 
 template <typename T>
 int add_ln(const float* x, const float* y, const float* gamma, const float* beta, float* out, T* out_t, int ld_t,
-           int64_t rows, int E, cudaStream_t s) {
+           int64_t rows, int E, cudaStream_t s, int y_div = 1) {
   ProfScope ps("energy.ln", 0, (double)rows * E * 12, s);
-  V4H_CUDA(launch_pdl(add_ln_kernel<T>, dim3((unsigned)ceil_div(rows, 8)), dim3(256), 0, s, x, y, gamma, beta, out, out_t,
-                      ld_t, rows, E));
+  V4H_CUDA(launch_pdl(add_ln_kernel<T>, dim3((unsigned)ceil_div(rows, 8)), dim3(256), 0, s, x, y, y_div, gamma, beta, out,
+                      out_t, ld_t, rows, E));
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }
@@ -286,6 +289,11 @@ int encode_impl(EnergyPlan& p, const v4h_energy_params& w, const char* arena, co
     const v4h_energy_dec_layer& L = w.dec[l];
     V4H_TRY(linear<T>(p, "energy.enc", ws.mem_t, E, L.ca_in_w + (size_t)E * E, p.dec[l].ca_in_w + (size_t)E * E, arena,
                       L.ca_in_b + E, ws.kv[l], TD, 2 * E, Ms, 2 * E, E, ACT_NONE, s));
+    // one memory token: the softmax over a single key is 1 whatever the query, so the cross-attention branch of
+    // this layer is the same vector out_proj(v) for every token of the sample -- computed here, once per batch
+    if (S == 1)
+      V4H_TRY(linear<T>(p, "energy.enc", ws.kv[l] + E, 2 * E, L.ca_out_w, p.dec[l].ca_out_w, arena, L.ca_out_b, ws.yca[l],
+                        DT_F32, E, Ms, E, E, ACT_NONE, s));
   }
   return V4H_OK;
 }
@@ -316,10 +324,14 @@ int forward_impl(EnergyPlan& p, const v4h_energy_params& w, const char* arena, c
     V4H_TRY(linear<T>(p, "energy.proj", ws.att, E, L.sa_out_w, p.dec[l].sa_out_w, arena, L.sa_out_b, ws.y_f, DT_F32, E, M, E, E, ACT_NONE, s));
     V4H_TRY(add_ln<T>(ws.x_f, ws.y_f, L.n1_w, L.n1_b, ws.x_f, ws.x_t, E, M, E, s));
     // cross attention over the encoded condition (K / V precomputed by energy_encode)
-    V4H_TRY(linear<T>(p, "energy.proj", ws.x_t, E, L.ca_in_w, p.dec[l].ca_in_w, arena, L.ca_in_b, ws.q, TD, E, M, E, E, ACT_NONE, s));
-    V4H_TRY(small_attention<T>(ws.q, E, ws.kv[l], ws.kv[l] + E, 2 * E, ws.att, E, M, Tn, S, H, dh, s));
-    V4H_TRY(linear<T>(p, "energy.proj", ws.att, E, L.ca_out_w, p.dec[l].ca_out_w, arena, L.ca_out_b, ws.y_f, DT_F32, E, M, E, E, ACT_NONE, s));
-    V4H_TRY(add_ln<T>(ws.x_f, ws.y_f, L.n2_w, L.n2_b, ws.x_f, ws.x_t, E, M, E, s));
+    if (S == 1) {
+      V4H_TRY(add_ln<T>(ws.x_f, ws.yca[l], L.n2_w, L.n2_b, ws.x_f, ws.x_t, E, M, E, s, Tn));
+    } else {
+      V4H_TRY(linear<T>(p, "energy.proj", ws.x_t, E, L.ca_in_w, p.dec[l].ca_in_w, arena, L.ca_in_b, ws.q, TD, E, M, E, E, ACT_NONE, s));
+      V4H_TRY(small_attention<T>(ws.q, E, ws.kv[l], ws.kv[l] + E, 2 * E, ws.att, E, M, Tn, S, H, dh, s));
+      V4H_TRY(linear<T>(p, "energy.proj", ws.att, E, L.ca_out_w, p.dec[l].ca_out_w, arena, L.ca_out_b, ws.y_f, DT_F32, E, M, E, E, ACT_NONE, s));
+      V4H_TRY(add_ln<T>(ws.x_f, ws.y_f, L.n2_w, L.n2_b, ws.x_f, ws.x_t, E, M, E, s));
+    }
     // feed forward
     V4H_TRY(linear<T>(p, "energy.ff1", ws.x_t, E, L.l1_w, p.dec[l].l1_w, arena, L.l1_b, ws.ff, TD, F, M, F, E, ACT_RELU, s));
     V4H_TRY(linear<T>(p, "energy.ff2", ws.ff, F, L.l2_w, p.dec[l].l2_w, arena, L.l2_b, ws.y_f, DT_F32, E, M, E, F, ACT_NONE, s));
