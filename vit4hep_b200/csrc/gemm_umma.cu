@@ -1134,6 +1134,12 @@ UmmaContext* umma_context_create() {
     int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) c->num_sms = n;
   }
+  // V4H_GEMM_SMS: persistent CTAs to launch (default: every SM).  A persistent CTA needs a whole SM; when another
+  // kernel (an NCCL all-reduce under the backward) holds some SMs, the CTAs that do not fit start a second round.
+  if (const char* e = getenv("V4H_GEMM_SMS")) {
+    const int v = atoi(e);
+    if (v >= 8 && v <= c->num_sms) c->num_sms = v;
+  }
   return c;
 }
 
