@@ -95,10 +95,12 @@ def test_attention_fwd_bwd(precision, engine, B, T, H, dh):
 
 
 @pytest.mark.parametrize("m,n,k,T", [(8640, 480, 480, 135), (8640, 480, 1920, 135), (19000, 480, 480, 135),
+                                     (34560, 480, 1920, 135), (19100, 256, 200, 88),
                                      (1000, 96, 96, 88), (300, 64, 200, 125), (540, 480, 480, 135), (4000, 224, 480, 450)])
 def test_gate_residual_gemm_with_layernorm_epilogue(m, n, k, T):
     """csrc/gemm_umma.cu gemm_gate_res_ln against torch: a 2-CTA cluster splits the columns when the row tiles do not
-    fill the GPU (first shapes), one CTA owns whole rows otherwise (m = 19000); ragged m / k, several samples per tile."""
+    fill the GPU (m < 18944), a cta_group::2 pair owns 256 whole rows otherwise (m >= 19000, odd tile counts
+    included); ragged m / k, several samples per tile."""
     from vit4hep_b200 import _cabi
     lib = _cabi.load()
     dev = torch.device("cuda:0")

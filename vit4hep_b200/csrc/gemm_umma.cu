@@ -758,7 +758,7 @@ __device__ __forceinline__ void tmem_alloc_n(uint32_t* slot, int cols) {
   if (cols <= COLS) tmem_alloc<COLS>(slot);
 }
 
-template <int CN>
+template <int CN, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_gate_res_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
                         const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmIn,
@@ -788,11 +788,16 @@ gemm_gate_res_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   uint64_t* in_empty = in_full + LN_MAX_SLOTS;  // [LN_MAX_SLOTS]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_empty + LN_MAX_SLOTS);
 
+  // CN = 2: the cluster splits the COLUMNS (rank = column half).  PAIR: the cluster is a cta_group::2 pair over
+  // 256 ROWS -- each CTA stages its own 128 rows of A and HALF of every W tile, the leader issues M = 256 MMAs and
+  // every CTA ends up with its 128 full rows in its own TMEM: 46 KB of operands per k-block and SM for 128 x 480
+  // outputs instead of 76 KB (the mainloop is bound by the SM's L2 ingest)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = CN == 2 ? cluster_ctarank() : 0u;
-  const int tile = (int)blockIdx.x / CN;
+  const uint32_t rank = (CN == 2 || PAIR) ? cluster_ctarank() : 0u;
+  const int tile = PAIR ? ((int)blockIdx.x / 2) * 2 + (int)rank : (int)blockIdx.x / CN;
   const int m0 = tile * BM;
-  const int col0 = g.col0[rank], wc = g.wc[rank], a0w = g.a0w[rank], a1w = g.a1w[rank];
+  const uint32_t crank = PAIR ? 0u : rank;  // which column range this CTA owns
+  const int col0 = g.col0[crank], wc = g.wc[crank], a0w = g.a0w[crank], a1w = g.a1w[crank];
   const int nch = wc / SLAB;
   const int nslots = g.nslots_pre + g.nslots_post;
   auto slot_of = [&](int j) { return j < g.nslots_pre ? j : g.nslots_pre + (j - g.nslots_pre) % g.nslots_post; };
@@ -812,7 +817,8 @@ gemm_gate_res_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     fence_barrier_init();
   }
   if (warp == 2) {
-    if (g.tmem_cols > 256) tmem_alloc<512>(tmem_slot);
+    if (PAIR) tmem_alloc_pair<512>(tmem_slot);
+    else if (g.tmem_cols > 256) tmem_alloc<512>(tmem_slot);
     else if (g.tmem_cols > 128) tmem_alloc<256>(tmem_slot);
     else if (g.tmem_cols > 64) tmem_alloc<128>(tmem_slot);
     else if (g.tmem_cols > 32) tmem_alloc<64>(tmem_slot);
@@ -820,7 +826,7 @@ gemm_gate_res_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   }
   tc_fence_before();
   __syncthreads();
-  if (CN == 2) cluster_sync_all();  // the peer's barriers exist before anything signals them
+  if (CN == 2 || PAIR) cluster_sync_all();  // the peer's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
@@ -834,24 +840,35 @@ gemm_gate_res_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* sa = smem + stage * g.stage_bytes;
         uint8_t* sb = sa + A_BYTES;
-        mbar_expect_tx(&full[stage], A_BYTES + (uint32_t)wc * BK * 2);
-        tma_load_2d(sa, &tmA, &full[stage], kb * BK, m0);
-        tma_load_2d(sb, tmB, &full[stage], kb * BK, col0);
-        if (a1w) tma_load_2d(sb + a0w * BK * 2, tmB, &full[stage], kb * BK, col0 + a0w);
+        if (PAIR) {
+          // both CTAs' bytes are counted on the LEADER's full barrier; each stages its half of the W rows of
+          // every accumulator
+          const uint32_t bar = map_to_cta(smem_u32(&full[stage]), 0);
+          const int h0 = a0w / 2, h1 = a1w / 2;
+          if (rank == 0) mbar_expect_tx(&full[stage], 2u * (A_BYTES + (uint32_t)(h0 + h1) * BK * 2));
+          tma_load_2d_pair(sa, &tmA, bar, kb * BK, m0);
+          tma_load_2d_pair(sb, tmB, bar, kb * BK, (int)rank * h0);
+          if (a1w) tma_load_2d_pair(sb + h0 * BK * 2, tmB, bar, kb * BK, a0w + (int)rank * h1);
+        } else {
+          mbar_expect_tx(&full[stage], A_BYTES + (uint32_t)wc * BK * 2);
+          tma_load_2d(sa, &tmA, &full[stage], kb * BK, m0);
+          tma_load_2d(sb, tmB, &full[stage], kb * BK, col0);
+          if (a1w) tma_load_2d(sb + a0w * BK * 2, tmB, &full[stage], kb * BK, col0 + a0w);
+        }
         if (++stage == g.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
+    // ===================================================================== MMA issuer (PAIR: the leader, for both CTAs)
+    if (lane == 0 && (!PAIR || rank == 0)) {
       int stage = 0; uint32_t phase = 0;
       const uint32_t sa0 = smem_u32(smem);
       const uint64_t adesc0 = make_smem_desc(sa0, 0, 1024), bdesc0 = make_smem_desc(sa0 + A_BYTES, 0, 1024);
       const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
       const uint32_t a_lo0 = (uint32_t)adesc0, b_lo0 = (uint32_t)bdesc0;
-      const uint32_t b1_off = (uint32_t)(a0w * BK * 2) >> 4;
-      const uint32_t idesc0 = make_idesc_bf16(BM, a0w, false, false);
-      const uint32_t idesc1 = make_idesc_bf16(BM, a1w ? a1w : 16, false, false);
+      const uint32_t b1_off = (uint32_t)((PAIR ? a0w / 2 : a0w) * BK * 2) >> 4;  // W rows of accumulator 0 held by this CTA
+      const uint32_t idesc0 = make_idesc_bf16(PAIR ? 2 * BM : BM, a0w, false, false);
+      const uint32_t idesc1 = make_idesc_bf16(PAIR ? 2 * BM : BM, a1w ? a1w : 16, false, false);
       const uint32_t stage_step = (uint32_t)g.stage_bytes >> 4;
       uint32_t stage_off = 0, accumulate = 0;
       for (int kb = 0; kb < g.kblocks; ++kb) {
@@ -861,12 +878,22 @@ gemm_gate_res_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         for (int k = 0; k < ksteps; ++k) {
           const uint64_t ad = ((uint64_t)a_hi << 32) | (a_lo0 + stage_off + k * 2u);
           const uint64_t bd = ((uint64_t)b_hi << 32) | (b_lo0 + stage_off + k * 2u);
-          umma_bf16(tmem_base, ad, bd, idesc0, k == 0 ? accumulate : 1u);
-          if (a1w) umma_bf16(tmem_base + 256u, ad, bd + b1_off, idesc1, k == 0 ? accumulate : 1u);
+          if (PAIR) {
+            umma_bf16_pair(tmem_base, ad, bd, idesc0, k == 0 ? accumulate : 1u);
+            if (a1w) umma_bf16_pair(tmem_base + 256u, ad, bd + b1_off, idesc1, k == 0 ? accumulate : 1u);
+          } else {
+            umma_bf16(tmem_base, ad, bd, idesc0, k == 0 ? accumulate : 1u);
+            if (a1w) umma_bf16(tmem_base + 256u, ad, bd + b1_off, idesc1, k == 0 ? accumulate : 1u);
+          }
         }
         accumulate = 1;
-        umma_commit(&empty[stage]);
-        if (kb == g.kblocks - 1) umma_commit(acc_full);
+        if (PAIR) {
+          umma_commit_pair(&empty[stage]);                       // frees the stage in both CTAs
+          if (kb == g.kblocks - 1) umma_commit_pair(acc_full);  // both epilogues
+        } else {
+          umma_commit(&empty[stage]);
+          if (kb == g.kblocks - 1) umma_commit(acc_full);
+        }
         stage_off += stage_step;
         if (++stage == g.stages) { stage = 0; stage_off = 0; phase ^= 1; }
       }
@@ -1007,7 +1034,7 @@ gemm_gate_res_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     const float inv_n = 1.f / (float)g.N;
     const float mean = t1 * inv_n;
     const float rstd = rsqrtf(fmaxf(t2 * inv_n - mean * mean, 0.f) + ep.ln_eps);
-    if (ep.ln_stats != nullptr && grp == 0 && rank == 0 && row < g.M) ep.ln_stats[row] = make_float2(mean, rstd);
+    if (ep.ln_stats != nullptr && grp == 0 && (PAIR || rank == 0) && row < g.M) ep.ln_stats[row] = make_float2(mean, rstd);
     // ---------------- pass 2
     uint8_t* stg = ln_stage + grp * LN_NBUF * LN_BOX;
     uint32_t it = 0;
@@ -1042,7 +1069,7 @@ gemm_gate_res_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       }
     }
     // the "ones" column of a wider pitch (layernorm.cu): turns the weight-gradient GEMM into [dW | bias gradient]
-    if (g.ld_ln > g.N && rank == CN - 1 && grp == 0 && row < g.M) {
+    if (g.ld_ln > g.N && (PAIR || rank == CN - 1) && grp == 0 && row < g.M) {
       bf16* orow = reinterpret_cast<bf16*>(ep.ln_out) + (size_t)row * g.ld_ln + g.N;
       for (int i = 0; i < g.ld_ln - g.N; ++i) orow[i] = __float2bfloat16_rn(i == 0 ? 1.f : 0.f);
     }
@@ -1052,10 +1079,11 @@ gemm_gate_res_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 
   tc_fence_before();
   __syncthreads();
-  if (CN == 2) cluster_sync_all();  // the peer may still write this CTA's partial sums / signal its barrier
+  if (CN == 2 || PAIR) cluster_sync_all();  // the peer may still write this CTA's partial sums / signal its barriers
   if (warp == 2) {
     tc_fence_after();
-    if (g.tmem_cols > 256) tmem_dealloc<512>(tmem_base);
+    if (PAIR) tmem_dealloc_pair<512>(tmem_base);
+    else if (g.tmem_cols > 256) tmem_dealloc<512>(tmem_base);
     else if (g.tmem_cols > 128) tmem_dealloc<256>(tmem_base);
     else if (g.tmem_cols > 64) tmem_dealloc<128>(tmem_base);
     else if (g.tmem_cols > 32) tmem_dealloc<64>(tmem_base);
@@ -1429,6 +1457,7 @@ int gemm_umma(UmmaContext* ctx, const GemmDesc& d, cudaStream_t s) {
 // gemm_gate_res_ln: host side
 // ------------------------------------------------------------------------------------------
 // tile / cluster / shared-memory plan of one problem; false: not representable (the caller runs the unfused path)
+// *cn_out: 1 = one CTA per row tile, 2 = 2-CTA cluster splitting the columns, 3 = cta_group::2 pair over 256 rows
 static bool ln_plan(const GemmDesc& d, int num_sms, LnArgs* out, int* cn_out) {
   LnArgs g;
   memset(&g, 0, sizeof(g));
@@ -1438,29 +1467,30 @@ static bool ln_plan(const GemmDesc& d, int num_sms, LnArgs* out, int* cn_out) {
   // one CTA per row tile when that fills the GPU; otherwise a 2-CTA cluster splits the columns so that twice as many
   // SMs work on the problem (V4H_GEMM_LN_CLUSTER = 1 / 2 forces the choice)
   static const int forced = [] { const char* e = getenv("V4H_GEMM_LN_CLUSTER"); return e ? atoi(e) : 0; }();
-  int cn = tiles_m >= num_sms ? 1 : 2;
-  if (forced == 1 || forced == 2) cn = forced;
+  int cn = tiles_m >= num_sms ? 3 : 2;
+  if (forced >= 1 && forced <= 3) cn = forced;
   if (d.N < 64) cn = 1;
+  const bool pair = cn == 3;
   auto split_acc = [&](int wc, int* a0, int* a1) {
     if (wc <= 256) { *a0 = wc; *a1 = 0; }
     else { *a0 = (int)ceil_div(wc / 2, 16) * 16; *a1 = wc - *a0; }
   };
-  if (cn == 1) {
+  if (cn == 1 || pair) {
     g.col0[0] = 0; g.wc[0] = d.N;
   } else {
     g.wc[0] = (int)ceil_div(d.N / 2, 32) * 32; g.wc[1] = d.N - g.wc[0];
     g.col0[0] = 0; g.col0[1] = g.wc[0];
   }
   int max_wc = 0, tmem_cols = 0;
-  for (int r = 0; r < cn; ++r) {
+  for (int r = 0; r < (cn == 2 ? 2 : 1); ++r) {
     split_acc(g.wc[r], &g.a0w[r], &g.a1w[r]);
     if (g.a1w[r] != 0 && g.a1w[r] != g.a0w[r]) return false;  // both halves come through one tensor map (same box)
     max_wc = std::max(max_wc, g.wc[r]);
     tmem_cols = std::max(tmem_cols, g.a1w[r] ? 256 + g.a1w[r] : g.a0w[r]);
   }
   g.vec_w = (int)align_up(max_wc, 4);
-  g.tmem_cols = tmem_cols;
-  g.stage_bytes = (int)align_up((size_t)A_BYTES + (size_t)max_wc * BK * 2, 1024);
+  g.tmem_cols = pair ? 512 : tmem_cols;
+  g.stage_bytes = (int)align_up((size_t)A_BYTES + (size_t)(pair ? max_wc / 2 : max_wc) * BK * 2, 1024);
   g.has_y = d.ep.out2 != nullptr;
   g.ld_ln = d.ep.ld_ln;
   // shared memory: [stages][dedicated residual slots][vectors + partial sums] ... [barriers]
@@ -1516,7 +1546,8 @@ int gemm_gate_res_ln(UmmaContext* ctx, const GemmDesc& d, cudaStream_t s) {
   CUtensorMap mB1, mLn;
   memset(&mB1, 0, sizeof(mB1)); memset(&mLn, 0, sizeof(mLn));
   V4H_TRY(get_map(ctx, d.A, d.K, d.M, d.lda, BK, BM, 2, &m.a));
-  V4H_TRY(get_map(ctx, d.B, d.K, d.N, d.ldb, BK, g.a0w[0], 2, &m.b));       // W rows of rank 0 (box = accumulator width)
+  // W rows of rank 0: box = accumulator width (half of it per CTA of a pair)
+  V4H_TRY(get_map(ctx, d.B, d.K, d.N, d.ldb, BK, cn == 3 ? g.a0w[0] / 2 : g.a0w[0], 2, &m.b));
   if (cn == 2) V4H_TRY(get_map(ctx, d.B, d.K, d.N, d.ldb, BK, g.a0w[1], 2, &mB1));
   V4H_TRY(get_map(ctx, d.ep.res_in, d.N, d.M, d.ep.ldo, SLAB, BM, 4, &m.in));
   V4H_TRY(get_map(ctx, d.ep.res_out, d.N, d.M, d.ep.ldo, SLAB, BM, 4, &m.out));
@@ -1527,13 +1558,13 @@ int gemm_gate_res_ln(UmmaContext* ctx, const GemmDesc& d, cudaStream_t s) {
   EpiParams ep = d.ep;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)(tiles_m * cn));
+  cfg.gridDim = dim3((unsigned)(cn == 3 ? (tiles_m + 1) / 2 * 2 : tiles_m * cn));
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = SMEM_LIMIT;
   cfg.stream = s;
   cudaLaunchAttribute attr[2];
   int na = 0;
-  if (cn == 2) {
+  if (cn >= 2) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
     attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
     ++na;
@@ -1545,20 +1576,27 @@ int gemm_gate_res_ln(UmmaContext* ctx, const GemmDesc& d, cudaStream_t s) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  if (cn == 2) {
+  if (cn == 3) {
     static bool configured = false;
     if (!configured) {
-      V4H_CUDA(cudaFuncSetAttribute(gemm_gate_res_ln_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+      V4H_CUDA(cudaFuncSetAttribute(gemm_gate_res_ln_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
       configured = true;
     }
-    V4H_CUDA(cudaLaunchKernelEx(&cfg, gemm_gate_res_ln_kernel<2>, m.a, m.b, mB1, m.in, m.out, mLn, g, ep));
+    V4H_CUDA(cudaLaunchKernelEx(&cfg, gemm_gate_res_ln_kernel<1, true>, m.a, m.b, m.b, m.in, m.out, mLn, g, ep));
+  } else if (cn == 2) {
+    static bool configured = false;
+    if (!configured) {
+      V4H_CUDA(cudaFuncSetAttribute(gemm_gate_res_ln_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+      configured = true;
+    }
+    V4H_CUDA(cudaLaunchKernelEx(&cfg, gemm_gate_res_ln_kernel<2, false>, m.a, m.b, mB1, m.in, m.out, mLn, g, ep));
   } else {
     static bool configured = false;
     if (!configured) {
-      V4H_CUDA(cudaFuncSetAttribute(gemm_gate_res_ln_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+      V4H_CUDA(cudaFuncSetAttribute(gemm_gate_res_ln_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
       configured = true;
     }
-    V4H_CUDA(cudaLaunchKernelEx(&cfg, gemm_gate_res_ln_kernel<1>, m.a, m.b, m.b, m.in, m.out, mLn, g, ep));
+    V4H_CUDA(cudaLaunchKernelEx(&cfg, gemm_gate_res_ln_kernel<1, false>, m.a, m.b, m.b, m.in, m.out, mLn, g, ep));
   }
   V4H_LAUNCH_CHECK();
   return V4H_OK;
