@@ -275,7 +275,7 @@ def gemm_class_roofline(lib, dev, M, param, tokens, peaks, fam_eager):
                 _cabi.check(lib.v4h_debug_gemm_ln(m, n, k, tokens, A.data_ptr(), Bm.data_ptr(), bias.data_ptr(),
                                                   out2.data_ptr(), res_in.data_ptr(), res_out.data_ptr(), gate.data_ptr(),
                                                   shift.data_ptr(), scale.data_ptr(), ln.data_ptr(), n + 8,
-                                                  stats.data_ptr(), s))
+                                                  stats.data_ptr(), None, s))
                 return
             _cabi.check(lib.v4h_debug_gemm(kind, m, n, k, tokens, A.data_ptr(), Bm.data_ptr(), bias.data_ptr(), out.data_ptr(),
                                            out2.data_ptr(), ptr(res_in), ptr(res_out), ptr(gate), ptr(aux), None, s))

@@ -329,10 +329,14 @@ int v4h_debug_gemm(int32_t kind, int32_t m, int32_t n, int32_t k, int32_t rows_p
  * gemm_gate_res_ln; reference nn/vit.py:331-332), stand-alone for kernel tests and benchmarks:
  *   y = A W^T + bias (bf16, optional);  res_out = res_in + gate[b] * y;  stats[row] = (mean, rstd) (optional);
  *   ln_out[row, :n] = LN(res_out[row]) * (1 + scale[b]) + shift[b]   (bf16, row pitch ld_ln, eps 1e-6)
- * A (m, k), W (n, k) bf16; gate / shift / scale (ceil(m / rows_per_sample), n) fp32; res_in / res_out (m, n) fp32. */
+ * A (m, k), W (n, k) bf16; gate / shift / scale (ceil(m / rows_per_sample), n) fp32; res_in / res_out (m, n) fp32.
+ * counters: optional device array of 8 int64 cycle counters of the first epilogue thread, summed over CTAs: wait
+ * accumulator; pass 1 TMEM loads, wait residual box, math + TMEM store, store / barrier; statistics; pass 2 math,
+ * store / barrier. */
 int v4h_debug_gemm_ln(int32_t m, int32_t n, int32_t k, int32_t rows_per_sample, const void* A, const void* W,
                       const float* bias, void* y, const float* res_in, float* res_out, const float* gate,
-                      const float* shift, const float* scale, void* ln_out, int32_t ld_ln, float* stats, v4h_stream_t s);
+                      const float* shift, const float* scale, void* ln_out, int32_t ld_ln, float* stats, int64_t* counters,
+                      v4h_stream_t s);
 
 /* Measurement hook: feed rate of a TMA + mbarrier ring without a consumer.  `ctas` persistent CTAs each pull
  * `iters` stages of `boxes` [box_rows x 64] bf16 boxes (box_rows 64 / 128 / 256: 8 / 16 / 32 KB, 128-byte

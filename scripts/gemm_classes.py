@@ -42,7 +42,7 @@ for name, kind, m, n, k in CLASSES:
         if kind == 7:
             _cabi.check(lib.v4h_debug_gemm_ln(m, n, k, T, A.data_ptr(), B.data_ptr(), bias.data_ptr(), out2.data_ptr(),
                                               res_in.data_ptr(), res_out.data_ptr(), gate.data_ptr(), shift.data_ptr(),
-                                              scale.data_ptr(), ln.data_ptr(), n + 8, stats.data_ptr(), s))
+                                              scale.data_ptr(), ln.data_ptr(), n + 8, stats.data_ptr(), None, s))
         else:
             _cabi.check(lib.v4h_debug_gemm(kind, m, n, k, T, A.data_ptr(), B.data_ptr(), bias.data_ptr(), out.data_ptr(),
                                            out2.data_ptr(), ptr(res_in), ptr(res_out), ptr(gate), ptr(aux), None, s))

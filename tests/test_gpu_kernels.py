@@ -119,7 +119,7 @@ def test_gate_residual_gemm_with_layernorm_epilogue(m, n, k, T):
     stats = torch.zeros(m, 2, device=dev)
     _cabi.check(lib.v4h_debug_gemm_ln(m, n, k, T, A.data_ptr(), W.data_ptr(), bias.data_ptr(), y.data_ptr(), res.data_ptr(),
                                       res_out.data_ptr(), gate.data_ptr(), shift.data_ptr(), scale.data_ptr(),
-                                      ln.data_ptr(), ld, stats.data_ptr(), torch.cuda.current_stream().cuda_stream))
+                                      ln.data_ptr(), ld, stats.data_ptr(), None, torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     sample = torch.arange(m, device=dev) // T
     want_y = A.double() @ W.double().T + bias.double()

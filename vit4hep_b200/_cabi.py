@@ -117,7 +117,7 @@ SIGNATURES = {
     "v4h_profile_end": (C.c_int, [C.POINTER(ProfileEntry), _i32, C.POINTER(_i32)]),
     "v4h_test_gemm": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "v4h_debug_gemm": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "v4h_debug_gemm_ln": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "v4h_debug_gemm_ln": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "v4h_debug_tma_probe": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "v4h_debug_attention_counters": (C.c_int, [_vp]),
     "v4h_test_attention_fwd": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),

@@ -458,7 +458,8 @@ int v4h_debug_gemm(int32_t kind, int32_t m, int32_t n, int32_t k, int32_t rows_p
 
 int v4h_debug_gemm_ln(int32_t m, int32_t n, int32_t k, int32_t rows_per_sample, const void* A, const void* W,
                       const float* bias, void* y, const float* res_in, float* res_out, const float* gate,
-                      const float* shift, const float* scale, void* ln_out, int32_t ld_ln, float* stats, v4h_stream_t s) {
+                      const float* shift, const float* scale, void* ln_out, int32_t ld_ln, float* stats, int64_t* counters,
+                      v4h_stream_t s) {
   V4H_REQUIRE(A && W && res_in && res_out && gate && shift && scale && ln_out, "debug_gemm_ln: null argument");
   static UmmaContext* ctx = umma_context_create();
   GemmDesc g;
@@ -468,6 +469,7 @@ int v4h_debug_gemm_ln(int32_t m, int32_t n, int32_t k, int32_t rows_per_sample, 
   g.ep.res_in = res_in; g.ep.res_out = res_out;
   g.ep.ln_shift = shift; g.ep.ln_scale = scale; g.ep.ln_out = ln_out; g.ep.ld_ln = ld_ln;
   g.ep.ln_stats = reinterpret_cast<float2*>(stats); g.ep.ln_eps = 1e-6f;
+  g.dbg = reinterpret_cast<long long*>(counters);
   V4H_REQUIRE(gemm_gate_res_ln_supported(g), "debug_gemm_ln: shape not supported by the fused kernel");
   return gemm_gate_res_ln(ctx, g, (cudaStream_t)s);
 }

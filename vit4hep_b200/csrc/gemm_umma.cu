@@ -736,6 +736,7 @@ struct LnArgs {
   int vec_w;            // floats per staged vector (max wc)
   int tmem_cols;
   int has_y, ld_ln;
+  long long* dbg;       // optional cycle counters of the first epilogue thread (v4h_debug_gemm_ln)
 };
 
 __device__ __forceinline__ void st_cluster_f2(uint32_t cluster_addr, float a, float b) {
@@ -938,8 +939,10 @@ gemm_gate_res_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     const float* gate_r = gate_s + sidx * g.vec_w;
     const float* shift_r = shift_s + sidx * g.vec_w;
     const float* scale_r = scale_s + sidx * g.vec_w;
+    Lap T(threadIdx.x == 128 ? g.dbg : nullptr);
     mbar_wait(acc_full, 0);
     tc_fence_after();
+    T.lap(0);
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
     // TMEM column of output column c of this CTA (second accumulator starts at column 256)
     auto tcol = [&](int c) { return (uint32_t)(c < a0w ? c : 256 + (c - a0w)); };
@@ -964,12 +967,14 @@ gemm_gate_res_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * c);
         v[4 * c] += b4.x; v[4 * c + 1] += b4.y; v[4 * c + 2] += b4.z; v[4 * c + 3] += b4.w;
       }
+      T.lap(1);
       if (g.has_y && row < g.M) {  // y = branch output, kept for the backward (d gate = sum dh * y)
         bf16* yrow = reinterpret_cast<bf16*>(ep.out2) + (size_t)row * ep.ldo + col0 + c0;
 #pragma unroll
         for (int c = 0; c < 4; ++c) reinterpret_cast<uint4*>(yrow)[c] = pack8(&v[8 * c]);
       }
       mbar_wait(&in_full[sl], (uint32_t)use_of(j) & 1u);
+      T.lap(2);
       uint8_t* box = slot_ptr(sl);
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -990,6 +995,7 @@ gemm_gate_res_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         tmem_st16(t_row + tcol(c0 + 16), hi);
       }
       fence_proxy_async();
+      T.lap(3);
       if (leader) {
         tma_store_wait_read1();                 // stores of two chunks ago have read their slot
         if (hist[1] >= 0) mbar_arrive(&in_empty[hist[1]]);
@@ -1000,6 +1006,7 @@ gemm_gate_res_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         tma_store_commit();
       }
       hist[1] = hist[0]; hist[0] = sl;
+      T.lap(4);
     }
     tmem_st_wait();
     if (leader) {
@@ -1031,6 +1038,7 @@ gemm_gate_res_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       t1 += peer_part[r * 2];
       t2 += peer_part[r * 2 + 1];
     }
+    T.lap(5);
     const float inv_n = 1.f / (float)g.N;
     const float mean = t1 * inv_n;
     const float rstd = rsqrtf(fmaxf(t2 * inv_n - mean * mean, 0.f) + ep.ln_eps);
@@ -1061,12 +1069,14 @@ gemm_gate_res_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       uint8_t* so = stg + (it % LN_NBUF) * LN_BOX;
       box_write<bf16>(so, r, v);
       fence_proxy_async();
+      T.lap(6);
       if (leader) tma_store_wait_read1();
       group_bar_sync(grp);
       if (leader) {
         tma_store_2d(&tmLn, so, col0 + c0, m0);
         tma_store_commit();
       }
+      T.lap(7);
     }
     // the "ones" column of a wider pitch (layernorm.cu): turns the weight-gradient GEMM into [dW | bias gradient]
     if (g.ld_ln > g.N && (PAIR || rank == CN - 1) && grp == 0 && row < g.M) {
@@ -1074,6 +1084,7 @@ gemm_gate_res_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       for (int i = 0; i < g.ld_ln - g.N; ++i) orow[i] = __float2bfloat16_rn(i == 0 ? 1.f : 0.f);
     }
     if (leader) tma_store_wait_read0();
+    T.flush(0, 8);
     tc_fence_before();
   }
 
@@ -1493,6 +1504,7 @@ static bool ln_plan(const GemmDesc& d, int num_sms, LnArgs* out, int* cn_out) {
   g.stage_bytes = (int)align_up((size_t)A_BYTES + (size_t)(pair ? max_wc / 2 : max_wc) * BK * 2, 1024);
   g.has_y = d.ep.out2 != nullptr;
   g.ld_ln = d.ep.ld_ln;
+  g.dbg = d.dbg;
   // shared memory: [stages][dedicated residual slots][vectors + partial sums] ... [barriers]
   const int vec_bytes = (int)align_up((size_t)(1 + 3 * LN_MAX_SAMPLES) * g.vec_w * 4 + (EG + 1) * BM * 2 * 4, 1024);
   const int in_box = BM * SLAB * 4, ln_box = BM * SLAB * 2;
@@ -1504,9 +1516,10 @@ static bool ln_plan(const GemmDesc& d, int num_sms, LnArgs* out, int* cn_out) {
     const int pre = std::min(std::min(left / in_box, nch_max), LN_MAX_SLOTS - 1);
     int post = 0;
     if (pre < nch_max) {
-      // the freed operand stages hold the pass-2 staging boxes and the remaining residual slots.  A slot is handed
-      // back two chunks of its group (four chunks) after its own, so a ring that wraps needs at least 5 slots
-      const int room = (st * g.stage_bytes - EG * LN_NBUF * ln_box) / in_box;
+      // the freed operand stages hold the remaining residual slots (pass 1) and then the pass-2 staging boxes: pass 2
+      // starts after every pass-1 store has read its slot, so the two may overlap.  A slot is handed back two chunks
+      // of its group (four chunks) after its own, so a ring that wraps needs at least 5 slots
+      const int room = st * g.stage_bytes / in_box;
       post = std::min(std::min(room, LN_MAX_SLOTS - pre), nch_max - pre);
       if (post < nch_max - pre && post < 5) continue;
       if (post < 1) continue;
