@@ -106,6 +106,10 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> N
     with torch.no_grad():
         for t in list(module.parameters()) + list(module.buffers()):
             dist.broadcast(t, src=src, group=group)
+    # a collective writes the storage without necessarily bumping Tensor._version: rebuild the bf16 operand copies
+    invalidate = getattr(module, "invalidate_weights", None)
+    if invalidate is not None:
+        invalidate()
 
 
 def enable_data_parallel(net, group=None, min_bucket_elems: int = 4_000_000, broadcast: bool = True):
