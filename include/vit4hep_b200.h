@@ -289,6 +289,24 @@ int v4h_postprocess_showers(const float* x, const float* cond, int64_t n, int32_
                             float* e_out, v4h_stream_t s);
 
 /* ------------------------------------------------------------------------------------
+ * Pre-processing of raw showers = the data feed (reference experiments/calochallenge/datasets.py:44-47 applies the
+ * transforms of configs/calochallenge/cfm/calochallenge_ds2.yaml:15-28 forwards, on the CPU, when the dataset is
+ * built; classes in experiments/calochallenge/transforms.py): NormalizeByElayer(eps), ScaleTotalEnergy(factor),
+ * CutValues (identity forwards), ExclusiveLogitTransform(delta, rescale=True), GlobalStandardizeFromFile,
+ * LogEnergy(alpha), ScaleEnergy(e_min, e_max), AddFeaturesToCond, Reshape.
+ * showers (n, voxels): raw energies per voxel; e_inc (n): incident energies; layer_bounds as above.
+ * mean_std: DEVICE float[2].  compute_stats == 0: it holds the (mean, std) that GlobalStandardizeFromFile loaded and
+ * everything happens in one kernel.  compute_stats != 0: the `written == False` branch (transforms.py:55-63) — mean
+ * and unbiased std of the non-saturated features of THIS call are computed on the device (stats: DEVICE double[3]
+ * scratch), written to mean_std, and applied by a second kernel.
+ * x (n, voxels): network-space showers; cond (n, n_layers + 1): the u features then the scaled log incident energy.
+ * ------------------------------------------------------------------------------------ */
+int v4h_preprocess_showers(const float* showers, const float* e_inc, int64_t n, int32_t voxels, int32_t n_layers,
+                           const int32_t* layer_bounds, float eps, float factor, float delta, float alpha, float e_min,
+                           float e_max, float* mean_std, int32_t compute_stats, double* stats, float* x, float* cond,
+                           v4h_stream_t s);
+
+/* ------------------------------------------------------------------------------------
  * Measurement hooks (bench.py): how many kernels the library launched, and per-kernel-class device
  * time from CUDA events recorded on the launching stream around each launch.
  * ------------------------------------------------------------------------------------ */

@@ -233,6 +233,45 @@ def golden_postprocess():
     print("postprocess golden: showers", tuple(x.shape), "nonzero frac", float((x > 0).float().mean()))
 
 
+def golden_preprocess():
+    """The same reference transform objects run FRONT TO BACK on synthetic raw showers, as the dataset constructor
+    does (experiments/calochallenge/datasets.py:44-47), GlobalStandardizeFromFile in its compute-and-write state
+    (transforms.py:55-63; write() replaced by a no-op, it only saves the two scalars)."""
+    import importlib
+    tr = importlib.import_module("experiments.calochallenge.transforms")
+    L, per = 45, 12
+    V = L * per
+    bounds = np.arange(0, V + 1, per)
+    norm = object.__new__(tr.NormalizeByElayer)
+    norm.eps, norm.cut, norm.layer_boundaries, norm.n_layers = 1.0e-10, 0.0, bounds, L
+    gs = object.__new__(tr.GlobalStandardizeFromFile)
+    gs.written, gs.exclude_zeros, gs.eps = False, True, torch.logit(torch.tensor(1.0e-6))
+    gs.write = lambda: None
+    chain = [norm, tr.ScaleTotalEnergy(factor=0.35, n_layers=L), tr.CutValues(cut=1.0e-7, n_layers=L),
+             tr.ExclusiveLogitTransform(delta=1.0e-6, rescale=True), gs, tr.LogEnergy(),
+             tr.ScaleEnergy(e_min=6.907755, e_max=13.815510), tr.AddFeaturesToCond(split_index=V),
+             tr.Reshape(shape=[1, L, 4, 3])]
+    g = torch.Generator().manual_seed(4048)
+    N = 96
+    raw = torch.exp(torch.randn(N, V, generator=g) * 2.0 + 3.0) * (torch.rand(N, V, generator=g) < 0.35)
+    raw = raw.reshape(N, L, per)
+    raw[torch.rand(N, L, generator=g) < 0.15] = 0.0             # empty layers
+    raw[:, -3:][torch.rand(N, 3, generator=g) < 0.5] = 0.0      # and showers that stop early
+    single = torch.rand(N, L, generator=g) < 0.05               # layers with a single hit (normalised value exactly 1)
+    raw[single] = raw[single] * torch.nn.functional.one_hot(torch.tensor(3), per)
+    raw = raw.reshape(N, V).contiguous()
+    e_inc = 10.0 ** (3.0 + 3.0 * torch.rand(N, 1, generator=g))
+    # a calorimeter sees about the incident energy: E_tot / E_inc in (0.3, 1.2), so that u_0 * factor stays below 1
+    raw = raw * (e_inc * (0.3 + 0.9 * torch.rand(N, 1, generator=g)) / raw.sum(1, keepdim=True))
+    x, c = raw.clone(), e_inc.clone()
+    for fn in chain:
+        x, c = fn(x, c, rank=1)
+    np.savez_compressed(os.path.join(OUT, "preprocess_ds2.npz"), showers=raw.numpy(), e_inc=e_inc.numpy(),
+                        bounds=bounds.astype(np.int32), mean=np.float32(gs.mean), std=np.float32(gs.std),
+                        x=x.numpy(), cond=c.numpy())
+    print("preprocess golden: x", tuple(x.shape), "cond", tuple(c.shape), "mean/std", float(gs.mean), float(gs.std))
+
+
 def golden_energy():
     """The reference's ParallelTransformer (nn/cfm/transformer_cfm.py) at a small size, dims_c = 1 and 3: velocity
     for per-sample times, and a CFM.sample_batch solve of the base class (models/base_model.py:220-244)."""
@@ -281,6 +320,7 @@ def main():
     golden_finetune(ref)
     golden_fixed_pos_embed(ref)
     golden_postprocess()
+    golden_preprocess()
     golden_energy()
 
 

@@ -40,12 +40,16 @@ def step():
 for _ in range(5):
     step()
 torch.cuda.synchronize(); dist.barrier()
-with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-    step()
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(4):  # the first profiled steps absorb the ranks' profiler start-up skew; the last one is printed
+        step()
     torch.cuda.synchronize()
 if rank == 0:
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    evs = [e for e in evs if not e.name.startswith(("nccl:", "Optimizer.", "Memcpy", "Memset"))]
     evs.sort(key=lambda e: e.time_range.start)
+    ends = [i for i, e in enumerate(evs) if "adamw_kernel" in e.name]
+    evs = evs[ends[-2] + 1: ends[-1] + 1]       # the last step: after the previous step's optimizer kernel
     t0 = evs[0].time_range.start
     print(f"# one eager data-parallel training step on rank 0 of {world} (ds2, batch 64 per GPU); times in us from the first kernel")
     print(f"# {'start':>9s} {'dur':>8s}  kernel")

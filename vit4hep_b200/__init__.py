@@ -10,5 +10,6 @@ from .cfm import (CFM, CaloChallengeCFM, CaloChallengeCFM_DS1, CaloGANCFM, CaloH
 from .optim import ExponentialMovingAverage, FusedAdamW  # noqa: F401
 from .energy import ParallelTransformer  # noqa: F401
 from .postprocess import FusedReverseTransforms  # noqa: F401
+from .preprocess import FusedForwardTransforms, ShowerDataset  # noqa: F401
 
 __version__ = "0.1.0"

@@ -107,6 +107,8 @@ SIGNATURES = {
     "v4h_energy_forward": (C.c_int, [_vp, C.POINTER(EnergyParams), _vp, _vp, _vp, _i32, _vp, _i64, _vp, _sz, _vp]),
     "v4h_postprocess_showers": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _fl, _fl, _fl, _fl, _fl, _fl, _fl, _fl, _fl,
                                           _fl, _vp, _vp, _vp]),
+    "v4h_preprocess_showers": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _fl, _fl, _fl, _fl, _fl, _fl, _vp, _i32, _vp,
+                                         _vp, _vp, _vp]),
     "v4h_grad_norm_sq": (C.c_int, [_vp, _i64, _vp, _vp]),
     "v4h_adamw_step": (C.c_int, [_vp, _i32, _i64, _vp, _fl, _fl, _fl, _fl, _fl, _fl, _i32, _vp, _vp, _fl, _i32, _vp, _vp]),
     "v4h_ema_update": (C.c_int, [_vp, _i32, _i64, _fl, _i32, _vp, _vp]),

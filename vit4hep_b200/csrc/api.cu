@@ -329,6 +329,19 @@ int v4h_postprocess_showers(const float* x, const float* cond, int64_t n, int32_
                              alpha, eps, norm_cut, out, e_out, (cudaStream_t)s);
 }
 
+// ------------------------------------------------------------------------------------ pre-processing
+int v4h_preprocess_showers(const float* showers, const float* e_inc, int64_t n, int32_t voxels, int32_t n_layers,
+                           const int32_t* layer_bounds, float eps, float factor, float delta, float alpha, float e_min,
+                           float e_max, float* mean_std, int32_t compute_stats, double* stats, float* x, float* cond,
+                           v4h_stream_t s) {
+  V4H_REQUIRE(showers && e_inc && layer_bounds && mean_std && x && cond && n > 0 && voxels > 0,
+              "preprocess_showers: bad arguments");
+  V4H_REQUIRE(!compute_stats || stats, "preprocess_showers: compute_stats needs the double[3] scratch");
+  V4H_REQUIRE(delta >= 0.f && delta < 0.5f && e_max != e_min, "preprocess_showers: bad transform parameters");
+  return preprocess_showers(showers, e_inc, n, voxels, n_layers, layer_bounds, eps, factor, delta, alpha, e_min, e_max,
+                            mean_std, compute_stats, stats, x, cond, (cudaStream_t)s);
+}
+
 // ------------------------------------------------------------------------------------ optimizer
 int v4h_grad_norm_sq(const float* flat, int64_t n, float* out, v4h_stream_t s) {
   V4H_REQUIRE(flat && out && n > 0, "grad_norm_sq: bad arguments");
