@@ -248,6 +248,7 @@ struct AttnArgs {
   int off[8];
   uint32_t dq2_col;
   int pf_stride;     // CTAs resident at a time (L2 prefetch distance); 0 = no prefetch
+  int stages;        // pipelined long-T kernels: shared-memory stages of the streamed operand pair (2 or 3)
 };
 
 struct ALap {  // cycle accounting of thread 0 of each CTA
@@ -802,6 +803,409 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_umma_kernel(const __
 }
 
 
+// ------------------------------------------------------------------------------------------ pipelined long-T backward
+// The two kernels above run load -> MMA -> exponentials -> MMA strictly one after the other, one CTA per SM
+// (ds3, T = 450: 154 TFLOP/s), and the thread that issues the MMAs is also one of the 128 softmax workers: the
+// products of a block are short on flops but long on operand fetches (M = 128, N = 80: 6.5 KB of shared memory per
+// 16-deep step), the tensor queue pushes back, and ~800 cycles of issue per block land on the critical path.
+// The *_pipe variants keep the arithmetic and the tile formats and reorganise the block loop (TMA operands only):
+//   - warp 8 is the ISSUER: one lane requests the TMA loads and issues every MMA; warps 0-7 are WORKERS (warps w
+//     and w + 4 own the same 32 rows / TMEM lane quadrant and split the columns of every tile).  The two sides
+//     meet on mbarriers only (no CTA barrier in the loop);
+//   - the streamed operand pair (K, V for dQ; Q, dO for dK / dV) sits in NS = 2 or 3 shared-memory stages, a stage
+//     is refilled as soon as the accumulating MMAs that read it have completed;
+//   - the score products S / dP alternate between two TMEM buffers: the tensor core works on block j + 1 while
+//     the workers turn block j into dS (and P^T).
+constexpr int PIPE_WORKERS = 256;
+constexpr int PIPE_THREADS = PIPE_WORKERS + 32;
+struct PipeCtl {
+  uint64_t ld[3];     // TMA: stage s holds its operand pair (dQ: its K block)            (issuer -> issuer)
+  uint64_t ldv[2];    // dQ kernel: V stage s
+  uint64_t sbar[2];   // score products of a block are in TMEM buffer u                   (tensor core -> workers)
+  uint64_t sfree[2];  // every worker warp has read TMEM buffer u                         (workers -> issuer)
+  uint64_t dsfull;    // dS (and P^T) of a block are in shared memory                     (workers -> issuer)
+  uint64_t acc;       // accumulating products of a block done: dS / P^T and its stage are free (tensor core -> all)
+  uint32_t tmem_slot;
+};
+__device__ __forceinline__ uint32_t pipe_prologue(PipeCtl* ctl, uint32_t tmem_cols) {
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 3; ++i) mbar_init(&ctl->ld[i], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&ctl->ldv[i], 1); mbar_init(&ctl->sbar[i], 1); mbar_init(&ctl->sfree[i], PIPE_WORKERS / 32); }
+    mbar_init(&ctl->dsfull, PIPE_WORKERS / 32);
+    mbar_init(&ctl->acc, 1);
+    fence_barrier_init();
+  }
+  if ((threadIdx.x >> 5) == 1) tmem_alloc_dyn(&ctl->tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  return ctl->tmem_slot;
+}
+// worker side: this warp has pulled its part of the block's score buffer into registers ...
+__device__ __forceinline__ void pipe_scores_read(PipeCtl* ctl, int blk) {
+  tc_fence_before();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(&ctl->sfree[blk & 1]);
+}
+// ... and has written its part of dS (and P^T) to shared memory
+__device__ __forceinline__ void pipe_worker_done(PipeCtl* ctl) {
+  fence_proxy_async();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(&ctl->dsfull);
+}
+
+template <int DHP>
+__global__ void __launch_bounds__(PIPE_THREADS) attn_bwd_dq_pipe_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                        const __grid_constant__ CUtensorMap tmKV,
+                                                                        const __grid_constant__ CUtensorMap tmdO,
+                                                                        const AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  PipeCtl* ctl = reinterpret_cast<PipeCtl*>(smem);
+  uint8_t* tiles = smem + 1024;
+  const int BN = a.BN, T = a.T, H = a.H, dh = a.dh, nb = a.nblocks;
+  // K (read by S = Q K^T and by dQ += dS K) lives until the block's accumulation is done: 3 stages.  V (read by
+  // dP = dO V^T only) is free as soon as the block's scores are: 2 stages.  Every load is then requested two
+  // blocks before its first use.
+  constexpr int NSK = 3, NSV = 2;
+  float* s_part = reinterpret_cast<float*>(smem + 256);     // [128] half-row partial sums of delta
+  uint8_t* pQ = tiles;
+  uint8_t* pdO = pQ + w_bytes(MT, DHP);
+  uint8_t* pKs = pdO + w_bytes(MT, DHP);
+  uint8_t* pVs = pKs + (size_t)NSK * w_bytes(BN, DHP);
+  uint8_t* sdS_ptr = pVs + (size_t)NSV * w_bytes(BN, DHP);
+  const uint32_t gsS = g8_stride(MT), kv_tile = w_bytes(BN, DHP);
+  const Opnd oQ = opnd_w(smem_u32(pQ), MT), odO = opnd_w(smem_u32(pdO), MT), odS = opnd_g8(smem_u32(sdS_ptr), gsS);
+
+  const int bh = blockIdx.y, b = bh / H, hd = bh % H;
+  const int q0 = blockIdx.x * MT;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const size_t ld = (size_t)3 * H * dh, ldo = (size_t)H * dh;
+
+  ALap L(a.dbg);
+  const uint32_t tmem = pipe_prologue(ctl, a.tmem_cols);
+  const uint32_t tdQ = tmem + 4u * (uint32_t)BN;            // buffer u: S at tmem + 2 u BN, dP at + BN
+  L.lap(0);
+
+  if (warp == PIPE_WORKERS / 32) {
+    // ------------------------------------------------------------------------------------ issuer
+    if ((tid & 31) == 0) {
+      auto load_k = [&](int j) {
+        const int st = j % NSK;
+        mbar_expect_tx(&ctl->ld[st], kv_tile + (j == 0 ? 2 * w_bytes(MT, DHP) : 0u));
+        if (j == 0) {
+          tma_load_w<DHP>(pQ, MT, &tmQ, &ctl->ld[st], hd * dh, q0, b);
+          tma_load_w<DHP>(pdO, MT, &tmdO, &ctl->ld[st], hd * dh, q0, b);
+        }
+        tma_load_w<DHP>(pKs + (size_t)st * kv_tile, BN, &tmKV, &ctl->ld[st], (H + hd) * dh, j * BN, b);
+      };
+      auto load_v = [&](int j) {
+        const int st = j % NSV;
+        mbar_expect_tx(&ctl->ldv[st], kv_tile);
+        tma_load_w<DHP>(pVs + (size_t)st * kv_tile, BN, &tmKV, &ctl->ldv[st], (2 * H + hd) * dh, j * BN, b);
+      };
+      auto issue_scores = [&](int j) {                      // S = Q K^T, dP = dO V^T of block j -> buffer j & 1
+        if (j >= 2) mbar_wait(&ctl->sfree[j & 1], (uint32_t)((j >> 1) - 1) & 1u);
+        mbar_wait(&ctl->ld[j % NSK], (uint32_t)(j / NSK) & 1u);
+        mbar_wait(&ctl->ldv[j % NSV], (uint32_t)(j / NSV) & 1u);
+        tc_fence_after();
+        const uint32_t tS = tmem + (uint32_t)(j & 1) * 2u * (uint32_t)BN;
+        issue_mma_x(tS, oQ, false, opnd_w(smem_u32(pKs + (size_t)(j % NSK) * kv_tile), BN), false, BN, DHP / 16, false);
+        issue_mma_x(tS + (uint32_t)BN, odO, false, opnd_w(smem_u32(pVs + (size_t)(j % NSV) * kv_tile), BN), false, BN,
+                    DHP / 16, false);
+        umma_commit(&ctl->sbar[j & 1]);
+      };
+      for (int j = 0; j < NSK && j < nb; ++j) {  // in the order of first use
+        load_k(j);
+        if (j < NSV) load_v(j);
+      }
+      issue_scores(0);
+      for (int blk = 0; blk < nb; ++blk) {
+        if (blk > 0) {  // dQ += dS K of block blk - 1 has completed: its K stage takes block blk - 1 + NSK
+          mbar_wait(&ctl->acc, (uint32_t)(blk - 1) & 1u);
+          if (blk - 1 + NSK < nb) load_k(blk - 1 + NSK);
+        }
+        if (blk + 1 < nb) issue_scores(blk + 1);
+        if (blk + NSV < nb) {  // dP of this block is complete: its V stage takes block blk + NSV
+          mbar_wait(&ctl->sbar[blk & 1], (uint32_t)(blk >> 1) & 1u);
+          load_v(blk + NSV);
+        }
+        mbar_wait(&ctl->dsfull, (uint32_t)blk & 1u);
+        tc_fence_after();
+        issue_mma_x(tdQ, odS, false, opnd_w(smem_u32(pKs + (size_t)(blk % NSK) * kv_tile), BN), true, DHP, BN / 16, blk > 0);
+        umma_commit(&ctl->acc);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------------------------ workers
+    const int half = warp >> 2, row = (warp & 3) * 32 + (tid & 31);
+    const int nch = BN / 16, ch0 = half ? (nch + 1) / 2 : 0, ch1 = half ? nch : (nch + 1) / 2;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const bf16* dobase = a.d_o + (size_t)b * T * ldo + (size_t)hd * dh;
+    const bf16* obase = a.o + (size_t)b * T * ldo + (size_t)hd * dh;
+    // row statistics: delta = sum_d dO * O (the two warps of a row take half of the head dims each and meet in
+    // shared memory), lse in log2 units
+    const int q = q0 + row;
+    float delta = 0.f, lse2 = 0.f;
+    {
+      constexpr int NC = DHP / 8, C0 = (NC + 1) / 2;
+      const int cb = half ? C0 : 0, ce = half ? NC : C0;
+      float part = 0.f;
+      if (q < T) {
+        const bf16* dor = dobase + (size_t)q * ldo;
+        const bf16* orow = obase + (size_t)q * ldo;
+        uint4 xv[C0], yv[C0];
+#pragma unroll
+        for (int c = 0; c < C0; ++c) {
+          const bool in = cb + c < ce && (cb + c) * 8 < dh;
+          xv[c] = in ? *reinterpret_cast<const uint4*>(dor + (cb + c) * 8) : make_uint4(0, 0, 0, 0);
+          yv[c] = in ? *reinterpret_cast<const uint4*>(orow + (cb + c) * 8) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int c = 0; c < C0; ++c) {
+          const uint32_t xs[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w}, ys[4] = {yv[c].x, yv[c].y, yv[c].z, yv[c].w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 fx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xs[i]));
+            const float2 fy = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ys[i]));
+            part = fmaf(fx.x, fy.x, part);
+            part = fmaf(fx.y, fy.y, part);
+          }
+        }
+        lse2 = a.lse[(size_t)bh * T + q] * 1.4426950408889634f;
+      }
+      if (half) s_part[row] = part;
+      asm volatile("bar.sync 1, %0;" ::"n"(PIPE_WORKERS) : "memory");
+      if (!half) s_part[row] = part = part + s_part[row];
+      asm volatile("bar.sync 1, %0;" ::"n"(PIPE_WORKERS) : "memory");
+      delta = s_part[row];
+      if (!half && q < T) a.delta[(size_t)bh * T + q] = delta;
+    }
+    L.lap(1);
+    for (int blk = 0; blk < nb; ++blk) {
+      const int nvalid = min(BN, T - blk * BN);
+      mbar_wait(&ctl->sbar[blk & 1], (uint32_t)(blk >> 1) & 1u);
+      tc_fence_after();
+      L.lap(2);
+      L.lap(3);
+      const uint32_t tS = tmem + (uint32_t)(blk & 1) * 2u * (uint32_t)BN, tdP = tS + (uint32_t)BN;
+      for (int c0 = ch0 * 16; c0 < ch1 * 16; c0 += 16) {
+        float s[16], dp[16];
+        tmem_ld16(tS + lane_off + c0, s);
+        tmem_ld16(tdP + lane_off + c0, dp);
+        tmem_ld_wait();
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          const float p0 = c0 + i < nvalid ? exp2_fast(fmaf(s[i], a.scale_log2, -lse2)) : 0.f;
+          const float p1 = c0 + i + 1 < nvalid ? exp2_fast(fmaf(s[i + 1], a.scale_log2, -lse2)) : 0.f;
+          w[i / 2] = pack_bf16(p0 * (dp[i] - delta), p1 * (dp[i + 1] - delta));
+        }
+        // dS of the previous block must have been consumed before the first store of this one
+        if (c0 == ch0 * 16 && blk > 0) mbar_wait(&ctl->acc, (uint32_t)(blk - 1) & 1u);
+        const uint32_t dst = odS.base + (uint32_t)(c0 / 8) * gsS + (uint32_t)row * 16u;
+        sts128(dst, w[0], w[1], w[2], w[3]);
+        sts128(dst + gsS, w[4], w[5], w[6], w[7]);
+      }
+      pipe_scores_read(ctl, blk);
+      L.lap(4);
+      pipe_worker_done(ctl);
+      L.lap(5);
+    }
+    mbar_wait(&ctl->acc, (uint32_t)(nb - 1) & 1u);
+    tc_fence_after();
+    L.lap(6);
+    bf16* out = a.dqkv + ((size_t)b * T + min(q, T - 1)) * ld + (size_t)hd * dh;
+    constexpr int OCH = DHP / 16;
+    for (int c0 = (half ? (OCH + 1) / 2 : 0) * 16; c0 < (half ? OCH : (OCH + 1) / 2) * 16; c0 += 16) {
+      float v[16];
+      tmem_ld16(tdQ + lane_off + c0, v);
+      tmem_ld_wait();
+      if (q < T) {
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          if (c0 + 8 * h8 < dh) {
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              w[i] = pack_bf16(v[8 * h8 + 2 * i] * a.scale, v[8 * h8 + 2 * i + 1] * a.scale);
+            *reinterpret_cast<uint4*>(out + c0 + 8 * h8) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+    }
+    L.lap(7);
+  }
+  attn_epilogue(tmem, a.tmem_cols);
+  L.lap(8);
+  L.flush();
+}
+
+template <int DHP>
+__global__ void __launch_bounds__(PIPE_THREADS) attn_bwd_dkv_pipe_kernel(const __grid_constant__ CUtensorMap tmK,
+                                                                         const __grid_constant__ CUtensorMap tmQ,
+                                                                         const __grid_constant__ CUtensorMap tmdO,
+                                                                         const AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  PipeCtl* ctl = reinterpret_cast<PipeCtl*>(smem);
+  const int BQ = a.BN, T = a.T, H = a.H, dh = a.dh, NS = a.stages, nb = a.nblocks;
+  uint8_t* tiles = smem + 3072;
+  uint8_t* pK = tiles;
+  uint8_t* pV = pK + w_bytes(MT, DHP);
+  uint8_t* pQdO = pV + w_bytes(MT, DHP);                     // stage s: Q at + s * 2 * w_bytes(BQ), dO right after
+  uint8_t* sPT_ptr = pQdO + (size_t)NS * 2 * w_bytes(BQ, DHP);
+  uint8_t* sdST_ptr = sPT_ptr + g8_bytes(MT, BQ);
+  float* s_lse = reinterpret_cast<float*>(sdST_ptr + g8_alloc(MT, BQ));  // [nb * BQ] lse * log2(e), +inf for padded queries
+  float* s_delta = s_lse + nb * BQ;                                      // [nb * BQ]
+  const uint32_t gsS = g8_stride(MT), q_stage = 2 * w_bytes(BQ, DHP);
+  const Opnd oK = opnd_w(smem_u32(pK), MT), oV = opnd_w(smem_u32(pV), MT), oPT = opnd_g8(smem_u32(sPT_ptr), gsS),
+             odST = opnd_g8(smem_u32(sdST_ptr), gsS);
+
+  const int bh = blockIdx.y, b = bh / H, hd = bh % H;
+  const int k0 = blockIdx.x * MT;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const size_t ld = (size_t)3 * H * dh;
+
+  ALap L(a.dbg);
+  const uint32_t tmem = pipe_prologue(ctl, a.tmem_cols);
+  L.lap(0);
+  const uint32_t tdV = tmem + 4u * (uint32_t)BQ, tdK = tdV + DHP;  // buffer u: S^T at tmem + 2 u BQ, dP^T at + BQ
+
+  if (warp == PIPE_WORKERS / 32) {
+    // ------------------------------------------------------------------------------------ issuer
+    if ((tid & 31) == 0) {
+      auto load = [&](int j) {
+        const int st = j % NS;
+        uint8_t* pQ = pQdO + (size_t)st * q_stage;
+        mbar_expect_tx(&ctl->ld[st], q_stage + (j == 0 ? 2 * w_bytes(MT, DHP) : 0u));
+        if (j == 0) {
+          tma_load_w<DHP>(pK, MT, &tmK, &ctl->ld[st], (H + hd) * dh, k0, b);
+          tma_load_w<DHP>(pV, MT, &tmK, &ctl->ld[st], (2 * H + hd) * dh, k0, b);
+        }
+        tma_load_w<DHP>(pQ, BQ, &tmQ, &ctl->ld[st], hd * dh, j * BQ, b);
+        tma_load_w<DHP>(pQ + w_bytes(BQ, DHP), BQ, &tmdO, &ctl->ld[st], hd * dh, j * BQ, b);
+      };
+      auto issue_scores = [&](int j) {                       // S^T = K Q^T, dP^T = V dO^T of block j
+        const int st = j % NS;
+        if (j >= 2) mbar_wait(&ctl->sfree[j & 1], (uint32_t)((j >> 1) - 1) & 1u);
+        mbar_wait(&ctl->ld[st], (uint32_t)(j / NS) & 1u);
+        tc_fence_after();
+        const uint32_t qb = smem_u32(pQdO + (size_t)st * q_stage);
+        const uint32_t tS = tmem + (uint32_t)(j & 1) * 2u * (uint32_t)BQ;
+        issue_mma_x(tS, oK, false, opnd_w(qb, BQ), false, BQ, DHP / 16, false);
+        issue_mma_x(tS + (uint32_t)BQ, oV, false, opnd_w(qb + w_bytes(BQ, DHP), BQ), false, BQ, DHP / 16, false);
+        umma_commit(&ctl->sbar[j & 1]);
+      };
+      for (int j = 0; j < NS && j < nb; ++j) load(j);
+      issue_scores(0);
+      for (int blk = 0; blk < nb; ++blk) {
+        if (blk > 0) {  // dV += P^T dO and dK += dS^T Q of block blk - 1 have completed
+          mbar_wait(&ctl->acc, (uint32_t)(blk - 1) & 1u);
+          if (blk - 1 + NS < nb) load(blk - 1 + NS);
+        }
+        if (blk + 1 < nb) issue_scores(blk + 1);
+        mbar_wait(&ctl->dsfull, (uint32_t)blk & 1u);
+        tc_fence_after();
+        const uint32_t qb = smem_u32(pQdO + (size_t)(blk % NS) * q_stage);
+        issue_mma_x(tdV, oPT, false, opnd_w(qb + w_bytes(BQ, DHP), BQ), true, DHP, BQ / 16, blk > 0);
+        issue_mma_x(tdK, odST, false, opnd_w(qb, BQ), true, DHP, BQ / 16, blk > 0);
+        umma_commit(&ctl->acc);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------------------------ workers
+    const int half = warp >> 2, row = (warp & 3) * 32 + (tid & 31);
+    const int nch = BQ / 16, ch0 = half ? (nch + 1) / 2 : 0, ch1 = half ? nch : (nch + 1) / 2;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    // lse / delta of every query of this (sample, head), once
+    for (int i = tid; i < nb * BQ; i += PIPE_WORKERS) {
+      const bool ok = i < T;
+      s_lse[i] = ok ? a.lse[(size_t)bh * T + i] * 1.4426950408889634f : INFINITY;
+      s_delta[i] = ok ? a.delta[(size_t)bh * T + i] : 0.f;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(PIPE_WORKERS) : "memory");
+    L.lap(1);
+    for (int blk = 0; blk < nb; ++blk) {
+      mbar_wait(&ctl->sbar[blk & 1], (uint32_t)(blk >> 1) & 1u);
+      tc_fence_after();
+      L.lap(2);
+      const uint32_t tS = tmem + (uint32_t)(blk & 1) * 2u * (uint32_t)BQ, tdP = tS + (uint32_t)BQ;
+      const float4* l4 = reinterpret_cast<const float4*>(s_lse + blk * BQ);
+      const float4* d4 = reinterpret_cast<const float4*>(s_delta + blk * BQ);
+      for (int c0 = ch0 * 16; c0 < ch1 * 16; c0 += 16) {
+        float s[16], dp[16];
+        tmem_ld16(tS + lane_off + c0, s);
+        tmem_ld16(tdP + lane_off + c0, dp);
+        tmem_ld_wait();
+        float l[16], d[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 lv = l4[c0 / 4 + i], dv = d4[c0 / 4 + i];
+          l[4 * i] = lv.x; l[4 * i + 1] = lv.y; l[4 * i + 2] = lv.z; l[4 * i + 3] = lv.w;
+          d[4 * i] = dv.x; d[4 * i + 1] = dv.y; d[4 * i + 2] = dv.z; d[4 * i + 3] = dv.w;
+        }
+        uint32_t wp[8], wd[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          const float p0 = exp2_fast(fmaf(s[i], a.scale_log2, -l[i]));       // padded query: exp2(-inf) = 0
+          const float p1 = exp2_fast(fmaf(s[i + 1], a.scale_log2, -l[i + 1]));
+          wp[i / 2] = pack_bf16(p0, p1);
+          wd[i / 2] = pack_bf16(p0 * (dp[i] - d[i]), p1 * (dp[i + 1] - d[i + 1]));
+        }
+        // P^T / dS^T of the previous block must have been consumed before the first store of this one
+        if (c0 == ch0 * 16 && blk > 0) mbar_wait(&ctl->acc, (uint32_t)(blk - 1) & 1u);
+        const uint32_t off = (uint32_t)(c0 / 8) * gsS + (uint32_t)row * 16u;
+        sts128(oPT.base + off, wp[0], wp[1], wp[2], wp[3]);
+        sts128(oPT.base + off + gsS, wp[4], wp[5], wp[6], wp[7]);
+        sts128(odST.base + off, wd[0], wd[1], wd[2], wd[3]);
+        sts128(odST.base + off + gsS, wd[4], wd[5], wd[6], wd[7]);
+      }
+      pipe_scores_read(ctl, blk);
+      L.lap(4);
+      pipe_worker_done(ctl);
+      L.lap(5);
+    }
+    mbar_wait(&ctl->acc, (uint32_t)(nb - 1) & 1u);
+    tc_fence_after();
+    L.lap(6);
+
+    const int key = k0 + row;
+    bf16* dkout = a.dqkv + ((size_t)b * T + min(key, T - 1)) * ld + (size_t)H * dh + (size_t)hd * dh;
+    bf16* dvout = dkout + (size_t)H * dh;
+    constexpr int OCH = DHP / 16;
+    for (int c0 = (half ? (OCH + 1) / 2 : 0) * 16; c0 < (half ? OCH : (OCH + 1) / 2) * 16; c0 += 16) {
+      float vk[16], vv[16];
+      tmem_ld16(tdK + lane_off + c0, vk);
+      tmem_ld16(tdV + lane_off + c0, vv);
+      tmem_ld_wait();
+      if (key < T) {
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          if (c0 + 8 * h8 < dh) {
+            uint32_t wk[4], wv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              wk[i] = pack_bf16(vk[8 * h8 + 2 * i] * a.scale, vk[8 * h8 + 2 * i + 1] * a.scale);
+              wv[i] = pack_bf16(vv[8 * h8 + 2 * i], vv[8 * h8 + 2 * i + 1]);
+            }
+            *reinterpret_cast<uint4*>(dkout + c0 + 8 * h8) = make_uint4(wk[0], wk[1], wk[2], wk[3]);
+            *reinterpret_cast<uint4*>(dvout + c0 + 8 * h8) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+          }
+        }
+      }
+    }
+    L.lap(7);
+  }
+  attn_epilogue(tmem, a.tmem_cols);
+  L.lap(8);
+  L.flush();
+}
+
+
 // ------------------------------------------------------------------------------------------ fused backward
 // Short sequences (T <= 160: every key fits one MMA N extent): ONE CTA per (sample, head) computes dQ,
 // dK and dV with S and P evaluated once, in ONE pass over the query rows: rows [0, 128) are the main M
@@ -1173,6 +1577,14 @@ uint32_t pow2_cols(int cols) {
   while ((int)c < cols) c <<= 1;
   return c;
 }
+// A / B measurements: V4H_ATTN_{FWD,DQ,DKV}_CAP shrink the key / query block of the multi-block kernels (smaller
+// tiles -> more CTAs per SM)
+int env_cap(const char* name, int T, int cap) {
+  const char* e = getenv(name);
+  if (!e || T <= 160) return cap;
+  const int v = atoi(e) / 16 * 16;
+  return v >= 16 && v < cap ? v : cap;
+}
 // block length: the fewest blocks of at most `cap` rows, rows rounded up to a multiple of 16
 void pick_block(int T, int cap, int* bn, int* nblocks) {
   const int nb = (int)ceil_div(T, cap);
@@ -1252,7 +1664,16 @@ int fwd_launch_one(AttnArgs a, int B, cudaStream_t s) {
 }
 template <int DHP>
 int fwd_launch(AttnArgs a, int B, cudaStream_t s) {
-  const int cap = std::min(160, 512 - DHP) / 16 * 16;
+  int cap = std::min(160, 512 - DHP) / 16 * 16;
+  if (a.T > cap) {
+    // several key blocks: the block loop is one dependent chain per CTA, so the block is sized for TWO CTAs per SM
+    // (ds3, T = 450: 3 blocks of 160 keys, one CTA per SM, 170 us; 5 blocks of 96, two per SM, 113 us)
+    for (int bn = cap; bn >= 32; bn -= 16) {
+      cap = bn;
+      if (2048 + w_bytes(MT, DHP) + 2 * w_bytes(bn, DHP) + g8_bytes(MT, bn) + 16 <= 113 * 1024) break;
+    }
+  }
+  cap = env_cap("V4H_ATTN_FWD_CAP", a.T, cap);
   pick_block(a.T, cap, &a.BN, &a.nblocks);
   a.tmem_cols = pow2_cols(a.BN + DHP);
   return a.nblocks == 1 ? fwd_launch_one<DHP, true>(a, B, s) : fwd_launch_one<DHP, false>(a, B, s);
@@ -1313,6 +1734,35 @@ bool fused_plan(AttnArgs& f, size_t* smem_bytes) {
   return *smem_bytes <= 227 * 1024;
 }
 
+bool pipe_enabled() {
+  static const int on = [] { const char* e = getenv("V4H_ATTN_PIPE"); return (e && e[0] == '0') ? 0 : 1; }();
+  return on != 0;
+}
+int pipe_stages() {
+  static const int n = [] { const char* e = getenv("V4H_ATTN_PIPE_STAGES"); return (e && e[0] == '3') ? 3 : 2; }();
+  return n;
+}
+// Block length / stage count of a pipelined long-T kernel: `acc_cols` TMEM columns of accumulators next to two
+// buffers of two score tiles (4 BN columns); shared memory = `fixed` + NS stages of BN rows of `row_stage` bytes +
+// `ntiles` thread-written [128][BN] tiles.  The wanted stage count falls back to 2 when 3 leaves less than 64 rows.
+bool pipe_plan(int T, int want_stages, int acc_cols, size_t fixed, size_t row_stage, int ntiles, AttnArgs* out,
+               size_t* smem_bytes) {
+  for (int ns = want_stages; ns >= (want_stages == 1 ? 1 : 2); --ns) {
+    int cap = 0;
+    for (int bn = 128; bn >= 16; bn -= 16) {
+      const size_t smem = fixed + (size_t)ns * bn * row_stage + (size_t)ntiles * g8_bytes(MT, bn) + 16;
+      if (4 * bn + acc_cols <= 512 && smem <= 227 * 1024) { cap = bn; break; }
+    }
+    if (cap == 0 || (ns == 3 && cap < 64)) continue;
+    pick_block(T, cap, &out->BN, &out->nblocks);
+    out->stages = ns;
+    out->tmem_cols = pow2_cols(4 * out->BN + acc_cols);
+    *smem_bytes = fixed + (size_t)ns * out->BN * row_stage + (size_t)ntiles * g8_bytes(MT, out->BN) + 16;
+    return true;
+  }
+  return false;
+}
+
 template <int DHP>
 int bwd_launch(AttnArgs a, int B, cudaStream_t s) {
   AttnArgs f = a;
@@ -1341,9 +1791,48 @@ int bwd_launch(AttnArgs a, int B, cudaStream_t s) {
   dim3 grid((unsigned)ceil_div(a.T, MT), (unsigned)(B * a.H));
   const int use_tma = (attn_tma_enabled() && a.dh == DHP) ? 1 : 0;
   const size_t ldq = (size_t)3 * a.H * a.dh, ldo = (size_t)a.H * a.dh;
+  if (use_tma && a.T > 160 && pipe_enabled()) {  // software-pipelined dQ and dK / dV
+    const int want = pipe_stages();
+    const char* skip = getenv("V4H_ATTN_SKIP");  // timing of one of the two kernels alone (results are then incomplete)
+    if (!(skip && skip[0] == 'q')) {
+      AttnArgs q = a;
+      size_t smem = 0;
+      // dQ: Q, dO tiles + NS x (K, V) blocks + dS; TMEM 2 x (S, dP) + dQ
+      V4H_REQUIRE(pipe_plan(a.T, 1, DHP, 2048 + 2 * (size_t)w_bytes(MT, DHP), 5 * (size_t)w_bytes(1, DHP), 1, &q, &smem),
+                  "attention: no pipelined dQ plan for T = %d", a.T);
+      q.use_tma = 1;
+      static size_t configured = 0;
+      if (smem > configured) { V4H_TRY(set_smem(attn_bwd_dq_pipe_kernel<DHP>, smem)); configured = smem; }
+      CUtensorMap mq, mkv, mdo;
+      V4H_TRY(make_w_map(a.qkv, B, a.T, 3 * a.H * a.dh, ldq, MT, &mq));
+      V4H_TRY(make_w_map(a.qkv, B, a.T, 3 * a.H * a.dh, ldq, q.BN, &mkv));
+      V4H_TRY(make_w_map(a.d_o, B, a.T, a.H * a.dh, ldo, MT, &mdo));
+      V4H_CUDA(launch_pdl(attn_bwd_dq_pipe_kernel<DHP>, dim3(grid), dim3(PIPE_THREADS), smem, s, mq, mkv, mdo, q));
+      V4H_LAUNCH_CHECK();
+    }
+    if (!(skip && skip[0] == 'k')) {
+      AttnArgs k = a;
+      size_t smem = 0;
+      // dK / dV: K, V tiles + NS x (Q, dO) blocks + P^T, dS^T; TMEM 2 x (S^T, dP^T) + dV + dK
+      V4H_REQUIRE(pipe_plan(a.T, want, 2 * DHP, 4096 + 2 * (size_t)w_bytes(MT, DHP), 2 * (size_t)w_bytes(1, DHP), 2, &k, &smem),
+                  "attention: no pipelined dK / dV plan for T = %d", a.T);
+      k.use_tma = 1;
+      smem += 128 + (size_t)k.nblocks * k.BN * 8;  // lse and delta of all queries
+      V4H_REQUIRE(smem <= 227 * 1024, "attention: T = %d is too long for the pipelined dK / dV kernel", a.T);
+      static size_t configured = 0;
+      if (smem > configured) { V4H_TRY(set_smem(attn_bwd_dkv_pipe_kernel<DHP>, smem)); configured = smem; }
+      CUtensorMap mk, mq, mdo;
+      V4H_TRY(make_w_map(a.qkv, B, a.T, 3 * a.H * a.dh, ldq, MT, &mk));
+      V4H_TRY(make_w_map(a.qkv, B, a.T, 3 * a.H * a.dh, ldq, k.BN, &mq));
+      V4H_TRY(make_w_map(a.d_o, B, a.T, a.H * a.dh, ldo, k.BN, &mdo));
+      V4H_CUDA(launch_pdl(attn_bwd_dkv_pipe_kernel<DHP>, dim3(grid), dim3(PIPE_THREADS), smem, s, mk, mq, mdo, k));
+      V4H_LAUNCH_CHECK();
+    }
+    return V4H_OK;
+  }
   {  // dQ + delta
     AttnArgs q = a;
-    const int cap = std::min(160, (512 - DHP) / 2) / 16 * 16;
+    const int cap = env_cap("V4H_ATTN_DQ_CAP", a.T, std::min(160, (512 - DHP) / 2) / 16 * 16);
     pick_block(a.T, cap, &q.BN, &q.nblocks);
     q.tmem_cols = pow2_cols(2 * q.BN + DHP);
     q.use_tma = use_tma;
@@ -1363,7 +1852,7 @@ int bwd_launch(AttnArgs a, int B, cudaStream_t s) {
   {  // dK, dV: K, V tiles of 128 keys; Q / dO stream through in blocks of at most 128 queries (the two [key][q]
      // tiles of P^T and dS^T plus four operand tiles have to fit the 227 KB)
     AttnArgs k = a;
-    const int cap = std::min(128, (512 - 2 * DHP) / 2) / 16 * 16;
+    const int cap = env_cap("V4H_ATTN_DKV_CAP", a.T, std::min(128, (512 - 2 * DHP) / 2) / 16 * 16);
     pick_block(a.T, cap, &k.BN, &k.nblocks);
     k.tmem_cols = pow2_cols(2 * k.BN + 2 * DHP);
     k.use_tma = use_tma;
