@@ -10,9 +10,19 @@ N > 1 is launched by torchrun (one rank per GPU, NCCL); rank 0 prints ONE JSON l
   ``zero_grad``, backward (with the bucketed gradient all-reduce when N > 1), ``clip_grad_norm_(1000)``,
   AdamW step.  ``value`` is timed with the batches already resident in HBM; ``e2e`` feeds pinned HOST
   batches through ``model._batch_loss`` (H2D inside the timed region) and reads the loss back every step.
-* ``roofline`` / ``kernels``: per-kernel-class device time from CUDA events recorded by the library on the
-  launching stream around each launch (v4h_profile_*), in a separate pass of the same steps so that the
-  event overhead does not leak into ``value``.
+* ``roofline``: the tcgen05 GEMM family.  Each of the 12 GEMM call sites of a transformer block (forward, dgrad and
+  wgrad of qkv / proj / fc1 / fc2, with the epilogues the step uses, proj and fc2 including the fused LayerNorm) is
+  replayed 20 times back to back between two CUDA events on the launching stream; ``achieved`` is the flops of one
+  block's 12 GEMMs over the sum of their times (``classes`` lists each).  ``kernels`` is the per-kernel-class device
+  time of whole steps from CUDA events the library records around each launch (v4h_profile_*, eager launches, a
+  separate pass so the event overhead does not leak into ``value``); the brackets overstate a kernel by ~3 us, so
+  ``frac_eager_brackets`` (the same roofline taken from that table) is a lower bound.
+* ``sampling``: BASELINE.json configs[3] as one sharded job — the conditions are split over the ranks, every rank
+  solves its batches of 256 with RK4 3/8 (80 network evaluations), the showers are all-gathered and copied to the
+  host on rank 0 (``e2e``); ``energy_model`` is the energy-ratio network's solve for the same conditions; with its
+  own ``roofline`` and ``cpu_baseline``.
+* ``fp32``: the reference-precision mode (SIMT fp32 kernels) on the same step; ``strong_scaling`` (N > 1): the
+  reference's ``batchsize // world_size`` split of a global batch of 64.
 * ``cpu_baseline`` / ``--impl reference``: the CPU oracle port of the same training step (oracle/, fp32,
   all host threads) on a bounded sample.
 """
@@ -501,6 +511,8 @@ def run_b200(args):
         except Exception as exc:
             fp32 = {"error": repr(exc)[:200]}
 
+    data_feed = measure_data_feed(args, dev, peaks) if rank == 0 and world == 1 and not args.no_sampling else None
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cms, threads = cpu_train_samples_per_s(args.config, args.cpu_batch, args.cpu_steps, 2)
@@ -539,6 +551,7 @@ def run_b200(args):
             "kernels": kernels[:40],
             "strong_scaling": strong,
             "sampling": sampling,
+            "data_feed": data_feed,
             "fp32": fp32,
             "cpu_baseline": cpu,
         }
@@ -551,6 +564,52 @@ def run_b200(args):
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
+
+
+def measure_data_feed(args, dev, peaks):
+    """Pre- and post-processing kernels of the data feed on 25 600 synthetic showers of the
+    configured grid: showers/s and the HBM roofline (algorithmic bytes: every voxel read once and written once)."""
+    from vit4hep_b200 import FusedForwardTransforms
+    try:
+        layers, per = 45, {"ds2": 144, "ds3": 900}[args.config]
+        V, N = layers * per, 25600 if args.config == "ds2" else 6400
+        chain = {"NormalizeByElayer": {}, "ScaleTotalEnergy": {"n_layers": layers, "factor": 0.35},
+                 "CutValues": {"cut": 1.0e-7, "n_layers": layers},
+                 "ExclusiveLogitTransform": {"delta": 1.0e-6, "rescale": True},
+                 "GlobalStandardizeFromFile": {"model_dir": None, "eps": 1.0e-6}, "LogEnergy": {},
+                 "ScaleEnergy": {"e_min": 6.907755, "e_max": 13.815510}, "AddFeaturesToCond": {"split_index": V},
+                 "Reshape": {"shape": [1, V]}}
+        g = torch.Generator(device=dev).manual_seed(11)
+        raw = torch.exp(torch.randn(N, V, device=dev, generator=g) * 2 + 3) * (torch.rand(N, V, device=dev, generator=g) < 0.3)
+        e_inc = 10.0 ** (3 + 3 * torch.rand(N, 1, device=dev, generator=g))
+        raw = raw * (e_inc * 0.8 / raw.sum(1, keepdim=True))
+        fwd = FusedForwardTransforms(chain, range(0, V + 1, per))
+        x, cond = fwd(raw, e_inc)           # first call: statistics from the data (two kernels)
+        rev = fwd.reverse()
+
+        def timed(fn, iters=10):
+            fn(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / iters
+        ms_pre, ms_post = timed(lambda: fwd(raw, e_inc)), timed(lambda: rev(x, cond))
+        back, _ = rev(x, cond)
+        keep = raw > 1e-6 * raw.sum(1, keepdim=True) / layers
+        err = float(((back - raw)[keep]).norm() / raw[keep].norm())
+        gb = 2 * N * V * 4 / 1e9
+        return {"showers": N, "voxels": V,
+                "preprocess": {"showers_per_s": N / (ms_pre * 1e-3), "ms": ms_pre, "gbs": gb / (ms_pre * 1e-3),
+                               "frac_of_hbm": gb / (ms_pre * 1e-3) / peaks["hbm_gbs"]},
+                "postprocess": {"showers_per_s": N / (ms_post * 1e-3), "ms": ms_post, "gbs": gb / (ms_post * 1e-3),
+                                "frac_of_hbm": gb / (ms_post * 1e-3) / peaks["hbm_gbs"]},
+                "round_trip_rel_l2": err,
+                "note": "v4h_preprocess_showers (statistics known: one kernel) / v4h_postprocess_showers, timings include "
+                        "the output allocations of the host classes; 8 B of HBM traffic per voxel"}
+    except Exception as exc:  # secondary measurement
+        return {"error": repr(exc)[:200]}
 
 
 def measure_sampling(args, model, K, world, rank, dev, timed, peaks, lib):
