@@ -1,5 +1,7 @@
 """Device timeline of one data-parallel training step: where the bucketed NCCL all-reduces sit relative to the
-backward kernels (torch.profiler / CUPTI kernel records of rank 0, eager launches so that every kernel is named).
+backward kernels (torch.profiler / CUPTI kernel records of rank 0).  The step is the CUDA graph bench.py replays
+(GraphedTrainStep), so the launches are not host-paced and the ranks do not drift apart under the profiler;
+`--eager` profiles eager launches instead.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         scripts/dp_timeline.py > profiles/r02_dp_timeline_nN.txt
@@ -10,7 +12,7 @@ os.environ.setdefault("NCCL_DEBUG", "WARN")
 import torch
 import torch.distributed as dist
 from torch.profiler import ProfilerActivity, profile
-from vit4hep_b200 import FusedAdamW, configs, dp
+from vit4hep_b200 import FusedAdamW, GraphedTrainStep, configs, dp
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -39,6 +41,11 @@ def step():
 
 for _ in range(5):
     step()
+if "--eager" not in sys.argv:
+    graphed = GraphedTrainStep(model, opt, x, c)
+    step = lambda: graphed.step(x, c)
+    for _ in range(5):
+        step()
 torch.cuda.synchronize(); dist.barrier()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     for _ in range(4):  # the first profiled steps absorb the ranks' profiler start-up skew; the last one is printed
@@ -51,7 +58,7 @@ if rank == 0:
     ends = [i for i, e in enumerate(evs) if "adamw_kernel" in e.name]
     evs = evs[ends[-2] + 1: ends[-1] + 1]       # the last step: after the previous step's optimizer kernel
     t0 = evs[0].time_range.start
-    print(f"# one eager data-parallel training step on rank 0 of {world} (ds2, batch 64 per GPU); times in us from the first kernel")
+    print(f"# one {'eager' if '--eager' in sys.argv else 'graph-replayed'} data-parallel training step on rank 0 of {world} (ds2, batch 64 per GPU); times in us from the first kernel")
     print(f"# {'start':>9s} {'dur':>8s}  kernel")
     nccl_busy, total_end = 0.0, 0.0
     for e in evs:
