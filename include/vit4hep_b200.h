@@ -280,11 +280,12 @@ int v4h_energy_forward(v4h_energy_plan* p, const v4h_energy_params* w, const voi
  * ScaleTotalEnergy(factor), NormalizeByElayer(eps, norm_cut) in ONE kernel.
  * x (n, voxels): sampled showers; cond (n, n_layers + 1): the u features then the scaled log incident energy (the
  * conditions the shape network was sampled with); layer_bounds (n_layers + 1) DEVICE int32 voxel offsets of the
- * calorimeter layers (XMLHandler.GetBinEdges in the reference).  out (n, voxels): energy per voxel; e_out (n):
- * incident energies.
+ * calorimeter layers (XMLHandler.GetBinEdges in the reference); max_layer_voxels: the largest layer (<= 1024 selects
+ * the kernels that keep a layer in registers and touch every voxel once; 0 = unknown, generic two-sweep kernel).
+ * out (n, voxels): energy per voxel; e_out (n): incident energies.
  * ------------------------------------------------------------------------------------ */
 int v4h_postprocess_showers(const float* x, const float* cond, int64_t n, int32_t voxels, int32_t n_layers,
-                            const int32_t* layer_bounds, float mean, float std, float delta, float cut, float factor,
+                            const int32_t* layer_bounds, int32_t max_layer_voxels, float mean, float std, float delta, float cut, float factor,
                             float e_min, float e_max, float alpha, float eps, float norm_cut, float* out,
                             float* e_out, v4h_stream_t s);
 
@@ -302,7 +303,7 @@ int v4h_postprocess_showers(const float* x, const float* cond, int64_t n, int32_
  * x (n, voxels): network-space showers; cond (n, n_layers + 1): the u features then the scaled log incident energy.
  * ------------------------------------------------------------------------------------ */
 int v4h_preprocess_showers(const float* showers, const float* e_inc, int64_t n, int32_t voxels, int32_t n_layers,
-                           const int32_t* layer_bounds, float eps, float factor, float delta, float alpha, float e_min,
+                           const int32_t* layer_bounds, int32_t max_layer_voxels, float eps, float factor, float delta, float alpha, float e_min,
                            float e_max, float* mean_std, int32_t compute_stats, double* stats, float* x, float* cond,
                            v4h_stream_t s);
 

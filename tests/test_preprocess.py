@@ -172,3 +172,30 @@ def test_device_resident_dataset_splits_and_batches(golden_dir):
     assert torch.equal(seen.sort(dim=0).values, full.energy.sort(dim=0).values)
     assert sum(xb.shape[0] for xb, _ in full.batches(20, drop_last=True)) == 80
     assert [xb.shape[0] for xb, _ in full.batches(40, shuffle=False)] == [40, 40, 16]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layers,per", [(5, 900), (3, 1500), (7, 33)])
+def test_fused_chains_for_other_layer_sizes(layers, per):
+    """layers of 900 voxels (ds3: the 32-registers-per-lane kernels), 1500 (generic two-sweep kernels) and a ragged 33:
+    forward and reverse against the oracle, and the round trip"""
+    from vit4hep_b200.preprocess import FusedForwardTransforms
+    V = layers * per
+    bounds = list(range(0, V + 1, per))
+    chain = dict(CHAIN)
+    chain["ScaleTotalEnergy"] = {"n_layers": layers, "factor": 0.35}
+    chain["CutValues"] = {"cut": 1.0e-7, "n_layers": layers}
+    chain["AddFeaturesToCond"] = {"split_index": V}
+    chain["Reshape"] = {"shape": [1, layers, per]}
+    raw, e_inc = _raw(300, bounds, 7)
+    f = FusedForwardTransforms(chain, bounds)
+    x, cond = f(raw.cuda(), e_inc.cuda())
+    xo, co, mean, std = to.forward_chain(raw, e_inc, bounds, shape=[1, layers, per], **PARAMS)
+    assert abs(f.mean - mean) < 1e-5 and abs(f.std - std) < 1e-5
+    assert vo.rel_l2(x.cpu(), xo) < 1e-5 and vo.rel_l2(cond.cpu(), co) < 1e-5
+    back, e = f.reverse()(x, cond)
+    bo, eo = to.reverse_chain(xo, co, bounds, mean=mean, std=std, cut=1.0e-7, **PARAMS)
+    assert vo.rel_l2(e.cpu(), eo) < 1e-5 and vo.rel_l2(back.cpu(), bo) < 1e-4
+    layer_e = raw.reshape(300, layers, per).sum(-1).repeat_interleave(per, dim=1)
+    kept = raw / (layer_e + 1e-10) > 2e-7
+    assert vo.rel_l2(back.cpu()[kept], raw[kept]) < 1e-3

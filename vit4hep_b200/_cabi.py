@@ -105,9 +105,9 @@ SIGNATURES = {
     "v4h_energy_prepare_weights": (C.c_int, [_vp, C.POINTER(EnergyParams), _vp, _vp]),
     "v4h_energy_encode": (C.c_int, [_vp, C.POINTER(EnergyParams), _vp, _vp, _i64, _vp, _sz, _vp]),
     "v4h_energy_forward": (C.c_int, [_vp, C.POINTER(EnergyParams), _vp, _vp, _vp, _i32, _vp, _i64, _vp, _sz, _vp]),
-    "v4h_postprocess_showers": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _fl, _fl, _fl, _fl, _fl, _fl, _fl, _fl, _fl,
+    "v4h_postprocess_showers": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _i32, _fl, _fl, _fl, _fl, _fl, _fl, _fl, _fl, _fl,
                                           _fl, _vp, _vp, _vp]),
-    "v4h_preprocess_showers": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _fl, _fl, _fl, _fl, _fl, _fl, _vp, _i32, _vp,
+    "v4h_preprocess_showers": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _i32, _fl, _fl, _fl, _fl, _fl, _fl, _vp, _i32, _vp,
                                          _vp, _vp, _vp]),
     "v4h_grad_norm_sq": (C.c_int, [_vp, _i64, _vp, _vp]),
     "v4h_adamw_step": (C.c_int, [_vp, _i32, _i64, _vp, _fl, _fl, _fl, _fl, _fl, _fl, _i32, _vp, _vp, _fl, _i32, _vp, _vp]),

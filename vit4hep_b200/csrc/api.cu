@@ -320,25 +320,25 @@ int v4h_energy_forward(v4h_energy_plan* p, const v4h_energy_params* w, const voi
 
 // ------------------------------------------------------------------------------------ post-processing
 int v4h_postprocess_showers(const float* x, const float* cond, int64_t n, int32_t voxels, int32_t n_layers,
-                            const int32_t* layer_bounds, float mean, float std, float delta, float cut, float factor,
+                            const int32_t* layer_bounds, int32_t max_layer_voxels, float mean, float std, float delta, float cut, float factor,
                             float e_min, float e_max, float alpha, float eps, float norm_cut, float* out,
                             float* e_out, v4h_stream_t s) {
   V4H_REQUIRE(x && cond && layer_bounds && out && e_out && n > 0 && voxels > 0, "postprocess_showers: bad arguments");
   V4H_REQUIRE(std != 0.f && factor != 0.f && delta >= 0.f && delta < 0.5f, "postprocess_showers: bad transform parameters");
-  return postprocess_showers(x, cond, n, voxels, n_layers, layer_bounds, mean, std, delta, cut, factor, e_min, e_max,
+  return postprocess_showers(x, cond, n, voxels, n_layers, layer_bounds, max_layer_voxels > 0 ? max_layer_voxels : voxels, mean, std, delta, cut, factor, e_min, e_max,
                              alpha, eps, norm_cut, out, e_out, (cudaStream_t)s);
 }
 
 // ------------------------------------------------------------------------------------ pre-processing
 int v4h_preprocess_showers(const float* showers, const float* e_inc, int64_t n, int32_t voxels, int32_t n_layers,
-                           const int32_t* layer_bounds, float eps, float factor, float delta, float alpha, float e_min,
+                           const int32_t* layer_bounds, int32_t max_layer_voxels, float eps, float factor, float delta, float alpha, float e_min,
                            float e_max, float* mean_std, int32_t compute_stats, double* stats, float* x, float* cond,
                            v4h_stream_t s) {
   V4H_REQUIRE(showers && e_inc && layer_bounds && mean_std && x && cond && n > 0 && voxels > 0,
               "preprocess_showers: bad arguments");
   V4H_REQUIRE(!compute_stats || stats, "preprocess_showers: compute_stats needs the double[3] scratch");
   V4H_REQUIRE(delta >= 0.f && delta < 0.5f && e_max != e_min, "preprocess_showers: bad transform parameters");
-  return preprocess_showers(showers, e_inc, n, voxels, n_layers, layer_bounds, eps, factor, delta, alpha, e_min, e_max,
+  return preprocess_showers(showers, e_inc, n, voxels, n_layers, layer_bounds, max_layer_voxels > 0 ? max_layer_voxels : voxels, eps, factor, delta, alpha, e_min, e_max,
                             mean_std, compute_stats, stats, x, cond, (cudaStream_t)s);
 }
 

@@ -117,14 +117,14 @@ int counter_increment(int* counter, cudaStream_t s);
 
 // postprocess.cu: reverse transform chain of the CaloChallenge ds2 / ds3 shape model, one fused pass
 int postprocess_showers(const float* x, const float* cond, int64_t n, int voxels, int n_layers, const int32_t* bounds_dev,
-                        float mean, float std, float delta, float cut, float factor, float e_min, float e_max, float alpha,
+                        int max_layer, float mean, float std, float delta, float cut, float factor, float e_min, float e_max, float alpha,
                         float eps, float norm_cut, float* out, float* e_out, cudaStream_t s);
 
 // preprocess.cu: forward transform chain of the same model (the data feed), one or two fused passes
 int preprocess_showers(const float* showers, const float* e_inc, int64_t n, int voxels, int n_layers,
-                       const int32_t* bounds_dev, float eps, float factor, float delta, float alpha, float e_min,
-                       float e_max, float* mean_std_dev, int compute_stats, double* stats_dev, float* x, float* cond,
-                       cudaStream_t s);
+                       const int32_t* bounds_dev, int max_layer, float eps, float factor, float delta, float alpha,
+                       float e_min, float e_max, float* mean_std_dev, int compute_stats, double* stats_dev, float* x,
+                       float* cond, cudaStream_t s);
 
 // patchify.cu:  dst[b, j] = src[b, table[j]] staged through shared memory per chunk
 int patch_permute(const float* src, float* dst, const int32_t* table, const int32_t* chunk_bounds,

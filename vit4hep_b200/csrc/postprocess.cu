@@ -44,6 +44,14 @@ __device__ __forceinline__ float voxel_value(float v, const PostArgs& a) {
   return (a.cut != 0.f && z <= a.cut) ? 0.f : z;  // CutValues rev (skipped entirely when cut == 0)
 }
 
+// the same with the two divisions per voxel as reciprocal multiplies (one more rounding each, 1e-7 relative; the IEEE
+// divisions made the kernel ALU-bound at 0.2 of the HBM rate)
+__device__ __forceinline__ float voxel_value_fast(float v, const PostArgs& a, float inv_scale) {
+  const float t = fmaf(v, a.std, a.mean);
+  const float z = (__frcp_rn(1.f + expf(-t)) - a.delta) * inv_scale;
+  return (a.cut != 0.f && z <= a.cut) ? 0.f : z;
+}
+
 __global__ void __launch_bounds__(PP_THREADS) postprocess_kernel(PostArgs a) {
   pdl_wait();
   __shared__ float lsum[PP_MAX_LAYERS];
@@ -100,10 +108,95 @@ __global__ void __launch_bounds__(PP_THREADS) postprocess_kernel(PostArgs a) {
   }
 }
 
+// ---- layers of at most 32 * CAP voxels: the layer energies only depend on the conditions, so they are computed first
+// and ONE sweep does the rest — a warp pulls a whole layer into registers (all loads in flight together), sums,
+// normalises and stores: every voxel is read once and written once.
+template <int CAP>
+__global__ void __launch_bounds__(PP_THREADS) postprocess_reg_kernel(PostArgs a) {
+  pdl_wait();
+  __shared__ float layer_e[PP_MAX_LAYERS];
+  __shared__ float us[PP_MAX_LAYERS];
+  __shared__ int lb[PP_MAX_LAYERS + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = PP_THREADS / 32;
+  for (int i = threadIdx.x; i <= a.n_layers; i += PP_THREADS) lb[i] = a.bounds[i];
+  const float inv_scale = __frcp_rn(a.one_minus_2delta);
+  __syncthreads();
+  for (int s = blockIdx.x; s < a.n; s += gridDim.x) {
+    const float* x = a.x + (size_t)s * a.voxels;
+    const float* c = a.cond + (size_t)s * (a.n_layers + 1);
+    // prefetch this warp's first layer while the layer energies are worked out
+    float v[CAP];
+    int l = warp;
+    if (l < a.n_layers) {
+      const int base = lb[l], len = lb[l + 1] - base;
+#pragma unroll
+      for (int k = 0; k < CAP; ++k) v[k] = lane + 32 * k < len ? __ldg(x + base + lane + 32 * k) : 0.f;
+    }
+    for (int i = threadIdx.x; i < a.n_layers; i += PP_THREADS) {
+      float u = unlogit(c[i], a);
+      if (i == 0) u = __fdiv_rn(u, a.factor);
+      else u = fminf(fmaxf(u, 0.f), 1.f);
+      us[i] = u;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      // ScaleEnergy rev, LogEnergy rev; then the layer energies from the u's (reference transforms.py:363-371)
+      const float e_inc = __fsub_rn(expf(__fadd_rn(__fmul_rn(c[a.n_layers], a.e_scale), a.e_min)), a.alpha);
+      a.e_out[s] = e_inc;
+      const float total = __fmul_rn(e_inc, us[0]);
+      float cum = 0.f;
+      for (int i = 0; i + 1 < a.n_layers; ++i) {
+        const float le = __fmul_rn(__fsub_rn(total, cum), us[i + 1]);
+        layer_e[i] = le;
+        cum = __fadd_rn(cum, le);
+      }
+      layer_e[a.n_layers - 1] = __fsub_rn(total, cum);
+    }
+    __syncthreads();
+    float* out = a.out + (size_t)s * a.voxels;
+    constexpr bool PF = CAP <= 8;  // small layers: the next layer's loads are issued before this one's arithmetic
+    float vn[PF ? CAP : 1];
+    for (; l < a.n_layers; l += nwarps) {
+      const int base = lb[l], len = lb[l + 1] - base;
+      if (PF) {
+        if (l + nwarps < a.n_layers) {
+          const int bn = lb[l + nwarps], ln = lb[l + nwarps + 1] - bn;
+#pragma unroll
+          for (int k = 0; k < CAP; ++k) vn[PF ? k : 0] = lane + 32 * k < ln ? __ldg(x + bn + lane + 32 * k) : 0.f;
+        }
+      } else if (l != warp) {
+#pragma unroll
+        for (int k = 0; k < CAP; ++k) v[k] = lane + 32 * k < len ? __ldg(x + base + lane + 32 * k) : 0.f;
+      }
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < CAP; ++k) {
+        v[k] = lane + 32 * k < len ? voxel_value_fast(v[k], a, inv_scale) : 0.f;
+        acc += v[k];
+      }
+      acc = warp_sum(acc);
+      const float inv_denom = __frcp_rn(__fadd_rn(acc, a.eps)), le = layer_e[l];
+#pragma unroll
+      for (int k = 0; k < CAP; ++k) {
+        if (lane + 32 * k < len) {
+          float z = v[k] * inv_denom;
+          if (z <= a.norm_cut) z = 0.f;
+          out[base + lane + 32 * k] = __fmul_rn(z, le);
+        }
+      }
+      if (PF) {
+#pragma unroll
+        for (int k = 0; k < CAP; ++k) v[k] = vn[PF ? k : 0];
+      }
+    }
+    __syncthreads();  // us / layer_e are rewritten for the next shower
+  }
+}
+
 }  // namespace
 
 int postprocess_showers(const float* x, const float* cond, int64_t n, int voxels, int n_layers, const int32_t* bounds_dev,
-                        float mean, float std, float delta, float cut, float factor, float e_min, float e_max, float alpha,
+                        int max_layer, float mean, float std, float delta, float cut, float factor, float e_min, float e_max, float alpha,
                         float eps, float norm_cut, float* out, float* e_out, cudaStream_t s) {
   V4H_REQUIRE(n_layers >= 1 && n_layers <= PP_MAX_LAYERS, "postprocess: 1 <= n_layers <= %d", PP_MAX_LAYERS);
   PostArgs a;
@@ -112,7 +205,9 @@ int postprocess_showers(const float* x, const float* cond, int64_t n, int voxels
   a.cut = cut; a.factor = factor; a.e_scale = (float)((double)e_max - (double)e_min); a.e_min = e_min; a.alpha = alpha;
   a.eps = eps; a.norm_cut = norm_cut; a.out = out; a.e_out = e_out;
   const int64_t grid = n < 148 * 8 ? n : 148 * 8;
-  V4H_CUDA(launch_pdl(postprocess_kernel, dim3((unsigned)grid), dim3(PP_THREADS), 0, s, a));
+  if (max_layer <= 32 * 8) V4H_CUDA(launch_pdl(postprocess_reg_kernel<8>, dim3((unsigned)grid), dim3(PP_THREADS), 0, s, a));
+  else if (max_layer <= 32 * 32) V4H_CUDA(launch_pdl(postprocess_reg_kernel<32>, dim3((unsigned)grid), dim3(PP_THREADS), 0, s, a));
+  else V4H_CUDA(launch_pdl(postprocess_kernel, dim3((unsigned)grid), dim3(PP_THREADS), 0, s, a));
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }

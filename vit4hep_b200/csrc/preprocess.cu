@@ -41,6 +41,18 @@ __device__ __forceinline__ float logit_rescaled(float v, float one_minus_2delta,
   return logf(__fdiv_rn(z, __fsub_rn(1.f, z)));
 }
 
+// the same with the division as a reciprocal multiply (one more rounding of the ratio: 1e-7 absolute on the logit)
+__device__ __forceinline__ float logit_fast(float v, float one_minus_2delta, float delta) {
+  const float z = __fadd_rn(__fmul_rn(v, one_minus_2delta), delta);
+  return logf(z * __frcp_rn(__fsub_rn(1.f, z)));
+}
+// v / d from r = 1 / d with one residual correction: the correctly rounded quotient (a voxel that holds all of its
+// layer's energy must give exactly 1: one ulp below moves its logit by 0.06)
+__device__ __forceinline__ float div_by(float v, float d, float r) {
+  const float q = v * r;
+  return fmaf(fmaf(-q, d, v), r, q);
+}
+
 __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreArgs a) {
   pdl_wait();
   __shared__ float lsum[PRE_MAX_LAYERS];
@@ -114,6 +126,112 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreArgs a) {
   }
 }
 
+// ---- layers of at most 32 * CAP voxels (ds2: 144, ds3: 900): a warp holds a whole layer in registers, so every voxel
+// is read ONCE (all loads of a layer in flight together) and written once, with one CTA barrier per shower: the u
+// features of shower s are finished by warp 0 while the other warps already sweep shower s + 1 (layer sums double
+// buffered).  The generic kernel above re-reads the voxels in a second sweep and chains one load per lane.
+template <int CAP>
+__global__ void __launch_bounds__(PRE_THREADS) preprocess_reg_kernel(PreArgs a) {
+  pdl_wait();
+  __shared__ float lsum[2][PRE_MAX_LAYERS];
+  __shared__ float rem[PRE_MAX_LAYERS];
+  __shared__ int lb[PRE_MAX_LAYERS + 1];
+  __shared__ double red[3][PRE_THREADS / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = PRE_THREADS / 32;
+  for (int i = threadIdx.x; i <= a.n_layers; i += PRE_THREADS) lb[i] = a.bounds[i];
+  float mean = 0.f, std = 1.f;
+  if (a.mean_std) { mean = a.mean_std[0]; std = a.mean_std[1]; }
+  const float inv_std = __frcp_rn(std);
+  // a zero voxel must land exactly on the lower saturation edge: same function as the voxels go through
+  const float sat = logit_fast(0.f, 1.f, 1.0e-6f);
+  double cnt = 0.0, sum = 0.0, sq = 0.0;
+  __syncthreads();
+  int par = 0;
+  for (int s = blockIdx.x; s < a.n; s += gridDim.x, par ^= 1) {
+    const float* in = a.showers + (size_t)s * a.voxels;
+    float* x = a.x + (size_t)s * a.voxels;
+    // small layers (CAP = 8): the loads of this warp's NEXT layer are issued before the arithmetic of the current
+    // one, otherwise half of the time no load is in flight (2.2 TB/s)
+    constexpr bool PF = CAP <= 8;
+    float v[CAP], vn[PF ? CAP : 1];
+    if (PF && warp < a.n_layers) {
+      const int base = lb[warp], len = lb[warp + 1] - base;
+#pragma unroll
+      for (int k = 0; k < CAP; ++k) v[k] = lane + 32 * k < len ? __ldg(in + base + lane + 32 * k) : 0.f;
+    }
+    for (int l = warp; l < a.n_layers; l += nwarps) {
+      const int base = lb[l], len = lb[l + 1] - base;
+      if (PF) {
+        if (l + nwarps < a.n_layers) {
+          const int bn = lb[l + nwarps], ln = lb[l + nwarps + 1] - bn;
+#pragma unroll
+          for (int k = 0; k < CAP; ++k) vn[PF ? k : 0] = lane + 32 * k < ln ? __ldg(in + bn + lane + 32 * k) : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < CAP; ++k) v[k] = lane + 32 * k < len ? __ldg(in + base + lane + 32 * k) : 0.f;
+      }
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < CAP; ++k) acc += v[k];
+      acc = warp_sum(acc);
+      if (lane == 0) lsum[par][l] = acc;
+      // the three divisions per voxel of the reference's tensor ops through reciprocals (with IEEE divisions the
+      // kernel was ALU-bound at 0.2 of the HBM rate)
+      const float denom = __fadd_rn(acc, a.eps), inv_denom = __frcp_rn(denom);
+#pragma unroll
+      for (int k = 0; k < CAP; ++k) {
+        if (lane + 32 * k < len) {
+          float t = logit_fast(div_by(v[k], denom, inv_denom), a.one_minus_2delta, a.delta);
+          if (a.stats && t > sat && t < -sat) { cnt += 1.0; sum += (double)t; sq += (double)t * (double)t; }
+          if (a.mean_std) t = (t - mean) * inv_std;
+          x[base + lane + 32 * k] = t;
+        }
+      }
+      if (PF) {
+#pragma unroll
+        for (int k = 0; k < CAP; ++k) v[k] = vn[PF ? k : 0];
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // u_0 = E_tot / E_inc (scaled), u_{l+1} = E_l / (sum_{j >= l} E_j + eps)     transforms.py:388-394, :197-199
+      float* c = a.cond + (size_t)s * (a.n_layers + 1);
+      const float e_inc = a.e_inc[s];
+      if (lane == 0) {
+        float r = 0.f;
+        for (int l = a.n_layers - 1; l >= 0; --l) { r = __fadd_rn(r, lsum[par][l]); rem[l] = r; }
+        // LogEnergy, ScaleEnergy                                                    transforms.py:162-163, :222-223
+        c[a.n_layers] = __fdiv_rn(__fsub_rn(logf(__fadd_rn(e_inc, a.alpha)), a.e_min), a.e_scale);
+      }
+      __syncwarp();
+      for (int i = lane; i < a.n_layers; i += 32) {
+        const float u = i == 0 ? __fmul_rn(__fdiv_rn(rem[0], e_inc), a.factor)
+                               : __fdiv_rn(lsum[par][i - 1], __fadd_rn(rem[i - 1], a.eps));
+        float t = logit_fast(u, a.one_minus_2delta, a.delta);
+        if (a.stats && t > sat && t < -sat) { cnt += 1.0; sum += (double)t; sq += (double)t * (double)t; }
+        if (a.mean_std) t = (t - mean) * inv_std;
+        c[i] = t;
+      }
+      __syncwarp();  // rem is rewritten for the next shower
+    }
+  }
+  if (a.stats) {
+    for (int o = 16; o > 0; o >>= 1) {
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    if (lane == 0) { red[0][warp] = cnt; red[1][warp] = sum; red[2][warp] = sq; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      double t = 0.0;
+      for (int w = 0; w < nwarps; ++w) t += red[threadIdx.x][w];
+      atomicAdd(a.stats + threadIdx.x, t);
+    }
+  }
+}
+
 // (count, sum, sum of squares) -> (mean, unbiased std) like Tensor.mean() / Tensor.std() (transforms.py:59-60)
 __global__ void preprocess_stats_kernel(const double* stats, float* mean_std) {
   pdl_wait();
@@ -127,9 +245,16 @@ __global__ void preprocess_stats_kernel(const double* stats, float* mean_std) {
 __global__ void __launch_bounds__(PRE_THREADS) preprocess_standardize_kernel(float* x, int64_t nx, float* cond, int64_t n,
                                                                              int n_layers, const float* mean_std) {
   pdl_wait();
-  const float mean = mean_std[0], std = mean_std[1];
+  const float mean = mean_std[0], std = mean_std[1], inv_std = __frcp_rn(std);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x, tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (int64_t i = tid; i < nx; i += stride) x[i] = __fdiv_rn(__fsub_rn(x[i], mean), std);
+  const int64_t n4 = (reinterpret_cast<uintptr_t>(x) & 15) == 0 ? nx / 4 : 0;
+  float4* x4 = reinterpret_cast<float4*>(x);
+  for (int64_t i = tid; i < n4; i += stride) {
+    float4 v = x4[i];
+    v.x = (v.x - mean) * inv_std; v.y = (v.y - mean) * inv_std; v.z = (v.z - mean) * inv_std; v.w = (v.w - mean) * inv_std;
+    x4[i] = v;
+  }
+  for (int64_t i = 4 * n4 + tid; i < nx; i += stride) x[i] = __fdiv_rn(__fsub_rn(x[i], mean), std);
   const int64_t nc = n * n_layers;
   for (int64_t i = tid; i < nc; i += stride) {
     float* p = cond + (i / n_layers) * (n_layers + 1) + (i % n_layers);
@@ -140,9 +265,9 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_standardize_kernel(flo
 }  // namespace
 
 int preprocess_showers(const float* showers, const float* e_inc, int64_t n, int voxels, int n_layers,
-                       const int32_t* bounds_dev, float eps, float factor, float delta, float alpha, float e_min,
-                       float e_max, float* mean_std_dev, int compute_stats, double* stats_dev, float* x, float* cond,
-                       cudaStream_t s) {
+                       const int32_t* bounds_dev, int max_layer, float eps, float factor, float delta, float alpha,
+                       float e_min, float e_max, float* mean_std_dev, int compute_stats, double* stats_dev, float* x,
+                       float* cond, cudaStream_t s) {
   V4H_REQUIRE(n_layers >= 1 && n_layers <= PRE_MAX_LAYERS, "preprocess: 1 <= n_layers <= %d", PRE_MAX_LAYERS);
   PreArgs a;
   a.showers = showers; a.e_inc = e_inc; a.n = (int)n; a.voxels = voxels; a.n_layers = n_layers; a.bounds = bounds_dev;
@@ -153,7 +278,9 @@ int preprocess_showers(const float* showers, const float* e_inc, int64_t n, int 
   a.x = x; a.cond = cond;
   if (compute_stats) V4H_CUDA(cudaMemsetAsync(stats_dev, 0, 3 * sizeof(double), s));
   const int64_t grid = n < 148 * 8 ? n : 148 * 8;
-  V4H_CUDA(launch_pdl(preprocess_kernel, dim3((unsigned)grid), dim3(PRE_THREADS), 0, s, a));
+  if (max_layer <= 32 * 8) V4H_CUDA(launch_pdl(preprocess_reg_kernel<8>, dim3((unsigned)grid), dim3(PRE_THREADS), 0, s, a));
+  else if (max_layer <= 32 * 32) V4H_CUDA(launch_pdl(preprocess_reg_kernel<32>, dim3((unsigned)grid), dim3(PRE_THREADS), 0, s, a));
+  else V4H_CUDA(launch_pdl(preprocess_kernel, dim3((unsigned)grid), dim3(PRE_THREADS), 0, s, a));
   V4H_LAUNCH_CHECK();
   if (compute_stats) {
     V4H_CUDA(launch_pdl(preprocess_stats_kernel, dim3(1), dim3(1), 0, s, (const double*)stats_dev, mean_std_dev));

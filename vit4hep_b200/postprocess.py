@@ -44,6 +44,7 @@ class FusedReverseTransforms:
         self.bounds = [int(b) for b in layer_boundaries]
         self.n_layers = len(self.bounds) - 1
         self.voxels = self.bounds[-1]
+        self.max_layer = max(b - a for a, b in zip(self.bounds, self.bounds[1:])) if self.n_layers else 0
         if self.bounds[0] != 0 or any(b <= a for a, b in zip(self.bounds, self.bounds[1:])):
             raise ValueError("layer_boundaries must start at 0 and increase")
         nb = kw["NormalizeByElayer"]
@@ -100,7 +101,8 @@ class FusedReverseTransforms:
             self._bounds_dev[dev] = torch.tensor(self.bounds, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             _cabi.check(_cabi.load().v4h_postprocess_showers(
-                x.data_ptr(), c.data_ptr(), N, self.voxels, self.n_layers, self._bounds_dev[dev].data_ptr(), self.mean,
+                x.data_ptr(), c.data_ptr(), N, self.voxels, self.n_layers, self._bounds_dev[dev].data_ptr(), self.max_layer,
+                self.mean,
                 self.std, self.delta, self.cut, self.factor, self.e_min, self.e_max, self.alpha, self.eps, self.norm_cut,
                 out.data_ptr(), e.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
         return out, e

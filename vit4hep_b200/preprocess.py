@@ -83,7 +83,7 @@ class FusedForwardTransforms:
             except FileNotFoundError:
                 pass
         self.mean, self.std = mean, std
-        self._bounds_dev = {}
+        self._bounds_dev, self._ms_dev = {}, {}
 
     @property
     def written(self) -> bool:
@@ -116,12 +116,15 @@ class FusedForwardTransforms:
         if dev not in self._bounds_dev:
             self._bounds_dev[dev] = torch.tensor(self._cfg.bounds, dtype=torch.int32, device=dev)
         compute = not self.written
-        mean_std = torch.tensor([0.0, 1.0] if compute else [self.mean, self.std], dtype=torch.float32, device=dev)
-        stats = torch.zeros(3, dtype=torch.float64, device=dev)
+        if compute or self._ms_dev.get(dev, (None,))[0] != (self.mean, self.std):
+            self._ms_dev[dev] = ((self.mean, self.std), torch.tensor([0.0, 1.0] if compute else [self.mean, self.std],
+                                                                     dtype=torch.float32, device=dev),
+                                 torch.zeros(3, dtype=torch.float64, device=dev))
+        _, mean_std, stats = self._ms_dev[dev]
         c = self._cfg
         with torch.cuda.device(dev):
             _cabi.check(_cabi.load().v4h_preprocess_showers(
-                raw.data_ptr(), e.data_ptr(), N, self.voxels, self.n_layers, self._bounds_dev[dev].data_ptr(), c.eps,
+                raw.data_ptr(), e.data_ptr(), N, self.voxels, self.n_layers, self._bounds_dev[dev].data_ptr(), c.max_layer, c.eps,
                 c.factor, c.delta, c.alpha, c.e_min, c.e_max, mean_std.data_ptr(), int(compute), stats.data_ptr(),
                 x.data_ptr(), cond.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
         if compute:
