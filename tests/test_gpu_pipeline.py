@@ -68,7 +68,9 @@ def test_dataset_training_sampling_postprocessing(dev, tmp_path):
             (first if epoch == 0 else last if epoch == 5 else []).append(loss.item())
     assert all(math.isfinite(v) for v in first + last)
     assert sum(last) / len(last) < 0.9 * sum(first) / len(first), (first, last)   # it learns
-    # the same step as one CUDA graph, fed from the dataset
+    # the same step as one CUDA graph, fed from the dataset (no autograd graph of the eager steps may be alive: its
+    # gradient-accumulation nodes are bound to the default stream)
+    del loss
     x0, c0 = next(train.batches(48, shuffle=False))
     graphed = v4.GraphedTrainStep(model, opt, x0, c0, warmup=1)
     for x, cond in train.batches(48, shuffle=True, drop_last=True, generator=gen):

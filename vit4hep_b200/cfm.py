@@ -397,7 +397,12 @@ class GraphedTrainStep:
 
     Extension for launch-bound regimes (the reference's ``BaseExperiment._step`` issues the same work
     eagerly, experiments/base_experiment.py:555-597).  ``step(x, c)`` copies the batch into the static input
-    buffers (host tensors should be pinned) and returns the static 0-dim loss tensor of the replay."""
+    buffers (host tensors should be pinned) and returns the static 0-dim loss tensor of the replay.
+
+    Construct it before any eager step of the same model on the default stream, or drop every reference to the
+    losses of such steps first: a live autograd graph keeps its gradient-accumulation nodes bound to the stream it was
+    built on, torch would make that (legacy) stream wait on the capture and the capture fails with
+    cudaErrorStreamCaptureImplicit (the usual rule for whole-step CUDA graphs in torch)."""
 
     def __init__(self, model, optimizer, x_example: torch.Tensor, c_example: torch.Tensor, warmup: int = 3):
         dev = getattr(model, "device", None) or next(model.parameters()).device
