@@ -124,6 +124,21 @@ def ds2_setup(config: str):
     return cfg["geom"], dict(cfg["param"])
 
 
+_SHAPES = {"ds2": (135, 48), "ds3": (450, 90)}  # (tokens, patch_dim) of the shipped shape-model configs
+
+
+def workload_config(name: str, batch: int, world: int) -> dict:
+    """The `config` object of the JSON line: the workload only, identical for the B200 arm and the reference arm
+    (how each arm executes it is under `details`)."""
+    tokens, patch_dim = _SHAPES[name]
+    return {"workload": f"CaloChallenge {name} shape CFM-ViT training step (BASELINE.json configs[1]): _batch_loss, "
+                        f"backward, clip_grad_norm(1000), AdamW; batch {batch} per GPU, data-parallel x{world}",
+            "global_batch": batch * world, "per_gpu_batch": batch, "tokens": tokens, "patch_dim": patch_dim,
+            "parallelism": f"dp{world}",
+            "l2": "no explicit flush: the per-step working set (activation workspace ~1 GB + 104 MB fp32 / 52 MB bf16 "
+                  "weights + 8 rotating input batches) exceeds the 126 MB L2"}
+
+
 def rerandomise(net, seed=1, std=0.02):
     """reference init leaves adaLN / output layers at zero (output identically 0): re-draw them so the
     benchmark exercises non-trivial values"""
@@ -177,11 +192,12 @@ def run_reference(args):
     steps, warmup = min(args.steps, 40), min(args.warmup, 3)  # bounded sample: about a second per step
     value, ms, threads = cpu_train_samples_per_s(args.config, batch, steps, warmup)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC.replace("ds2", args.config), "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"CaloChallenge {args.config} shape CFM-ViT training step (CPU oracle port of the "
-                               f"reference path, batch {batch} per step)", "batch_per_step": batch},
+        "config": workload_config(args.config, batch, args.gpus),
+        "details": {"execution": "CPU oracle port of the reference path (oracle/vit_oracle.py, torch fp32 on the host "
+                                 "cores), one process whatever --gpus says", "batch_per_step": batch},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{steps} training steps of batch {batch} (fwd+bwd+clip+AdamW) of the CPU oracle "
                                    f"port, {warmup} warm-up (bounded: --steps {args.steps} --warmup {args.warmup})"},
@@ -526,16 +542,12 @@ def run_b200(args):
             "metric": METRIC.replace("ds2", args.config), "value": value, "unit": UNIT, "n_gpus": world, "steps": S, "warmup": W,
             "ms_per_step": ms / S, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": f"CaloChallenge {args.config} shape CFM-ViT {args.precision} training, "
-                                   f"batch {B} per GPU, data-parallel x{world} (BASELINE.json configs[1])",
-                       "global_batch": B * world, "per_gpu_batch": B, "tokens": geom.tokens,
-                       "patch_dim": geom.patch_dim, "parallelism": f"dp{world}",
-                       "execution": ("one CUDA graph per training step (vit4hep_b200.GraphedTrainStep)"
-                                     if graphed is not None else "eager launches"),
-                       "optimizer": ("torch AdamW(fused) + clip_grad_norm_(1000)" if args.torch_optimizer else
-                                     "vit4hep_b200.FusedAdamW: clip_grad_norm(1000) + AdamW + bf16 weight refresh"),
-                       "l2": "no explicit flush: the per-step working set (activation workspace ~1 GB + 104 MB "
-                             "fp32 / 52 MB bf16 weights + 8 rotating input batches) exceeds the 126 MB L2"},
+            "config": workload_config(args.config, B, world),
+            "details": {"precision": args.precision,
+                        "execution": ("one CUDA graph per training step (vit4hep_b200.GraphedTrainStep)"
+                                      if graphed is not None else "eager launches"),
+                        "optimizer": ("torch AdamW(fused) + clip_grad_norm_(1000)" if args.torch_optimizer else
+                                      "vit4hep_b200.FusedAdamW: clip_grad_norm(1000) + AdamW + bf16 weight refresh")},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / S, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4,
