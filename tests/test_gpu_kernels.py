@@ -66,7 +66,10 @@ def test_simt_gemm_layouts(layout):
 
 @pytest.mark.parametrize("precision,engine", [(0, 0), (1, 0), (1, 1)])
 @pytest.mark.parametrize("B,T,H,dh", [(2, 135, 6, 80), (1, 450, 6, 80), (3, 84, 2, 24), (1, 606, 6, 80), (2, 33, 4, 32),
-                                      (2, 128, 2, 64), (1, 300, 3, 128), (1, 1, 1, 8), (2, 17, 3, 40)])
+                                      (2, 128, 2, 64), (1, 300, 3, 128), (1, 1, 1, 8), (2, 17, 3, 40),
+                                      # long sequences at other head sizes: two-CTA forward blocks and the pipelined
+                                      # dQ / dK-dV kernels (TMA tiles: dh 32, 64), the cp.async path (dh 24, 40)
+                                      (2, 200, 2, 64), (1, 257, 4, 32), (1, 180, 2, 24), (1, 161, 1, 40), (1, 1000, 1, 80)])
 def test_attention_fwd_bwd(precision, engine, B, T, H, dh):
     """engine 0 = SIMT kernels (fp32 mode arithmetic), 1 = tcgen05 / TMEM kernels (bf16 mode)"""
     from vit4hep_b200 import _cabi
