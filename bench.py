@@ -693,6 +693,19 @@ def measure_sampling(args, model, K, world, rank, dev, timed, peaks, lib):
         energy = {"metric": f"{args.config} energy-ratio CFM ODE-sampled vectors/s", "value": total / (ms_en * 1e-3),
                   "unit": "showers/s", "ms_total": ms_en, "batch": SB, "nfe_per_shower": 80,
                   "share_of_pipeline": ms_en / (ms_en + ms)}
+        # the network is launch-latency bound at the reference's sample batch (configs/training/default.yaml:3,
+        # batchsize_sample 256, shared with the shape model): the same job with a sample batch of 4096
+        try:
+            SBL = 4096
+            shard = e - b
+            em.sample_batch(econd[:min(SBL, shard)])
+            if shard > SBL and shard % SBL:
+                em.sample_batch(econd[: shard % SBL])
+            ms_big, _ = timed(lambda i: dp.sample_sharded(em, econd, SBL, gather=False), 1)
+            energy["large_batch"] = {"batch": SBL, "value": total / (ms_big * 1e-3), "ms_total": ms_big,
+                                     "share_of_pipeline": ms_big / (ms_big + ms)}
+        except Exception as exc:
+            energy["large_batch"] = {"error": repr(exc)[:200]}
         del em
     except Exception as exc:  # secondary measurement: never take the main line down
         energy = {"error": repr(exc)[:200]}
