@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 import torch
 
+from oracle import ref_stubs
 from oracle import transforms_oracle as to
 from oracle import vit_oracle as vo
 from tests.test_postprocess import CHAIN
@@ -54,6 +55,64 @@ def test_oracle_forward_then_reverse_restores_the_showers(golden_dir):
     # voxels below the normalised cut (1e-7 of their layer) are dropped by CutValues; the rest comes back
     kept = raw / (raw.reshape(len(raw), 45, -1).sum(-1).repeat_interleave(12, dim=1) + 1e-10) > 2e-7
     assert vo.rel_l2(back[kept], raw[kept]) < 1e-3
+
+
+@pytest.mark.skipif(not ref_stubs.reference_available(), reason="live reference not present")
+def test_oracle_chains_match_the_live_reference_at_ds2_size():
+    """the reference's own transform objects (experiments/calochallenge/transforms.py) at the real ds2 geometry, both
+    directions, against the restatement (the committed golden covers a small geometry)"""
+    ref_stubs.install()
+    import importlib
+    tr = importlib.import_module("experiments.calochallenge.transforms")
+    L, per = 45, 144
+    V = L * per
+    bounds = np.arange(0, V + 1, per)
+    norm = object.__new__(tr.NormalizeByElayer)
+    norm.eps, norm.cut, norm.layer_boundaries, norm.n_layers = 1.0e-10, 0.0, bounds, L
+    gs = object.__new__(tr.GlobalStandardizeFromFile)
+    gs.written, gs.exclude_zeros, gs.eps = False, True, torch.logit(torch.tensor(1.0e-6))
+    gs.write = lambda: None
+    chain = [norm, tr.ScaleTotalEnergy(factor=0.35, n_layers=L), tr.CutValues(cut=1.0e-7, n_layers=L),
+             tr.ExclusiveLogitTransform(delta=1.0e-6, rescale=True), gs, tr.LogEnergy(),
+             tr.ScaleEnergy(e_min=6.907755, e_max=13.815510), tr.AddFeaturesToCond(split_index=V),
+             tr.Reshape(shape=[1, 45, 16, 9])]
+    raw, e_inc = _raw(64, [int(b) for b in bounds], 13)
+    x, c = raw.clone(), e_inc.clone()
+    for fn in chain:
+        x, c = fn(x, c, rank=1)
+    xo, co, mean, std = to.forward_chain(raw, e_inc, [int(b) for b in bounds], shape=[1, 45, 16, 9], **PARAMS)
+    assert abs(mean - float(gs.mean)) < 1e-6 and abs(std - float(gs.std)) < 1e-6
+    assert vo.rel_l2(xo, x) < 1e-6 and vo.rel_l2(co, c) < 1e-6
+    xb, cb = x.clone().squeeze(1), c.clone()
+    for fn in chain[::-1]:
+        xb, cb = fn(xb, cb, rev=True)
+    bo, eo = to.reverse_chain(xo, co, [int(b) for b in bounds], mean=mean, std=std, cut=1.0e-7, **PARAMS)
+    assert vo.rel_l2(bo, xb) < 1e-5 and vo.rel_l2(eo, cb) < 1e-6
+    assert torch.equal(bo == 0, xb == 0)
+
+
+def test_dataset_host_logic_on_cpu_tensors():
+    """splits, indexing and batching of ShowerDataset do not depend on the device (no transform: nothing native runs)"""
+    from vit4hep_b200.preprocess import ShowerDataset
+    g = torch.Generator().manual_seed(0)
+    showers, e = torch.rand(50, 12, generator=g), torch.rand(50, 1, generator=g)
+    full = ShowerDataset.from_arrays(showers.numpy(), e.numpy(), split="full", device="cpu")
+    trn = ShowerDataset.from_arrays(showers, e, train_val_frac=[0.6, 0.2], split="training", device="cpu")
+    val = ShowerDataset.from_arrays(showers, e, train_val_frac=[0.6, 0.2], split="validation", device="cpu")
+    assert (len(full), len(trn), len(val)) == (50, 30, 10)
+    assert torch.equal(trn.layers, showers[:30]) and torch.equal(val.layers, showers[-10:]) and torch.equal(val.energy, e[-10:])
+    assert float(full.max_bounds) == float(showers.max()) and float(full.min_bounds) == float(showers.min())
+    x7, e7 = full[7]
+    assert torch.equal(x7, showers[7]) and torch.equal(e7, e[7])
+    assert [len(xb) for xb, _ in full.batches(16, shuffle=False)] == [16, 16, 16, 2]
+    assert [len(xb) for xb, _ in full.batches(16, shuffle=False, drop_last=True)] == [16, 16, 16]
+    gen = torch.Generator().manual_seed(1)
+    seen = torch.cat([eb for _, eb in full.batches(16, shuffle=True, generator=gen)])
+    assert not torch.equal(seen, e) and torch.equal(seen.sort(0).values, e.sort(0).values)
+    with pytest.raises(ValueError):
+        ShowerDataset.from_arrays(showers, e, split="test", device="cpu")
+    empty = ShowerDataset.from_arrays(showers[:0], e[:0], device="cpu")
+    assert len(empty) == 0 and empty.min_bounds is None and list(empty.batches(4)) == []
 
 
 def test_layer_boundaries_from_xml(tmp_path):

@@ -160,7 +160,9 @@ class ShowerDataset:
         assert split == "full" or train_val_frac[0] + train_val_frac[1] <= 1.0
         self.transform, self.device, self.dtype = transform, torch.device(device), dtype
         layers = torch.as_tensor(showers, dtype=torch.float32).to(self.device, non_blocking=True)
-        energy = torch.as_tensor(energy, dtype=torch.float32).reshape(len(layers), -1).to(self.device, non_blocking=True)
+        energy = torch.as_tensor(energy, dtype=torch.float32)
+        width = energy.numel() // len(layers) if len(layers) else (energy.shape[-1] if energy.dim() > 1 else 1)
+        energy = energy.reshape(len(layers), width).to(self.device, non_blocking=True)
         # pre-process ALL showers before the split, like the reference (the statistics of GlobalStandardizeFromFile
         # are those of the whole file)                                                          datasets.py:44-61
         if transform is not None:
