@@ -258,3 +258,20 @@ def test_fused_chains_for_other_layer_sizes(layers, per):
     layer_e = raw.reshape(300, layers, per).sum(-1).repeat_interleave(per, dim=1)
     kept = raw / (layer_e + 1e-10) > 2e-7
     assert vo.rel_l2(back.cpu()[kept], raw[kept]) < 1e-3
+
+
+@pytest.mark.skipif(not ref_stubs.reference_available(), reason="live reference not present")
+@pytest.mark.parametrize("cfg,voxels,shape", [("calochallenge_ds2.yaml", 6480, [1, 45, 16, 9]),
+                                               ("calochallenge_ds3.yaml", 40500, [1, 45, 50, 18])])
+def test_transform_objects_accept_the_reference_yaml_unchanged(cfg, voxels, shape):
+    """the `data.transforms` mapping of the reference's shipped experiment configs builds both fused chains as it is"""
+    import yaml
+    from vit4hep_b200 import FusedForwardTransforms, FusedReverseTransforms
+    with open(os.path.join(ref_stubs.REFERENCE_ROOT, "configs", "calochallenge", "cfm", cfg)) as fh:
+        transforms = yaml.safe_load(fh)["data"]["transforms"]
+    bounds = list(range(0, voxels + 1, voxels // 45))
+    fwd = FusedForwardTransforms(transforms, bounds, mean=-2.0, std=3.0)
+    rev = FusedReverseTransforms(transforms, bounds, -2.0, 3.0)
+    assert fwd.shape == shape and fwd.voxels == voxels == rev.voxels and fwd.n_layers == 45
+    assert (rev.factor, rev.delta, rev.cut) == (0.35, 1.0e-6, 1.0e-7) and rev.max_layer == voxels // 45
+    assert (fwd.reverse().mean, fwd.reverse().std) == (-2.0, 3.0)
