@@ -152,8 +152,11 @@ def test_forward_transforms_validate_their_configuration(tmp_path):
     assert (f.reverse().mean, f.reverse().std) == (-2.5, 3.0)
     with pytest.raises(RuntimeError):   # no CPU fallback
         f(torch.zeros(2, 540), torch.ones(2, 1))
-    with pytest.raises(ImportError):    # no h5py in this image: the HDF5 entry point says so
+    with pytest.raises(ImportError):    # no h5py in this image: the HDF5 entry points say so
         ShowerDataset("/nonexistent.hdf5")
+    from vit4hep_b200.preprocess import save_hdf5
+    with pytest.raises(ImportError):
+        save_hdf5(str(tmp_path / "samples.hdf5"), torch.zeros(2, 540), torch.ones(2, 1))
 
 
 # --------------------------------------------------------------------------------------------------- GPU

@@ -22,7 +22,7 @@ import torch
 from . import _cabi
 from .postprocess import FusedReverseTransforms
 
-__all__ = ["FusedForwardTransforms", "ShowerDataset", "layer_boundaries_from_xml", "load_hdf5"]
+__all__ = ["FusedForwardTransforms", "ShowerDataset", "layer_boundaries_from_xml", "load_hdf5", "save_hdf5"]
 
 
 def layer_boundaries_from_xml(xml_filename: str, particle_type: str) -> np.ndarray:
@@ -53,6 +53,19 @@ def load_hdf5(hdf5_file: str) -> Tuple[np.ndarray, np.ndarray]:
                           "instead") from e
     with h5py.File(hdf5_file, "r") as f:
         return f["showers"][:], f["incident_energies"][:].reshape(-1, 1)
+
+
+def save_hdf5(hdf5_file: str, showers, incident_energies) -> None:
+    """Write generated showers in the CaloChallenge layout (`showers`, `incident_energies`, gzip), what the reference's
+    ``save_sample`` does (experiments/calochallenge/experiment.py:305-310).  Device tensors are copied to the host."""
+    try:
+        import h5py
+    except ImportError as e:  # pragma: no cover - h5py is not part of this image
+        raise ImportError("writing CaloChallenge HDF5 files needs h5py") from e
+    to_np = lambda a: a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    with h5py.File(hdf5_file, "w") as f:
+        f.create_dataset("incident_energies", data=to_np(incident_energies), compression="gzip")
+        f.create_dataset("showers", data=to_np(showers), compression="gzip")
 
 
 class FusedForwardTransforms:
