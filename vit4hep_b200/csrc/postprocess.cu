@@ -108,88 +108,81 @@ __global__ void __launch_bounds__(PP_THREADS) postprocess_kernel(PostArgs a) {
   }
 }
 
-// ---- layers of at most 32 * CAP voxels: the layer energies only depend on the conditions, so they are computed first
-// and ONE sweep does the rest — a warp pulls a whole layer into registers (all loads in flight together), sums,
-// normalises and stores: every voxel is read once and written once.
-template <int CAP>
-__global__ void __launch_bounds__(PP_THREADS) postprocess_reg_kernel(PostArgs a) {
+// ---- layers of at most 32 * CAP voxels: the layer energies only depend on the conditions, so a first, tiny kernel
+// (one THREAD per shower) works them out and parks each in the output slot of its layer's first voxel; then ONE WARP
+// per (shower, layer) — two adjacent layers at a time when they are small — pulls the layer into registers (all loads
+// in flight together), sums, normalises, scales and stores: every voxel is read once and written once, no CTA barrier,
+// no serial section in the sweep.
+__global__ void __launch_bounds__(PP_THREADS) postprocess_energy_kernel(PostArgs a) {
   pdl_wait();
-  __shared__ float layer_e[PP_MAX_LAYERS];
-  __shared__ float us[PP_MAX_LAYERS];
+  __shared__ int lb[PP_MAX_LAYERS + 1];
+  for (int i = threadIdx.x; i <= a.n_layers; i += PP_THREADS) lb[i] = a.bounds[i];
+  __syncthreads();
+  const int L = a.n_layers;
+  for (int64_t s = (int64_t)blockIdx.x * PP_THREADS + threadIdx.x; s < a.n; s += (int64_t)gridDim.x * PP_THREADS) {
+    const float* c = a.cond + (size_t)s * (L + 1);
+    float* out = a.out + (size_t)s * a.voxels;
+    // ScaleEnergy rev, LogEnergy rev; then the layer energies from the u's (reference transforms.py:363-371)
+    const float e_inc = __fsub_rn(expf(__fadd_rn(__fmul_rn(c[L], a.e_scale), a.e_min)), a.alpha);
+    a.e_out[s] = e_inc;
+    const float total = __fmul_rn(e_inc, __fdiv_rn(unlogit(c[0], a), a.factor));
+    float cum = 0.f;
+    for (int i = 0; i + 1 < L; ++i) {
+      const float u = fminf(fmaxf(unlogit(c[i + 1], a), 0.f), 1.f);
+      const float le = __fmul_rn(__fsub_rn(total, cum), u);
+      out[lb[i]] = le;
+      cum = __fadd_rn(cum, le);
+    }
+    out[lb[L - 1]] = __fsub_rn(total, cum);
+  }
+}
+
+template <int CAP, int G>
+__global__ void __launch_bounds__(PP_THREADS) postprocess_layer_kernel(PostArgs a) {
+  pdl_wait();
   __shared__ int lb[PP_MAX_LAYERS + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = PP_THREADS / 32;
   for (int i = threadIdx.x; i <= a.n_layers; i += PP_THREADS) lb[i] = a.bounds[i];
   const float inv_scale = __frcp_rn(a.one_minus_2delta);
   __syncthreads();
-  for (int s = blockIdx.x; s < a.n; s += gridDim.x) {
-    const float* x = a.x + (size_t)s * a.voxels;
-    const float* c = a.cond + (size_t)s * (a.n_layers + 1);
-    // prefetch this warp's first layer while the layer energies are worked out
-    float v[CAP];
-    int l = warp;
-    if (l < a.n_layers) {
-      const int base = lb[l], len = lb[l + 1] - base;
+  const int64_t ntasks = (int64_t)a.n * a.n_layers, ngroups = (ntasks + G - 1) / G, stride = (int64_t)gridDim.x * nwarps;
+  for (int64_t grp = (int64_t)blockIdx.x * nwarps + warp; grp < ngroups; grp += stride) {
+    float v[G][CAP], le[G];
+    int len[G];
+    float* out[G];
 #pragma unroll
-      for (int k = 0; k < CAP; ++k) v[k] = lane + 32 * k < len ? __ldg(x + base + lane + 32 * k) : 0.f;
-    }
-    for (int i = threadIdx.x; i < a.n_layers; i += PP_THREADS) {
-      float u = unlogit(c[i], a);
-      if (i == 0) u = __fdiv_rn(u, a.factor);
-      else u = fminf(fmaxf(u, 0.f), 1.f);
-      us[i] = u;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      // ScaleEnergy rev, LogEnergy rev; then the layer energies from the u's (reference transforms.py:363-371)
-      const float e_inc = __fsub_rn(expf(__fadd_rn(__fmul_rn(c[a.n_layers], a.e_scale), a.e_min)), a.alpha);
-      a.e_out[s] = e_inc;
-      const float total = __fmul_rn(e_inc, us[0]);
-      float cum = 0.f;
-      for (int i = 0; i + 1 < a.n_layers; ++i) {
-        const float le = __fmul_rn(__fsub_rn(total, cum), us[i + 1]);
-        layer_e[i] = le;
-        cum = __fadd_rn(cum, le);
-      }
-      layer_e[a.n_layers - 1] = __fsub_rn(total, cum);
-    }
-    __syncthreads();
-    float* out = a.out + (size_t)s * a.voxels;
-    constexpr bool PF = CAP <= 8;  // small layers: the next layer's loads are issued before this one's arithmetic
-    float vn[PF ? CAP : 1];
-    for (; l < a.n_layers; l += nwarps) {
-      const int base = lb[l], len = lb[l + 1] - base;
-      if (PF) {
-        if (l + nwarps < a.n_layers) {
-          const int bn = lb[l + nwarps], ln = lb[l + nwarps + 1] - bn;
+    for (int j = 0; j < G; ++j) {
+      const int64_t task = grp * G + j, s = task / a.n_layers;
+      const int l = (int)(task - s * a.n_layers);
+      const int base = lb[l];
+      len[j] = task < ntasks ? lb[l + 1] - base : 0;
+      const float* x = a.x + (size_t)s * a.voxels + base;
+      out[j] = a.out + (size_t)s * a.voxels + base;
 #pragma unroll
-          for (int k = 0; k < CAP; ++k) vn[PF ? k : 0] = lane + 32 * k < ln ? __ldg(x + bn + lane + 32 * k) : 0.f;
-        }
-      } else if (l != warp) {
+      for (int k = 0; k < CAP; ++k) v[j][k] = lane + 32 * k < len[j] ? __ldg(x + lane + 32 * k) : 0.f;
+      // the layer energy parked by postprocess_energy_kernel
+      le[j] = __shfl_sync(0xffffffffu, (lane == 0 && len[j] > 0) ? out[j][0] : 0.f, 0);
+    }
 #pragma unroll
-        for (int k = 0; k < CAP; ++k) v[k] = lane + 32 * k < len ? __ldg(x + base + lane + 32 * k) : 0.f;
-      }
+    for (int j = 0; j < G; ++j) {
+      if (len[j] == 0) break;
       float acc = 0.f;
 #pragma unroll
       for (int k = 0; k < CAP; ++k) {
-        v[k] = lane + 32 * k < len ? voxel_value_fast(v[k], a, inv_scale) : 0.f;
-        acc += v[k];
+        v[j][k] = lane + 32 * k < len[j] ? voxel_value_fast(v[j][k], a, inv_scale) : 0.f;
+        acc += v[j][k];
       }
       acc = warp_sum(acc);
-      const float inv_denom = __frcp_rn(__fadd_rn(acc, a.eps)), le = layer_e[l];
+      const float inv_denom = __frcp_rn(__fadd_rn(acc, a.eps));
 #pragma unroll
       for (int k = 0; k < CAP; ++k) {
-        if (lane + 32 * k < len) {
-          float z = v[k] * inv_denom;
+        if (lane + 32 * k < len[j]) {
+          float z = v[j][k] * inv_denom;
           if (z <= a.norm_cut) z = 0.f;
-          out[base + lane + 32 * k] = __fmul_rn(z, le);
+          out[j][lane + 32 * k] = __fmul_rn(z, le[j]);
         }
       }
-      if (PF) {
-#pragma unroll
-        for (int k = 0; k < CAP; ++k) v[k] = vn[PF ? k : 0];
-      }
     }
-    __syncthreads();  // us / layer_e are rewritten for the next shower
   }
 }
 
@@ -205,9 +198,18 @@ int postprocess_showers(const float* x, const float* cond, int64_t n, int voxels
   a.cut = cut; a.factor = factor; a.e_scale = (float)((double)e_max - (double)e_min); a.e_min = e_min; a.alpha = alpha;
   a.eps = eps; a.norm_cut = norm_cut; a.out = out; a.e_out = e_out;
   const int64_t grid = n < 148 * 8 ? n : 148 * 8;
-  if (max_layer <= 32 * 8) V4H_CUDA(launch_pdl(postprocess_reg_kernel<8>, dim3((unsigned)grid), dim3(PP_THREADS), 0, s, a));
-  else if (max_layer <= 32 * 32) V4H_CUDA(launch_pdl(postprocess_reg_kernel<32>, dim3((unsigned)grid), dim3(PP_THREADS), 0, s, a));
-  else V4H_CUDA(launch_pdl(postprocess_kernel, dim3((unsigned)grid), dim3(PP_THREADS), 0, s, a));
+  if (max_layer <= 32 * 32) {
+    V4H_CUDA(launch_pdl(postprocess_energy_kernel, dim3((unsigned)((n + PP_THREADS - 1) / PP_THREADS)), dim3(PP_THREADS), 0, s, a));
+    V4H_LAUNCH_CHECK();
+    // G = 2 (two adjacent small layers per warp) measured slower at ds2: 0.60 / 0.57 ms against 0.57 / 0.49
+    const int G = 1;
+    const int64_t groups = (n * n_layers + G - 1) / G, want = (groups + PP_THREADS / 32 - 1) / (PP_THREADS / 32);
+    const unsigned grid2 = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+    if (max_layer <= 32 * 8) V4H_CUDA(launch_pdl(postprocess_layer_kernel<8, 1>, dim3(grid2), dim3(PP_THREADS), 0, s, a));
+    else V4H_CUDA(launch_pdl(postprocess_layer_kernel<32, 1>, dim3(grid2), dim3(PP_THREADS), 0, s, a));
+  } else {
+    V4H_CUDA(launch_pdl(postprocess_kernel, dim3((unsigned)grid), dim3(PP_THREADS), 0, s, a));
+  }
   V4H_LAUNCH_CHECK();
   return V4H_OK;
 }

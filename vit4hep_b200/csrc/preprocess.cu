@@ -126,15 +126,32 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreArgs a) {
   }
 }
 
-// ---- layers of at most 32 * CAP voxels (ds2: 144, ds3: 900): a warp holds a whole layer in registers, so every voxel
-// is read ONCE (all loads of a layer in flight together) and written once, with one CTA barrier per shower: the u
-// features of shower s are finished by warp 0 while the other warps already sweep shower s + 1 (layer sums double
-// buffered).  The generic kernel above re-reads the voxels in a second sweep and chains one load per lane.
-template <int CAP>
-__global__ void __launch_bounds__(PRE_THREADS) preprocess_reg_kernel(PreArgs a) {
+// ---- layers of at most 32 * CAP voxels (ds2: 144, ds3: 900): ONE WARP per (shower, layer) keeps the layer in
+// registers, so every voxel is read once (all loads of the layer in flight together) and written once, and nothing
+// in the kernel waits for anything else: no CTA barrier, no serial section (the first version ran one CTA per shower
+// with a barrier and a one-warp tail per shower).  Small layers (G = 2 at CAP = 8) are taken two ADJACENT ones at a
+// time: ten loads per lane in flight over 1.1 KB of contiguous memory.  The layer sums are parked in the shower's row
+// of `cond`; a second, tiny kernel (one THREAD per shower) turns them into the u features in place.  The generic
+// kernel above re-reads the voxels in a second sweep and chains one load per lane.
+__device__ __forceinline__ void stats_reduce(double cnt, double sum, double sq, double* stats, double (*red)[PRE_THREADS / 32]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  }
+  if (lane == 0) { red[0][warp] = cnt; red[1][warp] = sum; red[2][warp] = sq; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int w = 0; w < PRE_THREADS / 32; ++w) t += red[threadIdx.x][w];
+    atomicAdd(stats + threadIdx.x, t);
+  }
+}
+
+template <int CAP, int G>
+__global__ void __launch_bounds__(PRE_THREADS) preprocess_layer_kernel(PreArgs a) {
   pdl_wait();
-  __shared__ float lsum[2][PRE_MAX_LAYERS];
-  __shared__ float rem[PRE_MAX_LAYERS];
   __shared__ int lb[PRE_MAX_LAYERS + 1];
   __shared__ double red[3][PRE_THREADS / 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = PRE_THREADS / 32;
@@ -146,90 +163,80 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_reg_kernel(PreArgs a) 
   const float sat = logit_fast(0.f, 1.f, 1.0e-6f);
   double cnt = 0.0, sum = 0.0, sq = 0.0;
   __syncthreads();
-  int par = 0;
-  for (int s = blockIdx.x; s < a.n; s += gridDim.x, par ^= 1) {
-    const float* in = a.showers + (size_t)s * a.voxels;
-    float* x = a.x + (size_t)s * a.voxels;
-    // small layers (CAP = 8): the loads of this warp's NEXT layer are issued before the arithmetic of the current
-    // one, otherwise half of the time no load is in flight (2.2 TB/s)
-    constexpr bool PF = CAP <= 8;
-    float v[CAP], vn[PF ? CAP : 1];
-    if (PF && warp < a.n_layers) {
-      const int base = lb[warp], len = lb[warp + 1] - base;
+  const int64_t ntasks = (int64_t)a.n * a.n_layers, ngroups = (ntasks + G - 1) / G, stride = (int64_t)gridDim.x * nwarps;
+  for (int64_t grp = (int64_t)blockIdx.x * nwarps + warp; grp < ngroups; grp += stride) {
+    float v[G][CAP];
+    int base[G], len[G];
+    int64_t sh[G];
 #pragma unroll
-      for (int k = 0; k < CAP; ++k) v[k] = lane + 32 * k < len ? __ldg(in + base + lane + 32 * k) : 0.f;
+    for (int j = 0; j < G; ++j) {
+      const int64_t task = grp * G + j;
+      sh[j] = task / a.n_layers;
+      const int l = (int)(task - sh[j] * a.n_layers);
+      base[j] = lb[l];
+      len[j] = task < ntasks ? lb[l + 1] - base[j] : 0;
+      const float* in = a.showers + (size_t)sh[j] * a.voxels + base[j];
+#pragma unroll
+      for (int k = 0; k < CAP; ++k) v[j][k] = lane + 32 * k < len[j] ? __ldg(in + lane + 32 * k) : 0.f;
     }
-    for (int l = warp; l < a.n_layers; l += nwarps) {
-      const int base = lb[l], len = lb[l + 1] - base;
-      if (PF) {
-        if (l + nwarps < a.n_layers) {
-          const int bn = lb[l + nwarps], ln = lb[l + nwarps + 1] - bn;
 #pragma unroll
-          for (int k = 0; k < CAP; ++k) vn[PF ? k : 0] = lane + 32 * k < ln ? __ldg(in + bn + lane + 32 * k) : 0.f;
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < CAP; ++k) v[k] = lane + 32 * k < len ? __ldg(in + base + lane + 32 * k) : 0.f;
-      }
+    for (int j = 0; j < G; ++j) {
+      if (grp * G + j >= ntasks) break;
       float acc = 0.f;
 #pragma unroll
-      for (int k = 0; k < CAP; ++k) acc += v[k];
+      for (int k = 0; k < CAP; ++k) acc += v[j][k];
       acc = warp_sum(acc);
-      if (lane == 0) lsum[par][l] = acc;
+      const int l = (int)(grp * G + j - sh[j] * a.n_layers);
+      if (lane == 0) a.cond[(size_t)sh[j] * (a.n_layers + 1) + l] = acc;  // layer energy, for preprocess_cond_kernel
       // the three divisions per voxel of the reference's tensor ops through reciprocals (with IEEE divisions the
       // kernel was ALU-bound at 0.2 of the HBM rate)
       const float denom = __fadd_rn(acc, a.eps), inv_denom = __frcp_rn(denom);
+      float* x = a.x + (size_t)sh[j] * a.voxels + base[j];
 #pragma unroll
       for (int k = 0; k < CAP; ++k) {
-        if (lane + 32 * k < len) {
-          float t = logit_fast(div_by(v[k], denom, inv_denom), a.one_minus_2delta, a.delta);
+        if (lane + 32 * k < len[j]) {
+          float t = logit_fast(div_by(v[j][k], denom, inv_denom), a.one_minus_2delta, a.delta);
           if (a.stats && t > sat && t < -sat) { cnt += 1.0; sum += (double)t; sq += (double)t * (double)t; }
           if (a.mean_std) t = (t - mean) * inv_std;
-          x[base + lane + 32 * k] = t;
+          x[lane + 32 * k] = t;
         }
       }
-      if (PF) {
-#pragma unroll
-        for (int k = 0; k < CAP; ++k) v[k] = vn[PF ? k : 0];
-      }
-    }
-    __syncthreads();
-    if (warp == 0) {
-      // u_0 = E_tot / E_inc (scaled), u_{l+1} = E_l / (sum_{j >= l} E_j + eps)     transforms.py:388-394, :197-199
-      float* c = a.cond + (size_t)s * (a.n_layers + 1);
-      const float e_inc = a.e_inc[s];
-      if (lane == 0) {
-        float r = 0.f;
-        for (int l = a.n_layers - 1; l >= 0; --l) { r = __fadd_rn(r, lsum[par][l]); rem[l] = r; }
-        // LogEnergy, ScaleEnergy                                                    transforms.py:162-163, :222-223
-        c[a.n_layers] = __fdiv_rn(__fsub_rn(logf(__fadd_rn(e_inc, a.alpha)), a.e_min), a.e_scale);
-      }
-      __syncwarp();
-      for (int i = lane; i < a.n_layers; i += 32) {
-        const float u = i == 0 ? __fmul_rn(__fdiv_rn(rem[0], e_inc), a.factor)
-                               : __fdiv_rn(lsum[par][i - 1], __fadd_rn(rem[i - 1], a.eps));
-        float t = logit_fast(u, a.one_minus_2delta, a.delta);
-        if (a.stats && t > sat && t < -sat) { cnt += 1.0; sum += (double)t; sq += (double)t * (double)t; }
-        if (a.mean_std) t = (t - mean) * inv_std;
-        c[i] = t;
-      }
-      __syncwarp();  // rem is rewritten for the next shower
     }
   }
-  if (a.stats) {
-    for (int o = 16; o > 0; o >>= 1) {
-      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-      sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  if (a.stats) stats_reduce(cnt, sum, sq, a.stats, red);
+}
+
+// one thread per shower: layer energies (parked in cond[s][0 .. L-1]) -> u features, in place from the last layer down;
+// u_0 = E_tot / E_inc (scaled), u_{l+1} = E_l / (sum_{j >= l} E_j + eps)          transforms.py:388-394, :197-199
+__global__ void __launch_bounds__(PRE_THREADS) preprocess_cond_kernel(PreArgs a) {
+  pdl_wait();
+  __shared__ double red[3][PRE_THREADS / 32];
+  float mean = 0.f, std = 1.f;
+  if (a.mean_std) { mean = a.mean_std[0]; std = a.mean_std[1]; }
+  const float inv_std = __frcp_rn(std);
+  const float sat = logit_fast(0.f, 1.f, 1.0e-6f);
+  double cnt = 0.0, sum = 0.0, sq = 0.0;
+  const int L = a.n_layers;
+  for (int64_t s = (int64_t)blockIdx.x * PRE_THREADS + threadIdx.x; s < a.n; s += (int64_t)gridDim.x * PRE_THREADS) {
+    float* c = a.cond + (size_t)s * (L + 1);
+    const float e_inc = a.e_inc[s];
+    auto emit = [&](int i, float u) {
+      float t = logit_fast(u, a.one_minus_2delta, a.delta);
+      if (a.stats && t > sat && t < -sat) { cnt += 1.0; sum += (double)t; sq += (double)t * (double)t; }
+      if (a.mean_std) t = (t - mean) * inv_std;
+      c[i] = t;
+    };
+    float r = c[L - 1];                    // E_{L-1}: part of every suffix sum, gives no u of its own
+    for (int l = L - 2; l >= 0; --l) {
+      const float e_l = c[l];              // read before slot l + 1 (already consumed) is overwritten
+      r = __fadd_rn(r, e_l);
+      emit(l + 1, __fdiv_rn(e_l, __fadd_rn(r, a.eps)));
     }
-    if (lane == 0) { red[0][warp] = cnt; red[1][warp] = sum; red[2][warp] = sq; }
-    __syncthreads();
-    if (threadIdx.x < 3) {
-      double t = 0.0;
-      for (int w = 0; w < nwarps; ++w) t += red[threadIdx.x][w];
-      atomicAdd(a.stats + threadIdx.x, t);
-    }
+    emit(0, __fmul_rn(__fdiv_rn(r, e_inc), a.factor));
+    // LogEnergy, ScaleEnergy                                                        transforms.py:162-163, :222-223
+    c[L] = __fdiv_rn(__fsub_rn(logf(__fadd_rn(e_inc, a.alpha)), a.e_min), a.e_scale);
   }
+  if (a.stats) stats_reduce(cnt, sum, sq, a.stats, red);
 }
 
 // (count, sum, sum of squares) -> (mean, unbiased std) like Tensor.mean() / Tensor.std() (transforms.py:59-60)
@@ -277,10 +284,20 @@ int preprocess_showers(const float* showers, const float* e_inc, int64_t n, int 
   a.stats = compute_stats ? stats_dev : nullptr;
   a.x = x; a.cond = cond;
   if (compute_stats) V4H_CUDA(cudaMemsetAsync(stats_dev, 0, 3 * sizeof(double), s));
-  const int64_t grid = n < 148 * 8 ? n : 148 * 8;
-  if (max_layer <= 32 * 8) V4H_CUDA(launch_pdl(preprocess_reg_kernel<8>, dim3((unsigned)grid), dim3(PRE_THREADS), 0, s, a));
-  else if (max_layer <= 32 * 32) V4H_CUDA(launch_pdl(preprocess_reg_kernel<32>, dim3((unsigned)grid), dim3(PRE_THREADS), 0, s, a));
-  else V4H_CUDA(launch_pdl(preprocess_kernel, dim3((unsigned)grid), dim3(PRE_THREADS), 0, s, a));
+  if (max_layer <= 32 * 32) {
+    // G = 2 (two adjacent small layers per warp) measured slower at ds2: 0.60 / 0.57 ms against 0.57 / 0.49
+    const int G = 1;
+    const int64_t groups = (n * n_layers + G - 1) / G, want = (groups + PRE_THREADS / 32 - 1) / (PRE_THREADS / 32);
+    const unsigned grid = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+    if (max_layer <= 32 * 8) V4H_CUDA(launch_pdl(preprocess_layer_kernel<8, 1>, dim3(grid), dim3(PRE_THREADS), 0, s, a));
+    else V4H_CUDA(launch_pdl(preprocess_layer_kernel<32, 1>, dim3(grid), dim3(PRE_THREADS), 0, s, a));
+    V4H_LAUNCH_CHECK();
+    const unsigned gridc = (unsigned)((n + PRE_THREADS - 1) / PRE_THREADS);
+    V4H_CUDA(launch_pdl(preprocess_cond_kernel, dim3(gridc), dim3(PRE_THREADS), 0, s, a));
+  } else {
+    const int64_t grid = n < 148 * 8 ? n : 148 * 8;
+    V4H_CUDA(launch_pdl(preprocess_kernel, dim3((unsigned)grid), dim3(PRE_THREADS), 0, s, a));
+  }
   V4H_LAUNCH_CHECK();
   if (compute_stats) {
     V4H_CUDA(launch_pdl(preprocess_stats_kernel, dim3(1), dim3(1), 0, s, (const double*)stats_dev, mean_std_dev));
