@@ -277,7 +277,7 @@ int v4h_energy_forward(v4h_energy_plan* p, const v4h_energy_params* w, const voi
  * configs/calochallenge/cfm/calochallenge_ds2.yaml:15-28 applied in reverse; classes in
  * experiments/calochallenge/transforms.py): Reshape, AddFeaturesToCond, ScaleEnergy(e_min, e_max), LogEnergy(alpha),
  * GlobalStandardizeFromFile(mean, std), ExclusiveLogitTransform(delta, rescale=True), CutValues(cut),
- * ScaleTotalEnergy(factor), NormalizeByElayer(eps, norm_cut) in ONE kernel.
+ * ScaleTotalEnergy(factor), NormalizeByElayer(eps, norm_cut), fused: every voxel is read once and written once.
  * x (n, voxels): sampled showers; cond (n, n_layers + 1): the u features then the scaled log incident energy (the
  * conditions the shape network was sampled with); layer_bounds (n_layers + 1) DEVICE int32 voxel offsets of the
  * calorimeter layers (XMLHandler.GetBinEdges in the reference); max_layer_voxels: the largest layer (<= 1024 selects

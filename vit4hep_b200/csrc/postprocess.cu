@@ -4,10 +4,10 @@
 //   Reshape, AddFeaturesToCond, ScaleEnergy, LogEnergy, GlobalStandardizeFromFile, ExclusiveLogitTransform(rescale),
 //   CutValues, ScaleTotalEnergy, NormalizeByElayer        (reference experiments/calochallenge/transforms.py)
 // The reference runs these as ~10 elementwise passes plus two 45-iteration Python loops on the CPU after
-// `.cpu()`; here one CTA per shower does all of it in two sweeps over the voxels (first sweep: per-layer sums of
-// the un-standardised, un-logited, cut voxels; second: the same values normalised per layer and scaled by the
-// layer energies that the u-recursion of NormalizeByElayer gives).  HBM-bound: 4 B read twice (the second read
-// hits L2) + 4 B written per voxel.
+// `.cpu()`; here a one-thread-per-shower kernel derives the layer energies from the conditions (the u-recursion of
+// NormalizeByElayer) and one warp per (shower, layer) does the rest with the layer in registers: un-standardise,
+// un-logit, cut, sum, normalise to unit layer sum, scale to the layer energy (layers longer than 1024 voxels: a
+// generic one-CTA-per-shower kernel with two sweeps).  HBM-bound: 4 B read + 4 B written per voxel.
 #include "kernels.cuh"
 
 namespace v4h {

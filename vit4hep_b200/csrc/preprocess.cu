@@ -4,12 +4,13 @@
 // configs/calochallenge/cfm/calochallenge_ds2.yaml:15-28, classes in experiments/calochallenge/transforms.py):
 //   NormalizeByElayer, ScaleTotalEnergy, CutValues (identity forwards), ExclusiveLogitTransform(rescale),
 //   GlobalStandardizeFromFile, LogEnergy, ScaleEnergy, AddFeaturesToCond, Reshape
-// One CTA per shower: sweep 1 sums the voxels of each layer, one thread turns the layer energies into the u
-// features, sweep 2 writes logit(voxel / layer energy).  GlobalStandardizeFromFile either applies a known
+// One warp per (shower, layer) keeps the layer in registers: it sums the voxels, writes logit(voxel / layer energy)
+// and leaves the layer energy for a one-thread-per-shower kernel that forms the u features (layers longer than 1024
+// voxels: a generic one-CTA-per-shower kernel with two sweeps).  GlobalStandardizeFromFile either applies a known
 // (mean, std) in the same sweep, or — its `written == False` branch, transforms.py:55-63 — the sweep accumulates
 // count / sum / sum of squares of the non-saturated features in fp64, a one-thread kernel turns them into
 // (mean, unbiased std) on the device, and a second elementwise kernel standardises in place.
-// HBM-bound: 4 B read twice (second read from L2) + 4 B written per voxel, + 8 B per voxel for the second kernel.
+// HBM-bound: 4 B read + 4 B written per voxel, + 8 B per voxel for the second kernel.
 #include "kernels.cuh"
 
 namespace v4h {
