@@ -109,6 +109,18 @@ def test_dataset_host_logic_on_cpu_tensors():
     gen = torch.Generator().manual_seed(1)
     seen = torch.cat([eb for _, eb in full.batches(16, shuffle=True, generator=gen)])
     assert not torch.equal(seen, e) and torch.equal(seen.sort(0).values, e.sort(0).values)
+    # data-parallel sharding: same permutation on every rank, disjoint strided shares, equal step counts
+    shares = []
+    for r in range(3):
+        gen = torch.Generator().manual_seed(5)
+        shares.append(torch.cat([eb for _, eb in full.batches(4, shuffle=True, generator=gen, rank=r, world_size=3)]))
+    assert [len(sh) for sh in shares] == [16, 16, 16]                       # 50 -> 48 = 3 x 16
+    both = torch.cat(shares)
+    assert len(torch.unique(both)) == 48 and set(both.flatten().tolist()) <= set(e.flatten().tolist())
+    fixed = [torch.cat([eb for _, eb in full.batches(8, shuffle=False, rank=r, world_size=2)]) for r in range(2)]
+    assert torch.equal(fixed[0], e[0:50:2]) and torch.equal(fixed[1], e[1:50:2])
+    with pytest.raises(ValueError):
+        next(full.batches(4, rank=2, world_size=2))
     with pytest.raises(ValueError):
         ShowerDataset.from_arrays(showers, e, split="test", device="cpu")
     empty = ShowerDataset.from_arrays(showers[:0], e[:0], device="cpu")

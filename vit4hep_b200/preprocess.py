@@ -198,11 +198,26 @@ class ShowerDataset:
         return self.layers[idx], self.energy[idx]
 
     def batches(self, batch_size: int, shuffle: bool = True, drop_last: bool = False,
-                generator: Optional[torch.Generator] = None) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
+                generator: Optional[torch.Generator] = None, rank: int = 0,
+                world_size: int = 1) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
         """One epoch of ``(x, cond)`` batches gathered on the device (the permutation is drawn on the device too;
-        ``generator`` must then be a generator of that device)."""
+        ``generator`` must then be a generator of that device).
+
+        Data-parallel training (``world_size`` > 1): every rank draws the SAME permutation — pass generators seeded
+        alike, as ``DistributedSampler`` does with its epoch seed — and takes the indices ``rank, rank + world_size,
+        ...`` of it; the tail that does not divide by ``world_size`` is dropped so that all ranks run the same
+        number of steps."""
         n = len(self)
-        order = torch.randperm(n, device=self.device, generator=generator) if shuffle else None
+        if not 0 <= rank < world_size:
+            raise ValueError(f"rank {rank} outside world_size {world_size}")
+        if world_size > 1 or shuffle:
+            order = (torch.randperm(n, device=self.device, generator=generator) if shuffle
+                     else torch.arange(n, device=self.device))
+            if world_size > 1:
+                order = order[: n - n % world_size][rank::world_size]
+        else:
+            order = None
+        n = n if order is None else len(order)
         stop = n - (n % batch_size) if drop_last else n
         for lo in range(0, stop, batch_size):
             hi = min(lo + batch_size, n)
