@@ -418,8 +418,17 @@ class GraphedTrainStep:
         torch.cuda.current_stream(dev).wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         # relaxed: the optimizer may allocate a pinned job table, the autograd thread runs the backward
-        with torch.cuda.graph(self.graph, capture_error_mode="relaxed"):
-            self.loss = self._eager()
+        try:
+            with torch.cuda.graph(self.graph, capture_error_mode="relaxed"):
+                self.loss = self._eager()
+        except RuntimeError as e:  # torch.AcceleratorError is a RuntimeError
+            if "capture" in str(e).lower():
+                raise RuntimeError(
+                    "GraphedTrainStep: the CUDA-graph capture of the training step failed. The usual cause is an autograd "
+                    "graph of an earlier EAGER step of this model that is still alive (e.g. a `loss` tensor still "
+                    "referenced): its gradient-accumulation nodes are bound to the stream that step ran on. Drop those "
+                    "references (del loss) or build the GraphedTrainStep before the first eager step.") from e
+            raise
 
     def _eager(self):
         self.optimizer.zero_grad(set_to_none=True)
